@@ -1,0 +1,260 @@
+"""ctypes loader for the CPU oracle -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  The product package (cmax_slam_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libcmax_oracle.so")
+_REF = os.path.join(_HERE, "_ref", "libref_basalt.so")
+
+EVENT_DTYPE = np.dtype(
+    [("x", "<u2"), ("y", "<u2"), ("sec", "<u4"), ("nsec", "<u4"), ("polarity", "u1"), ("pad", "u1", (3,))]
+)
+assert EVENT_DTYPE.itemsize == 16
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int32)
+
+
+class FeArgs(C.Structure):
+    _fields_ = [("events", C.c_void_p), ("n_events", C.c_int64), ("t_ref_sec", C.c_double),
+                ("lut_xyz", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("batch_size", C.c_int32), ("blur_sigma", C.c_double), ("contrast_measure", C.c_int32)]
+
+
+class FeOut(C.Structure):
+    _fields_ = [("contrast", C.c_double), ("grad", C.c_double * 3), ("iwe", C.c_void_p),
+                ("deriv", C.c_void_p), ("iwe_raw", C.c_void_p), ("deriv_raw", C.c_void_p),
+                ("cells", C.c_void_p), ("n_inbounds", C.c_int64)]
+
+
+class BeArgs(C.Structure):
+    _fields_ = [("events", C.c_void_p), ("n_events", C.c_int64), ("lut_xyz", C.c_void_p),
+                ("sensor_width", C.c_int32), ("sensor_height", C.c_int32),
+                ("pano_width", C.c_int32), ("pano_height", C.c_int32),
+                ("knots_xyzw", C.c_void_p), ("n_knots", C.c_int32),
+                ("t0_ns", C.c_int64), ("dt_ns", C.c_int64), ("spline_order", C.c_int32),
+                ("n_fixed", C.c_int32), ("tnext_sec", C.c_uint32), ("tnext_nsec", C.c_uint32),
+                ("IGp", C.c_void_p), ("alpha", C.c_double),
+                ("batch_size", C.c_int32), ("event_sample_rate", C.c_int32),
+                ("blur_sigma", C.c_double), ("contrast_measure", C.c_int32)]
+
+
+class BeOut(C.Structure):
+    _fields_ = [("contrast", C.c_double), ("grad", C.c_void_p), ("iwe", C.c_void_p),
+                ("bands", C.c_void_p), ("bands_raw", C.c_void_p), ("il_old", C.c_void_p),
+                ("il_new", C.c_void_p), ("cells", C.c_void_p), ("n_inbounds", C.c_int64)]
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(
+            os.path.join(_HERE, "cmax_oracle.cpp")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CXX": "g++"})
+    return _LIB
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.orc_fe_eval.restype = C.c_int
+        L.orc_fe_eval.argtypes = [C.POINTER(FeArgs), _dp, C.c_int, C.POINTER(FeOut)]
+        L.orc_fe_eval_batch.restype = C.c_int
+        L.orc_fe_eval_batch.argtypes = [C.POINTER(FeArgs), _dp, C.c_int, C.c_int, _dp, _dp, C.c_int]
+        L.orc_be_eval.restype = C.c_int
+        L.orc_be_eval.argtypes = [C.POINTER(BeArgs), _dp, C.c_int, C.POINTER(BeOut)]
+        L.orc_update_alpha.restype = C.c_double
+        L.orc_update_alpha.argtypes = [_fp, _fp, C.c_int64]
+        L.orc_gaussian_kernel.restype = C.c_int
+        L.orc_gaussian_kernel.argtypes = [C.c_double, _fp]
+        L.orc_gaussian_blur.restype = None
+        L.orc_gaussian_blur.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.orc_mean_stddev.restype = None
+        L.orc_mean_stddev.argtypes = [_fp, C.c_int64, _dp, _dp]
+        L.orc_so3_spline_eval.restype = C.c_int
+        L.orc_so3_spline_eval.argtypes = [C.c_int, _dp, C.c_int, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _ip, _dp]
+        L.orc_so3_exp.argtypes = [_dp, _dp]
+        L.orc_so3_log.argtypes = [_dp, _dp]
+        L.orc_batch_mid_time.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)] * 2
+        L.orc_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def have_ref():
+    return os.path.exists(_REF)
+
+
+def ref():
+    """The REAL basalt/Sophus code of the reference (oracle/_ref), or None."""
+    global _ref
+    if _ref is None and have_ref():
+        L = C.CDLL(_REF)
+        L.ref_so3_spline_eval.restype = C.c_int
+        L.ref_so3_spline_eval.argtypes = [C.c_int, _dp, C.c_int, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _ip, _dp]
+        L.ref_so3_exp.argtypes = [_dp, _dp]
+        L.ref_so3_log.argtypes = [_dp, _dp]
+        L.ref_knot_update.argtypes = [_dp, _dp, _dp]
+        L.ref_left_jacobians.argtypes = [_dp, _dp, _dp]
+        _ref = L
+    return _ref
+
+
+def _p(a, t=C.c_void_p):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def fe_args(events, t_ref_sec, lut, W, H, K4, batch_size=100, blur_sigma=1.0, measure=0):
+    events = np.ascontiguousarray(events)
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    a = FeArgs(events.ctypes.data, len(events), float(t_ref_sec), lut.ctypes.data, W, H,
+               K4[0], K4[1], K4[2], K4[3], batch_size, blur_sigma, measure)
+    a._keep = (events, lut)
+    return a
+
+
+def fe_eval(args, omega, want_grad=True, images=False, cells=False):
+    """Returns dict(contrast, grad, [iwe, deriv, iwe_raw, deriv_raw], [cells], n_inbounds)."""
+    W, H = args.width, args.height
+    o = FeOut()
+    res = {}
+    if images:
+        res["iwe"] = np.zeros((H, W), np.float32)
+        res["iwe_raw"] = np.zeros((H, W), np.float32)
+        o.iwe, o.iwe_raw = res["iwe"].ctypes.data, res["iwe_raw"].ctypes.data
+        if want_grad:
+            res["deriv"] = np.zeros((H, W, 3), np.float32)
+            res["deriv_raw"] = np.zeros((H, W, 3), np.float32)
+            o.deriv, o.deriv_raw = res["deriv"].ctypes.data, res["deriv_raw"].ctypes.data
+    if cells:
+        res["cells"] = np.zeros(args.n_events, np.int32)
+        o.cells = res["cells"].ctypes.data
+    om = np.ascontiguousarray(omega, dtype=np.float64)
+    rc = lib().orc_fe_eval(C.byref(args), _d(om), int(want_grad), C.byref(o))
+    if rc != 0:
+        raise RuntimeError("oracle: " + lib().orc_last_error().decode())
+    res["contrast"] = o.contrast
+    res["grad"] = np.array(list(o.grad)) if want_grad else None
+    res["n_inbounds"] = o.n_inbounds
+    return res
+
+
+def fe_eval_batch(args, omegas, want_grad=True, n_threads=1):
+    om = np.ascontiguousarray(omegas, dtype=np.float64).reshape(-1, 3)
+    k = om.shape[0]
+    c = np.zeros(k)
+    g = np.zeros((k, 3))
+    rc = lib().orc_fe_eval_batch(C.byref(args), _d(om), k, int(want_grad), _d(c), _d(g), n_threads)
+    if rc != 0:
+        raise RuntimeError("oracle: " + lib().orc_last_error().decode())
+    return c, (g if want_grad else None)
+
+
+def be_args(events, lut, SW, SH, PW, PH, knots_xyzw, t0_ns, dt_ns, order, n_fixed, tnext, IGp=None,
+            alpha=0.0, batch_size=100, sample_rate=1, blur_sigma=1.0, measure=0):
+    events = np.ascontiguousarray(events)
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    knots = np.ascontiguousarray(knots_xyzw, dtype=np.float64)
+    igp = None if IGp is None else np.ascontiguousarray(IGp, dtype=np.float32)
+    a = BeArgs(events.ctypes.data, len(events), lut.ctypes.data, SW, SH, PW, PH, knots.ctypes.data,
+               knots.shape[0], int(t0_ns), int(dt_ns), order, n_fixed, int(tnext[0]), int(tnext[1]),
+               None if igp is None else igp.ctypes.data, float(alpha), batch_size, sample_rate,
+               blur_sigma, measure)
+    a._keep = (events, lut, knots, igp)
+    return a
+
+
+def be_eval(args, x=None, want_grad=True, images=False, cells=False):
+    W, H = args.pano_width, args.pano_height
+    P = 3 * (args.n_knots - args.n_fixed)
+    o = BeOut()
+    res = {}
+    g = np.zeros(max(P, 1))
+    if want_grad:
+        o.grad = g.ctypes.data
+    if images:
+        for k in ("iwe", "il_old", "il_new"):
+            res[k] = np.zeros((H, W), np.float32)
+            setattr(o, k, res[k].ctypes.data)
+        if want_grad:
+            res["bands"] = np.zeros((P, H, W), np.float32)
+            res["bands_raw"] = np.zeros((P, H, W), np.float32)
+            o.bands, o.bands_raw = res["bands"].ctypes.data, res["bands_raw"].ctypes.data
+    if cells:
+        res["cells"] = np.zeros(args.n_events, np.int32)
+        o.cells = res["cells"].ctypes.data
+    xx = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+    rc = lib().orc_be_eval(C.byref(args), None if xx is None else _d(xx), int(want_grad), C.byref(o))
+    if rc != 0:
+        raise RuntimeError("oracle: " + lib().orc_last_error().decode())
+    res["contrast"] = o.contrast
+    res["grad"] = g[:P].copy() if want_grad else None
+    res["n_inbounds"] = o.n_inbounds
+    return res
+
+
+def gaussian_blur(img, sigma):
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    H, W = img.shape[:2]
+    Cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty_like(img)
+    lib().orc_gaussian_blur(img.ctypes.data_as(_fp), out.ctypes.data_as(_fp), W, H, Cn, float(sigma))
+    return out
+
+
+def gaussian_kernel(sigma):
+    t = np.zeros(64, np.float32)
+    k = lib().orc_gaussian_kernel(float(sigma), t.ctypes.data_as(_fp))
+    return t[:k].copy()
+
+
+def mean_stddev(img):
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    m, s = C.c_double(), C.c_double()
+    lib().orc_mean_stddev(img.ctypes.data_as(_fp), img.size, C.byref(m), C.byref(s))
+    return m.value, s.value
+
+
+def _spline_eval(fn, order, knots, t0_ns, dt_ns, t_ns, want_J=True):
+    knots = np.ascontiguousarray(knots, dtype=np.float64)
+    q = np.zeros(4)
+    R = np.zeros(9)
+    J = np.zeros(9 * order)
+    idx = C.c_int32(0)
+    rc = fn(order, _d(knots), knots.shape[0], int(t0_ns), int(dt_ns), int(t_ns), _d(q), _d(R),
+            C.byref(idx), _d(J) if want_J else None)
+    if rc != 0:
+        return None
+    return q, R.reshape(3, 3), idx.value, J.reshape(order, 3, 3)
+
+
+def spline_eval(order, knots, t0_ns, dt_ns, t_ns, want_J=True):
+    return _spline_eval(lib().orc_so3_spline_eval, order, knots, t0_ns, dt_ns, t_ns, want_J)
+
+
+def ref_spline_eval(order, knots, t0_ns, dt_ns, t_ns, want_J=True):
+    return _spline_eval(ref().ref_so3_spline_eval, order, knots, t0_ns, dt_ns, t_ns, want_J)
+
+
+def update_alpha(IGp, IL):
+    a = np.ascontiguousarray(IGp, dtype=np.float32)
+    b = np.ascontiguousarray(IL, dtype=np.float32)
+    return lib().orc_update_alpha(a.ctypes.data_as(_fp), b.ctypes.data_as(_fp), a.size)
