@@ -1,0 +1,120 @@
+"""ctypes binding of libcmax_b200.so (include/cmax_b200.h).  No CPU fallback: if the library is
+missing or there is no CUDA device the product fails loudly."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+K_NAMES = ["zero", "fe_scatter", "fe_gather", "blur_reduce", "adjoint_blur", "be_poses", "be_scatter",
+           "be_gather", "be_grad_reduce", "misc"]
+K_COUNT = len(K_NAMES)
+
+GRAD_DENSE, GRAD_ADJOINT = 0, 1
+CONTRAST_VARIANCE, CONTRAST_MEAN_SQUARE = 0, 1
+
+ERR = {-1: "CMAXB_ERR_INVALID", -2: "CMAXB_ERR_CUDA", -3: "CMAXB_ERR_EVENT_RANGE", -4: "CMAXB_ERR_TIME_ORDER",
+       -5: "CMAXB_ERR_SPLINE_RANGE", -6: "CMAXB_ERR_STATE"}
+
+
+class CmaxbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERR.get(code, code)}: {msg}")
+        self.code = code
+
+
+class FeCfg(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("lut_xyz", C.c_void_p), ("blur_sigma", C.c_double), ("batch_size", C.c_int32),
+                ("contrast_measure", C.c_int32), ("grad_mode", C.c_int32), ("device", C.c_int32),
+                ("stream", C.c_void_p), ("max_hypotheses", C.c_int32)]
+
+
+class BeCfg(C.Structure):
+    _fields_ = [("sensor_width", C.c_int32), ("sensor_height", C.c_int32), ("lut_xyz", C.c_void_p),
+                ("pano_width", C.c_int32), ("pano_height", C.c_int32), ("blur_sigma", C.c_double),
+                ("batch_size", C.c_int32), ("event_sample_rate", C.c_int32), ("spline_order", C.c_int32),
+                ("contrast_measure", C.c_int32), ("grad_mode", C.c_int32), ("device", C.c_int32),
+                ("stream", C.c_void_p)]
+
+
+class BeWindow(C.Structure):
+    _fields_ = [("events", C.c_void_p), ("n_events", C.c_size_t), ("knots_xyzw", C.c_void_p),
+                ("n_knots", C.c_int32), ("t0_ns", C.c_int64), ("dt_ns", C.c_int64), ("n_fixed", C.c_int32),
+                ("tnext_sec", C.c_uint32), ("tnext_nsec", C.c_uint32), ("IGp", C.c_void_p), ("alpha", C.c_double)]
+
+
+# every symbol include/cmax_b200.h declares
+EXPORTS = [
+    "cmaxb_fe_create", "cmaxb_fe_destroy", "cmaxb_fe_set_packet", "cmaxb_fe_eval", "cmaxb_fe_eval_batch",
+    "cmaxb_fe_eval_launch", "cmaxb_fe_eval_fetch", "cmaxb_fe_get_iwe", "cmaxb_fe_get_deriv", "cmaxb_fe_get_cells",
+    "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_get_alpha",
+    "cmaxb_be_get_il", "cmaxb_be_get_iwe", "cmaxb_be_get_bands", "cmaxb_be_get_cells", "cmaxb_be_get_poses",
+    "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
+    "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
+]
+
+_lib = None
+
+
+def lib():
+    """Load (building if needed) libcmax_b200.so.  Raises if it cannot be had -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    L = C.CDLL(path)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    L.cmaxb_fe_create.argtypes = [C.POINTER(FeCfg), C.POINTER(vp)]
+    L.cmaxb_fe_destroy.argtypes = [vp]
+    L.cmaxb_fe_destroy.restype = None
+    L.cmaxb_fe_set_packet.argtypes = [vp, vp, C.c_size_t, C.c_double]
+    L.cmaxb_fe_eval.argtypes = [vp, dp, dp, dp]
+    L.cmaxb_fe_eval_batch.argtypes = [vp, dp, C.c_int, dp, dp]
+    L.cmaxb_fe_eval_launch.argtypes = [vp, dp, C.c_int, C.c_int]
+    L.cmaxb_fe_eval_fetch.argtypes = [vp, dp, dp]
+    L.cmaxb_fe_get_iwe.argtypes = [vp, dp, C.c_int, vp]
+    L.cmaxb_fe_get_deriv.argtypes = [vp, dp, C.c_int, vp]
+    L.cmaxb_fe_get_cells.argtypes = [vp, dp, vp]
+    L.cmaxb_last_error.restype = C.c_char_p
+    L.cmaxb_launch_count.restype = C.c_uint64
+    L.cmaxb_kernel_name.restype = C.c_char_p
+    L.cmaxb_kernel_name.argtypes = [C.c_int]
+    L.cmaxb_fe_profile.argtypes = [vp, C.c_int]
+    L.cmaxb_fe_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
+    if not hasattr(L, "cmaxb_be_create"):
+        raise RuntimeError("libcmax_b200.so is stale (no back-end symbols): rebuild with cmax_slam_b200/build.py --force")
+    L.cmaxb_be_create.argtypes = [C.POINTER(BeCfg), C.POINTER(vp)]
+    L.cmaxb_be_destroy.argtypes = [vp]
+    L.cmaxb_be_destroy.restype = None
+    L.cmaxb_be_set_window.argtypes = [vp, C.POINTER(BeWindow)]
+    L.cmaxb_be_eval.argtypes = [vp, dp, C.c_int, dp, dp]
+    L.cmaxb_be_get_alpha.argtypes = [vp, dp]
+    L.cmaxb_be_get_il.argtypes = [vp, dp, C.c_int, vp, vp]
+    L.cmaxb_be_get_iwe.argtypes = [vp, dp, C.c_int, C.c_int, vp]
+    L.cmaxb_be_get_bands.argtypes = [vp, dp, C.c_int, C.c_int, vp]
+    L.cmaxb_be_get_cells.argtypes = [vp, dp, C.c_int, vp]
+    L.cmaxb_be_get_poses.argtypes = [vp, dp, C.c_int, C.POINTER(C.c_int64), vp, vp, vp, C.c_int64]
+    L.cmaxb_be_profile.argtypes = [vp, C.c_int]
+    L.cmaxb_be_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise CmaxbError(rc, lib().cmaxb_last_error().decode())
+
+
+def dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def launch_count():
+    return int(lib().cmaxb_launch_count())
+
+
+def device_count():
+    return int(lib().cmaxb_device_count())

@@ -1,0 +1,151 @@
+"""Host-side mirror of the reference's back-end cost interface over the C ABI.
+
+Reference surface mirrored:
+  EventWarper::computeImageOfWarpedEvents        src/backend/event_pano_warper.cpp:167-231
+  cmax_slam::computeContrast (global)            src/backend/global_focus_funcs.cpp:52-80
+  global_contrast_fdf / _f / _df (GSL callbacks) src/backend/global_optim_contrast_gsl_analytical.cpp:17-81
+  PoseGraphOptimizer::copyAndUpdateTraj           src/backend/pose_graph_optimizer.cpp:239-242
+All arithmetic happens in libcmax_b200.so on the GPU; this module only marshals pointers.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _capi
+from ._capi import GRAD_ADJOINT, GRAD_DENSE, CmaxbError  # noqa: F401
+
+
+class EventWarperCMax:
+    """Device-resident back-end contrast functor for one sliding window at a time."""
+
+    def __init__(self, sensor_width, sensor_height, lut_xyz, pano_width, pano_height, blur_sigma=1.0,
+                 event_batch_size=100, event_sample_rate=1, spline_order=2, contrast_measure=0,
+                 grad_mode=GRAD_ADJOINT, device=0, stream=None):
+        self._L = _capi.lib()
+        lut = np.ascontiguousarray(lut_xyz, dtype=np.float64).reshape(-1, 3)
+        if lut.shape[0] != sensor_width * sensor_height:
+            raise ValueError("lut_xyz must hold sensor_width*sensor_height bearing vectors")
+        cfg = _capi.BeCfg(sensor_width, sensor_height, lut.ctypes.data, pano_width, pano_height, float(blur_sigma),
+                          int(event_batch_size), int(event_sample_rate), int(spline_order), int(contrast_measure),
+                          int(grad_mode), int(device), None if stream is None else C.c_void_p(int(stream)))
+        h = C.c_void_p()
+        _capi.check(self._L.cmaxb_be_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.pano_width, self.pano_height = pano_width, pano_height
+        self.spline_order = spline_order
+        self.n_events = 0
+        self.n_params = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cmaxb_be_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_window(self, events, knots_xyzw, t0_ns, dt_ns, n_fixed, t_next_win_beg, IGp=None, alpha=float("nan")):
+        """events: 16-byte dvs_msgs::Event records of the window; knots_xyzw: (K,4) control poses of the
+        temporary trajectory; t_next_win_beg: (sec, nsec); alpha=NaN => updateAlpha on the first eval."""
+        ev = np.ascontiguousarray(events)
+        if ev.dtype.itemsize != 16:
+            raise ValueError("events must be 16-byte dvs_msgs::Event records")
+        kn = np.ascontiguousarray(knots_xyzw, dtype=np.float64).reshape(-1, 4)
+        igp = None if IGp is None else np.ascontiguousarray(IGp, dtype=np.float32)
+        if igp is not None and igp.size != self.pano_width * self.pano_height:
+            raise ValueError("IGp must be a pano_height x pano_width float image")
+        w = _capi.BeWindow(ev.ctypes.data, len(ev), kn.ctypes.data, kn.shape[0], int(t0_ns), int(dt_ns), int(n_fixed),
+                           int(t_next_win_beg[0]), int(t_next_win_beg[1]), None if igp is None else igp.ctypes.data,
+                           float(alpha))
+        self._keep = (ev, kn, igp)
+        _capi.check(self._L.cmaxb_be_set_window(self._h, C.byref(w)))
+        self.n_events = len(ev)
+        self.n_knots = kn.shape[0]
+        self.n_params = 3 * (kn.shape[0] - n_fixed)
+
+    def _x(self, x):
+        if x is None:
+            return None, 0
+        xx = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        return xx, xx.size
+
+    def eval(self, x=None, want_grad=True):
+        """(+contrast, +gradient[3*K_opt] or None) at incremental rotation vectors x (None = zeros)."""
+        xx, n = self._x(x)
+        c = C.c_double()
+        g = np.zeros(max(self.n_params, 1))
+        _capi.check(self._L.cmaxb_be_eval(self._h, None if xx is None else _capi.dptr(xx), n, C.byref(c),
+                                          _capi.dptr(g) if want_grad else None))
+        return c.value, (g[: self.n_params] if want_grad else None)
+
+    @property
+    def alpha(self):
+        a = C.c_double()
+        _capi.check(self._L.cmaxb_be_get_alpha(self._h, C.byref(a)))
+        return a.value
+
+    def computeImageOfWarpedEvents(self, x=None, blurred=True):
+        xx, n = self._x(x)
+        out = np.empty((self.pano_height, self.pano_width), np.float32)
+        _capi.check(self._L.cmaxb_be_get_iwe(self._h, None if xx is None else _capi.dptr(xx), n, int(blurred),
+                                             C.c_void_p(out.ctypes.data)))
+        return out
+
+    def local_iwe(self, x=None):
+        """(IL_old_, IL_new_) -- what updateIG consumes (event_pano_warper.cpp:109-126)."""
+        xx, n = self._x(x)
+        a = np.empty((self.pano_height, self.pano_width), np.float32)
+        b = np.empty_like(a)
+        _capi.check(self._L.cmaxb_be_get_il(self._h, None if xx is None else _capi.dptr(xx), n,
+                                            C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data)))
+        return a, b
+
+    def derivative_bands(self, x=None, blurred=True):
+        xx, n = self._x(x)
+        out = np.empty((self.n_params, self.pano_height, self.pano_width), np.float32)
+        _capi.check(self._L.cmaxb_be_get_bands(self._h, None if xx is None else _capi.dptr(xx), n, int(blurred),
+                                               C.c_void_p(out.ctypes.data)))
+        return out
+
+    def warped_cells(self, x=None):
+        xx, n = self._x(x)
+        out = np.empty(self.n_events, np.int32)
+        _capi.check(self._L.cmaxb_be_get_cells(self._h, None if xx is None else _capi.dptr(xx), n, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def batch_poses(self, x=None):
+        """Per-batch (R [nb,3,3] f64, Jk [nb,3,3*order] f32, idx_cp_beg [nb]) of the device So3Spline."""
+        xx, n = self._x(x)
+        nb = C.c_int64()
+        xp = None if xx is None else _capi.dptr(xx)
+        _capi.check(self._L.cmaxb_be_get_poses(self._h, xp, n, C.byref(nb), None, None, None, 0))
+        R = np.zeros((nb.value, 3, 3))
+        Jk = np.zeros((nb.value, 3, 3 * self.spline_order), np.float32)
+        idx = np.zeros(nb.value, np.int32)
+        _capi.check(self._L.cmaxb_be_get_poses(self._h, xp, n, C.byref(nb), C.c_void_p(R.ctypes.data),
+                                               C.c_void_p(Jk.ctypes.data), C.c_void_p(idx.ctypes.data), nb.value))
+        return R, Jk, idx
+
+    def profile(self, enable=True):
+        _capi.check(self._L.cmaxb_be_profile(self._h, int(enable)))
+
+    def kernel_times(self):
+        ms = np.zeros(_capi.K_COUNT)
+        n = np.zeros(_capi.K_COUNT, np.uint64)
+        _capi.check(self._L.cmaxb_be_kernel_times(self._h, _capi.dptr(ms), n.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return {_capi.K_NAMES[i]: (float(ms[i]), int(n[i])) for i in range(_capi.K_COUNT) if n[i] > 0}
+
+
+# GSL callback triple with the reference's semantics: -contrast / -gradient
+# (global_optim_contrast_gsl_analytical.cpp:56-66); want_df=False is the `df == nullptr` path.
+def global_contrast_fdf(v, warper, want_df=True):
+    c, g = warper.eval(v, want_grad=want_df)
+    return -c, (None if g is None else -g)
+
+
+def global_contrast_f(v, warper):
+    return global_contrast_fdf(v, warper, want_df=False)[0]
+
+
+def global_contrast_df(v, warper):
+    return global_contrast_fdf(v, warper, want_df=True)[1]

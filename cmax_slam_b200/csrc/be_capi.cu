@@ -1,0 +1,489 @@
+// be_capi.cu -- C ABI of the back-end (panoramic CMax bundle adjustment) path, include/cmax_b200.h.
+#include "capi_common.cuh"
+#include "be_kernels.cuh"
+#include "image_kernels.cuh"
+
+using namespace cmaxb;
+
+struct cmaxb_be {
+  cmaxb_be_cfg cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  long long A = 0, SA = 0;
+  int N = 2;                 // spline order
+  Taps taps{};
+  double4* d_lut = nullptr;
+  uint4* d_ev = nullptr; size_t ev_cap = 0;
+  long long n = 0, n_eff = 0, nb = 0;
+  BeBatchTime* d_bt = nullptr; BePose* d_poses = nullptr; double* d_wgrad = nullptr; size_t nb_cap = 0;
+  Quat* d_knots0 = nullptr; Quat* d_knots = nullptr; double* d_x = nullptr; double* d_grad = nullptr; size_t knots_cap = 0;
+  double* h_x = nullptr; double* h_grad = nullptr; size_t hx_cap = 0;
+  int n_knots = 0, n_fixed = 0, n_opt = 0;
+  long long t0_ns = 0, dt_ns = 0;
+  uint32_t tnext_sec = 0, tnext_nsec = 0;
+  float* d_igp = nullptr; bool have_igp = false;
+  double alpha = 0.0; bool alpha_pending = false;
+  float* d_il_old = nullptr; float* d_il_new = nullptr; float* d_blur = nullptr; float* d_G = nullptr;
+  float* d_bands = nullptr; float* d_bands_blur = nullptr; size_t bands_cap = 0;
+  double* d_acc = nullptr; unsigned int* d_ticket = nullptr; double* d_result = nullptr; double* d_mean = nullptr;
+  double* d_bacc = nullptr; unsigned int* d_bticket = nullptr; double* d_bresult = nullptr; double* d_bmean = nullptr; size_t bacc_cap = 0;
+  double* d_alpha_sums = nullptr;
+  double* h_result = nullptr; double* h_alpha_sums = nullptr;
+  int* d_flags = nullptr; int* h_flags = nullptr;
+  int* d_cells = nullptr; size_t cells_cap = 0;
+  bool have_window = false;
+  KernelProfiler prof;
+};
+
+static BeGeom be_geom(const cmaxb_be* be) {
+  BeGeom g;
+  g.ev = be->d_ev; g.n_eff = be->n_eff; g.nb = be->nb;
+  g.batch_size = be->cfg.batch_size; g.sample_rate = be->cfg.event_sample_rate;
+  g.lut = be->d_lut; g.SW = be->cfg.sensor_width; g.SH = be->cfg.sensor_height;
+  g.W = be->cfg.pano_width; g.H = be->cfg.pano_height;
+  // EquirectangularCamera(pano_size, 360, 180)            equirectangular_camera.h:11-16,64-67
+  g.cx = (double)g.W / 2.0; g.cy = (double)g.H / 2.0;
+  g.fx = (double)((g.W / 360.0) * 180.0 / 3.1415926535897932384626433832795);
+  g.fy = (double)((g.H / 180.0) * 180.0 / 3.1415926535897932384626433832795);
+  g.tnext_sec = be->tnext_sec; g.tnext_nsec = be->tnext_nsec;
+  g.n_fixed = be->n_fixed; g.Nk = be->N;
+  return g;
+}
+
+extern "C" int cmaxb_be_create(const cmaxb_be_cfg* cfg, cmaxb_be** out) {
+  if (!cfg || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->sensor_width < 1 || cfg->sensor_height < 1 || cfg->pano_width < 4 || cfg->pano_height < 4 || !cfg->lut_xyz ||
+      cfg->batch_size <= 0 || cfg->event_sample_rate <= 0)
+    return set_error(CMAXB_ERR_INVALID, "bad back-end configuration");
+  if (cfg->spline_order != 2 && cfg->spline_order != 4) return set_error(CMAXB_ERR_INVALID, "spline_order must be 2 (linear) or 4 (cubic)");
+  if (cfg->grad_mode != CMAXB_GRAD_DENSE && cfg->grad_mode != CMAXB_GRAD_ADJOINT) return set_error(CMAXB_ERR_INVALID, "bad grad_mode");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return set_error(CMAXB_ERR_CUDA, "no CUDA device: libcmax_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return set_error(CMAXB_ERR_INVALID, "bad device ordinal");
+  CMAXB_CUDA_TRY(cudaSetDevice(cfg->device));
+  cmaxb_be* be = new cmaxb_be();
+  be->cfg = *cfg;
+  be->cfg.lut_xyz = nullptr;
+  be->device = cfg->device;
+  be->N = cfg->spline_order;
+  be->A = (long long)cfg->pano_width * cfg->pano_height;
+  be->SA = (long long)cfg->sensor_width * cfg->sensor_height;
+  int rc = make_taps(cfg->blur_sigma, &be->taps);
+  if (rc != CMAXB_OK) { delete be; return rc; }
+  auto fail = [&](int code) { cmaxb_be_destroy(be); return code; };
+  if (cfg->stream) be->stream = (cudaStream_t)cfg->stream;
+  else {
+    if (cudaStreamCreateWithFlags(&be->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "cudaStreamCreate failed"));
+    be->own_stream = true;
+  }
+  if (be->prof.init() != CMAXB_OK) return fail(CMAXB_ERR_CUDA);
+  {
+    std::vector<double4> lut((size_t)be->SA);
+    for (long long i = 0; i < be->SA; ++i) lut[i] = make_double4(cfg->lut_xyz[3 * i], cfg->lut_xyz[3 * i + 1], cfg->lut_xyz[3 * i + 2], 0.0);
+    if (dev_alloc(&be->d_lut, (size_t)be->SA) != CMAXB_OK) return fail(CMAXB_ERR_CUDA);
+    if (cudaMemcpy(be->d_lut, lut.data(), sizeof(double4) * be->SA, cudaMemcpyHostToDevice) != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "LUT upload failed"));
+  }
+  const size_t A = (size_t)be->A;
+  bool ok = true;
+  ok = ok && dev_alloc(&be->d_il_old, A) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_il_new, A) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_blur, A) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_G, A) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_igp, A) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_acc, (size_t)kNAcc) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_ticket, 1) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_result, 4) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_mean, 1) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_alpha_sums, 8) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_flags, 1) == CMAXB_OK;
+  if (!ok) return fail(CMAXB_ERR_CUDA);
+  ok = ok && cudaMallocHost((void**)&be->h_result, sizeof(double) * 4) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&be->h_alpha_sums, sizeof(double) * 8) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&be->h_flags, sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMemset(be->d_acc, 0, sizeof(double) * kNAcc) == cudaSuccess;
+  ok = ok && cudaMemset(be->d_ticket, 0, sizeof(unsigned)) == cudaSuccess;
+  ok = ok && cudaMemset(be->d_result, 0, sizeof(double) * 4) == cudaSuccess;
+  if (!ok) return fail(set_error(CMAXB_ERR_CUDA, "back-end buffer allocation failed"));
+  const int r = be->taps.r;
+  cudaFuncSetAttribute(blur_reduce_kernel<1, SrcBeI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<1>(r));
+  cudaFuncSetAttribute(blur_reduce_kernel<1, SrcPlane, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<1>(r));
+  cudaFuncSetAttribute(adjoint_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjoint_smem_bytes(r));
+  if (cudaGetLastError() != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "cudaFuncSetAttribute failed"));
+  *out = be;
+  return CMAXB_OK;
+}
+
+extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
+  if (!be) return;
+  cudaSetDevice(be->device);
+  if (be->stream) cudaStreamSynchronize(be->stream);
+  cudaFree(be->d_lut); cudaFree(be->d_ev); cudaFree(be->d_bt); cudaFree(be->d_poses); cudaFree(be->d_wgrad);
+  cudaFree(be->d_knots0); cudaFree(be->d_knots); cudaFree(be->d_x); cudaFree(be->d_grad);
+  cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
+  cudaFree(be->d_bands); cudaFree(be->d_bands_blur);
+  cudaFree(be->d_acc); cudaFree(be->d_ticket); cudaFree(be->d_result); cudaFree(be->d_mean);
+  cudaFree(be->d_bacc); cudaFree(be->d_bticket); cudaFree(be->d_bresult); cudaFree(be->d_bmean);
+  cudaFree(be->d_alpha_sums); cudaFree(be->d_flags); cudaFree(be->d_cells);
+  if (be->h_x) cudaFreeHost(be->h_x);
+  if (be->h_grad) cudaFreeHost(be->h_grad);
+  if (be->h_result) cudaFreeHost(be->h_result);
+  if (be->h_alpha_sums) cudaFreeHost(be->h_alpha_sums);
+  if (be->h_flags) cudaFreeHost(be->h_flags);
+  be->prof.destroy();
+  if (be->own_stream && be->stream) cudaStreamDestroy(be->stream);
+  delete be;
+}
+
+extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
+  if (!be || !w || (!w->events && w->n_events > 0) || !w->knots_xyzw) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (w->n_knots < be->N || w->n_fixed < 0 || w->n_fixed > w->n_knots || w->dt_ns <= 0)
+    return set_error(CMAXB_ERR_INVALID, "bad window description");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  cudaStream_t s = be->stream;
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  be->have_window = false;
+  const long long n = (long long)w->n_events, bs = be->cfg.batch_size;
+  // the reference loop `for (beg = begin; beg < end-1; beg += bs)` never visits a trailing batch
+  // of exactly one event (event_pano_warper.cpp:188-196)
+  const long long n_eff = (n >= 1 && (n - 1) % bs == 0) ? n - 1 : n;
+  const long long nb = (n_eff + bs - 1) / bs;
+  be->n = n; be->n_eff = n_eff; be->nb = nb;
+  if ((size_t)n > be->ev_cap) {
+    cudaFree(be->d_ev); be->d_ev = nullptr; be->ev_cap = 0;
+    CMAXB_TRY(dev_alloc(&be->d_ev, (size_t)n));
+    be->ev_cap = (size_t)n;
+  }
+  if ((size_t)nb > be->nb_cap) {
+    cudaFree(be->d_bt); cudaFree(be->d_poses); cudaFree(be->d_wgrad);
+    be->d_bt = nullptr; be->d_poses = nullptr; be->d_wgrad = nullptr; be->nb_cap = 0;
+    CMAXB_TRY(dev_alloc(&be->d_bt, (size_t)nb));
+    CMAXB_TRY(dev_alloc(&be->d_poses, (size_t)nb));
+    CMAXB_TRY(dev_alloc(&be->d_wgrad, (size_t)nb * 12));
+    be->nb_cap = (size_t)nb;
+  }
+  if ((size_t)w->n_knots > be->knots_cap) {
+    cudaFree(be->d_knots0); cudaFree(be->d_knots); cudaFree(be->d_x); cudaFree(be->d_grad);
+    if (be->h_x) cudaFreeHost(be->h_x);
+    if (be->h_grad) cudaFreeHost(be->h_grad);
+    be->h_x = be->h_grad = nullptr; be->knots_cap = 0;
+    const size_t K = (size_t)w->n_knots;
+    CMAXB_TRY(dev_alloc(&be->d_knots0, K));
+    CMAXB_TRY(dev_alloc(&be->d_knots, K));
+    CMAXB_TRY(dev_alloc(&be->d_x, 3 * K));
+    CMAXB_TRY(dev_alloc(&be->d_grad, 3 * K));
+    CMAXB_CUDA_TRY(cudaMallocHost((void**)&be->h_x, sizeof(double) * 3 * K));
+    CMAXB_CUDA_TRY(cudaMallocHost((void**)&be->h_grad, sizeof(double) * 3 * K));
+    be->knots_cap = K;
+  }
+  be->n_knots = w->n_knots; be->n_fixed = w->n_fixed; be->n_opt = w->n_knots - w->n_fixed;
+  be->t0_ns = w->t0_ns; be->dt_ns = w->dt_ns;
+  be->tnext_sec = w->tnext_sec; be->tnext_nsec = w->tnext_nsec;
+  static_assert(sizeof(Quat) == 4 * sizeof(double), "Quat must be 4 packed doubles (x,y,z,w)");
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_knots0, w->knots_xyzw, sizeof(Quat) * w->n_knots, cudaMemcpyHostToDevice, s));
+  if (w->IGp) {
+    CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_igp, w->IGp, sizeof(float) * be->A, cudaMemcpyHostToDevice, s));
+    be->have_igp = true;
+  } else {
+    CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_igp, 0, sizeof(float) * be->A, s));
+    be->have_igp = false;
+  }
+  if (std::isnan(w->alpha)) { be->alpha = 0.0; be->alpha_pending = true; }
+  else { be->alpha = w->alpha; be->alpha_pending = false; }
+  if (n > 0) {
+    CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_ev, w->events, sizeof(cmaxb_event) * n, cudaMemcpyHostToDevice, s));
+    CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_flags, 0, sizeof(int), s));
+    const uint4* ev = be->d_ev; int* flags = be->d_flags;
+    const int SW = be->cfg.sensor_width, SH = be->cfg.sensor_height;
+    CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+      validate_events_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ev, n, SW, SH, flags);
+    }));
+    if (nb > 0) {
+      CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+        be_batch_time_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ev, n, n_eff, (int)bs, nb, be->t0_ns, be->dt_ns,
+                                                                             be->n_knots, be->N, be->d_bt, flags);
+      }));
+    }
+    CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_flags, be->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+    if (*be->h_flags & 2) return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor");
+    if (*be->h_flags & 4) return set_error(CMAXB_ERR_SPLINE_RANGE, "batch time outside the spline's valid range");
+  } else {
+    CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  }
+  be->have_window = true;
+  return CMAXB_OK;
+}
+
+static unsigned be_warp_grid(const cmaxb_be* be) {
+  long long blocks = (be->nb + kBeWarps - 1) / kBeWarps;
+  const long long cap = 148LL * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+static dim3 be_img_grid(const cmaxb_be* be, int z = 1) {
+  return dim3((be->cfg.pano_width + kTW - 1) / kTW, (be->cfg.pano_height + kTH - 1) / kTH, z);
+}
+
+// x -> updated knots -> per-batch pose table
+static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
+  if (x && n != 3 * be->n_opt) return set_error(CMAXB_ERR_INVALID, "x must have 3*(n_knots-n_fixed) entries");
+  cudaStream_t s = be->stream;
+  for (int i = 0; i < 3 * be->n_opt; ++i) be->h_x[i] = x ? x[i] : 0.0;
+  if (be->n_opt > 0) CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_x, be->h_x, sizeof(double) * 3 * be->n_opt, cudaMemcpyHostToDevice, s));
+  CMAXB_TRY(be->prof.run(CMAXB_K_BE_POSES, s, true, [&] {
+    be_update_knots_kernel<<<(be->n_knots + 127) / 128, 128, 0, s>>>(be->d_knots0, be->d_x, be->n_knots, be->n_fixed, be->d_knots);
+  }));
+  if (be->nb > 0) {
+    const unsigned grid = (unsigned)((be->nb + 127) / 128);
+    CMAXB_TRY(be->prof.run(CMAXB_K_BE_POSES, s, true, [&] {
+      if (be->N == 2) be_pose_kernel<2><<<grid, 128, 0, s>>>(be->d_knots, be->d_bt, be->nb, want_grad, be->d_poses);
+      else be_pose_kernel<4><<<grid, 128, 0, s>>>(be->d_knots, be->d_bt, be->nb, want_grad, be->d_poses);
+    }));
+  }
+  return CMAXB_OK;
+}
+
+static int be_run_scatter(cmaxb_be* be) {
+  cudaStream_t s = be->stream;
+  CMAXB_TRY(be->prof.run(CMAXB_K_ZERO, s, false, [&] {
+    cudaMemsetAsync(be->d_il_old, 0, sizeof(float) * be->A, s);
+    cudaMemsetAsync(be->d_il_new, 0, sizeof(float) * be->A, s);
+  }));
+  if (be->nb > 0) {
+    const BeGeom g = be_geom(be);
+    CMAXB_TRY(be->prof.run(CMAXB_K_BE_SCATTER, s, true, [&] {
+      be_scatter_kernel<<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_il_old, be->d_il_new);
+    }));
+  }
+  // first evaluation of a window with alpha unspecified: updateAlpha            (:201-210)
+  if (be->alpha_pending) {
+    CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_alpha_sums, 0, sizeof(double) * 8, s));
+    CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+      be_alpha_sums_kernel<<<148 * 4, 256, 0, s>>>(be->d_igp, be->d_il_old, be->d_il_new, be->A, be->d_alpha_sums);
+    }));
+    CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_alpha_sums, be->d_alpha_sums, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
+    CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+    const double* v = be->h_alpha_sums;
+    if (v[4] < 1.0) be->alpha = 0.0;                                              // countNonZero(IGp_) < 1
+    else be->alpha = (v[3] / v[2]) / (v[1] / v[0]);
+    be->alpha_pending = false;
+  }
+  return CMAXB_OK;
+}
+
+// blur(I) + contrast; leaves the blurred image in d_blur and its mean in d_mean
+static int be_run_image(cmaxb_be* be) {
+  cudaStream_t s = be->stream;
+  const SrcBeI src{be->d_il_old, be->d_il_new, be->have_igp ? be->d_igp : nullptr, (float)be->alpha};
+  const ReduceOut ro{be->d_acc, be->d_ticket, be->d_result, be->d_mean};
+  const int W = be->cfg.pano_width, H = be->cfg.pano_height, r = be->taps.r;
+  CMAXB_TRY(be->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+    blur_reduce_kernel<1, SrcBeI, true><<<be_img_grid(be), kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, be->taps, be->d_blur, 0, ro, be->cfg.contrast_measure);
+  }));
+  return CMAXB_OK;
+}
+
+static int be_ensure_bands(cmaxb_be* be) {
+  const size_t need = (size_t)3 * be->n_opt * (size_t)be->A;
+  if (need > be->bands_cap) {
+    cudaFree(be->d_bands); cudaFree(be->d_bands_blur);
+    be->d_bands = be->d_bands_blur = nullptr; be->bands_cap = 0;
+    CMAXB_TRY(dev_alloc(&be->d_bands, need));
+    CMAXB_TRY(dev_alloc(&be->d_bands_blur, need));
+    be->bands_cap = need;
+  }
+  const size_t P = (size_t)3 * be->n_opt;
+  if (P > be->bacc_cap) {
+    cudaFree(be->d_bacc); cudaFree(be->d_bticket); cudaFree(be->d_bresult); cudaFree(be->d_bmean);
+    CMAXB_TRY(dev_alloc(&be->d_bacc, P * kNAcc));
+    CMAXB_TRY(dev_alloc(&be->d_bticket, P));
+    CMAXB_TRY(dev_alloc(&be->d_bresult, P * 4));
+    CMAXB_TRY(dev_alloc(&be->d_bmean, P));
+    CMAXB_CUDA_TRY(cudaMemset(be->d_bacc, 0, sizeof(double) * P * kNAcc));
+    CMAXB_CUDA_TRY(cudaMemset(be->d_bticket, 0, sizeof(unsigned) * P));
+    be->bacc_cap = P;
+  }
+  return CMAXB_OK;
+}
+
+// dense bands at the current pose table: scatter, then blur into d_bands_blur
+static int be_run_bands(cmaxb_be* be, bool blur) {
+  CMAXB_TRY(be_ensure_bands(be));
+  cudaStream_t s = be->stream;
+  const int P = 3 * be->n_opt;
+  if (P == 0) return CMAXB_OK;
+  CMAXB_TRY(be->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(be->d_bands, 0, sizeof(float) * (size_t)P * be->A, s); }));
+  if (be->nb > 0) {
+    const BeGeom g = be_geom(be);
+    CMAXB_TRY(be->prof.run(CMAXB_K_BE_SCATTER, s, true, [&] {
+      if (be->N == 2) be_scatter_bands_kernel<2><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_bands, be->A, P);
+      else be_scatter_bands_kernel<4><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_bands, be->A, P);
+    }));
+  }
+  if (blur) {
+    const SrcPlane src{be->d_bands, be->A};
+    const ReduceOut ro{be->d_bacc, be->d_bticket, be->d_bresult, be->d_bmean};
+    const int W = be->cfg.pano_width, H = be->cfg.pano_height, r = be->taps.r;
+    // blockIdx.z is limited to 65535 planes
+    CMAXB_TRY(be->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+      blur_reduce_kernel<1, SrcPlane, true><<<be_img_grid(be, P), kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, be->taps, be->d_bands_blur, be->A, ro, be->cfg.contrast_measure);
+    }));
+  }
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contrast, double* grad) {
+  if (!be || !contrast) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window: call cmaxb_be_set_window first");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  const bool want_grad = grad != nullptr;
+  cudaStream_t s = be->stream;
+  CMAXB_TRY(be_run_poses(be, x, n, want_grad));
+  CMAXB_TRY(be_run_scatter(be));
+  CMAXB_TRY(be_run_image(be));
+  const int P = 3 * be->n_opt;
+  if (want_grad && P > 0) {
+    const int W = be->cfg.pano_width, H = be->cfg.pano_height, r = be->taps.r;
+    if (be->cfg.grad_mode == CMAXB_GRAD_ADJOINT) {
+      CMAXB_TRY(be->prof.run(CMAXB_K_ADJOINT_BLUR, s, true, [&] {
+        adjoint_blur_kernel<<<be_img_grid(be), kImgThreads, adjoint_smem_bytes(r), s>>>(be->d_blur, 0, W, H, be->taps, be->d_mean, be->cfg.contrast_measure, be->d_G);
+      }));
+      if (be->nb > 0) {
+        const BeGeom g = be_geom(be);
+        CMAXB_TRY(be->prof.run(CMAXB_K_BE_GATHER, s, true, [&] {
+          if (be->N == 2) be_gather_kernel<2><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, be->d_wgrad);
+          else be_gather_kernel<4><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, be->d_wgrad);
+        }));
+      }
+      const double inv_np = 1.0 / ((double)W * (double)H);
+      CMAXB_TRY(be->prof.run(CMAXB_K_BE_GRAD_REDUCE, s, true, [&] {
+        if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, 256, 0, s>>>(be->d_poses, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+        else be_grad_reduce_kernel<4><<<be->n_opt, 256, 0, s>>>(be->d_poses, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+      }));
+    } else {
+      CMAXB_TRY(be_run_bands(be, true));
+      CMAXB_TRY(be->prof.run(CMAXB_K_BE_GRAD_REDUCE, s, true, [&] {
+        be_band_reduce_kernel<<<P, 256, 0, s>>>(be->d_blur, be->d_bands_blur, be->A, be->d_mean, be->cfg.contrast_measure, be->d_grad);
+      }));
+    }
+    CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_grad, be->d_grad, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
+  }
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_result, be->d_result, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  *contrast = be->h_result[0];
+  if (want_grad) for (int i = 0; i < P; ++i) grad[i] = be->h_grad[i];
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_get_alpha(cmaxb_be* be, double* alpha) {
+  if (!be || !alpha) return set_error(CMAXB_ERR_INVALID, "null argument");
+  *alpha = be->alpha_pending ? NAN : be->alpha;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_get_il(cmaxb_be* be, const double* x, int n, float* il_old, float* il_new) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_run_poses(be, x, n, false));
+  CMAXB_TRY(be_run_scatter(be));
+  cudaStream_t s = be->stream;
+  if (il_old) CMAXB_CUDA_TRY(cudaMemcpyAsync(il_old, be->d_il_old, sizeof(float) * be->A, cudaMemcpyDeviceToHost, s));
+  if (il_new) CMAXB_CUDA_TRY(cudaMemcpyAsync(il_new, be->d_il_new, sizeof(float) * be->A, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_get_iwe(cmaxb_be* be, const double* x, int n, int blurred, float* out) {
+  if (!be || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_run_poses(be, x, n, false));
+  CMAXB_TRY(be_run_scatter(be));
+  cudaStream_t s = be->stream;
+  if (blurred) {
+    CMAXB_TRY(be_run_image(be));
+  } else {
+    // un-blurred I = IL + alpha*IGp: run the same kernel with a radius-0 filter
+    Taps t0{}; t0.r = 0; t0.w[0] = 1.0f;
+    const SrcBeI src{be->d_il_old, be->d_il_new, be->have_igp ? be->d_igp : nullptr, (float)be->alpha};
+    const ReduceOut ro{be->d_acc, be->d_ticket, be->d_result, be->d_mean};
+    CMAXB_TRY(be->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+      blur_reduce_kernel<1, SrcBeI, true><<<be_img_grid(be), kImgThreads, blur_smem_bytes<1>(0), s>>>(src, be->cfg.pano_width, be->cfg.pano_height, t0, be->d_blur, 0, ro, be->cfg.contrast_measure);
+    }));
+  }
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(out, be->d_blur, sizeof(float) * be->A, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_get_bands(cmaxb_be* be, const double* x, int n, int blurred, float* out) {
+  if (!be || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_run_poses(be, x, n, true));
+  const bool do_blur = blurred && be->taps.r > 0;
+  CMAXB_TRY(be_run_bands(be, do_blur));
+  cudaStream_t s = be->stream;
+  const size_t bytes = sizeof(float) * (size_t)3 * be->n_opt * be->A;
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(out, do_blur ? be->d_bands_blur : be->d_bands, bytes, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_get_cells(cmaxb_be* be, const double* x, int n, int32_t* out) {
+  if (!be || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  if (be->n == 0) return CMAXB_OK;
+  CMAXB_TRY(be_run_poses(be, x, n, false));
+  if ((size_t)be->n > be->cells_cap) {
+    cudaFree(be->d_cells); be->d_cells = nullptr; be->cells_cap = 0;
+    CMAXB_TRY(dev_alloc(&be->d_cells, (size_t)be->n));
+    be->cells_cap = (size_t)be->n;
+  }
+  cudaStream_t s = be->stream;
+  const BeGeom g = be_geom(be);
+  CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+    be_cells_kernel<<<(unsigned)((be->n + 255) / 256), 256, 0, s>>>(g, be->d_poses, be->n, be->d_cells);
+  }));
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(out, be->d_cells, sizeof(int) * be->n, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_get_poses(cmaxb_be* be, const double* x, int n, int64_t* n_batches, double* R9, float* Jk,
+                                  int32_t* idx_cp_beg, int64_t capacity) {
+  if (!be || !n_batches) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  *n_batches = be->nb;
+  if (capacity < be->nb || be->nb == 0) return CMAXB_OK;
+  CMAXB_TRY(be_run_poses(be, x, n, true));
+  std::vector<BePose> h((size_t)be->nb);
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(h.data(), be->d_poses, sizeof(BePose) * be->nb, cudaMemcpyDeviceToHost, be->stream));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(be->stream));
+  const int nj = 9 * be->N;
+  for (long long b = 0; b < be->nb; ++b) {
+    if (R9) for (int i = 0; i < 9; ++i) R9[9 * b + i] = h[b].R[i];
+    if (Jk) for (int i = 0; i < nj; ++i) Jk[nj * b + i] = h[b].Jk[i];
+    if (idx_cp_beg) idx_cp_beg[b] = h[b].idx_cp_beg;
+  }
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_profile(cmaxb_be* be, int enable) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  be->prof.enabled = enable != 0;
+  be->prof.reset();
+  return CMAXB_OK;
+}
+extern "C" int cmaxb_be_kernel_times(cmaxb_be* be, double* ms, uint64_t* launches) {
+  if (!be || !ms || !launches) return set_error(CMAXB_ERR_INVALID, "null argument");
+  for (int i = 0; i < CMAXB_K_COUNT; ++i) { ms[i] = be->prof.ms[i]; launches[i] = be->prof.launches[i]; }
+  return CMAXB_OK;
+}

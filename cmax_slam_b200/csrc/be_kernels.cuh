@@ -1,0 +1,369 @@
+// be_kernels.cuh -- back-end (panoramic bundle adjustment) event kernels.
+//
+// Per cost evaluation the reference runs EventWarper::computeImageOfWarpedEvents ->
+// warpAndAccumulateEvents (src/backend/event_pano_warper.cpp:167-336): one spline pose and knot
+// Jacobian per batch of `event_batch_size` events (Trajectory::evaluate, src/backend/
+// trajectory.cpp:86-110,329-355 -> basalt So3Spline<N>::evaluate), then per event a rotation of
+// the bearing vector, the equirectangular projection with its 2x3 Jacobian
+// (include/backend/equirectangular_camera.h:18-45), bilinear votes into IL_old_/IL_new_ and into
+// 3*Nk derivative bands.
+//
+// Mapping here: one WARP per batch (the pose is loaded once and broadcast; no division by the
+// batch size; the 16-byte event records of a batch are one coalesced run), lanes stride over the
+// batch's events.
+#pragma once
+#include "common.cuh"
+#include "so3_math.cuh"
+
+namespace cmaxb {
+
+struct BePose {            // per batch, 232 bytes
+  double R[9];             // so3.matrix()                                   (:254)
+  float Jk[36];            // 3 x 3Nk, row-major with row stride 3Nk         (trajectory.cpp:99-106,342-351)
+  int idx_cp_beg;          // J.start_idx
+  int valid;               // 0: batch not processed
+};
+
+struct BeBatchTime {       // per batch, fixed for a window
+  long long s;             // segment index  (so3_spline.h:224)
+  double u;                // fractional position (:225)
+};
+
+struct BeGeom {
+  const uint4* ev;
+  long long n_eff;         // events actually visited by the reference loop (:188-196)
+  long long nb;
+  int batch_size, sample_rate;
+  const double4* lut;
+  int SW, SH;              // sensor
+  int W, H;                // panorama
+  double fx, fy, cx, cy;   // equirectangular focal lengths / centre      (equirectangular_camera.h:11-16,64-67)
+  uint32_t tnext_sec, tnext_nsec;
+  int n_fixed, Nk;
+};
+
+// t_mid of each batch -> (s, u); flags |= 4 when outside the spline (BASALT_ASSERT, so3_spline.h:221-230)
+__global__ void be_batch_time_kernel(const uint4* __restrict__ ev, long long n, long long n_eff, int bs, long long nb,
+                                     long long t0_ns, long long dt_ns, int n_knots, int order,
+                                     BeBatchTime* __restrict__ out, int* flags) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const long long beg = b * bs;
+  long long end = beg + bs;
+  if (n - beg <= bs) end = n;                                             // (:192-194)
+  const uint4 e0 = ev[beg], e1 = ev[end - 1];
+  RosTime mid;
+  ros_batch_mid(RosTime{e0.y, e0.z}, RosTime{e1.y, e1.z}, &mid);
+  const long long t_ns = (long long)((unsigned long long)mid.sec * 1000000000ull + (unsigned long long)mid.nsec);  // toNSec()
+  const long long st = t_ns - t0_ns;
+  BeBatchTime bt;
+  bt.s = 0; bt.u = 0.0;
+  if (st < 0) { atomicOr(flags, 4); }
+  else {
+    bt.s = st / dt_ns;
+    bt.u = (double)(st % dt_ns) / (double)dt_ns;
+    if (bt.s + order > (long long)n_knots) { atomicOr(flags, 4); bt.s = 0; }
+  }
+  out[b] = bt;
+}
+
+// temp trajectory: K_i <- exp(x_i) * K_i for the optimised knots
+// (CopyAndIncrementalUpdate / incrementalUpdate, trajectory.cpp:221-263,491-522)
+__global__ void be_update_knots_kernel(const Quat* __restrict__ knots0, const double* __restrict__ x, int n_knots,
+                                       int n_fixed, Quat* __restrict__ knots) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_knots) return;
+  Quat q = knots0[i];
+  if (i >= n_fixed) {
+    const int j = i - n_fixed;
+    Vec3 d; d.x = x[3 * j]; d.y = x[3 * j + 1]; d.z = x[3 * j + 2];
+    q = quat_mul(so3_exp(d), q);
+  }
+  knots[i] = q;
+}
+
+template <int N>
+__global__ void be_pose_kernel(const Quat* __restrict__ knots, const BeBatchTime* __restrict__ bt, long long nb,
+                               int want_grad, BePose* __restrict__ poses) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const BeBatchTime t = bt[b];
+  Mat3 J[N];
+  const Quat q = so3_spline_eval<N>(knots, (int)t.s, t.u, want_grad ? J : nullptr);
+  const Mat3 R = quat_to_mat(q);
+  BePose* p = poses + b;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) p->R[i] = R.m[i];
+  if (want_grad) {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) p->Jk[r * (3 * N) + 3 * k + c] = (float)J[k].m[r * 3 + c];
+  }
+  p->idx_cp_beg = (int)t.s;
+  p->valid = 1;
+}
+
+struct BeWarp {
+  bool in;
+  int xx, yy;
+  float dx, dy;
+  bool is_old;
+  float dd[2][3];   // dpm_ddrot = dpm_drb * drb_ddrot (2x3, f32)            (:273-282)
+};
+
+template <bool GRAD>
+__device__ __forceinline__ BeWarp be_warp(const BeGeom& g, const double* R, uint4 e) {
+  BeWarp o;
+  const int ex = e.x & 0xffff, ey = e.x >> 16;
+  const double2* lp = reinterpret_cast<const double2*>(g.lut + (ey * g.SW + ex));
+  const double2 bxy = __ldg(lp);
+  const double bz = __ldg(reinterpret_cast<const double*>(lp + 1));
+  const double bx = bxy.x, by = bxy.y;
+  // e_ray_w = R * e_ray_cam                                               (:269)
+  const double wx = R[0] * bx + R[1] * by + R[2] * bz;
+  const double wy = R[3] * bx + R[4] * by + R[5] * bz;
+  const double wz = R[6] * bx + R[7] * by + R[8] * bz;
+  // projectToImage                                                        (equirectangular_camera.h:18-45)
+  const double phi = atan2(wx, wz);
+  const double n2 = wx * wx + wy * wy + wz * wz;
+  const double rho = sqrt(n2);
+  const double theta = asin(wy / rho);
+  const double px = g.cx + phi * g.fx;
+  const double py = g.cy + theta * g.fy;
+  o.in = false;
+  o.xx = o.yy = 0;
+  o.dx = o.dy = 0.f;
+  if (fabs(px) < 2e9 && fabs(py) < 2e9) {
+    const int xx = (int)px, yy = (int)py;                                  // (:290-291)
+    if (1 <= xx && xx < g.W - 2 && 1 <= yy && yy < g.H - 2) {              // (:296)
+      o.in = true;
+      o.xx = xx; o.yy = yy;
+      o.dx = (float)(px - (double)xx);
+      o.dy = (float)(py - (double)yy);
+    }
+  }
+  o.is_old = (e.y < g.tnext_sec) || (e.y == g.tnext_sec && e.z < g.tnext_nsec);   // ev->ts < t_next_win_beg_ (:298)
+  if (GRAD) {
+    const double Ydivrho = wy / rho;
+    const double XdivZ = wx / wz;
+    const double tmp1 = g.fx / ((1 + XdivZ * XdivZ) * wz);
+    const double tmp2 = -g.fy / sqrt(1 - Ydivrho * Ydivrho);
+    const double tmp3 = Ydivrho / (rho * rho);
+    const float j00 = (float)tmp1, j02 = (float)(-tmp1 * XdivZ);
+    const float j10 = (float)(tmp2 * tmp3 * wx), j11 = (float)(tmp2 * (tmp3 * wy - 1 / rho)), j12 = (float)(tmp2 * tmp3 * wz);
+    // drb_ddrot = [0 rb.z -rb.y; -rb.z 0 rb.x; rb.y -rb.x 0] as f32          (:280-281)
+    const float rx = (float)wx, ry = (float)wy, rz = (float)wz;
+    const float nrx = (float)(-wx), nry = (float)(-wy), nrz = (float)(-wz);
+    // dpm_ddrot = dpm_drb * drb_ddrot, f32, s = 0; s += a*b  (j01 == 0)      (:282)
+    o.dd[0][0] = j00 * 0.f + 0.f * nrz + j02 * ry;
+    o.dd[0][1] = j00 * rz + 0.f * 0.f + j02 * nrx;
+    o.dd[0][2] = j00 * nry + 0.f * rx + j02 * 0.f;
+    o.dd[1][0] = j10 * 0.f + j11 * nrz + j12 * ry;
+    o.dd[1][1] = j10 * rz + j11 * 0.f + j12 * nrx;
+    o.dd[1][2] = j10 * nry + j11 * rx + j12 * 0.f;
+  }
+  return o;
+}
+
+constexpr int kBeThreads = 256;
+constexpr int kBeWarps = kBeThreads / 32;
+
+// value scatter: IL_old_ / IL_new_
+__global__ void __launch_bounds__(kBeThreads)
+be_scatter_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict__ il_old, float* __restrict__ il_new) {
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * kBeWarps;
+  for (long long b = blockIdx.x * (long long)kBeWarps + (threadIdx.x >> 5); b < g.nb; b += wstride) {
+    const long long beg = b * g.batch_size;
+    long long end = beg + g.batch_size;
+    if (end > g.n_eff || g.n_eff - beg <= g.batch_size) end = g.n_eff;
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = __ldg(&poses[b].R[i]);
+    for (long long i = beg + (long long)lane * g.sample_rate; i < end; i += 32LL * g.sample_rate) {
+      const uint4 e = load_event(g.ev, i);
+      const BeWarp w = be_warp<false>(g, R, e);
+      if (!w.in) continue;
+      float* il = w.is_old ? il_old : il_new;
+      const float dx = w.dx, dy = w.dy;
+      const long long p = (long long)w.yy * g.W + w.xx;
+      atomicAdd(il + p, (1.f - dx) * (1.f - dy));
+      atomicAdd(il + p + 1, dx * (1.f - dy));
+      atomicAdd(il + p + g.W, (1.f - dx) * dy);
+      atomicAdd(il + p + g.W + 1, dx * dy);
+    }
+  }
+}
+
+// dense derivative bands (reference-faithful DENSE mode / parity): planar bands[P][A]
+template <int N>
+__global__ void __launch_bounds__(kBeThreads)
+be_scatter_bands_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict__ bands, long long A, int P) {
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * kBeWarps;
+  for (long long b = blockIdx.x * (long long)kBeWarps + (threadIdx.x >> 5); b < g.nb; b += wstride) {
+    const long long beg = b * g.batch_size;
+    long long end = beg + g.batch_size;
+    if (end > g.n_eff || g.n_eff - beg <= g.batch_size) end = g.n_eff;
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = __ldg(&poses[b].R[i]);
+    const int idx = poses[b].idx_cp_beg;
+    const float* Jk = poses[b].Jk;
+    for (long long i = beg + (long long)lane * g.sample_rate; i < end; i += 32LL * g.sample_rate) {
+      const uint4 e = load_event(g.ev, i);
+      const BeWarp w = be_warp<true>(g, R, e);
+      if (!w.in) continue;
+      const float dx = w.dx, dy = w.dy;
+      const long long p = (long long)w.yy * g.W + w.xx;
+      for (int c = 0; c < 3 * N; ++c) {
+        const int j = 3 * (idx - g.n_fixed) + c;                            // (:322)
+        if (j < 0 || j >= P) continue;
+        // jac = dpm_ddrot * ddrot_ddrot_cp: cv::gemm CV_32F accumulates in double   (:285)
+        double s0 = 0, s1 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double jk = (double)__ldg(Jk + k * (3 * N) + c);
+          s0 += (double)w.dd[0][k] * jk;
+          s1 += (double)w.dd[1][k] * jk;
+        }
+        const float r0 = (float)s0, r1 = (float)s1;
+        float* bd = bands + (long long)j * A + p;
+        atomicAdd(bd, r0 * (-(1.f - dy)) + r1 * (-(1.f - dx)));                // (:327-330)
+        atomicAdd(bd + 1, r0 * (1.f - dy) + r1 * (-dx));
+        atomicAdd(bd + g.W, r0 * (-dy) + r1 * (1.f - dx));
+        atomicAdd(bd + g.W + 1, r0 * dy + r1 * dx);
+      }
+    }
+  }
+}
+
+// debug / parity: per-event cell (-1 rejected, -2 never visited)
+__global__ void be_cells_kernel(BeGeom g, const BePose* __restrict__ poses, long long n_total, int* __restrict__ cells) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  int out = -2;
+  if (i < g.n_eff) {
+    const long long b = i / g.batch_size;
+    if ((i - b * g.batch_size) % g.sample_rate == 0) {
+      double R[9];
+      for (int k = 0; k < 9; ++k) R[k] = poses[b].R[k];
+      const BeWarp w = be_warp<false>(g, R, load_event(g.ev, i));
+      out = w.in ? w.yy * g.W + w.xx : -1;
+    }
+  }
+  cells[i] = out;
+}
+
+// Adjoint gather.  For an event with derivative-vote weights (s_c, t_c) (:327-330) and
+// jac = dd * Jk, the contribution to g_j is  (a*dd[0,:] + b*dd[1,:]) . Jk[:, j]  with
+// a = sum_c s_c G(c), b = sum_c t_c G(c).  The bracket is summed over the batch first (3 numbers),
+// then multiplied by the batch's Jk once: wgrad[b][c] = V_b . Jk[:, c].
+template <int N>
+__global__ void __launch_bounds__(kBeThreads)
+be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __restrict__ G, double* __restrict__ wgrad) {
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * kBeWarps;
+  for (long long b = blockIdx.x * (long long)kBeWarps + (threadIdx.x >> 5); b < g.nb; b += wstride) {
+    const long long beg = b * g.batch_size;
+    long long end = beg + g.batch_size;
+    if (end > g.n_eff || g.n_eff - beg <= g.batch_size) end = g.n_eff;
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = __ldg(&poses[b].R[i]);
+    double v0 = 0, v1 = 0, v2 = 0;
+    for (long long i = beg + (long long)lane * g.sample_rate; i < end; i += 32LL * g.sample_rate) {
+      const uint4 e = load_event(g.ev, i);
+      const BeWarp w = be_warp<true>(g, R, e);
+      if (!w.in) continue;
+      const float* p = G + (long long)w.yy * g.W + w.xx;
+      const double g00 = __ldg(p), g01 = __ldg(p + 1), g10 = __ldg(p + g.W), g11 = __ldg(p + g.W + 1);
+      const double dx = w.dx, dy = w.dy;
+      const double a = (1.0 - dy) * (g01 - g00) + dy * (g11 - g10);
+      const double bb = (1.0 - dx) * (g10 - g00) + dx * (g11 - g01);
+      v0 += a * (double)w.dd[0][0] + bb * (double)w.dd[1][0];
+      v1 += a * (double)w.dd[0][1] + bb * (double)w.dd[1][1];
+      v2 += a * (double)w.dd[0][2] + bb * (double)w.dd[1][2];
+    }
+    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+    if (lane < 3 * N) {
+      const float* Jk = poses[b].Jk;
+      wgrad[b * (3 * N) + lane] = v0 * (double)Jk[lane] + v1 * (double)Jk[3 * N + lane] + v2 * (double)Jk[6 * N + lane];
+    }
+  }
+}
+
+// g[3*kk + c] = (1/Np) * sum over batches touching knot (kk + n_fixed) of wgrad[b][3*(knot-idx_b)+c].
+// One CTA per optimised knot; fixed summation order (deterministic).
+template <int N>
+__global__ void __launch_bounds__(256)
+be_grad_reduce_kernel(const BePose* __restrict__ poses, const double* __restrict__ wgrad, long long nb, int n_fixed,
+                      double inv_np, double* __restrict__ grad) {
+  __shared__ double s_red[8 * 3];
+  const int knot = blockIdx.x + n_fixed;
+  double a[3] = {0.0, 0.0, 0.0};
+  for (long long b = threadIdx.x; b < nb; b += blockDim.x) {
+    const int rel = knot - poses[b].idx_cp_beg;
+    if (rel >= 0 && rel < N) {
+      const double* w = wgrad + b * (3 * N) + 3 * rel;
+      a[0] += w[0]; a[1] += w[1]; a[2] += w[2];
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) a[c] = warp_sum(a[c]);
+  if (lane == 0) { s_red[wid * 3] = a[0]; s_red[wid * 3 + 1] = a[1]; s_red[wid * 3 + 2] = a[2]; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += s_red[w * 3 + threadIdx.x];
+    grad[3 * blockIdx.x + threadIdx.x] = s * inv_np;
+  }
+}
+
+// DENSE mode: reduce blurred bands against the blurred image.
+// g_j = mean( 2(I-mu) .* (D_j - mean(D_j)) ) = 2*(mean(I*D_j) - mu*mean(D_j))   (global_focus_funcs.cpp:39-43)
+// or 2*mean(I*D_j) (mean square, :22).  One CTA per band.
+__global__ void __launch_bounds__(256)
+be_band_reduce_kernel(const float* __restrict__ I, const float* __restrict__ bands, long long A, const double* mean,
+                      int measure, double* __restrict__ grad) {
+  __shared__ double s_red[8 * 2];
+  const float* D = bands + (long long)blockIdx.x * A;
+  double sd = 0, sid = 0;
+  for (long long i = threadIdx.x; i < A; i += blockDim.x) {
+    const double d = D[i];
+    sd += d; sid += (double)I[i] * d;
+  }
+  sd = warp_sum(sd); sid = warp_sum(sid);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s_red[wid * 2] = sd; s_red[wid * 2 + 1] = sid; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += s_red[w * 2]; b += s_red[w * 2 + 1]; }
+    const double Np = (double)A;
+    grad[blockIdx.x] = (measure == CMAXB_CONTRAST_MEAN_SQUARE) ? 2.0 * (b / Np) : 2.0 * (b / Np - mean[0] * (a / Np));
+  }
+}
+
+// updateAlpha sums (event_pano_warper.cpp:134-165): out[0..4] = sum(1-exp(-IGp)), sum(IGp),
+// sum(1-exp(-IL)), sum(IL), countNonZero(IGp); IL = IL_old + IL_new.
+__global__ void __launch_bounds__(256)
+be_alpha_sums_kernel(const float* __restrict__ igp, const float* __restrict__ il_old, const float* __restrict__ il_new,
+                     long long A, double* __restrict__ out) {
+  __shared__ double s_red[8 * 5];
+  double v[5] = {0, 0, 0, 0, 0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A; i += (long long)gridDim.x * blockDim.x) {
+    const float a = igp[i];
+    const float l = il_old[i] + il_new[i];
+    v[0] += (double)(1.f - expf(-1.0f * a));
+    v[1] += (double)a;
+    v[2] += (double)(1.f - expf(-1.0f * l));
+    v[3] += (double)l;
+    v[4] += (a != 0.f) ? 1.0 : 0.0;
+  }
+  block_atomic_add<5>(v, out, s_red);
+}
+
+}  // namespace cmaxb

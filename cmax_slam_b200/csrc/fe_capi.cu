@@ -1,0 +1,372 @@
+// fe_capi.cu -- C ABI of the front-end path (see include/cmax_b200.h).
+#include "capi_common.cuh"
+#include "fe_kernels.cuh"
+#include "image_kernels.cuh"
+
+using namespace cmaxb;
+
+namespace cmaxb {
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launch_count{0};
+}  // namespace cmaxb
+
+struct cmaxb_fe {
+  cmaxb_fe_cfg cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  long long A = 0;          // pixels
+  int kmax = 1;
+  Taps taps{};
+  double4* d_lut = nullptr;
+  uint4* d_ev = nullptr; size_t ev_cap = 0;
+  double* d_dt = nullptr; size_t dt_cap = 0;
+  long long n = 0, nb = 0;
+  bool have_packet = false;
+  int* d_flags = nullptr; int* h_flags = nullptr;
+  float* d_img1 = nullptr; float* d_blur1 = nullptr; float* d_G = nullptr;
+  float4* d_img4 = nullptr; float4* d_blur4 = nullptr;
+  int* d_cells = nullptr; size_t cells_cap = 0;
+  double* d_omegas = nullptr; double* h_omegas = nullptr;
+  double* d_acc = nullptr; unsigned int* d_ticket = nullptr; unsigned int* d_ticket2 = nullptr;
+  double* d_gacc = nullptr; double* d_result = nullptr; double* d_mean = nullptr; double* h_result = nullptr;
+  int last_k = 0; bool last_grad = false; bool pending = false;
+  KernelProfiler prof;
+};
+
+static FeGeom fe_geom(const cmaxb_fe* fe) {
+  FeGeom g;
+  g.ev = fe->d_ev; g.n = fe->n; g.batch_size = fe->cfg.batch_size; g.dt_tab = fe->d_dt; g.lut = fe->d_lut;
+  g.W = fe->cfg.width; g.H = fe->cfg.height;
+  g.fx = fe->cfg.fx; g.fy = fe->cfg.fy; g.cx = fe->cfg.cx; g.cy = fe->cfg.cy;
+  return g;
+}
+
+extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
+  if (!cfg || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->width < 4 || cfg->height < 4 || !cfg->lut_xyz || cfg->batch_size <= 0)
+    return set_error(CMAXB_ERR_INVALID, "bad front-end configuration");
+  if (cfg->grad_mode != CMAXB_GRAD_DENSE && cfg->grad_mode != CMAXB_GRAD_ADJOINT)
+    return set_error(CMAXB_ERR_INVALID, "bad grad_mode");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return set_error(CMAXB_ERR_CUDA, "no CUDA device: libcmax_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return set_error(CMAXB_ERR_INVALID, "bad device ordinal");
+  CMAXB_CUDA_TRY(cudaSetDevice(cfg->device));
+  cmaxb_fe* fe = new cmaxb_fe();
+  fe->cfg = *cfg;
+  fe->cfg.lut_xyz = nullptr;
+  fe->device = cfg->device;
+  fe->A = (long long)cfg->width * cfg->height;
+  fe->kmax = cfg->max_hypotheses > 0 ? cfg->max_hypotheses : 1;
+  int rc = make_taps(cfg->blur_sigma, &fe->taps);
+  if (rc != CMAXB_OK) { delete fe; return rc; }
+  if (fe->taps.r + 2 > cfg->width || fe->taps.r + 2 > cfg->height) { delete fe; return set_error(CMAXB_ERR_INVALID, "image smaller than the blur kernel"); }
+  auto fail = [&](int code) { cmaxb_fe_destroy(fe); return code; };
+  if (cfg->stream) fe->stream = (cudaStream_t)cfg->stream;
+  else {
+    if (cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "cudaStreamCreate failed"));
+    fe->own_stream = true;
+  }
+  if (fe->prof.init() != CMAXB_OK) return fail(CMAXB_ERR_CUDA);
+  // LUT padded to 32-byte records
+  {
+    std::vector<double4> lut((size_t)fe->A);
+    for (long long i = 0; i < fe->A; ++i) lut[i] = make_double4(cfg->lut_xyz[3 * i], cfg->lut_xyz[3 * i + 1], cfg->lut_xyz[3 * i + 2], 0.0);
+    if (dev_alloc(&fe->d_lut, (size_t)fe->A) != CMAXB_OK) return fail(CMAXB_ERR_CUDA);
+    if (cudaMemcpy(fe->d_lut, lut.data(), sizeof(double4) * fe->A, cudaMemcpyHostToDevice) != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "LUT upload failed"));
+  }
+  const size_t k = (size_t)fe->kmax, A = (size_t)fe->A;
+  bool ok = true;
+  ok = ok && dev_alloc(&fe->d_flags, 1) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_img1, k * A) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_omegas, k * 3) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_acc, k * kNAcc) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_ticket, k) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_ticket2, k) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_gacc, k * 3) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_result, k * 4) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_mean, k) == CMAXB_OK;
+  if (cfg->grad_mode == CMAXB_GRAD_ADJOINT) {
+    ok = ok && dev_alloc(&fe->d_blur1, k * A) == CMAXB_OK;
+    ok = ok && dev_alloc(&fe->d_G, k * A) == CMAXB_OK;
+  } else {
+    ok = ok && dev_alloc(&fe->d_img4, k * A) == CMAXB_OK;
+  }
+  if (!ok) return fail(CMAXB_ERR_CUDA);
+  ok = ok && cudaMallocHost((void**)&fe->h_flags, sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&fe->h_omegas, sizeof(double) * 3 * k) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&fe->h_result, sizeof(double) * 4 * k) == cudaSuccess;
+  ok = ok && cudaMemset(fe->d_acc, 0, sizeof(double) * k * kNAcc) == cudaSuccess;
+  ok = ok && cudaMemset(fe->d_ticket, 0, sizeof(unsigned) * k) == cudaSuccess;
+  ok = ok && cudaMemset(fe->d_ticket2, 0, sizeof(unsigned) * k) == cudaSuccess;
+  ok = ok && cudaMemset(fe->d_gacc, 0, sizeof(double) * k * 3) == cudaSuccess;
+  ok = ok && cudaMemset(fe->d_result, 0, sizeof(double) * k * 4) == cudaSuccess;
+  if (!ok) return fail(set_error(CMAXB_ERR_CUDA, "front-end buffer allocation failed"));
+  // opt in to large dynamic shared memory for the image kernels
+  const int r = fe->taps.r;
+  cudaFuncSetAttribute(blur_reduce_kernel<1, SrcPlane, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<1>(r));
+  cudaFuncSetAttribute(blur_reduce_kernel<1, SrcPlane, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<1>(r));
+  cudaFuncSetAttribute(blur_reduce_kernel<4, SrcPlane4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<4>(r));
+  cudaFuncSetAttribute(blur_reduce_kernel<4, SrcPlane4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<4>(r));
+  cudaFuncSetAttribute(adjoint_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjoint_smem_bytes(r));
+  if (cudaGetLastError() != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "cudaFuncSetAttribute failed (blur radius too large for shared memory?)"));
+  *out = fe;
+  return CMAXB_OK;
+}
+
+extern "C" void cmaxb_fe_destroy(cmaxb_fe* fe) {
+  if (!fe) return;
+  cudaSetDevice(fe->device);
+  if (fe->stream) cudaStreamSynchronize(fe->stream);
+  cudaFree(fe->d_lut); cudaFree(fe->d_ev); cudaFree(fe->d_dt); cudaFree(fe->d_flags);
+  cudaFree(fe->d_img1); cudaFree(fe->d_blur1); cudaFree(fe->d_G); cudaFree(fe->d_img4); cudaFree(fe->d_blur4);
+  cudaFree(fe->d_cells); cudaFree(fe->d_omegas); cudaFree(fe->d_acc); cudaFree(fe->d_ticket); cudaFree(fe->d_ticket2);
+  cudaFree(fe->d_gacc); cudaFree(fe->d_result); cudaFree(fe->d_mean);
+  if (fe->h_flags) cudaFreeHost(fe->h_flags);
+  if (fe->h_omegas) cudaFreeHost(fe->h_omegas);
+  if (fe->h_result) cudaFreeHost(fe->h_result);
+  fe->prof.destroy();
+  if (fe->own_stream && fe->stream) cudaStreamDestroy(fe->stream);
+  delete fe;
+}
+
+extern "C" int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec) {
+  if (!fe || (!events && n > 0)) return set_error(CMAXB_ERR_INVALID, "null argument");
+  CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream)); fe->pending = false; }
+  fe->have_packet = false;
+  const long long bs = fe->cfg.batch_size;
+  const long long nb = ((long long)n + bs - 1) / bs;
+  if (n > fe->ev_cap) {
+    cudaFree(fe->d_ev); fe->d_ev = nullptr; fe->ev_cap = 0;
+    CMAXB_TRY(dev_alloc(&fe->d_ev, n));
+    fe->ev_cap = n;
+  }
+  if ((size_t)nb > fe->dt_cap) {
+    cudaFree(fe->d_dt); fe->d_dt = nullptr; fe->dt_cap = 0;
+    CMAXB_TRY(dev_alloc(&fe->d_dt, (size_t)nb));
+    fe->dt_cap = (size_t)nb;
+  }
+  fe->n = (long long)n; fe->nb = nb;
+  if (n > 0) {
+    cudaStream_t s = fe->stream;
+    CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->d_ev, events, sizeof(cmaxb_event) * n, cudaMemcpyHostToDevice, s));
+    CMAXB_CUDA_TRY(cudaMemsetAsync(fe->d_flags, 0, sizeof(int), s));
+    const uint4* ev = fe->d_ev; const long long nn = fe->n; int* flags = fe->d_flags;
+    const int W = fe->cfg.width, H = fe->cfg.height; double* dt = fe->d_dt; const int ibs = (int)bs;
+    CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
+      validate_events_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(ev, nn, W, H, flags);
+    }));
+    CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
+      fe_batch_dt_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ev, nn, ibs, t_ref_sec, dt, nb, flags);
+    }));
+    CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->h_flags, fe->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+    if (*fe->h_flags & 2) return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor");
+    if (*fe->h_flags & 1) return set_error(CMAXB_ERR_TIME_ORDER, "Events must span a non-negative time interval");
+  }
+  fe->have_packet = true;
+  return CMAXB_OK;
+}
+
+static int fe_upload_omegas(cmaxb_fe* fe, const double* omegas, int k) {
+  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream)); fe->pending = false; }
+  std::memcpy(fe->h_omegas, omegas, sizeof(double) * 3 * k);
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->d_omegas, fe->h_omegas, sizeof(double) * 3 * k, cudaMemcpyHostToDevice, fe->stream));
+  return CMAXB_OK;
+}
+
+static dim3 fe_event_grid(const cmaxb_fe* fe, int k) {
+  long long blocks = (fe->n + kFeThreads - 1) / kFeThreads;
+  const long long cap = 148LL * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return dim3((unsigned)blocks, (unsigned)k, 1);
+}
+static dim3 img_grid(int W, int H, int k) { return dim3((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, k); }
+
+// scatter the value plane(s) of k hypotheses into d_img1
+static int fe_run_scatter_value(cmaxb_fe* fe, int k) {
+  cudaStream_t s = fe->stream;
+  CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(fe->d_img1, 0, sizeof(float) * fe->A * k, s); }));
+  if (fe->n > 0) {
+    const FeGeom g = fe_geom(fe);
+    CMAXB_TRY(fe->prof.run(CMAXB_K_FE_SCATTER, s, true, [&] {
+      fe_scatter_kernel<0><<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, fe->d_img1, nullptr, fe->A);
+    }));
+  }
+  return CMAXB_OK;
+}
+static int fe_run_scatter_dense(cmaxb_fe* fe, int k) {
+  cudaStream_t s = fe->stream;
+  if (!fe->d_img4) CMAXB_TRY(dev_alloc(&fe->d_img4, (size_t)fe->kmax * fe->A));
+  CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(fe->d_img4, 0, sizeof(float4) * fe->A * k, s); }));
+  if (fe->n > 0) {
+    const FeGeom g = fe_geom(fe);
+    CMAXB_TRY(fe->prof.run(CMAXB_K_FE_SCATTER, s, true, [&] {
+      fe_scatter_kernel<1><<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, nullptr, fe->d_img4, fe->A);
+    }));
+  }
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, int want_grad) {
+  if (!fe || !omegas) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!fe->have_packet) return set_error(CMAXB_ERR_STATE, "no event packet: call cmaxb_fe_set_packet first");
+  if (k < 1 || k > fe->kmax) return set_error(CMAXB_ERR_INVALID, "k exceeds cfg.max_hypotheses");
+  CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  CMAXB_TRY(fe_upload_omegas(fe, omegas, k));
+  cudaStream_t s = fe->stream;
+  const int W = fe->cfg.width, H = fe->cfg.height, r = fe->taps.r, measure = fe->cfg.contrast_measure;
+  const ReduceOut ro{fe->d_acc, fe->d_ticket, fe->d_result, fe->d_mean};
+  const dim3 ig = img_grid(W, H, k);
+  if (want_grad && fe->cfg.grad_mode == CMAXB_GRAD_DENSE) {
+    CMAXB_TRY(fe_run_scatter_dense(fe, k));
+    const SrcPlane4 src{fe->d_img4, fe->A};
+    CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+      blur_reduce_kernel<4, SrcPlane4, false><<<ig, kImgThreads, blur_smem_bytes<4>(r), s>>>(src, W, H, fe->taps, nullptr, 0, ro, measure);
+    }));
+  } else {
+    CMAXB_TRY(fe_run_scatter_value(fe, k));
+    const SrcPlane src{fe->d_img1, fe->A};
+    if (!want_grad) {
+      CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+        blur_reduce_kernel<1, SrcPlane, false><<<ig, kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, fe->taps, nullptr, 0, ro, measure);
+      }));
+    } else {
+      CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+        blur_reduce_kernel<1, SrcPlane, true><<<ig, kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, fe->taps, fe->d_blur1, fe->A, ro, measure);
+      }));
+      CMAXB_TRY(fe->prof.run(CMAXB_K_ADJOINT_BLUR, s, true, [&] {
+        adjoint_blur_kernel<<<ig, kImgThreads, adjoint_smem_bytes(r), s>>>(fe->d_blur1, fe->A, W, H, fe->taps, fe->d_mean, measure, fe->d_G);
+      }));
+      const FeGeom g = fe_geom(fe);
+      CMAXB_TRY(fe->prof.run(CMAXB_K_FE_GATHER, s, true, [&] {
+        fe_gather_kernel<<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, fe->d_G, fe->A, fe->d_gacc, fe->d_ticket2, fe->d_result);
+      }));
+    }
+  }
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->h_result, fe->d_result, sizeof(double) * 4 * k, cudaMemcpyDeviceToHost, s));
+  fe->last_k = k; fe->last_grad = want_grad != 0; fe->pending = true;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grads3k) {
+  if (!fe || !contrasts) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (fe->last_k <= 0) return set_error(CMAXB_ERR_STATE, "no evaluation launched");
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+  fe->pending = false;
+  for (int h = 0; h < fe->last_k; ++h) {
+    contrasts[h] = fe->h_result[4 * h];
+    if (grads3k && fe->last_grad)
+      for (int c = 0; c < 3; ++c) grads3k[3 * h + c] = fe->h_result[4 * h + 1 + c];
+  }
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_eval_batch(cmaxb_fe* fe, const double* omegas, int k, double* contrasts, double* grads3k) {
+  CMAXB_TRY(cmaxb_fe_eval_launch(fe, omegas, k, grads3k != nullptr));
+  return cmaxb_fe_eval_fetch(fe, contrasts, grads3k);
+}
+
+extern "C" int cmaxb_fe_eval(cmaxb_fe* fe, const double omega[3], double* contrast, double* grad3) {
+  return cmaxb_fe_eval_batch(fe, omega, 1, contrast, grad3);
+}
+
+extern "C" int cmaxb_fe_get_iwe(cmaxb_fe* fe, const double omega[3], int blurred, float* out) {
+  if (!fe || !omega || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!fe->have_packet) return set_error(CMAXB_ERR_STATE, "no event packet");
+  CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  CMAXB_TRY(fe_upload_omegas(fe, omega, 1));
+  CMAXB_TRY(fe_run_scatter_value(fe, 1));
+  cudaStream_t s = fe->stream;
+  const float* src_ptr = fe->d_img1;
+  if (blurred && fe->taps.r > 0) {
+    if (!fe->d_blur1) CMAXB_TRY(dev_alloc(&fe->d_blur1, (size_t)fe->kmax * fe->A));
+    const SrcPlane src{fe->d_img1, fe->A};
+    const ReduceOut ro{fe->d_acc, fe->d_ticket, fe->d_result, fe->d_mean};
+    const int W = fe->cfg.width, H = fe->cfg.height, r = fe->taps.r;
+    CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+      blur_reduce_kernel<1, SrcPlane, true><<<img_grid(W, H, 1), kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, fe->taps, fe->d_blur1, fe->A, ro, fe->cfg.contrast_measure);
+    }));
+    src_ptr = fe->d_blur1;
+  }
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(out, src_ptr, sizeof(float) * fe->A, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_get_deriv(cmaxb_fe* fe, const double omega[3], int blurred, float* out) {
+  if (!fe || !omega || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!fe->have_packet) return set_error(CMAXB_ERR_STATE, "no event packet");
+  CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  CMAXB_TRY(fe_upload_omegas(fe, omega, 1));
+  CMAXB_TRY(fe_run_scatter_dense(fe, 1));
+  cudaStream_t s = fe->stream;
+  const float4* src_ptr = fe->d_img4;
+  if (blurred && fe->taps.r > 0) {
+    if (!fe->d_blur4) CMAXB_TRY(dev_alloc(&fe->d_blur4, (size_t)fe->A));
+    const SrcPlane4 src{fe->d_img4, fe->A};
+    const ReduceOut ro{fe->d_acc, fe->d_ticket, fe->d_result, fe->d_mean};
+    const int W = fe->cfg.width, H = fe->cfg.height, r = fe->taps.r;
+    CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+      blur_reduce_kernel<4, SrcPlane4, true><<<img_grid(W, H, 1), kImgThreads, blur_smem_bytes<4>(r), s>>>(src, W, H, fe->taps, fe->d_blur4, fe->A, ro, fe->cfg.contrast_measure);
+    }));
+    src_ptr = fe->d_blur4;
+  }
+  std::vector<float4> tmp((size_t)fe->A);
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(tmp.data(), src_ptr, sizeof(float4) * fe->A, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  for (long long i = 0; i < fe->A; ++i) { out[3 * i] = tmp[i].y; out[3 * i + 1] = tmp[i].z; out[3 * i + 2] = tmp[i].w; }
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_get_cells(cmaxb_fe* fe, const double omega[3], int32_t* out) {
+  if (!fe || !omega || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!fe->have_packet) return set_error(CMAXB_ERR_STATE, "no event packet");
+  CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  if (fe->n == 0) return CMAXB_OK;
+  CMAXB_TRY(fe_upload_omegas(fe, omega, 1));
+  if ((size_t)fe->n > fe->cells_cap) {
+    cudaFree(fe->d_cells); fe->d_cells = nullptr; fe->cells_cap = 0;
+    CMAXB_TRY(dev_alloc(&fe->d_cells, (size_t)fe->n));
+    fe->cells_cap = (size_t)fe->n;
+  }
+  cudaStream_t s = fe->stream;
+  const FeGeom g = fe_geom(fe);
+  CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
+    fe_cells_kernel<<<(unsigned)((fe->n + 255) / 256), 256, 0, s>>>(g, fe->d_omegas, fe->d_cells);
+  }));
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(out, fe->d_cells, sizeof(int) * fe->n, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_profile(cmaxb_fe* fe, int enable) {
+  if (!fe) return set_error(CMAXB_ERR_INVALID, "null argument");
+  fe->prof.enabled = enable != 0;
+  fe->prof.reset();
+  return CMAXB_OK;
+}
+extern "C" int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms, uint64_t* launches) {
+  if (!fe || !ms || !launches) return set_error(CMAXB_ERR_INVALID, "null argument");
+  for (int i = 0; i < CMAXB_K_COUNT; ++i) { ms[i] = fe->prof.ms[i]; launches[i] = fe->prof.launches[i]; }
+  return CMAXB_OK;
+}
+
+// ---- diagnostics ----------------------------------------------------------------------------------
+extern "C" const char* cmaxb_last_error(void) { return g_last_error.c_str(); }
+extern "C" int cmaxb_version(void) { return CMAXB_VERSION; }
+extern "C" int cmaxb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" uint64_t cmaxb_launch_count(void) { return g_launch_count.load(); }
+extern "C" const char* cmaxb_kernel_name(int kind) {
+  static const char* names[CMAXB_K_COUNT] = {"zero(memset)", "fe_scatter", "fe_gather", "blur_reduce", "adjoint_blur",
+                                             "be_poses", "be_scatter", "be_gather", "be_grad_reduce", "misc"};
+  return (kind >= 0 && kind < CMAXB_K_COUNT) ? names[kind] : "?";
+}

@@ -1,0 +1,129 @@
+"""Host-side mirror of the reference's front-end cost interface over the C ABI.
+
+Reference surface mirrored (same names, argument meaning and sign conventions):
+  AngVelEstimator::computeImageOfWarpedEvents   src/frontend/local_image_warped_events.cpp:10-57
+  cmax_slam::computeContrast                    src/frontend/local_focus_funcs.cpp:82-120
+  local_contrast_fdf / _f / _df (GSL callbacks) src/frontend/local_optim_contrast_gsl.cpp:20-70
+All arithmetic happens in libcmax_b200.so on the GPU; this module only marshals pointers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import GRAD_ADJOINT, GRAD_DENSE, CmaxbError  # noqa: F401
+
+
+class AngVelEstimatorCMax:
+    """Device-resident front-end contrast functor (one handle = one CUDA stream)."""
+
+    def __init__(self, width, height, K4, lut_xyz, blur_sigma=1.0, event_batch_size=100, contrast_measure=0,
+                 grad_mode=GRAD_ADJOINT, device=0, stream=None, max_hypotheses=1):
+        self._L = _capi.lib()
+        lut = np.ascontiguousarray(lut_xyz, dtype=np.float64).reshape(-1, 3)
+        if lut.shape[0] != width * height:
+            raise ValueError("lut_xyz must hold width*height bearing vectors")
+        cfg = _capi.FeCfg(width, height, K4[0], K4[1], K4[2], K4[3], lut.ctypes.data, float(blur_sigma),
+                          int(event_batch_size), int(contrast_measure), int(grad_mode), int(device),
+                          None if stream is None else C.c_void_p(int(stream)), int(max_hypotheses))
+        h = C.c_void_p()
+        _capi.check(self._L.cmaxb_fe_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.width, self.height = width, height
+        self.max_hypotheses = max(1, int(max_hypotheses))
+        self.n_events = 0
+        self._res_c = np.zeros(self.max_hypotheses)
+        self._res_g = np.zeros((self.max_hypotheses, 3))
+        self._om = np.zeros((self.max_hypotheses, 3))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cmaxb_fe_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- packet ---------------------------------------------------------------------------------
+    def set_packet(self, events, t_ref_sec):
+        """events: numpy structured array with the 16-byte dvs_msgs::Event layout (synth.EVENT_DTYPE)
+        or a (ptr, n) tuple of pinned host memory; t_ref_sec = time_packet_.toSec()."""
+        if isinstance(events, tuple):
+            ptr, n = events
+        else:
+            ev = np.ascontiguousarray(events)
+            if ev.dtype.itemsize != 16:
+                raise ValueError("events must be 16-byte dvs_msgs::Event records")
+            self._ev_keep = ev
+            ptr, n = ev.ctypes.data, len(ev)
+        _capi.check(self._L.cmaxb_fe_set_packet(self._h, C.c_void_p(ptr), n, float(t_ref_sec)))
+        self.n_events = n
+
+    # -- cost ------------------------------------------------------------------------------------
+    def eval(self, ang_vel, want_grad=True):
+        """(+contrast, +gradient[3] or None) at one angular velocity."""
+        om = np.ascontiguousarray(ang_vel, dtype=np.float64).reshape(3)
+        c = C.c_double()
+        g = np.zeros(3)
+        _capi.check(self._L.cmaxb_fe_eval(self._h, _capi.dptr(om), C.byref(c), _capi.dptr(g) if want_grad else None))
+        return c.value, (g if want_grad else None)
+
+    def eval_batch(self, ang_vels, want_grad=True):
+        om = np.ascontiguousarray(ang_vels, dtype=np.float64).reshape(-1, 3)
+        k = om.shape[0]
+        c = np.zeros(k)
+        g = np.zeros((k, 3))
+        _capi.check(self._L.cmaxb_fe_eval_batch(self._h, _capi.dptr(om), k, _capi.dptr(c), _capi.dptr(g) if want_grad else None))
+        return c, (g if want_grad else None)
+
+    def eval_launch(self, ang_vels, want_grad=True):
+        om = np.ascontiguousarray(ang_vels, dtype=np.float64).reshape(-1, 3)
+        self._k = om.shape[0]
+        self._om[: self._k] = om
+        _capi.check(self._L.cmaxb_fe_eval_launch(self._h, _capi.dptr(self._om), self._k, int(want_grad)))
+
+    def eval_fetch(self):
+        _capi.check(self._L.cmaxb_fe_eval_fetch(self._h, _capi.dptr(self._res_c), _capi.dptr(self._res_g)))
+        return self._res_c[: self._k].copy(), self._res_g[: self._k].copy()
+
+    # -- reference-named entry points ------------------------------------------------------------
+    def computeImageOfWarpedEvents(self, ang_vel, with_deriv=False, blurred=True):
+        """IWE (H,W) float32 [and derivative image (H,W,3)] as the reference function fills them."""
+        om = np.ascontiguousarray(ang_vel, dtype=np.float64).reshape(3)
+        iwe = np.empty((self.height, self.width), np.float32)
+        _capi.check(self._L.cmaxb_fe_get_iwe(self._h, _capi.dptr(om), int(blurred), C.c_void_p(iwe.ctypes.data)))
+        if not with_deriv:
+            return iwe
+        d = np.empty((self.height, self.width, 3), np.float32)
+        _capi.check(self._L.cmaxb_fe_get_deriv(self._h, _capi.dptr(om), int(blurred), C.c_void_p(d.ctypes.data)))
+        return iwe, d
+
+    def warped_cells(self, ang_vel):
+        om = np.ascontiguousarray(ang_vel, dtype=np.float64).reshape(3)
+        out = np.empty(self.n_events, np.int32)
+        _capi.check(self._L.cmaxb_fe_get_cells(self._h, _capi.dptr(om), C.c_void_p(out.ctypes.data)))
+        return out
+
+    # -- profiling -------------------------------------------------------------------------------
+    def profile(self, enable=True):
+        _capi.check(self._L.cmaxb_fe_profile(self._h, int(enable)))
+
+    def kernel_times(self):
+        ms = np.zeros(_capi.K_COUNT)
+        n = np.zeros(_capi.K_COUNT, np.uint64)
+        _capi.check(self._L.cmaxb_fe_kernel_times(self._h, _capi.dptr(ms), n.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return {_capi.K_NAMES[i]: (float(ms[i]), int(n[i])) for i in range(_capi.K_COUNT) if n[i] > 0}
+
+
+# GSL callback triple with the reference's exact semantics: returns -contrast / -gradient
+# (local_optim_contrast_gsl.cpp:48-54); df=None means value only (:32,40).
+def local_contrast_fdf(v, estimator, want_df=True):
+    c, g = estimator.eval(v, want_grad=want_df)
+    return -c, (None if g is None else -g)
+
+
+def local_contrast_f(v, estimator):
+    return local_contrast_fdf(v, estimator, want_df=False)[0]
+
+
+def local_contrast_df(v, estimator):
+    return local_contrast_fdf(v, estimator, want_df=True)[1]

@@ -1,0 +1,185 @@
+/*
+ * cmax_b200.h -- C ABI of libcmax_b200.so: the B200-native (sm_100a) contrast-maximisation
+ * inner loop of CMax-SLAM (reference: tub-rip/cmax_slam @ 12342de).
+ *
+ * The library replaces, beneath the reference's GSL f/df/fdf cost callbacks, the pair of calls
+ *   computeImageOfWarpedEvents(...) + computeContrast(...)
+ * made by
+ *   front-end: local_contrast_fdf            src/frontend/local_optim_contrast_gsl.cpp:20-56
+ *   back-end : global_contrast_fdf           src/backend/global_optim_contrast_gsl_analytical.cpp:17-68
+ * Plain C: pointers and sizes only, no C++ / OpenCV / ROS / GSL / torch types.  Every function
+ * returns 0 on success or a negative cmaxb_status; the message is in cmaxb_last_error()
+ * (thread local).  The library returns +contrast / +gradient; the GSL adapter negates, as the
+ * reference does (local_optim_contrast_gsl.cpp:48-54).  There is NO CPU fallback: without a CUDA
+ * device every create() fails with CMAXB_ERR_CUDA.
+ *
+ * Threading: one handle = one CUDA stream + private device buffers.  Calls on different handles
+ * may run concurrently (FE thread / BE thread, src/cmax_slam.cpp:92); one handle is not
+ * re-entrant (neither are the reference functions: function-local statics).
+ */
+#ifndef CMAX_B200_H_
+#define CMAX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMAXB_VERSION 100
+
+typedef enum cmaxb_status {
+  CMAXB_OK = 0,
+  CMAXB_ERR_INVALID = -1,      /* bad argument */
+  CMAXB_ERR_CUDA = -2,         /* CUDA runtime error / no device */
+  CMAXB_ERR_EVENT_RANGE = -3,  /* event pixel outside the sensor (reference: vector::at throws) */
+  CMAXB_ERR_TIME_ORDER = -4,   /* a batch spans a negative time (reference: CHECK_GE aborts,
+                                  local_image_warped_events.cpp:72) */
+  CMAXB_ERR_SPLINE_RANGE = -5, /* batch time outside the spline (reference: BASALT_ASSERT aborts,
+                                  so3_spline.h:221-230) */
+  CMAXB_ERR_STATE = -6         /* call order (e.g. eval before set_packet) */
+} cmaxb_status;
+
+/* dvs_msgs::Event exactly as the ROS C++ generator lays it out (uint16 x, uint16 y,
+ * ros::Time ts{uint32 sec, uint32 nsec}, bool polarity, 3 pad bytes): 16 bytes, so a
+ * std::vector<dvs_msgs::Event>::data() can be passed as is (event_subset_,
+ * include/frontend/ang_vel_estimator.h, include/backend/pose_graph_optimizer.h). */
+typedef struct cmaxb_event {
+  uint16_t x, y;
+  uint32_t sec, nsec;
+  uint8_t polarity;
+  uint8_t pad_[3];
+} cmaxb_event;
+
+enum { CMAXB_CONTRAST_VARIANCE = 0, CMAXB_CONTRAST_MEAN_SQUARE = 1 }; /* local_focus_funcs.h:7-11 */
+
+/* How the analytic gradient is evaluated (identical mathematics, different data movement):
+ *   DENSE   : accumulate the derivative images, blur them, reduce -- what the reference does
+ *             (local_image_warped_events.cpp:153-167, local_focus_funcs.cpp:34-42).
+ *   ADJOINT : g = sum_events sum_corners dw_c * [blur^T(2(I-mu))/Np](corner): one extra image and a
+ *             gather pass over the events; no derivative images exist.                       */
+enum { CMAXB_GRAD_DENSE = 0, CMAXB_GRAD_ADJOINT = 1 };
+
+/* ------------------------------------------------------------------ front-end ------------ */
+typedef struct cmaxb_fe cmaxb_fe;
+
+typedef struct cmaxb_fe_cfg {
+  int32_t width, height;     /* cam_width_, cam_height_ */
+  double fx, fy, cx, cy;     /* camera_matrix_ (0,0),(1,1),(0,2),(1,2); ang_vel_estimator.cpp:42 */
+  const double* lut_xyz;     /* precomputed_bearing_vectors_: width*height*3 doubles, copied */
+  double blur_sigma;         /* params.warp_opt.blur_sigma (<=0: no blur) */
+  int32_t batch_size;        /* params.warp_opt.event_batch_size */
+  int32_t contrast_measure;  /* params.process_opt.contrast_measure */
+  int32_t grad_mode;         /* CMAXB_GRAD_* */
+  int32_t device;            /* CUDA device ordinal */
+  void* stream;              /* optional cudaStream_t to run on; NULL = library-owned stream */
+  int32_t max_hypotheses;    /* capacity of eval_batch (<=0: 1) */
+} cmaxb_fe_cfg;
+
+int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out);
+void cmaxb_fe_destroy(cmaxb_fe* fe);
+
+/* Upload one event packet (replaces the copy into event_subset_, ang_vel_estimator.cpp:137-147)
+ * and its reference time time_packet_.toSec().  `events` is host memory (pinned memory makes
+ * the copy asynchronous).  Validates pixel range and batch time order. */
+int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec);
+
+/* One cost evaluation = computeImageOfWarpedEvents + computeContrast.  grad3 == NULL => value
+ * only (the local_contrast_f path, local_optim_contrast_gsl.cpp:58-63). */
+int cmaxb_fe_eval(cmaxb_fe* fe, const double omega[3], double* contrast, double* grad3);
+
+/* k hypotheses on the resident packet in one pass over the events (BASELINE config C3). */
+int cmaxb_fe_eval_batch(cmaxb_fe* fe, const double* omegas, int k, double* contrasts, double* grads3k);
+
+/* Asynchronous pair used by the multi-GPU driver and the benchmark: launch returns as soon as
+ * the work is queued on the stream; fetch waits and returns the results of the last launch. */
+int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, int want_grad);
+int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grads3k);
+
+/* IWE for display / parity (publishEventImage, ang_vel_estimator.cpp:203-233).  blurred=0: raw
+ * accumulator; 1: after the Gaussian blur.  out: height*width floats. */
+int cmaxb_fe_get_iwe(cmaxb_fe* fe, const double omega[3], int blurred, float* out);
+/* Derivative images (height*width*3 floats, interleaved like CV_32FC3).  Parity / debugging. */
+int cmaxb_fe_get_deriv(cmaxb_fe* fe, const double omega[3], int blurred, float* out);
+/* Per-event integer cell yy*width+xx (-1 = rejected by the bounds test,
+ * local_image_warped_events.cpp:139-142).  n ints.  Parity / debugging. */
+int cmaxb_fe_get_cells(cmaxb_fe* fe, const double omega[3], int32_t* out);
+
+/* ------------------------------------------------------------------ back-end ------------- */
+typedef struct cmaxb_be cmaxb_be;
+
+typedef struct cmaxb_be_cfg {
+  int32_t sensor_width, sensor_height;
+  const double* lut_xyz;        /* sensor_width*sensor_height*3, copied */
+  int32_t pano_width, pano_height; /* map_opt_.pano_width / pano_height */
+  double blur_sigma;
+  int32_t batch_size;           /* warp_opt_.event_batch_size */
+  int32_t event_sample_rate;    /* warp_opt_.event_sample_rate */
+  int32_t spline_order;         /* 2 = LinearTrajectory (So3Spline<2>), 4 = CubicTrajectory (So3Spline<4>) */
+  int32_t contrast_measure;
+  int32_t grad_mode;            /* CMAXB_GRAD_* (DENSE keeps 3*K_opt band images: small problems only) */
+  int32_t device;
+  void* stream;
+} cmaxb_be_cfg;
+
+typedef struct cmaxb_be_window {
+  const cmaxb_event* events;    /* event_subset_ of the window (host) */
+  size_t n_events;
+  const double* knots_xyzw;     /* n_knots unit quaternions (x,y,z,w): control poses
+                                   idx_cp_traj_beg_ .. end (trajectory.cpp:249-254) */
+  int32_t n_knots;
+  int64_t t0_ns;                /* int64_t(1e9 * t_traj_temp_beg)   trajectory.cpp:60-61,255 */
+  int64_t dt_ns;                /* int64_t(1e9 * dt_knots)          trajectory.cpp:60 */
+  int32_t n_fixed;              /* num_cps_fixed_ = idx_cp_opt_beg_ - idx_cp_traj_beg_ */
+  uint32_t tnext_sec, tnext_nsec; /* t_next_win_beg_ (pose_graph_optimizer.cpp:290) */
+  const float* IGp;             /* pano floats or NULL (= zeros) */
+  double alpha;                 /* alpha_; NaN => computed on the first eval from IGp and that
+                                   eval's IL exactly as updateAlpha (event_pano_warper.cpp:134-165,
+                                   201-210) and then frozen for the window */
+} cmaxb_be_window;
+
+int cmaxb_be_create(const cmaxb_be_cfg* cfg, cmaxb_be** out);
+void cmaxb_be_destroy(cmaxb_be* be);
+int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w);
+/* x: 3*(n_knots-n_fixed) incremental rotation vectors (the gsl_vector of global_contrast_fdf);
+ * grad: same length or NULL (value only). */
+int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contrast, double* grad);
+int cmaxb_be_get_alpha(cmaxb_be* be, double* alpha);
+/* IL_old_ / IL_new_ at x (needed by updateIG, event_pano_warper.cpp:109-126); either may be NULL */
+int cmaxb_be_get_il(cmaxb_be* be, const double* x, int n, float* il_old, float* il_new);
+/* final image I = blur(IL + alpha*IGp) at x */
+int cmaxb_be_get_iwe(cmaxb_be* be, const double* x, int n, int blurred, float* out);
+/* dense derivative bands (3*(n_knots-n_fixed) planes of pano floats, planar). Parity / debugging;
+ * allocates the band images on first use. */
+int cmaxb_be_get_bands(cmaxb_be* be, const double* x, int n, int blurred, float* out);
+int cmaxb_be_get_cells(cmaxb_be* be, const double* x, int n, int32_t* out);
+/* per-batch pose table at x: R (9 doubles, row-major), Jk (3 x 3*order floats, row-major),
+ * idx_cp_beg.  Parity / debugging of the device So3Spline. Arrays sized n_batches. */
+int cmaxb_be_get_poses(cmaxb_be* be, const double* x, int n, int64_t* n_batches, double* R9,
+                       float* Jk, int32_t* idx_cp_beg, int64_t capacity);
+
+/* ------------------------------------------------------------------ diagnostics ---------- */
+const char* cmaxb_last_error(void);
+int cmaxb_version(void);
+int cmaxb_device_count(void);
+/* number of kernels THIS LIBRARY launched since load (all handles) */
+uint64_t cmaxb_launch_count(void);
+
+/* Per-kernel device timing with CUDA events on the handle's stream.  Enable, run evaluations,
+ * then read accumulated milliseconds / launch counts per kernel kind. */
+enum {
+  CMAXB_K_ZERO = 0, CMAXB_K_FE_SCATTER, CMAXB_K_FE_GATHER, CMAXB_K_BLUR_REDUCE, CMAXB_K_ADJOINT_BLUR,
+  CMAXB_K_BE_POSES, CMAXB_K_BE_SCATTER, CMAXB_K_BE_GATHER, CMAXB_K_BE_GRAD_REDUCE, CMAXB_K_MISC,
+  CMAXB_K_COUNT
+};
+int cmaxb_fe_profile(cmaxb_fe* fe, int enable);
+int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms /*CMAXB_K_COUNT*/, uint64_t* launches /*CMAXB_K_COUNT*/);
+int cmaxb_be_profile(cmaxb_be* be, int enable);
+int cmaxb_be_kernel_times(cmaxb_be* be, double* ms, uint64_t* launches);
+const char* cmaxb_kernel_name(int kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMAX_B200_H_ */
