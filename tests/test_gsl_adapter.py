@@ -1,0 +1,76 @@
+"""The reference-side C++ binding (include/cmax_b200_gsl.hpp) compiles against the C header and a
+stand-in gsl_vector, resolves the library by dlopen and keeps the reference's sign convention.
+CPU part: compile + dlopen + symbol table.  GPU part (marked): one evaluation through the GSL-shaped
+callbacks, compared with the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_SRC = r'''
+#include "cmax_b200_gsl.hpp"
+static cmaxb_gsl::Api g_api;
+extern "C" int adapter_load(const char* path) { return g_api.load(path) ? 0 : -1; }
+extern "C" int adapter_fe_roundtrip(const cmaxb_fe_cfg* cfg, const cmaxb_event* ev, size_t n, double t_ref,
+                                    const double* omega, double* f_only, double* f, double* df3) {
+  cmaxb_fe* fe = nullptr;
+  if (g_api.fe_create(cfg, &fe) != CMAXB_OK) return -1;
+  if (g_api.fe_set_packet(fe, ev, n, t_ref) != CMAXB_OK) { g_api.fe_destroy(fe); return -2; }
+  cmaxb_gsl::FeParams p{&g_api, fe};
+  double xv[3] = {omega[0], omega[1], omega[2]};
+  gsl_vector x{3, 1, xv, nullptr, 0};
+  double gv[3];
+  gsl_vector g{3, 1, gv, nullptr, 0};
+  *f_only = cmaxb_gsl::local_contrast_f(&x, &p);
+  cmaxb_gsl::local_contrast_fdf(&x, &p, f, &g);
+  for (int i = 0; i < 3; ++i) df3[i] = gv[i];
+  cmaxb_gsl::local_contrast_df(&x, &p, &g);
+  for (int i = 0; i < 3; ++i) if (gv[i] != df3[i] && !(gv[i] - df3[i] < 1e-6 && df3[i] - gv[i] < 1e-6)) { g_api.fe_destroy(fe); return -3; }
+  g_api.fe_destroy(fe);
+  return 0;
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def adapter(tmp_path_factory):
+    d = tmp_path_factory.mktemp("gsl")
+    src = d / "adapter.cpp"
+    src.write_text(_SRC)
+    out = d / "libadapter.so"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wall", "-Werror",
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "stubs"),
+                           "-o", str(out), str(src), "-ldl"])
+    return C.CDLL(str(out))
+
+
+def test_adapter_compiles_and_resolves_symbols(adapter):
+    from cmax_slam_b200 import build
+    assert adapter.adapter_load(build.build().encode()) == 0
+    assert adapter.adapter_load(b"/nonexistent/libcmax_b200.so") == -1
+
+
+@pytest.mark.gpu
+def test_adapter_gsl_callbacks_on_device(adapter, oracle):
+    from cmax_slam_b200 import _capi, build, synth
+    assert adapter.adapter_load(build.build().encode()) == 0
+    pk = synth.fe_config("C1", scale=0.1)
+    lut = np.ascontiguousarray(pk.lut)
+    cfg = _capi.FeCfg(pk.width, pk.height, *pk.K, lut.ctypes.data, 1.0, 100, 0, 1, 0, None, 1)
+    om = np.array([0.3, -0.9, 2.0])
+    f0, f = C.c_double(), C.c_double()
+    df = np.zeros(3)
+    dp = C.POINTER(C.c_double)
+    adapter.adapter_fe_roundtrip.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, dp, dp, dp, dp]
+    rc = adapter.adapter_fe_roundtrip(C.addressof(cfg), pk.events.ctypes.data, len(pk.events), pk.t_ref_sec,
+                                      om.ctypes.data_as(dp), C.byref(f0), C.byref(f), df.ctypes.data_as(dp))
+    assert rc == 0
+    a = oracle.fe_args(pk.events, pk.t_ref_sec, pk.lut, pk.width, pk.height, pk.K)
+    ro = oracle.fe_eval(a, om, True)
+    assert abs(f.value + ro["contrast"]) <= 1e-5 * ro["contrast"]          # callbacks return MINUS contrast
+    assert abs(f0.value + ro["contrast"]) <= 1e-5 * ro["contrast"]
+    assert np.abs(df + ro["grad"]).max() <= 1e-5 * np.abs(ro["grad"]).max()
