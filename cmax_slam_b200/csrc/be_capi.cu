@@ -25,6 +25,8 @@ struct cmaxb_be {
   float* d_igp = nullptr; bool have_igp = false;
   double alpha = 0.0; bool alpha_pending = false;
   float* d_il_old = nullptr; float* d_il_new = nullptr; float* d_blur = nullptr; float* d_G = nullptr;
+  float4* d_ilq = nullptr; float4* d_GQ = nullptr;   // corner-split accumulator / adjoint image (event-dense windows)
+  bool use_quad = false; bool il_is_quad = false;
   float* d_bands = nullptr; float* d_bands_blur = nullptr; size_t bands_cap = 0;
   double* d_acc = nullptr; unsigned int* d_ticket = nullptr; double* d_result = nullptr; double* d_mean = nullptr;
   double* d_bacc = nullptr; unsigned int* d_bticket = nullptr; double* d_bresult = nullptr; double* d_bmean = nullptr; size_t bacc_cap = 0;
@@ -93,7 +95,7 @@ extern "C" int cmaxb_be_create(const cmaxb_be_cfg* cfg, cmaxb_be** out) {
   ok = ok && dev_alloc(&be->d_blur, A) == CMAXB_OK;
   ok = ok && dev_alloc(&be->d_G, A) == CMAXB_OK;
   ok = ok && dev_alloc(&be->d_igp, A) == CMAXB_OK;
-  ok = ok && dev_alloc(&be->d_acc, (size_t)kNAcc) == CMAXB_OK;
+  ok = ok && dev_alloc(&be->d_acc, (size_t)kNAcc * kMaxImgCtas) == CMAXB_OK;
   ok = ok && dev_alloc(&be->d_ticket, 1) == CMAXB_OK;
   ok = ok && dev_alloc(&be->d_result, 4) == CMAXB_OK;
   ok = ok && dev_alloc(&be->d_mean, 1) == CMAXB_OK;
@@ -103,15 +105,9 @@ extern "C" int cmaxb_be_create(const cmaxb_be_cfg* cfg, cmaxb_be** out) {
   ok = ok && cudaMallocHost((void**)&be->h_result, sizeof(double) * 4) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&be->h_alpha_sums, sizeof(double) * 8) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&be->h_flags, sizeof(int)) == cudaSuccess;
-  ok = ok && cudaMemset(be->d_acc, 0, sizeof(double) * kNAcc) == cudaSuccess;
   ok = ok && cudaMemset(be->d_ticket, 0, sizeof(unsigned)) == cudaSuccess;
   ok = ok && cudaMemset(be->d_result, 0, sizeof(double) * 4) == cudaSuccess;
   if (!ok) return fail(set_error(CMAXB_ERR_CUDA, "back-end buffer allocation failed"));
-  const int r = be->taps.r;
-  cudaFuncSetAttribute(blur_reduce_kernel<1, SrcBeI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<1>(r));
-  cudaFuncSetAttribute(blur_reduce_kernel<1, SrcPlane, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<1>(r));
-  cudaFuncSetAttribute(adjoint_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjoint_smem_bytes(r));
-  if (cudaGetLastError() != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "cudaFuncSetAttribute failed"));
   *out = be;
   return CMAXB_OK;
 }
@@ -123,7 +119,7 @@ extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
   cudaFree(be->d_lut); cudaFree(be->d_ev); cudaFree(be->d_bt); cudaFree(be->d_poses); cudaFree(be->d_wgrad);
   cudaFree(be->d_knots0); cudaFree(be->d_knots); cudaFree(be->d_x); cudaFree(be->d_grad);
   cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
-  cudaFree(be->d_bands); cudaFree(be->d_bands_blur);
+  cudaFree(be->d_bands); cudaFree(be->d_bands_blur); cudaFree(be->d_ilq); cudaFree(be->d_GQ);
   cudaFree(be->d_acc); cudaFree(be->d_ticket); cudaFree(be->d_result); cudaFree(be->d_mean);
   cudaFree(be->d_bacc); cudaFree(be->d_bticket); cudaFree(be->d_bresult); cudaFree(be->d_bmean);
   cudaFree(be->d_alpha_sums); cudaFree(be->d_flags); cudaFree(be->d_cells);
@@ -151,6 +147,13 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
   const long long n_eff = (n >= 1 && (n - 1) % bs == 0) ? n - 1 : n;
   const long long nb = (n_eff + bs - 1) / bs;
   be->n = n; be->n_eff = n_eff; be->nb = nb;
+  // Event-dense windows accumulate IL in a corner-split float4 image (1 vector reduction per event,
+  // 4x the image bytes); sparse windows on a big panorama keep float planes (4 reductions per event).
+  be->use_quad = (2 * n_eff >= be->A);
+  if (be->use_quad && !be->d_ilq) {
+    CMAXB_TRY(dev_alloc(&be->d_ilq, (size_t)be->A));
+    CMAXB_TRY(dev_alloc(&be->d_GQ, (size_t)be->A));
+  }
   if ((size_t)n > be->ev_cap) {
     cudaFree(be->d_ev); be->d_ev = nullptr; be->ev_cap = 0;
     CMAXB_TRY(dev_alloc(&be->d_ev, (size_t)n));
@@ -224,9 +227,6 @@ static unsigned be_warp_grid(const cmaxb_be* be) {
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
 }
-static dim3 be_img_grid(const cmaxb_be* be, int z = 1) {
-  return dim3((be->cfg.pano_width + kTW - 1) / kTW, (be->cfg.pano_height + kTH - 1) / kTH, z);
-}
 
 // x -> updated knots -> per-batch pose table
 static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
@@ -247,23 +247,30 @@ static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
   return CMAXB_OK;
 }
 
-static int be_run_scatter(cmaxb_be* be) {
+static int be_run_scatter(cmaxb_be* be, bool allow_quad) {
   cudaStream_t s = be->stream;
+  const bool quad = allow_quad && be->use_quad;
+  be->il_is_quad = quad;
   CMAXB_TRY(be->prof.run(CMAXB_K_ZERO, s, false, [&] {
-    cudaMemsetAsync(be->d_il_old, 0, sizeof(float) * be->A, s);
-    cudaMemsetAsync(be->d_il_new, 0, sizeof(float) * be->A, s);
+    if (quad) cudaMemsetAsync(be->d_ilq, 0, sizeof(float4) * be->A, s);
+    else {
+      cudaMemsetAsync(be->d_il_old, 0, sizeof(float) * be->A, s);
+      cudaMemsetAsync(be->d_il_new, 0, sizeof(float) * be->A, s);
+    }
   }));
   if (be->nb > 0) {
     const BeGeom g = be_geom(be);
     CMAXB_TRY(be->prof.run(CMAXB_K_BE_SCATTER, s, true, [&] {
-      be_scatter_kernel<<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_il_old, be->d_il_new);
+      if (quad) be_scatter_kernel<2><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, nullptr, be->d_ilq);
+      else be_scatter_kernel<0><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_il_old, be->d_il_new, nullptr);
     }));
   }
   // first evaluation of a window with alpha unspecified: updateAlpha            (:201-210)
   if (be->alpha_pending) {
     CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_alpha_sums, 0, sizeof(double) * 8, s));
     CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
-      be_alpha_sums_kernel<<<148 * 4, 256, 0, s>>>(be->d_igp, be->d_il_old, be->d_il_new, be->A, be->d_alpha_sums);
+      be_alpha_sums_kernel<<<148 * 4, 256, 0, s>>>(be->d_igp, be->d_il_old, be->d_il_new, quad ? be->d_ilq : nullptr,
+                                                   be->cfg.pano_width, be->A, be->d_alpha_sums);
     }));
     CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_alpha_sums, be->d_alpha_sums, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
     CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
@@ -276,14 +283,22 @@ static int be_run_scatter(cmaxb_be* be) {
 }
 
 // blur(I) + contrast; leaves the blurred image in d_blur and its mean in d_mean
-static int be_run_image(cmaxb_be* be) {
+static int be_run_image(cmaxb_be* be, const Taps& taps) {
   cudaStream_t s = be->stream;
-  const SrcBeI src{be->d_il_old, be->d_il_new, be->have_igp ? be->d_igp : nullptr, (float)be->alpha};
   const ReduceOut ro{be->d_acc, be->d_ticket, be->d_result, be->d_mean};
-  const int W = be->cfg.pano_width, H = be->cfg.pano_height, r = be->taps.r;
+  const int W = be->cfg.pano_width, H = be->cfg.pano_height;
+  const float* igp = be->have_igp ? be->d_igp : nullptr;
+  cudaError_t le = cudaSuccess;
   CMAXB_TRY(be->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
-    blur_reduce_kernel<1, SrcBeI, true><<<be_img_grid(be), kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, be->taps, be->d_blur, 0, ro, be->cfg.contrast_measure);
+    if (be->il_is_quad) {
+      const SrcBeQuad src{SrcQuad{be->d_ilq, 0}, igp, (float)be->alpha};
+      le = launch_blur_reduce<1, SrcBeQuad, true>(s, 1, src, W, H, taps, be->d_blur, 0, ro, be->cfg.contrast_measure);
+    } else {
+      const SrcBeI src{be->d_il_old, be->d_il_new, igp, (float)be->alpha};
+      le = launch_blur_reduce<1, SrcBeI, true>(s, 1, src, W, H, taps, be->d_blur, 0, ro, be->cfg.contrast_measure);
+    }
   }));
+  if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("blur_reduce launch: ") + cudaGetErrorString(le));
   return CMAXB_OK;
 }
 
@@ -299,11 +314,10 @@ static int be_ensure_bands(cmaxb_be* be) {
   const size_t P = (size_t)3 * be->n_opt;
   if (P > be->bacc_cap) {
     cudaFree(be->d_bacc); cudaFree(be->d_bticket); cudaFree(be->d_bresult); cudaFree(be->d_bmean);
-    CMAXB_TRY(dev_alloc(&be->d_bacc, P * kNAcc));
+    CMAXB_TRY(dev_alloc(&be->d_bacc, P * kNAcc * kMaxImgCtas));
     CMAXB_TRY(dev_alloc(&be->d_bticket, P));
     CMAXB_TRY(dev_alloc(&be->d_bresult, P * 4));
     CMAXB_TRY(dev_alloc(&be->d_bmean, P));
-    CMAXB_CUDA_TRY(cudaMemset(be->d_bacc, 0, sizeof(double) * P * kNAcc));
     CMAXB_CUDA_TRY(cudaMemset(be->d_bticket, 0, sizeof(unsigned) * P));
     be->bacc_cap = P;
   }
@@ -327,11 +341,13 @@ static int be_run_bands(cmaxb_be* be, bool blur) {
   if (blur) {
     const SrcPlane src{be->d_bands, be->A};
     const ReduceOut ro{be->d_bacc, be->d_bticket, be->d_bresult, be->d_bmean};
-    const int W = be->cfg.pano_width, H = be->cfg.pano_height, r = be->taps.r;
+    const int W = be->cfg.pano_width, H = be->cfg.pano_height;
     // blockIdx.z is limited to 65535 planes
+    cudaError_t le = cudaSuccess;
     CMAXB_TRY(be->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
-      blur_reduce_kernel<1, SrcPlane, true><<<be_img_grid(be, P), kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, be->taps, be->d_bands_blur, be->A, ro, be->cfg.contrast_measure);
+      le = launch_blur_reduce<1, SrcPlane, true>(s, P, src, W, H, be->taps, be->d_bands_blur, be->A, ro, be->cfg.contrast_measure);
     }));
+    if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("blur_reduce launch: ") + cudaGetErrorString(le));
   }
   return CMAXB_OK;
 }
@@ -343,20 +359,29 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
   const bool want_grad = grad != nullptr;
   cudaStream_t s = be->stream;
   CMAXB_TRY(be_run_poses(be, x, n, want_grad));
-  CMAXB_TRY(be_run_scatter(be));
-  CMAXB_TRY(be_run_image(be));
+  CMAXB_TRY(be_run_scatter(be, true));
+  CMAXB_TRY(be_run_image(be, be->taps));
   const int P = 3 * be->n_opt;
   if (want_grad && P > 0) {
-    const int W = be->cfg.pano_width, H = be->cfg.pano_height, r = be->taps.r;
+    const int W = be->cfg.pano_width, H = be->cfg.pano_height;
     if (be->cfg.grad_mode == CMAXB_GRAD_ADJOINT) {
+      const bool quad = be->use_quad;
+      cudaError_t le = cudaSuccess;
       CMAXB_TRY(be->prof.run(CMAXB_K_ADJOINT_BLUR, s, true, [&] {
-        adjoint_blur_kernel<<<be_img_grid(be), kImgThreads, adjoint_smem_bytes(r), s>>>(be->d_blur, 0, W, H, be->taps, be->d_mean, be->cfg.contrast_measure, be->d_G);
+        le = quad ? launch_adjoint_blur<true>(s, 1, be->d_blur, 0, W, H, be->taps, be->d_mean, be->cfg.contrast_measure, nullptr, be->d_GQ)
+                  : launch_adjoint_blur<false>(s, 1, be->d_blur, 0, W, H, be->taps, be->d_mean, be->cfg.contrast_measure, be->d_G, nullptr);
       }));
+      if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("adjoint_blur launch: ") + cudaGetErrorString(le));
       if (be->nb > 0) {
         const BeGeom g = be_geom(be);
         CMAXB_TRY(be->prof.run(CMAXB_K_BE_GATHER, s, true, [&] {
-          if (be->N == 2) be_gather_kernel<2><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, be->d_wgrad);
-          else be_gather_kernel<4><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, be->d_wgrad);
+          if (be->N == 2) {
+            if (quad) be_gather_kernel<2, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, be->d_GQ, be->d_wgrad);
+            else be_gather_kernel<2, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, nullptr, be->d_wgrad);
+          } else {
+            if (quad) be_gather_kernel<4, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, be->d_GQ, be->d_wgrad);
+            else be_gather_kernel<4, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, nullptr, be->d_wgrad);
+          }
         }));
       }
       const double inv_np = 1.0 / ((double)W * (double)H);
@@ -390,7 +415,7 @@ extern "C" int cmaxb_be_get_il(cmaxb_be* be, const double* x, int n, float* il_o
   if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window");
   CMAXB_CUDA_TRY(cudaSetDevice(be->device));
   CMAXB_TRY(be_run_poses(be, x, n, false));
-  CMAXB_TRY(be_run_scatter(be));
+  CMAXB_TRY(be_run_scatter(be, false));
   cudaStream_t s = be->stream;
   if (il_old) CMAXB_CUDA_TRY(cudaMemcpyAsync(il_old, be->d_il_old, sizeof(float) * be->A, cudaMemcpyDeviceToHost, s));
   if (il_new) CMAXB_CUDA_TRY(cudaMemcpyAsync(il_new, be->d_il_new, sizeof(float) * be->A, cudaMemcpyDeviceToHost, s));
@@ -403,19 +428,10 @@ extern "C" int cmaxb_be_get_iwe(cmaxb_be* be, const double* x, int n, int blurre
   if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window");
   CMAXB_CUDA_TRY(cudaSetDevice(be->device));
   CMAXB_TRY(be_run_poses(be, x, n, false));
-  CMAXB_TRY(be_run_scatter(be));
+  CMAXB_TRY(be_run_scatter(be, true));
   cudaStream_t s = be->stream;
-  if (blurred) {
-    CMAXB_TRY(be_run_image(be));
-  } else {
-    // un-blurred I = IL + alpha*IGp: run the same kernel with a radius-0 filter
-    Taps t0{}; t0.r = 0; t0.w[0] = 1.0f;
-    const SrcBeI src{be->d_il_old, be->d_il_new, be->have_igp ? be->d_igp : nullptr, (float)be->alpha};
-    const ReduceOut ro{be->d_acc, be->d_ticket, be->d_result, be->d_mean};
-    CMAXB_TRY(be->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
-      blur_reduce_kernel<1, SrcBeI, true><<<be_img_grid(be), kImgThreads, blur_smem_bytes<1>(0), s>>>(src, be->cfg.pano_width, be->cfg.pano_height, t0, be->d_blur, 0, ro, be->cfg.contrast_measure);
-    }));
-  }
+  Taps t0{}; t0.r = 0; t0.w[0] = 1.0f;   // un-blurred I = IL + alpha*IGp: the same kernel with a radius-0 filter
+  CMAXB_TRY(be_run_image(be, blurred ? be->taps : t0));
   CMAXB_CUDA_TRY(cudaMemcpyAsync(out, be->d_blur, sizeof(float) * be->A, cudaMemcpyDeviceToHost, s));
   CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
   return CMAXB_OK;

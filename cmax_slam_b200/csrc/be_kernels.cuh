@@ -169,9 +169,13 @@ __device__ __forceinline__ BeWarp be_warp(const BeGeom& g, const double* R, uint
 constexpr int kBeThreads = 256;
 constexpr int kBeWarps = kBeThreads / 32;
 
-// value scatter: IL_old_ / IL_new_
+// value scatter.  MODE 0: IL_old_ / IL_new_ as two float planes (what updateIG needs).
+// MODE 2: IL = old + new as ONE corner-split float4 image, one vector reduction per event (the cost
+// evaluation only ever uses the sum, event_pano_warper.cpp:199).
+template <int MODE>
 __global__ void __launch_bounds__(kBeThreads)
-be_scatter_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict__ il_old, float* __restrict__ il_new) {
+be_scatter_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict__ il_old, float* __restrict__ il_new,
+                  float4* __restrict__ il_quad) {
   const int lane = threadIdx.x & 31;
   const long long wstride = (long long)gridDim.x * kBeWarps;
   for (long long b = blockIdx.x * (long long)kBeWarps + (threadIdx.x >> 5); b < g.nb; b += wstride) {
@@ -185,13 +189,17 @@ be_scatter_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict_
       const uint4 e = load_event(g.ev, i);
       const BeWarp w = be_warp<false>(g, R, e);
       if (!w.in) continue;
-      float* il = w.is_old ? il_old : il_new;
       const float dx = w.dx, dy = w.dy;
       const long long p = (long long)w.yy * g.W + w.xx;
-      atomicAdd(il + p, (1.f - dx) * (1.f - dy));
-      atomicAdd(il + p + 1, dx * (1.f - dy));
-      atomicAdd(il + p + g.W, (1.f - dx) * dy);
-      atomicAdd(il + p + g.W + 1, dx * dy);
+      if (MODE == 2) {
+        atomicAdd(il_quad + p, make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy));
+      } else {
+        float* il = w.is_old ? il_old : il_new;
+        atomicAdd(il + p, (1.f - dx) * (1.f - dy));
+        atomicAdd(il + p + 1, dx * (1.f - dy));
+        atomicAdd(il + p + g.W, (1.f - dx) * dy);
+        atomicAdd(il + p + g.W + 1, dx * dy);
+      }
     }
   }
 }
@@ -260,9 +268,10 @@ __global__ void be_cells_kernel(BeGeom g, const BePose* __restrict__ poses, long
 // jac = dd * Jk, the contribution to g_j is  (a*dd[0,:] + b*dd[1,:]) . Jk[:, j]  with
 // a = sum_c s_c G(c), b = sum_c t_c G(c).  The bracket is summed over the batch first (3 numbers),
 // then multiplied by the batch's Jk once: wgrad[b][c] = V_b . Jk[:, c].
-template <int N>
+template <int N, bool QUAD>
 __global__ void __launch_bounds__(kBeThreads)
-be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __restrict__ G, double* __restrict__ wgrad) {
+be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __restrict__ G, const float4* __restrict__ GQ,
+                 double* __restrict__ wgrad) {
   const int lane = threadIdx.x & 31;
   const long long wstride = (long long)gridDim.x * kBeWarps;
   for (long long b = blockIdx.x * (long long)kBeWarps + (threadIdx.x >> 5); b < g.nb; b += wstride) {
@@ -277,8 +286,14 @@ be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __rest
       const uint4 e = load_event(g.ev, i);
       const BeWarp w = be_warp<true>(g, R, e);
       if (!w.in) continue;
-      const float* p = G + (long long)w.yy * g.W + w.xx;
-      const double g00 = __ldg(p), g01 = __ldg(p + 1), g10 = __ldg(p + g.W), g11 = __ldg(p + g.W + 1);
+      double g00, g01, g10, g11;
+      if (QUAD) {
+        const float4 q = __ldg(GQ + (long long)w.yy * g.W + w.xx);
+        g00 = q.x; g01 = q.y; g10 = q.z; g11 = q.w;
+      } else {
+        const float* p = G + (long long)w.yy * g.W + w.xx;
+        g00 = __ldg(p); g01 = __ldg(p + 1); g10 = __ldg(p + g.W); g11 = __ldg(p + g.W + 1);
+      }
       const double dx = w.dx, dy = w.dy;
       const double a = (1.0 - dy) * (g01 - g00) + dy * (g11 - g10);
       const double bb = (1.0 - dx) * (g10 - g00) + dx * (g11 - g01);
@@ -349,14 +364,23 @@ be_band_reduce_kernel(const float* __restrict__ I, const float* __restrict__ ban
 
 // updateAlpha sums (event_pano_warper.cpp:134-165): out[0..4] = sum(1-exp(-IGp)), sum(IGp),
 // sum(1-exp(-IL)), sum(IL), countNonZero(IGp); IL = IL_old + IL_new.
+// il_quad != nullptr: IL is re-assembled from the corner-split accumulator.
 __global__ void __launch_bounds__(256)
 be_alpha_sums_kernel(const float* __restrict__ igp, const float* __restrict__ il_old, const float* __restrict__ il_new,
-                     long long A, double* __restrict__ out) {
+                     const float4* __restrict__ il_quad, int W, long long A, double* __restrict__ out) {
   __shared__ double s_red[8 * 5];
   double v[5] = {0, 0, 0, 0, 0};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A; i += (long long)gridDim.x * blockDim.x) {
     const float a = igp[i];
-    const float l = il_old[i] + il_new[i];
+    float l;
+    if (il_quad) {
+      const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+      l = il_quad[i].x;
+      if (x > 0) l += il_quad[i - 1].y;
+      if (y > 0) { l += il_quad[i - W].z; if (x > 0) l += il_quad[i - W - 1].w; }
+    } else {
+      l = il_old[i] + il_new[i];
+    }
     v[0] += (double)(1.f - expf(-1.0f * a));
     v[1] += (double)a;
     v[2] += (double)(1.f - expf(-1.0f * l));

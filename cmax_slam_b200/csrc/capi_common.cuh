@@ -55,8 +55,13 @@ struct KernelProfiler {
   template <class F>
   int run(int kind, cudaStream_t s, bool is_kernel, F&& f) {
     if (enabled) CMAXB_CUDA_TRY(cudaEventRecord(e0, s));
+    (void)cudaGetLastError();   // do not inherit a stale error of another library in this process
     f();
-    CMAXB_CUDA_TRY(cudaGetLastError());
+    {
+      cudaError_t err = cudaGetLastError();
+      if (err != cudaSuccess)
+        return set_error(CMAXB_ERR_CUDA, std::string("launch of kernel kind ") + std::to_string(kind) + " failed: " + cudaGetErrorString(err));
+    }
     if (is_kernel) g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (enabled) {
       CMAXB_CUDA_TRY(cudaEventRecord(e1, s));

@@ -24,8 +24,12 @@ struct cmaxb_fe {
   long long n = 0, nb = 0;
   bool have_packet = false;
   int* d_flags = nullptr; int* h_flags = nullptr;
-  float* d_img1 = nullptr; float* d_blur1 = nullptr; float* d_G = nullptr;
-  float4* d_img4 = nullptr; float4* d_blur4 = nullptr;
+  // value accumulators: two corner-split ("quad") images used alternately; the blur kernel of one
+  // evaluation clears the image the next evaluation scatters into (no memset in steady state)
+  float4* d_quad[2] = {nullptr, nullptr}; int quad_cur = 0; int quad_dirty[2] = {0, 0};
+  float* d_blur1 = nullptr;        // blurred IWE (adjoint mode, get_iwe)
+  float4* d_GQ = nullptr;          // adjoint image, one float4 per cell
+  float4* d_img4 = nullptr; float4* d_blur4 = nullptr;   // DENSE mode: (I, dI/dw) accumulators
   int* d_cells = nullptr; size_t cells_cap = 0;
   double* d_omegas = nullptr; double* h_omegas = nullptr;
   double* d_acc = nullptr; unsigned int* d_ticket = nullptr; unsigned int* d_ticket2 = nullptr;
@@ -80,17 +84,18 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   const size_t k = (size_t)fe->kmax, A = (size_t)fe->A;
   bool ok = true;
   ok = ok && dev_alloc(&fe->d_flags, 1) == CMAXB_OK;
-  ok = ok && dev_alloc(&fe->d_img1, k * A) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_quad[0], k * A) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_quad[1], k * A) == CMAXB_OK;
   ok = ok && dev_alloc(&fe->d_omegas, k * 3) == CMAXB_OK;
-  ok = ok && dev_alloc(&fe->d_acc, k * kNAcc) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_acc, k * kNAcc * kMaxImgCtas) == CMAXB_OK;
   ok = ok && dev_alloc(&fe->d_ticket, k) == CMAXB_OK;
   ok = ok && dev_alloc(&fe->d_ticket2, k) == CMAXB_OK;
-  ok = ok && dev_alloc(&fe->d_gacc, k * 3) == CMAXB_OK;
+  ok = ok && dev_alloc(&fe->d_gacc, k * 3 * kMaxEventCtas) == CMAXB_OK;
   ok = ok && dev_alloc(&fe->d_result, k * 4) == CMAXB_OK;
   ok = ok && dev_alloc(&fe->d_mean, k) == CMAXB_OK;
   if (cfg->grad_mode == CMAXB_GRAD_ADJOINT) {
     ok = ok && dev_alloc(&fe->d_blur1, k * A) == CMAXB_OK;
-    ok = ok && dev_alloc(&fe->d_G, k * A) == CMAXB_OK;
+    ok = ok && dev_alloc(&fe->d_GQ, k * A) == CMAXB_OK;
   } else {
     ok = ok && dev_alloc(&fe->d_img4, k * A) == CMAXB_OK;
   }
@@ -98,20 +103,12 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   ok = ok && cudaMallocHost((void**)&fe->h_flags, sizeof(int)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&fe->h_omegas, sizeof(double) * 3 * k) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&fe->h_result, sizeof(double) * 4 * k) == cudaSuccess;
-  ok = ok && cudaMemset(fe->d_acc, 0, sizeof(double) * k * kNAcc) == cudaSuccess;
   ok = ok && cudaMemset(fe->d_ticket, 0, sizeof(unsigned) * k) == cudaSuccess;
   ok = ok && cudaMemset(fe->d_ticket2, 0, sizeof(unsigned) * k) == cudaSuccess;
-  ok = ok && cudaMemset(fe->d_gacc, 0, sizeof(double) * k * 3) == cudaSuccess;
   ok = ok && cudaMemset(fe->d_result, 0, sizeof(double) * k * 4) == cudaSuccess;
+  ok = ok && cudaMemset(fe->d_quad[0], 0, sizeof(float4) * k * A) == cudaSuccess;
+  ok = ok && cudaMemset(fe->d_quad[1], 0, sizeof(float4) * k * A) == cudaSuccess;
   if (!ok) return fail(set_error(CMAXB_ERR_CUDA, "front-end buffer allocation failed"));
-  // opt in to large dynamic shared memory for the image kernels
-  const int r = fe->taps.r;
-  cudaFuncSetAttribute(blur_reduce_kernel<1, SrcPlane, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<1>(r));
-  cudaFuncSetAttribute(blur_reduce_kernel<1, SrcPlane, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<1>(r));
-  cudaFuncSetAttribute(blur_reduce_kernel<4, SrcPlane4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<4>(r));
-  cudaFuncSetAttribute(blur_reduce_kernel<4, SrcPlane4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem_bytes<4>(r));
-  cudaFuncSetAttribute(adjoint_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjoint_smem_bytes(r));
-  if (cudaGetLastError() != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "cudaFuncSetAttribute failed (blur radius too large for shared memory?)"));
   *out = fe;
   return CMAXB_OK;
 }
@@ -121,7 +118,7 @@ extern "C" void cmaxb_fe_destroy(cmaxb_fe* fe) {
   cudaSetDevice(fe->device);
   if (fe->stream) cudaStreamSynchronize(fe->stream);
   cudaFree(fe->d_lut); cudaFree(fe->d_ev); cudaFree(fe->d_dt); cudaFree(fe->d_flags);
-  cudaFree(fe->d_img1); cudaFree(fe->d_blur1); cudaFree(fe->d_G); cudaFree(fe->d_img4); cudaFree(fe->d_blur4);
+  cudaFree(fe->d_quad[0]); cudaFree(fe->d_quad[1]); cudaFree(fe->d_blur1); cudaFree(fe->d_GQ); cudaFree(fe->d_img4); cudaFree(fe->d_blur4);
   cudaFree(fe->d_cells); cudaFree(fe->d_omegas); cudaFree(fe->d_acc); cudaFree(fe->d_ticket); cudaFree(fe->d_ticket2);
   cudaFree(fe->d_gacc); cudaFree(fe->d_result); cudaFree(fe->d_mean);
   if (fe->h_flags) cudaFreeHost(fe->h_flags);
@@ -180,23 +177,49 @@ static int fe_upload_omegas(cmaxb_fe* fe, const double* omegas, int k) {
 
 static dim3 fe_event_grid(const cmaxb_fe* fe, int k) {
   long long blocks = (fe->n + kFeThreads - 1) / kFeThreads;
-  const long long cap = 148LL * 16;
+  const long long cap = kMaxEventCtas;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return dim3((unsigned)blocks, (unsigned)k, 1);
 }
-static dim3 img_grid(int W, int H, int k) { return dim3((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, k); }
 
-// scatter the value plane(s) of k hypotheses into d_img1
+// scatter the value votes of k hypotheses into the current quad accumulator
 static int fe_run_scatter_value(cmaxb_fe* fe, int k) {
   cudaStream_t s = fe->stream;
-  CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(fe->d_img1, 0, sizeof(float) * fe->A * k, s); }));
+  const int cur = fe->quad_cur;
+  if (fe->quad_dirty[cur] > 0) {   // only after start-up / a change of k / a debug call: steady state skips this
+    const int planes = fe->quad_dirty[cur];
+    CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(fe->d_quad[cur], 0, sizeof(float4) * fe->A * planes, s); }));
+    fe->quad_dirty[cur] = 0;
+  }
   if (fe->n > 0) {
     const FeGeom g = fe_geom(fe);
     CMAXB_TRY(fe->prof.run(CMAXB_K_FE_SCATTER, s, true, [&] {
-      fe_scatter_kernel<0><<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, fe->d_img1, nullptr, fe->A);
+      fe_scatter_kernel<2><<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, nullptr, fe->d_quad[cur], fe->A);
     }));
+    fe->quad_dirty[cur] = k;
   }
+  return CMAXB_OK;
+}
+// blur + reduce the current quad accumulator (k planes); optionally keep the blurred image; clears the
+// OTHER quad accumulator and makes it current.
+static int fe_run_value_image(cmaxb_fe* fe, int k, const Taps& taps, bool write_out) {
+  cudaStream_t s = fe->stream;
+  const int cur = fe->quad_cur, oth = cur ^ 1;
+  const SrcQuad src{fe->d_quad[cur], fe->A};
+  const ReduceOut ro{fe->d_acc, fe->d_ticket, fe->d_result, fe->d_mean};
+  const int W = fe->cfg.width, H = fe->cfg.height, measure = fe->cfg.contrast_measure;
+  // the other image can be cleared by this kernel if its dirty planes are covered by our k planes
+  float4* zero_ptr = (fe->quad_dirty[oth] > 0 && fe->quad_dirty[oth] <= k) ? fe->d_quad[oth] : nullptr;
+  if (write_out && !fe->d_blur1) CMAXB_TRY(dev_alloc(&fe->d_blur1, (size_t)fe->kmax * fe->A));
+  cudaError_t le = cudaSuccess;
+  CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+    le = write_out ? launch_blur_reduce<1, SrcQuad, true>(s, k, src, W, H, taps, fe->d_blur1, fe->A, ro, measure, zero_ptr, fe->A)
+                   : launch_blur_reduce<1, SrcQuad, false>(s, k, src, W, H, taps, nullptr, 0, ro, measure, zero_ptr, fe->A);
+  }));
+  if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("blur_reduce launch: ") + cudaGetErrorString(le));
+  if (zero_ptr) fe->quad_dirty[oth] = 0;
+  fe->quad_cur = oth;
   return CMAXB_OK;
 }
 static int fe_run_scatter_dense(cmaxb_fe* fe, int k) {
@@ -219,32 +242,29 @@ extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, i
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
   CMAXB_TRY(fe_upload_omegas(fe, omegas, k));
   cudaStream_t s = fe->stream;
-  const int W = fe->cfg.width, H = fe->cfg.height, r = fe->taps.r, measure = fe->cfg.contrast_measure;
-  const ReduceOut ro{fe->d_acc, fe->d_ticket, fe->d_result, fe->d_mean};
-  const dim3 ig = img_grid(W, H, k);
+  const int W = fe->cfg.width, H = fe->cfg.height, measure = fe->cfg.contrast_measure;
   if (want_grad && fe->cfg.grad_mode == CMAXB_GRAD_DENSE) {
     CMAXB_TRY(fe_run_scatter_dense(fe, k));
     const SrcPlane4 src{fe->d_img4, fe->A};
+    const ReduceOut ro{fe->d_acc, fe->d_ticket, fe->d_result, fe->d_mean};
+    cudaError_t le = cudaSuccess;
     CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
-      blur_reduce_kernel<4, SrcPlane4, false><<<ig, kImgThreads, blur_smem_bytes<4>(r), s>>>(src, W, H, fe->taps, nullptr, 0, ro, measure);
+      le = launch_blur_reduce<4, SrcPlane4, false>(s, k, src, W, H, fe->taps, nullptr, 0, ro, measure);
     }));
+    if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("blur_reduce launch: ") + cudaGetErrorString(le));
   } else {
     CMAXB_TRY(fe_run_scatter_value(fe, k));
-    const SrcPlane src{fe->d_img1, fe->A};
-    if (!want_grad) {
-      CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
-        blur_reduce_kernel<1, SrcPlane, false><<<ig, kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, fe->taps, nullptr, 0, ro, measure);
-      }));
-    } else {
-      CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
-        blur_reduce_kernel<1, SrcPlane, true><<<ig, kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, fe->taps, fe->d_blur1, fe->A, ro, measure);
-      }));
+    CMAXB_TRY(fe_run_value_image(fe, k, fe->taps, want_grad != 0));
+    if (want_grad) {
+      if (!fe->d_GQ) CMAXB_TRY(dev_alloc(&fe->d_GQ, (size_t)fe->kmax * fe->A));
+      cudaError_t le = cudaSuccess;
       CMAXB_TRY(fe->prof.run(CMAXB_K_ADJOINT_BLUR, s, true, [&] {
-        adjoint_blur_kernel<<<ig, kImgThreads, adjoint_smem_bytes(r), s>>>(fe->d_blur1, fe->A, W, H, fe->taps, fe->d_mean, measure, fe->d_G);
+        le = launch_adjoint_blur<true>(s, k, fe->d_blur1, fe->A, W, H, fe->taps, fe->d_mean, measure, nullptr, fe->d_GQ);
       }));
+      if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("adjoint_blur launch: ") + cudaGetErrorString(le));
       const FeGeom g = fe_geom(fe);
       CMAXB_TRY(fe->prof.run(CMAXB_K_FE_GATHER, s, true, [&] {
-        fe_gather_kernel<<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, fe->d_G, fe->A, fe->d_gacc, fe->d_ticket2, fe->d_result);
+        fe_gather_kernel<true><<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, nullptr, fe->d_GQ, fe->A, fe->d_gacc, fe->d_ticket2, fe->d_result);
       }));
     }
   }
@@ -281,19 +301,10 @@ extern "C" int cmaxb_fe_get_iwe(cmaxb_fe* fe, const double omega[3], int blurred
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
   CMAXB_TRY(fe_upload_omegas(fe, omega, 1));
   CMAXB_TRY(fe_run_scatter_value(fe, 1));
+  Taps t0{}; t0.r = 0; t0.w[0] = 1.0f;   // raw image: the same kernel with a radius-0 filter
+  CMAXB_TRY(fe_run_value_image(fe, 1, (blurred && fe->taps.r > 0) ? fe->taps : t0, true));
   cudaStream_t s = fe->stream;
-  const float* src_ptr = fe->d_img1;
-  if (blurred && fe->taps.r > 0) {
-    if (!fe->d_blur1) CMAXB_TRY(dev_alloc(&fe->d_blur1, (size_t)fe->kmax * fe->A));
-    const SrcPlane src{fe->d_img1, fe->A};
-    const ReduceOut ro{fe->d_acc, fe->d_ticket, fe->d_result, fe->d_mean};
-    const int W = fe->cfg.width, H = fe->cfg.height, r = fe->taps.r;
-    CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
-      blur_reduce_kernel<1, SrcPlane, true><<<img_grid(W, H, 1), kImgThreads, blur_smem_bytes<1>(r), s>>>(src, W, H, fe->taps, fe->d_blur1, fe->A, ro, fe->cfg.contrast_measure);
-    }));
-    src_ptr = fe->d_blur1;
-  }
-  CMAXB_CUDA_TRY(cudaMemcpyAsync(out, src_ptr, sizeof(float) * fe->A, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(out, fe->d_blur1, sizeof(float) * fe->A, cudaMemcpyDeviceToHost, s));
   CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
   return CMAXB_OK;
 }
@@ -310,10 +321,12 @@ extern "C" int cmaxb_fe_get_deriv(cmaxb_fe* fe, const double omega[3], int blurr
     if (!fe->d_blur4) CMAXB_TRY(dev_alloc(&fe->d_blur4, (size_t)fe->A));
     const SrcPlane4 src{fe->d_img4, fe->A};
     const ReduceOut ro{fe->d_acc, fe->d_ticket, fe->d_result, fe->d_mean};
-    const int W = fe->cfg.width, H = fe->cfg.height, r = fe->taps.r;
+    const int W = fe->cfg.width, H = fe->cfg.height;
+    cudaError_t le = cudaSuccess;
     CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
-      blur_reduce_kernel<4, SrcPlane4, true><<<img_grid(W, H, 1), kImgThreads, blur_smem_bytes<4>(r), s>>>(src, W, H, fe->taps, fe->d_blur4, fe->A, ro, fe->cfg.contrast_measure);
+      le = launch_blur_reduce<4, SrcPlane4, true>(s, 1, src, W, H, fe->taps, fe->d_blur4, fe->A, ro, fe->cfg.contrast_measure);
     }));
+    if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("blur_reduce launch: ") + cudaGetErrorString(le));
     src_ptr = fe->d_blur4;
   }
   std::vector<float4> tmp((size_t)fe->A);

@@ -95,6 +95,8 @@ __global__ void fe_batch_dt_kernel(const uint4* __restrict__ ev, long long n, in
 
 constexpr int kFeThreads = 256;
 
+// MODE 2: value only  -> corner-split float4 accumulator quad[h] (one vector reduction per event;
+//                        image_kernels.cuh SrcQuad re-assembles the image)
 // MODE 0: value only  -> float plane img1[h]
 // MODE 1: dense       -> float4 plane img4[h] = (I, dI/dwx, dI/dwy, dI/dwz), one 16-byte vector
 //                        reduction per bilinear corner (red.global.add.v4.f32, sm_90+)
@@ -114,7 +116,9 @@ fe_scatter_kernel(FeGeom g, const double* __restrict__ omegas, float* __restrict
     const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy);
     const float w10 = (1.f - dx) * dy, w11 = dx * dy;
     const long long p = h * stride_h + (long long)w.yy * g.W + w.xx;
-    if (MODE == 0) {
+    if (MODE == 2) {
+      atomicAdd(img4 + p, make_float4(w00, w01, w10, w11));
+    } else if (MODE == 0) {
       atomicAdd(img1 + p, w00);
       atomicAdd(img1 + p + 1, w01);
       atomicAdd(img1 + p + g.W, w10);
@@ -151,14 +155,18 @@ __global__ void fe_cells_kernel(FeGeom g, const double* __restrict__ omegas, int
 // Adjoint gather: g_c = (1/Np) * sum_events [ r0_c * a + r1_c * b ],
 //   a = sum_corners s_corner * G(corner), b = sum_corners t_corner * G(corner)
 // (s, t = the derivative-vote weights of :163-166).  Last CTA finalises into result[h][1..3].
+constexpr int kMaxEventCtas = 148 * 8;
+
+template <bool QUAD>
 __global__ void __launch_bounds__(kFeThreads)
-fe_gather_kernel(FeGeom g, const double* __restrict__ omegas, const float* __restrict__ G, long long stride_h,
-                 double* gacc, unsigned int* ticket, double* result) {
+fe_gather_kernel(FeGeom g, const double* __restrict__ omegas, const float* __restrict__ G, const float4* __restrict__ GQ,
+                 long long stride_h, double* partials /*[n_hyp][kMaxEventCtas][3]*/, unsigned int* ticket, double* result) {
   __shared__ double s_red[(kFeThreads / 32) * 3];
   __shared__ bool is_last;
   const int h = blockIdx.y;
   const double ox = omegas[3 * h], oy = omegas[3 * h + 1], oz = omegas[3 * h + 2];
-  const float* Gh = G + h * stride_h;
+  const float* Gh = QUAD ? nullptr : G + h * stride_h;
+  const float4* GQh = QUAD ? GQ + h * stride_h : nullptr;
   double acc[3] = {0.0, 0.0, 0.0};
   const long long stride = (long long)gridDim.x * kFeThreads;
   for (long long i = blockIdx.x * (long long)kFeThreads + threadIdx.x; i < g.n; i += stride) {
@@ -166,24 +174,56 @@ fe_gather_kernel(FeGeom g, const double* __restrict__ omegas, const float* __res
     const double dt = __ldg(g.dt_tab + i / g.batch_size);
     const FeWarp w = fe_warp<true>(g, e, dt, ox, oy, oz);
     if (!w.in) continue;
-    const float* p = Gh + (long long)w.yy * g.W + w.xx;
-    const double g00 = __ldg(p), g01 = __ldg(p + 1), g10 = __ldg(p + g.W), g11 = __ldg(p + g.W + 1);
+    double g00, g01, g10, g11;
+    if (QUAD) {
+      const float4 q = __ldg(GQh + (long long)w.yy * g.W + w.xx);
+      g00 = q.x; g01 = q.y; g10 = q.z; g11 = q.w;
+    } else {
+      const float* p = Gh + (long long)w.yy * g.W + w.xx;
+      g00 = __ldg(p); g01 = __ldg(p + 1); g10 = __ldg(p + g.W); g11 = __ldg(p + g.W + 1);
+    }
     const double dx = w.dx, dy = w.dy;
     const double a = (1.0 - dy) * (g01 - g00) + dy * (g11 - g10);
     const double b = (1.0 - dx) * (g10 - g00) + dx * (g11 - g01);
 #pragma unroll
     for (int c = 0; c < 3; ++c) acc[c] += (double)w.r0[c] * a + (double)w.r1[c] * b;
   }
-  block_atomic_add<3>(acc, gacc + 3 * h, s_red);
-  __threadfence();
+  // one partial record per CTA, fixed-order final sum by the last CTA (no same-address atomics)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) acc[c] = warp_sum(acc[c]);
+  if (lane == 0) { s_red[wid * 3] = acc[0]; s_red[wid * 3 + 1] = acc[1]; s_red[wid * 3 + 2] = acc[2]; }
   __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket + h, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  double* part = partials + ((long long)h * kMaxEventCtas + blockIdx.x) * 3;
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 3; ++c) {
+      double s = 0;
+      for (int w = 0; w < kFeThreads / 32; ++w) s += s_red[w * 3 + c];
+      part[c] = s;
+    }
     __threadfence();
-    volatile double* va = gacc + 3 * h;
+    is_last = (atomicAdd(ticket + h, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const volatile double* all = partials + (long long)h * kMaxEventCtas * 3;
+  double t[3] = {0.0, 0.0, 0.0};
+  for (int c = threadIdx.x; c < (int)gridDim.x; c += kFeThreads) {
+    t[0] += all[3 * c]; t[1] += all[3 * c + 1]; t[2] += all[3 * c + 2];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) t[c] = warp_sum(t[c]);
+  __syncthreads();
+  if (lane == 0) { s_red[wid * 3] = t[0]; s_red[wid * 3 + 1] = t[1]; s_red[wid * 3 + 2] = t[2]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     const double Np = (double)g.W * (double)g.H;
-    for (int c = 0; c < 3; ++c) { result[4 * h + 1 + c] = va[c] / Np; va[c] = 0.0; }
+    for (int c = 0; c < 3; ++c) {
+      double s = 0;
+      for (int w = 0; w < kFeThreads / 32; ++w) s += s_red[w * 3 + c];
+      result[4 * h + 1 + c] = s / Np;
+    }
     ticket[h] = 0u;
     __threadfence();
   }
