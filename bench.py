@@ -166,7 +166,12 @@ def run_ours(args, rank, world, local_rank):
     oms = synth.fe_hypotheses(pkt, max(world, 1), seed=3, sigma=0.05)
     omega = oms[rank]
     grad_mode = GRAD_ADJOINT if args.grad_mode == "adjoint" else GRAD_DENSE
-    stream = torch.cuda.current_stream(dev)
+    # A dedicated (non-default) torch stream: the library is handed THIS stream, so the L2 flush, the
+    # evaluation kernels, the NCCL all-reduce and the timing events are all ordered on one stream.
+    # (torch's default stream has handle 0, which the C ABI reads as "create your own stream".)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     fe = AngVelEstimatorCMax(pkt.width, pkt.height, pkt.K, pkt.lut, blur_sigma=pkt.blur_sigma,
                              event_batch_size=pkt.batch_size, grad_mode=grad_mode, device=local_rank,
                              stream=stream.cuda_stream)
@@ -259,12 +264,13 @@ def run_ours(args, rank, world, local_rank):
         kern = {k: v for k, v in per_kernel.items() if k != "zero"}
         dom = max(kern, key=lambda k: kern[k]["avg_us"] * kern[k]["launches"])
         # algorithmic bytes of the dominant kernel per launch (DESIGN.md section "Kernels")
-        planes = 4 if grad_mode == GRAD_DENSE else 1
         alg = {
-            "fe_scatter": 16 * n_ev + 24 * A + 4 * A * planes,   # events + f64 LUT + accumulator written once
-            "fe_gather": 16 * n_ev + 24 * A + 4 * A,             # events + LUT + adjoint image G
-            "blur_reduce": 4 * A * planes + (4 * A if grad_mode == GRAD_ADJOINT else 0),
-            "adjoint_blur": 8 * A,
+            # fused evaluation (ADJOINT f+g): events + f64 LUT read by the scatter AND the gather pass;
+            # quad accumulator cleared + read (16 B/cell each), blurred image written + read (4 B),
+            # adjoint image GQ written + read (16 B)  -- DESIGN.md section 4
+            "fe_eval_fused": 2 * (16 * n_ev + 24 * A) + (16 + 16 + 4 + 4 + 16 + 16) * A,
+            "fe_scatter": 16 * n_ev + 24 * A + 16 * A,           # DENSE: events + LUT + (I,dI) accumulator
+            "blur_reduce": 16 * A,
         }.get(dom, 0)
         dur_s = kern[dom]["avg_us"] * 1e-6
         achieved = alg / dur_s / 1e9 if dur_s > 0 else 0.0
@@ -308,7 +314,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grad-mode", default="dense", choices=["dense", "adjoint"])
+    ap.add_argument("--grad-mode", default="adjoint", choices=["dense", "adjoint"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -8,7 +8,7 @@ import numpy as np
 from . import build as _build
 
 K_NAMES = ["zero", "fe_scatter", "fe_gather", "blur_reduce", "adjoint_blur", "be_poses", "be_scatter",
-           "be_gather", "be_grad_reduce", "misc"]
+           "be_gather", "be_grad_reduce", "misc", "fe_eval_fused", "be_eval_fused"]
 K_COUNT = len(K_NAMES)
 
 GRAD_DENSE, GRAD_ADJOINT = 0, 1
@@ -53,7 +53,7 @@ EXPORTS = [
     "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_get_alpha",
     "cmaxb_be_get_il", "cmaxb_be_get_iwe", "cmaxb_be_get_bands", "cmaxb_be_get_cells", "cmaxb_be_get_poses",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
-    "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
+    "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_fe_phase_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
 ]
 
 _lib = None
@@ -84,6 +84,7 @@ def lib():
     L.cmaxb_kernel_name.argtypes = [C.c_int]
     L.cmaxb_fe_profile.argtypes = [vp, C.c_int]
     L.cmaxb_fe_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
+    L.cmaxb_fe_phase_times.argtypes = [vp, dp]
     if not hasattr(L, "cmaxb_be_create"):
         raise RuntimeError("libcmax_b200.so is stale (no back-end symbols): rebuild with cmax_slam_b200/build.py --force")
     L.cmaxb_be_create.argtypes = [C.POINTER(BeCfg), C.POINTER(vp)]

@@ -16,7 +16,7 @@ struct cmaxb_be {
   double4* d_lut = nullptr;
   uint4* d_ev = nullptr; size_t ev_cap = 0;
   long long n = 0, n_eff = 0, nb = 0;
-  BeBatchTime* d_bt = nullptr; BePose* d_poses = nullptr; double* d_wgrad = nullptr; size_t nb_cap = 0;
+  BeBatchTime* d_bt = nullptr; BePose* d_poses = nullptr; double* d_wgrad = nullptr; int* d_idx = nullptr; size_t nb_cap = 0;
   Quat* d_knots0 = nullptr; Quat* d_knots = nullptr; double* d_x = nullptr; double* d_grad = nullptr; size_t knots_cap = 0;
   double* h_x = nullptr; double* h_grad = nullptr; size_t hx_cap = 0;
   int n_knots = 0, n_fixed = 0, n_opt = 0;
@@ -116,7 +116,7 @@ extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
   if (!be) return;
   cudaSetDevice(be->device);
   if (be->stream) cudaStreamSynchronize(be->stream);
-  cudaFree(be->d_lut); cudaFree(be->d_ev); cudaFree(be->d_bt); cudaFree(be->d_poses); cudaFree(be->d_wgrad);
+  cudaFree(be->d_lut); cudaFree(be->d_ev); cudaFree(be->d_bt); cudaFree(be->d_poses); cudaFree(be->d_wgrad); cudaFree(be->d_idx);
   cudaFree(be->d_knots0); cudaFree(be->d_knots); cudaFree(be->d_x); cudaFree(be->d_grad);
   cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
   cudaFree(be->d_bands); cudaFree(be->d_bands_blur); cudaFree(be->d_ilq); cudaFree(be->d_GQ);
@@ -160,8 +160,9 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
     be->ev_cap = (size_t)n;
   }
   if ((size_t)nb > be->nb_cap) {
-    cudaFree(be->d_bt); cudaFree(be->d_poses); cudaFree(be->d_wgrad);
-    be->d_bt = nullptr; be->d_poses = nullptr; be->d_wgrad = nullptr; be->nb_cap = 0;
+    cudaFree(be->d_bt); cudaFree(be->d_poses); cudaFree(be->d_wgrad); cudaFree(be->d_idx);
+    be->d_bt = nullptr; be->d_poses = nullptr; be->d_wgrad = nullptr; be->d_idx = nullptr; be->nb_cap = 0;
+    CMAXB_TRY(dev_alloc(&be->d_idx, (size_t)nb));
     CMAXB_TRY(dev_alloc(&be->d_bt, (size_t)nb));
     CMAXB_TRY(dev_alloc(&be->d_poses, (size_t)nb));
     CMAXB_TRY(dev_alloc(&be->d_wgrad, (size_t)nb * 12));
@@ -240,8 +241,8 @@ static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
   if (be->nb > 0) {
     const unsigned grid = (unsigned)((be->nb + 127) / 128);
     CMAXB_TRY(be->prof.run(CMAXB_K_BE_POSES, s, true, [&] {
-      if (be->N == 2) be_pose_kernel<2><<<grid, 128, 0, s>>>(be->d_knots, be->d_bt, be->nb, want_grad, be->d_poses);
-      else be_pose_kernel<4><<<grid, 128, 0, s>>>(be->d_knots, be->d_bt, be->nb, want_grad, be->d_poses);
+      if (be->N == 2) be_pose_kernel<2><<<grid, 128, 0, s>>>(be->d_knots, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx);
+      else be_pose_kernel<4><<<grid, 128, 0, s>>>(be->d_knots, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx);
     }));
   }
   return CMAXB_OK;
@@ -386,8 +387,8 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
       }
       const double inv_np = 1.0 / ((double)W * (double)H);
       CMAXB_TRY(be->prof.run(CMAXB_K_BE_GRAD_REDUCE, s, true, [&] {
-        if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, 256, 0, s>>>(be->d_poses, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
-        else be_grad_reduce_kernel<4><<<be->n_opt, 256, 0, s>>>(be->d_poses, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+        if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+        else be_grad_reduce_kernel<4><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
       }));
     } else {
       CMAXB_TRY(be_run_bands(be, true));

@@ -84,7 +84,7 @@ __global__ void be_update_knots_kernel(const Quat* __restrict__ knots0, const do
 
 template <int N>
 __global__ void be_pose_kernel(const Quat* __restrict__ knots, const BeBatchTime* __restrict__ bt, long long nb,
-                               int want_grad, BePose* __restrict__ poses) {
+                               int want_grad, BePose* __restrict__ poses, int* __restrict__ idx_out) {
   const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (b >= nb) return;
   const BeBatchTime t = bt[b];
@@ -102,6 +102,7 @@ __global__ void be_pose_kernel(const Quat* __restrict__ knots, const BeBatchTime
   }
   p->idx_cp_beg = (int)t.s;
   p->valid = 1;
+  idx_out[b] = (int)t.s;     // packed copy for the per-knot reduction (coalesced scan)
 }
 
 struct BeWarp {
@@ -313,13 +314,13 @@ be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __rest
 // One CTA per optimised knot; fixed summation order (deterministic).
 template <int N>
 __global__ void __launch_bounds__(256)
-be_grad_reduce_kernel(const BePose* __restrict__ poses, const double* __restrict__ wgrad, long long nb, int n_fixed,
+be_grad_reduce_kernel(const int* __restrict__ idx, const double* __restrict__ wgrad, long long nb, int n_fixed,
                       double inv_np, double* __restrict__ grad) {
   __shared__ double s_red[8 * 3];
   const int knot = blockIdx.x + n_fixed;
   double a[3] = {0.0, 0.0, 0.0};
   for (long long b = threadIdx.x; b < nb; b += blockDim.x) {
-    const int rel = knot - poses[b].idx_cp_beg;
+    const int rel = knot - __ldg(idx + b);
     if (rel >= 0 && rel < N) {
       const double* w = wgrad + b * (3 * N) + 3 * rel;
       a[0] += w[0]; a[1] += w[1]; a[2] += w[2];

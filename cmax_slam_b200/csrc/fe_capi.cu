@@ -2,6 +2,7 @@
 #include "capi_common.cuh"
 #include "fe_kernels.cuh"
 #include "image_kernels.cuh"
+#include "fe_mega.cuh"
 
 using namespace cmaxb;
 
@@ -34,6 +35,15 @@ struct cmaxb_fe {
   double* d_omegas = nullptr; double* h_omegas = nullptr;
   double* d_acc = nullptr; unsigned int* d_ticket = nullptr; unsigned int* d_ticket2 = nullptr;
   double* d_gacc = nullptr; double* d_result = nullptr; double* d_mean = nullptr; double* h_result = nullptr;
+  // fused (single cooperative kernel) evaluation
+  int mega_grid = 0; bool mega_ok = false;
+  double* d_part_img = nullptr; double* d_part_ev = nullptr;
+  double* h_mega_result = nullptr; double* d_mega_result = nullptr;   // mapped pinned memory
+  bool last_mega = false;
+  unsigned long long* h_phase = nullptr; unsigned long long* d_phase = nullptr;   // mapped: phase boundary timestamps
+  unsigned long long* h_done = nullptr; unsigned long long* d_done = nullptr;     // mapped: completion sequence number
+  unsigned long long seq = 0;
+  bool force_multi_kernel = false;   // CMAXB_FE_MULTI_KERNEL=1: stand-alone kernels (profiling / A-B comparison)
   int last_k = 0; bool last_grad = false; bool pending = false;
   KernelProfiler prof;
 };
@@ -64,6 +74,10 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   fe->device = cfg->device;
   fe->A = (long long)cfg->width * cfg->height;
   fe->kmax = cfg->max_hypotheses > 0 ? cfg->max_hypotheses : 1;
+  {
+    const char* mk = getenv("CMAXB_FE_MULTI_KERNEL");
+    fe->force_multi_kernel = mk && mk[0] == '1';
+  }
   int rc = make_taps(cfg->blur_sigma, &fe->taps);
   if (rc != CMAXB_OK) { delete fe; return rc; }
   if (fe->taps.r + 2 > cfg->width || fe->taps.r + 2 > cfg->height) { delete fe; return set_error(CMAXB_ERR_INVALID, "image smaller than the blur kernel"); }
@@ -109,6 +123,39 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   ok = ok && cudaMemset(fe->d_quad[0], 0, sizeof(float4) * k * A) == cudaSuccess;
   ok = ok && cudaMemset(fe->d_quad[1], 0, sizeof(float4) * k * A) == cudaSuccess;
   if (!ok) return fail(set_error(CMAXB_ERR_CUDA, "front-end buffer allocation failed"));
+  // fused evaluation kernel: co-resident grid size from the occupancy API
+  {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, fe->device);
+    int nsm = 0;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, fe->device);
+    const size_t smem = mega_smem_bytes(fe->taps.r);
+    int occ = 0;
+    cudaError_t e1 = cudaFuncSetAttribute(fe_eval_megakernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e2 = cudaFuncSetAttribute(fe_eval_megakernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e3 = (fe->taps.r == 4)
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fe_eval_megakernel<4>, kMegaThreads, smem)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fe_eval_megakernel<-1>, kMegaThreads, smem);
+    if (coop && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && occ > 0) {
+      int grid = occ * nsm;
+      if (grid > kMegaMaxCtas) grid = kMegaMaxCtas;
+      fe->mega_grid = grid;
+      const size_t kk = (size_t)fe->kmax;
+      bool okm = dev_alloc(&fe->d_part_img, kk * kMegaMaxCtas * 2) == CMAXB_OK && dev_alloc(&fe->d_part_ev, kk * kMegaMaxCtas * 3) == CMAXB_OK;
+      okm = okm && cudaHostAlloc((void**)&fe->h_mega_result, sizeof(double) * 4 * kk, cudaHostAllocMapped) == cudaSuccess;
+      okm = okm && cudaHostGetDevicePointer((void**)&fe->d_mega_result, fe->h_mega_result, 0) == cudaSuccess;
+      okm = okm && cudaHostAlloc((void**)&fe->h_done, sizeof(unsigned long long) * 8, cudaHostAllocMapped) == cudaSuccess;
+      okm = okm && cudaHostGetDevicePointer((void**)&fe->d_done, fe->h_done, 0) == cudaSuccess;
+      if (okm) fe->h_done[0] = 0;
+      okm = okm && cudaHostAlloc((void**)&fe->h_phase, sizeof(unsigned long long) * 16, cudaHostAllocMapped) == cudaSuccess;
+      okm = okm && cudaHostGetDevicePointer((void**)&fe->d_phase, fe->h_phase, 0) == cudaSuccess;
+      if (okm && !fe->d_blur1) okm = dev_alloc(&fe->d_blur1, kk * A) == CMAXB_OK;
+      if (okm && !fe->d_GQ) okm = dev_alloc(&fe->d_GQ, kk * A) == CMAXB_OK;
+      fe->mega_ok = okm;
+    }
+    (void)cudaGetLastError();
+    if (!fe->mega_ok) return fail(set_error(CMAXB_ERR_CUDA, "cooperative launch unavailable: the fused evaluation kernel cannot run on this device"));
+  }
   *out = fe;
   return CMAXB_OK;
 }
@@ -124,6 +171,10 @@ extern "C" void cmaxb_fe_destroy(cmaxb_fe* fe) {
   if (fe->h_flags) cudaFreeHost(fe->h_flags);
   if (fe->h_omegas) cudaFreeHost(fe->h_omegas);
   if (fe->h_result) cudaFreeHost(fe->h_result);
+  if (fe->h_mega_result) cudaFreeHost(fe->h_mega_result);
+  if (fe->h_phase) cudaFreeHost(fe->h_phase);
+  if (fe->h_done) cudaFreeHost(fe->h_done);
+  cudaFree(fe->d_part_img); cudaFree(fe->d_part_ev);
   fe->prof.destroy();
   if (fe->own_stream && fe->stream) cudaStreamDestroy(fe->stream);
   delete fe;
@@ -235,12 +286,62 @@ static int fe_run_scatter_dense(cmaxb_fe* fe, int k) {
   return CMAXB_OK;
 }
 
+// One cooperative launch per <= kMegaMaxHyp hypotheses; omegas travel as kernel parameters and the
+// results land in mapped pinned memory.
+static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int want_grad) {
+  cudaStream_t s = fe->stream;
+  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(s)); fe->pending = false; }
+  const int cur = fe->quad_cur, oth = cur ^ 1;
+  if (fe->quad_dirty[cur] > 0) {
+    const int planes = fe->quad_dirty[cur];
+    CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(fe->d_quad[cur], 0, sizeof(float4) * fe->A * planes, s); }));
+    fe->quad_dirty[cur] = 0;
+  }
+  const bool clear_next = fe->quad_dirty[oth] > 0 && fe->quad_dirty[oth] <= k;
+  for (int c0 = 0; c0 < k; c0 += kMegaMaxHyp) {
+    const int kc = (k - c0 < kMegaMaxHyp) ? k - c0 : kMegaMaxHyp;
+    FeMegaParams p;
+    p.g = fe_geom(fe);
+    p.k = kc; p.want_grad = want_grad; p.measure = fe->cfg.contrast_measure; p.taps = fe->taps;
+    for (int i = 0; i < 3 * kc; ++i) p.omegas[i] = omegas[3 * c0 + i];
+    p.quad = fe->d_quad[cur] + (long long)c0 * fe->A;
+    p.quad_next = clear_next ? fe->d_quad[oth] + (long long)c0 * fe->A : nullptr;
+    p.blurred = fe->d_blur1 + (long long)c0 * fe->A;
+    p.GQ = fe->d_GQ + (long long)c0 * fe->A;
+    p.A = fe->A;
+    p.part_img = fe->d_part_img + (long long)c0 * kMegaMaxCtas * 2;
+    p.part_ev = fe->d_part_ev + (long long)c0 * kMegaMaxCtas * 3;
+    p.result = fe->d_mega_result + 4 * c0;
+    p.done_flag = fe->d_done;
+    p.seq = ++fe->seq;
+    p.phase_ns = fe->prof.enabled ? fe->d_phase : nullptr;
+    if (fe->prof.enabled) for (int i = 0; i < 16; ++i) fe->h_phase[i] = 0;
+    void* args[] = {&p};
+    const size_t smem = mega_smem_bytes(fe->taps.r);
+    cudaError_t le = cudaSuccess;
+    CMAXB_TRY(fe->prof.run(CMAXB_K_FE_EVAL_FUSED, s, true, [&] {
+      le = (fe->taps.r == 4)
+          ? cudaLaunchCooperativeKernel((void*)fe_eval_megakernel<4>, dim3(fe->mega_grid), dim3(kMegaThreads), args, smem, s)
+          : cudaLaunchCooperativeKernel((void*)fe_eval_megakernel<-1>, dim3(fe->mega_grid), dim3(kMegaThreads), args, smem, s);
+    }));
+    if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("fused evaluation launch: ") + cudaGetErrorString(le));
+  }
+  if (clear_next) fe->quad_dirty[oth] = 0;
+  if (fe->n > 0) fe->quad_dirty[cur] = k;
+  fe->quad_cur = oth;
+  fe->last_k = k; fe->last_grad = want_grad != 0; fe->pending = true; fe->last_mega = true;
+  return CMAXB_OK;
+}
+
 extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, int want_grad) {
   if (!fe || !omegas) return set_error(CMAXB_ERR_INVALID, "null argument");
   if (!fe->have_packet) return set_error(CMAXB_ERR_STATE, "no event packet: call cmaxb_fe_set_packet first");
   if (k < 1 || k > fe->kmax) return set_error(CMAXB_ERR_INVALID, "k exceeds cfg.max_hypotheses");
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  if (!(want_grad && fe->cfg.grad_mode == CMAXB_GRAD_DENSE) && !fe->force_multi_kernel)
+    return fe_eval_launch_fused(fe, omegas, k, want_grad);
   CMAXB_TRY(fe_upload_omegas(fe, omegas, k));
+  fe->last_mega = false;
   cudaStream_t s = fe->stream;
   const int W = fe->cfg.width, H = fe->cfg.height, measure = fe->cfg.contrast_measure;
   if (want_grad && fe->cfg.grad_mode == CMAXB_GRAD_DENSE) {
@@ -276,12 +377,30 @@ extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, i
 extern "C" int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grads3k) {
   if (!fe || !contrasts) return set_error(CMAXB_ERR_INVALID, "null argument");
   if (fe->last_k <= 0) return set_error(CMAXB_ERR_STATE, "no evaluation launched");
-  CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+  if (fe->last_mega && fe->pending) {
+    // The fused kernel publishes its results in mapped pinned memory and then stores its sequence
+    // number: spin on that word (~1 us) instead of paying the driver's stream-synchronise latency;
+    // check the stream now and then so that a faulted kernel cannot hang the caller.
+    volatile unsigned long long* done = fe->h_done;
+    unsigned long long spins = 0;
+    while (*done != fe->seq) {
+      if ((++spins & 0x3fff) == 0) {
+        cudaError_t q = cudaStreamQuery(fe->stream);
+        if (q == cudaSuccess) break;                       // finished (flag write raced the query) or faulted
+        if (q != cudaErrorNotReady) return set_error(CMAXB_ERR_CUDA, std::string("fused evaluation kernel: ") + cudaGetErrorString(q));
+      }
+    }
+    if (*done != fe->seq) CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+    if (*done != fe->seq) return set_error(CMAXB_ERR_CUDA, "fused evaluation kernel finished without publishing its result");
+  } else {
+    CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+  }
   fe->pending = false;
+  const double* res = fe->last_mega ? fe->h_mega_result : fe->h_result;
   for (int h = 0; h < fe->last_k; ++h) {
-    contrasts[h] = fe->h_result[4 * h];
+    contrasts[h] = res[4 * h];
     if (grads3k && fe->last_grad)
-      for (int c = 0; c < 3; ++c) grads3k[3 * h + c] = fe->h_result[4 * h + 1 + c];
+      for (int c = 0; c < 3; ++c) grads3k[3 * h + c] = res[4 * h + 1 + c];
   }
   return CMAXB_OK;
 }
@@ -363,6 +482,13 @@ extern "C" int cmaxb_fe_profile(cmaxb_fe* fe, int enable) {
   fe->prof.reset();
   return CMAXB_OK;
 }
+extern "C" int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10) {
+  if (!fe || !us10) return set_error(CMAXB_ERR_INVALID, "null argument");
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+  for (int i = 0; i < 10; ++i)
+    us10[i] = (fe->h_phase && fe->h_phase[i] && fe->h_phase[0]) ? (double)(fe->h_phase[i] - fe->h_phase[0]) * 1e-3 : -1.0;
+  return CMAXB_OK;
+}
 extern "C" int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms, uint64_t* launches) {
   if (!fe || !ms || !launches) return set_error(CMAXB_ERR_INVALID, "null argument");
   for (int i = 0; i < CMAXB_K_COUNT; ++i) { ms[i] = fe->prof.ms[i]; launches[i] = fe->prof.launches[i]; }
@@ -380,6 +506,7 @@ extern "C" int cmaxb_device_count(void) {
 extern "C" uint64_t cmaxb_launch_count(void) { return g_launch_count.load(); }
 extern "C" const char* cmaxb_kernel_name(int kind) {
   static const char* names[CMAXB_K_COUNT] = {"zero(memset)", "fe_scatter", "fe_gather", "blur_reduce", "adjoint_blur",
-                                             "be_poses", "be_scatter", "be_gather", "be_grad_reduce", "misc"};
+                                             "be_poses", "be_scatter", "be_gather", "be_grad_reduce", "misc",
+                                             "fe_eval_fused", "be_eval_fused"};
   return (kind >= 0 && kind < CMAXB_K_COUNT) ? names[kind] : "?";
 }

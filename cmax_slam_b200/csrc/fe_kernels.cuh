@@ -28,14 +28,10 @@ struct FeWarp {
 };
 
 // One event, one hypothesis.  No FMA contraction (see common.cuh).
+// (bx,by,bz) = bearing vector of the event's pixel, already loaded.
 template <bool GRAD>
-__device__ __forceinline__ FeWarp fe_warp(const FeGeom& g, uint4 e, double dt, double ox, double oy, double oz) {
+__device__ __forceinline__ FeWarp fe_warp_b(const FeGeom& g, double bx, double by, double bz, double dt, double ox, double oy, double oz) {
   FeWarp o;
-  const int ex = e.x & 0xffff, ey = e.x >> 16;
-  const double2* lp = reinterpret_cast<const double2*>(g.lut + (ey * g.W + ex));
-  const double2 bxy = __ldg(lp);
-  const double bz = __ldg(reinterpret_cast<const double*>(lp + 1));
-  const double bx = bxy.x, by = bxy.y;
   // delta_rot = ang_vel * dt ; p' = p + delta_rot x p                     (:76,101)
   const double dlx = ox * dt, dly = oy * dt, dlz = oz * dt;
   const double px3 = bx + (dly * bz - dlz * by);
@@ -76,6 +72,15 @@ __device__ __forceinline__ FeWarp fe_warp(const FeGeom& g, uint4 e, double dt, d
     o.r1[0] = (float)(g.fy * c10); o.r1[1] = (float)(g.fy * c11); o.r1[2] = (float)(g.fy * c12);
   }
   return o;
+}
+
+template <bool GRAD>
+__device__ __forceinline__ FeWarp fe_warp(const FeGeom& g, uint4 e, double dt, double ox, double oy, double oz) {
+  const int ex = e.x & 0xffff, ey = e.x >> 16;
+  const double2* lp = reinterpret_cast<const double2*>(g.lut + (ey * g.W + ex));
+  const double2 bxy = __ldg(lp);
+  const double bz = __ldg(reinterpret_cast<const double*>(lp + 1));
+  return fe_warp_b<GRAD>(g, bxy.x, bxy.y, bz, dt, ox, oy, oz);
 }
 
 // per-batch reference time offsets; flags[0] |= 1 on a negative batch span (:72)

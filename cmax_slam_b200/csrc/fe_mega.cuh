@@ -1,0 +1,393 @@
+// fe_mega.cuh -- the front-end cost evaluation as ONE persistent cooperative kernel.
+//
+// ncu on the multi-kernel pipeline (profiles/r01b_*) showed that each of its four small kernels
+// keeps the SMs busy for only 5-10 us while its launch / ramp / tail costs another 5-8 us, and the
+// gaps between them add ~24 us per evaluation.  Here the whole evaluation
+//     scatter -> | -> blur + sums (+ clear next accumulator) -> | -> adjoint blur -> | -> gather -> | -> final
+// runs in one launch of co-resident CTAs (cooperative launch, one grid barrier per '|'), the
+// hypotheses come in as kernel parameters (no H2D copy) and the result is stored straight into
+// mapped pinned host memory (no D2H copy).  Work decomposition, arithmetic and operation order are
+// exactly those of the stand-alone kernels (fe_kernels.cuh, image_kernels.cuh).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "fe_kernels.cuh"
+#include "image_kernels.cuh"
+
+namespace cmaxb {
+
+namespace cg = cooperative_groups;
+
+constexpr int kMegaThreads = 256;
+constexpr int kMegaMaxHyp = 32;       // hypotheses per launch (kernel-parameter space)
+constexpr int kMegaMaxCtas = 148 * 8;
+
+struct FeMegaParams {
+  FeGeom g;
+  int k;                      // hypotheses in this launch
+  int want_grad;
+  int measure;
+  Taps taps;
+  double omegas[3 * kMegaMaxHyp];
+  float4* quad;               // [k][A]  accumulator being filled and consumed (clean on entry)
+  float4* quad_next;          // [k][A]  accumulator of the next evaluation: cleared here (or null)
+  float* blurred;             // [k][A]
+  float4* GQ;                 // [k][A]
+  long long A;
+  double* part_img;           // [k][kMegaMaxCtas][2]
+  double* part_ev;            // [k][kMegaMaxCtas][3]
+  double* result;             // [k][4] mapped pinned host memory (device pointer)
+  unsigned long long* done_flag; // mapped host word: receives `seq` after the results are visible to the host
+  unsigned long long seq;
+  unsigned long long* phase_ns; // optional [8]: %globaltimer of CTA 0 at every phase boundary (mapped host memory)
+};
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define CMAXB_PHASE_MARK(idx) do { if (p.phase_ns && blockIdx.x == 0 && threadIdx.x == 0) p.phase_ns[idx] = global_timer_ns(); } while (0)
+
+constexpr int kEvUnroll = 4;
+
+__device__ __forceinline__ void mega_scatter(const FeMegaParams& p) {
+  const FeGeom& g = p.g;
+  const long long stride = (long long)gridDim.x * kMegaThreads;
+  const long long i0 = blockIdx.x * (long long)kMegaThreads + threadIdx.x;
+  // kEvUnroll events per iteration: all event records, dt entries and LUT sectors are requested
+  // before the first dependent use (the loop is latency-bound on L2, not throughput-bound)
+  for (long long i = i0; i < g.n; i += kEvUnroll * stride) {
+    uint4 e[kEvUnroll];
+    double dt[kEvUnroll];
+    double2 bxy[kEvUnroll];
+    double bz[kEvUnroll];
+    bool ok[kEvUnroll];
+#pragma unroll
+    for (int u = 0; u < kEvUnroll; ++u) {
+      const long long j = i + u * stride;
+      ok[u] = j < g.n;
+      e[u] = load_event(g.ev, ok[u] ? j : i);
+    }
+#pragma unroll
+    for (int u = 0; u < kEvUnroll; ++u) {
+      const long long j = ok[u] ? i + u * stride : i;
+      dt[u] = __ldg(g.dt_tab + (unsigned)j / (unsigned)g.batch_size);
+      const int ex = e[u].x & 0xffff, ey = e[u].x >> 16;
+      const double2* lp = reinterpret_cast<const double2*>(g.lut + (ey * g.W + ex));
+      bxy[u] = __ldg(lp);
+      bz[u] = __ldg(reinterpret_cast<const double*>(lp + 1));
+    }
+    for (int h = 0; h < p.k; ++h) {
+      const double ox = p.omegas[3 * h], oy = p.omegas[3 * h + 1], oz = p.omegas[3 * h + 2];
+      float4* q = p.quad + h * p.A;
+#pragma unroll
+      for (int u = 0; u < kEvUnroll; ++u) {
+        const FeWarp w = fe_warp_b<false>(g, bxy[u].x, bxy[u].y, bz[u], dt[u], ox, oy, oz);
+        if (ok[u] && w.in) {
+          const float dx = w.dx, dy = w.dy;
+          atomicAdd(q + (long long)w.yy * g.W + w.xx,
+                    make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy));
+        }
+      }
+    }
+  }
+}
+
+// blur + S1,S2 partial sums of hypothesis h; clears the same tiles of the next accumulator.
+// The quad cells of the tile (+halo+1) are staged ONCE in shared memory as float4 (one 16-byte L2
+// request per cell, all requests of a thread issued back to back), cells outside the image staged as
+// zero, and the image pixels -- including the BORDER_REFLECT_101 halo -- are assembled from there.
+template <int R>
+__device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned char* smem_raw, bool write_out) {
+  const int W = p.g.W, H = p.g.H;
+  const int r = (R >= 0) ? R : p.taps.r;
+  const int IW = kTW + 2 * r, IH = kTH + 2 * r;
+  const int QW = IW + 1, QH = IH + 1;
+  float4* s_q = reinterpret_cast<float4*>(smem_raw);          // [QH][QW] cells at image coords (tx0-r-1.., ty0-r-1..)
+  float* s_in = reinterpret_cast<float*>(s_q + QW * QH);      // [IH][IW]
+  float* s_tmp = s_in + IW * IH;                              // [IH][kTW]
+  double* s_red = reinterpret_cast<double*>(s_tmp + IH * kTW);
+  const int tid = threadIdx.x;
+  const int ntx = (W + kTW - 1) / kTW, nty = (H + kTH - 1) / kTH;
+  const float4* quad = p.quad + h * p.A;
+  float* out = p.blurred + h * p.A;
+  float4* zero_ptr = p.quad_next ? p.quad_next + h * p.A : nullptr;
+  double a[2] = {0.0, 0.0};
+  for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
+    const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * kTH;
+    const int qx0 = tx0 - r - 1, qy0 = ty0 - r - 1;
+    __syncthreads();
+    for (int i = tid; i < QW * QH; i += kMegaThreads) {
+      const int ly = i / QW, lx = i - ly * QW;
+      const int gx = qx0 + lx, gy = qy0 + ly;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = __ldcg(quad + (long long)gy * W + gx);
+      s_q[i] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < IW * IH; i += kMegaThreads) {
+      const int ly = i / IW, lx = i - ly * IW;
+      const int gx = reflect101(min(tx0 + lx - r, W + r), W);
+      const int gy = reflect101(min(ty0 + ly - r, H + r), H);
+      const int cx = gx - qx0, cy = gy - qy0;                 // >= 1 by construction
+      float v = 0.f;
+      if (cx >= 1 && cy >= 1 && cx < QW && cy < QH) {          // always true for pixels that feed a valid output
+        const float4* c = s_q + cy * QW + cx;
+        v = c[0].x;
+        v += c[-1].y;
+        v += c[-QW].z;
+        v += c[-QW - 1].w;
+      }
+      s_in[i] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < IH * kTW; i += kMegaThreads) {
+      const int ly = i / kTW, lx = i - ly * kTW;
+      const float* q = s_in + ly * IW + lx;
+      float s = p.taps.w[0] * q[0];
+#pragma unroll
+      for (int j = 1; j <= 2 * r; ++j) s = fmaf(p.taps.w[j], q[j], s);
+      s_tmp[i] = s;
+    }
+    __syncthreads();
+    const int lx = tid & (kTW - 1);
+    for (int ly = tid / kTW; ly < kTH; ly += kMegaThreads / kTW) {
+      const int gx = tx0 + lx, gy = ty0 + ly;
+      if (gx < W && gy < H) {
+        const float* c = s_tmp + (ly + r) * kTW + lx;
+        float s = p.taps.w[r] * c[0];
+#pragma unroll
+        for (int j = 1; j <= r; ++j) s = fmaf(p.taps.w[r + j], c[j * kTW] + c[-j * kTW], s);
+        if (write_out) out[(long long)gy * W + gx] = s;
+        const double v = (double)s;
+        a[0] += v; a[1] += v * v;
+        if (zero_ptr) zero_ptr[(long long)gy * W + gx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  block_sum<2>(a, s_red);
+  if (tid == 0) {
+    double* part = p.part_img + ((long long)h * kMegaMaxCtas + blockIdx.x) * 2;
+    part[0] = a[0]; part[1] = a[1];
+  }
+}
+
+// every CTA adds the per-CTA records of hypothesis h in the same fixed order -> identical S1, S2
+__device__ __forceinline__ void mega_image_sums(const FeMegaParams& p, int h, double* s_red, double* S1, double* S2) {
+  const double* all = p.part_img + (long long)h * kMegaMaxCtas * 2;
+  double t[2] = {0.0, 0.0};
+  for (int c = threadIdx.x; c < (int)gridDim.x; c += kMegaThreads) {
+    t[0] += __ldcg(all + 2 * c); t[1] += __ldcg(all + 2 * c + 1);
+  }
+  block_sum<2>(t, s_red);
+  __shared__ double s_bc[2];
+  if (threadIdx.x == 0) { s_bc[0] = t[0]; s_bc[1] = t[1]; }
+  __syncthreads();
+  *S1 = s_bc[0]; *S2 = s_bc[1];
+  __syncthreads();
+}
+
+template <int R>
+__device__ __forceinline__ void mega_adjoint(const FeMegaParams& p, int h, double mean, unsigned char* smem_raw) {
+  const int W = p.g.W, H = p.g.H;
+  const int r = (R >= 0) ? R : p.taps.r;
+  const int IW = kTW + 1 + 2 * r, IH = kTH + 1 + 2 * r;
+  constexpr int OW = kTW + 1, OH = kTH + 1;
+  float* s_in = reinterpret_cast<float*>(smem_raw);
+  float* s_tmp = s_in + IW * IH;
+  float* s_g = s_tmp + IH * OW;
+  const int tid = threadIdx.x;
+  const float a2 = 2.0f;
+  const float b2 = (p.measure == CMAXB_CONTRAST_MEAN_SQUARE) ? 0.0f : (float)(-2.0 * mean);
+  const float* img = p.blurred + h * p.A;
+  float4* GQ = p.GQ + h * p.A;
+  const int ntx = (W + kTW - 1) / kTW, nty = (H + kTH - 1) / kTH;
+  for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
+    const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * kTH;
+    __syncthreads();
+    for (int i = tid; i < IW * IH; i += kMegaThreads) {
+      const int ly = i / IW, lx = i - ly * IW;
+      const int gx = tx0 + lx - r, gy = ty0 + ly - r;
+      float z = 0.f;
+      if (gx >= 0 && gx < W && gy >= 0 && gy < H) z = __ldcg(img + (long long)gy * W + gx) * a2 + b2;
+      s_in[i] = z;
+    }
+    __syncthreads();
+    for (int i = tid; i < IH * OW; i += kMegaThreads) {
+      const int ly = i / OW, lx = i - ly * OW;
+      const int q = tx0 + lx;
+      const float* row = s_in + ly * IW;
+      float s = 0.f;
+      if (q < W) {
+#pragma unroll
+        for (int d = -r; d <= r; ++d) s = fmaf(p.taps.w[r + d], row[lx + r + d], s);
+        if (q >= 1 && q <= r)
+          for (int d = q; d <= r; ++d) s = fmaf(p.taps.w[r + d], row[(-q + d) - tx0 + r], s);
+        if (q <= W - 2 && q >= W - 1 - r)
+          for (int d = -r; d <= q - (W - 1); ++d) s = fmaf(p.taps.w[r + d], row[(2 * (W - 1) - q + d) - tx0 + r], s);
+      }
+      s_tmp[i] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < OH * OW; i += kMegaThreads) {
+      const int ly = i / OW, lx = i - ly * OW;
+      const int gx = tx0 + lx, q = ty0 + ly;
+      float s = 0.f;
+      if (gx < W && q < H) {
+        const float* col = s_tmp + lx;
+#pragma unroll
+        for (int d = -r; d <= r; ++d) s = fmaf(p.taps.w[r + d], col[(ly + r + d) * OW], s);
+        if (q >= 1 && q <= r)
+          for (int d = q; d <= r; ++d) s = fmaf(p.taps.w[r + d], col[((-q + d) - ty0 + r) * OW], s);
+        if (q <= H - 2 && q >= H - 1 - r)
+          for (int d = -r; d <= q - (H - 1); ++d) s = fmaf(p.taps.w[r + d], col[((2 * (H - 1) - q + d) - ty0 + r) * OW], s);
+      }
+      s_g[i] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < kTW * kTH; i += kMegaThreads) {
+      const int ly = i / kTW, lx = i & (kTW - 1);
+      const int gx = tx0 + lx, gy = ty0 + ly;
+      if (gx < W && gy < H) {
+        const float* q = s_g + ly * OW + lx;
+        GQ[(long long)gy * W + gx] = make_float4(q[0], q[1], q[OW], q[OW + 1]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void mega_gather(const FeMegaParams& p, int h, double* s_red) {
+  const FeGeom& g = p.g;
+  const double ox = p.omegas[3 * h], oy = p.omegas[3 * h + 1], oz = p.omegas[3 * h + 2];
+  const float4* GQh = p.GQ + h * p.A;
+  double acc[3] = {0.0, 0.0, 0.0};
+  constexpr int U = 2;
+  const long long stride = (long long)gridDim.x * kMegaThreads;
+  for (long long i = blockIdx.x * (long long)kMegaThreads + threadIdx.x; i < g.n; i += U * stride) {
+    uint4 e[U]; double dt[U]; double2 bxy[U]; double bz[U]; bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long j = i + u * stride;
+      ok[u] = j < g.n;
+      e[u] = load_event(g.ev, ok[u] ? j : i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long j = ok[u] ? i + u * stride : i;
+      dt[u] = __ldg(g.dt_tab + (unsigned)j / (unsigned)g.batch_size);
+      const int ex = e[u].x & 0xffff, ey = e[u].x >> 16;
+      const double2* lp = reinterpret_cast<const double2*>(g.lut + (ey * g.W + ex));
+      bxy[u] = __ldg(lp);
+      bz[u] = __ldg(reinterpret_cast<const double*>(lp + 1));
+    }
+    FeWarp w[U];
+    float4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      w[u] = fe_warp_b<true>(g, bxy[u].x, bxy[u].y, bz[u], dt[u], ox, oy, oz);
+      q[u] = (ok[u] && w[u].in) ? __ldcg(GQh + (long long)w[u].yy * g.W + w[u].xx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!(ok[u] && w[u].in)) continue;
+      const double g00 = q[u].x, g01 = q[u].y, g10 = q[u].z, g11 = q[u].w;
+      const double dx = w[u].dx, dy = w[u].dy;
+      const double a = (1.0 - dy) * (g01 - g00) + dy * (g11 - g10);
+      const double b = (1.0 - dx) * (g10 - g00) + dx * (g11 - g01);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += (double)w[u].r0[c] * a + (double)w[u].r1[c] * b;
+    }
+  }
+  block_sum<3>(acc, s_red);
+  if (threadIdx.x == 0) {
+    double* part = p.part_ev + ((long long)h * kMegaMaxCtas + blockIdx.x) * 3;
+    part[0] = acc[0]; part[1] = acc[1]; part[2] = acc[2];
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kMegaThreads)
+fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_red[(kMegaThreads / 32) * 3];
+  __shared__ double s_mean[kMegaMaxHyp];
+  cg::grid_group grid = cg::this_grid();
+  const double Np = (double)p.g.W * (double)p.g.H;
+
+  CMAXB_PHASE_MARK(0);
+  if (p.g.n > 0) mega_scatter(p);
+  CMAXB_PHASE_MARK(1);
+  grid.sync();
+  CMAXB_PHASE_MARK(2);
+  for (int h = 0; h < p.k; ++h) mega_blur<R>(p, h, smem_raw, p.want_grad != 0);
+  CMAXB_PHASE_MARK(3);
+  grid.sync();
+  CMAXB_PHASE_MARK(4);
+  for (int h = 0; h < p.k; ++h) {
+    double S1, S2;
+    mega_image_sums(p, h, s_red, &S1, &S2);
+    const double mean = S1 / Np;
+    if (threadIdx.x == 0) s_mean[h] = mean;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      double contrast;
+      if (p.measure == CMAXB_CONTRAST_MEAN_SQUARE) contrast = S2 / Np;
+      else {
+        double var = S2 / Np - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double sd = sqrt(var);
+        contrast = sd * sd;
+      }
+      p.result[4 * h] = contrast;
+    }
+  }
+  __syncthreads();
+  if (!p.want_grad) {
+    CMAXB_PHASE_MARK(5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(p.done_flag) = p.seq;
+    }
+    return;
+  }
+  for (int h = 0; h < p.k; ++h) mega_adjoint<R>(p, h, s_mean[h], smem_raw);
+  CMAXB_PHASE_MARK(5);
+  grid.sync();
+  CMAXB_PHASE_MARK(6);
+  for (int h = 0; h < p.k; ++h) {
+    __syncthreads();
+    mega_gather(p, h, s_red);
+  }
+  CMAXB_PHASE_MARK(7);
+  grid.sync();
+  CMAXB_PHASE_MARK(8);
+  if (blockIdx.x == 0) {
+    for (int h = 0; h < p.k; ++h) {
+      const double* all = p.part_ev + (long long)h * kMegaMaxCtas * 3;
+      double t[3] = {0.0, 0.0, 0.0};
+      for (int c = threadIdx.x; c < (int)gridDim.x; c += kMegaThreads) {
+        t[0] += __ldcg(all + 3 * c); t[1] += __ldcg(all + 3 * c + 1); t[2] += __ldcg(all + 3 * c + 2);
+      }
+      __syncthreads();
+      block_sum<3>(t, s_red);
+      if (threadIdx.x == 0) {
+        p.result[4 * h + 1] = t[0] / Np; p.result[4 * h + 2] = t[1] / Np; p.result[4 * h + 3] = t[2] / Np;
+      }
+    }
+    CMAXB_PHASE_MARK(9);
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long*>(p.done_flag) = p.seq;
+    }
+  }
+}
+
+inline size_t mega_smem_bytes(int r) {
+  const int IW = kTW + 2 * r, IH = kTH + 2 * r;
+  const size_t a = sizeof(float4) * (size_t)(IW + 1) * (IH + 1) + sizeof(float) * ((size_t)IW * IH + (size_t)IH * kTW) +
+                   sizeof(double) * (kMegaThreads / 32) * kNAcc;
+  const size_t b = adjoint_smem_bytes(r);
+  return a > b ? a : b;
+}
+
+}  // namespace cmaxb

@@ -46,13 +46,15 @@ struct SrcPlane4 {           // interleaved (I, D0, D1, D2)
 // re-assembled here, at load time, in a fixed order.
 struct SrcQuad {
   const float4* base; long long stride_h;
+  // __ldcg (L2-coherent) rather than the read-only path: in the fused evaluation kernel the image
+  // was written by other SMs earlier in the SAME launch.
   __device__ __forceinline__ float load(int h, int x, int y, int W) const {
     const float4* q = base + h * stride_h + (long long)y * W + x;
-    float v = __ldg(q).x;
-    if (x > 0) v += __ldg(q - 1).y;
+    float v = __ldcg(q).x;
+    if (x > 0) v += __ldcg(q - 1).y;
     if (y > 0) {
-      v += __ldg(q - W).z;
-      if (x > 0) v += __ldg(q - W - 1).w;
+      v += __ldcg(q - W).z;
+      if (x > 0) v += __ldcg(q - W - 1).w;
     }
     return v;
   }

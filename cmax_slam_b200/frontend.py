@@ -107,6 +107,12 @@ class AngVelEstimatorCMax:
     def profile(self, enable=True):
         _capi.check(self._L.cmaxb_fe_profile(self._h, int(enable)))
 
+    def phase_times(self):
+        """Fused kernel (profiling on): us from kernel entry to each phase boundary of the last launch."""
+        t = np.zeros(10)
+        _capi.check(self._L.cmaxb_fe_phase_times(self._h, _capi.dptr(t)))
+        return t
+
     def kernel_times(self):
         ms = np.zeros(_capi.K_COUNT)
         n = np.zeros(_capi.K_COUNT, np.uint64)

@@ -171,10 +171,14 @@ uint64_t cmaxb_launch_count(void);
 enum {
   CMAXB_K_ZERO = 0, CMAXB_K_FE_SCATTER, CMAXB_K_FE_GATHER, CMAXB_K_BLUR_REDUCE, CMAXB_K_ADJOINT_BLUR,
   CMAXB_K_BE_POSES, CMAXB_K_BE_SCATTER, CMAXB_K_BE_GATHER, CMAXB_K_BE_GRAD_REDUCE, CMAXB_K_MISC,
+  CMAXB_K_FE_EVAL_FUSED, CMAXB_K_BE_EVAL_FUSED,
   CMAXB_K_COUNT
 };
 int cmaxb_fe_profile(cmaxb_fe* fe, int enable);
 int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms /*CMAXB_K_COUNT*/, uint64_t* launches /*CMAXB_K_COUNT*/);
+/* Fused evaluation kernel, profiling enabled: microseconds from kernel entry (CTA 0) to each of its 10
+ * phase boundaries (scatter end, barrier, blur end, barrier, ...; -1 = not reached) of the LAST launch. */
+int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10);
 int cmaxb_be_profile(cmaxb_be* be, int enable);
 int cmaxb_be_kernel_times(cmaxb_be* be, double* ms, uint64_t* launches);
 const char* cmaxb_kernel_name(int kind);

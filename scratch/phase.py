@@ -1,0 +1,16 @@
+import sys; sys.path.insert(0,'.')
+import numpy as np
+from cmax_slam_b200 import synth
+from cmax_slam_b200.frontend import AngVelEstimatorCMax
+for name, scale in (("C1", 0.2), ("C2", 1.0)):
+    pk = synth.fe_config(name, scale)
+    fe = AngVelEstimatorCMax(pk.width, pk.height, pk.K, pk.lut, grad_mode=1)
+    fe.set_packet(pk.events, pk.t_ref_sec)
+    w = pk.omega_true + np.array([0.2,-0.1,0.15])
+    for i in range(5): fe.eval(w, True)
+    fe.profile(True)
+    for want in (True, False):
+        for i in range(3):
+            fe.eval(w, want)
+            print(name, want, np.round(fe.phase_times(), 2))
+    fe.close()

@@ -197,5 +197,5 @@ def test_native_library_is_what_ran():
     fe = _mk(pk)
     fe.eval(pk.omega_true, True)
     fe.close()
-    assert _capi.launch_count() - n0 >= 5
+    assert _capi.launch_count() - n0 >= 3      # validate + batch-dt kernels + the fused evaluation kernel
     assert "libcmax_b200.so" in open("/proc/self/maps").read()
