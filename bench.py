@@ -182,17 +182,19 @@ def run_ours(args, rank, world, local_rank):
     fe.set_packet(ev_host, pkt.t_ref_sec)
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
+    # multi-GPU: the evaluation kernel also writes its (contrast, g) row into `mine` on the device; ONE NCCL
+    # collective per step combines the rows of all ranks (an all-gather == the all-reduce of a zero-padded
+    # [N,4] buffer the north star words) on the same stream, with no host hop.
     gathered = torch.zeros(max(world, 1), 4, dtype=torch.float64, device=dev)
-    row = torch.zeros(4, dtype=torch.float64)
+    mine = torch.zeros(4, dtype=torch.float64, device=dev)
+    if world > 1:
+        fe.set_result_mirror(mine.data_ptr())
 
     def step_resident():
         fe.eval_launch(omega[None, :], True)
-        c, g = fe.eval_fetch()
         if world > 1:
-            gathered.zero_()
-            row[0] = c[0]; row[1:] = torch.from_numpy(g[0])
-            gathered[rank].copy_(row, non_blocking=True)
-            dist.all_reduce(gathered)
+            dist.all_gather_into_tensor(gathered.view(-1), mine)
+        c, g = fe.eval_fetch()
         return c[0], g[0]
 
     def step_e2e():
@@ -236,6 +238,14 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(lc)
             launches = int(lc.item())
         return total_ms, launches, wall, ms
+
+    # sanity: the collective really delivers every rank's row
+    c_chk, g_chk = step_resident()
+    barrier()
+    if world > 1:
+        rows = gathered.cpu().numpy()
+        assert abs(rows[rank, 0] - c_chk) <= 1e-12 * abs(c_chk) and np.allclose(rows[rank, 1:], g_chk, rtol=1e-12), "mirror row != fetched result"
+        assert np.all(rows[:, 0] > 0), "a rank's row is missing from the gathered buffer"
 
     K, Wm = args.steps, args.warmup
     total_ms, launches, wall, ms = timed(step_resident, K, Wm, True)
@@ -283,7 +293,7 @@ def run_ours(args, rank, world, local_rank):
                        "events": n_ev, "image": [W, H], "batch_size": pkt.batch_size, "blur_sigma": pkt.blur_sigma,
                        "grad_mode": args.grad_mode, "l2": "flushed between timed iterations (256 MiB fill)",
                        "parallelism": f"hypothesis-sharded x{world}" if world > 1 else "single GPU",
-                       "collective": "1 NCCL all-reduce of [N,4] f64 per step" if world > 1 else "none"},
+                       "collective": "1 NCCL all-gather of the [N,4] f64 result rows per step, device-resident" if world > 1 else "none"},
             "l2_warm": {"ms_per_step": warm_ms / K, "value": world * n_ev / (warm_ms / K * 1e-3),
                         "note": "no L2 flush between iterations (optimiser regime)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_ev + 24, "d2h_bytes_per_step": 32 + 4,

@@ -49,7 +49,7 @@ class BeWindow(C.Structure):
 # every symbol include/cmax_b200.h declares
 EXPORTS = [
     "cmaxb_fe_create", "cmaxb_fe_destroy", "cmaxb_fe_set_packet", "cmaxb_fe_eval", "cmaxb_fe_eval_batch",
-    "cmaxb_fe_eval_launch", "cmaxb_fe_eval_fetch", "cmaxb_fe_get_iwe", "cmaxb_fe_get_deriv", "cmaxb_fe_get_cells",
+    "cmaxb_fe_eval_launch", "cmaxb_fe_eval_fetch", "cmaxb_fe_set_result_mirror", "cmaxb_fe_get_iwe", "cmaxb_fe_get_deriv", "cmaxb_fe_get_cells",
     "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_get_alpha",
     "cmaxb_be_get_il", "cmaxb_be_get_iwe", "cmaxb_be_get_bands", "cmaxb_be_get_cells", "cmaxb_be_get_poses",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
@@ -75,6 +75,7 @@ def lib():
     L.cmaxb_fe_eval_batch.argtypes = [vp, dp, C.c_int, dp, dp]
     L.cmaxb_fe_eval_launch.argtypes = [vp, dp, C.c_int, C.c_int]
     L.cmaxb_fe_eval_fetch.argtypes = [vp, dp, dp]
+    L.cmaxb_fe_set_result_mirror.argtypes = [vp, vp]
     L.cmaxb_fe_get_iwe.argtypes = [vp, dp, C.c_int, vp]
     L.cmaxb_fe_get_deriv.argtypes = [vp, dp, C.c_int, vp]
     L.cmaxb_fe_get_cells.argtypes = [vp, dp, vp]

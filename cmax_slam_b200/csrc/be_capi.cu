@@ -18,6 +18,7 @@ struct cmaxb_be {
   long long n = 0, n_eff = 0, nb = 0;
   BeBatchTime* d_bt = nullptr; BePose* d_poses = nullptr; double* d_wgrad = nullptr; int* d_idx = nullptr; size_t nb_cap = 0;
   Quat* d_knots0 = nullptr; Quat* d_knots = nullptr; double* d_x = nullptr; double* d_grad = nullptr; size_t knots_cap = 0;
+  int* d_seg_lo = nullptr; int* d_seg_hi = nullptr;
   double* h_x = nullptr; double* h_grad = nullptr; size_t hx_cap = 0;
   int n_knots = 0, n_fixed = 0, n_opt = 0;
   long long t0_ns = 0, dt_ns = 0;
@@ -27,6 +28,8 @@ struct cmaxb_be {
   float* d_il_old = nullptr; float* d_il_new = nullptr; float* d_blur = nullptr; float* d_G = nullptr;
   float4* d_ilq = nullptr; float4* d_GQ = nullptr;   // corner-split accumulator / adjoint image (event-dense windows)
   bool use_quad = false; bool il_is_quad = false;
+  int* d_ccell = nullptr; float4* d_ca = nullptr; float4* d_cb = nullptr; size_t cache_cap = 0;   // per-event gather cache
+  long long n_visit = 0; int m_visit = 1;
   float* d_bands = nullptr; float* d_bands_blur = nullptr; size_t bands_cap = 0;
   double* d_acc = nullptr; unsigned int* d_ticket = nullptr; double* d_result = nullptr; double* d_mean = nullptr;
   double* d_bacc = nullptr; unsigned int* d_bticket = nullptr; double* d_bresult = nullptr; double* d_bmean = nullptr; size_t bacc_cap = 0;
@@ -50,6 +53,7 @@ static BeGeom be_geom(const cmaxb_be* be) {
   g.fy = (double)((g.H / 180.0) * 180.0 / 3.1415926535897932384626433832795);
   g.tnext_sec = be->tnext_sec; g.tnext_nsec = be->tnext_nsec;
   g.n_fixed = be->n_fixed; g.Nk = be->N;
+  g.m = be->m_visit; g.n_visit = be->n_visit;
   return g;
 }
 
@@ -118,8 +122,10 @@ extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
   if (be->stream) cudaStreamSynchronize(be->stream);
   cudaFree(be->d_lut); cudaFree(be->d_ev); cudaFree(be->d_bt); cudaFree(be->d_poses); cudaFree(be->d_wgrad); cudaFree(be->d_idx);
   cudaFree(be->d_knots0); cudaFree(be->d_knots); cudaFree(be->d_x); cudaFree(be->d_grad);
+  cudaFree(be->d_seg_lo); cudaFree(be->d_seg_hi);
   cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
   cudaFree(be->d_bands); cudaFree(be->d_bands_blur); cudaFree(be->d_ilq); cudaFree(be->d_GQ);
+  cudaFree(be->d_ccell); cudaFree(be->d_ca); cudaFree(be->d_cb);
   cudaFree(be->d_acc); cudaFree(be->d_ticket); cudaFree(be->d_result); cudaFree(be->d_mean);
   cudaFree(be->d_bacc); cudaFree(be->d_bticket); cudaFree(be->d_bresult); cudaFree(be->d_bmean);
   cudaFree(be->d_alpha_sums); cudaFree(be->d_flags); cudaFree(be->d_cells);
@@ -147,6 +153,12 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
   const long long n_eff = (n >= 1 && (n - 1) % bs == 0) ? n - 1 : n;
   const long long nb = (n_eff + bs - 1) / bs;
   be->n = n; be->n_eff = n_eff; be->nb = nb;
+  {
+    const long long sr = be->cfg.event_sample_rate;
+    be->m_visit = (int)((bs + sr - 1) / sr);
+    const long long len_last = nb > 0 ? n_eff - (nb - 1) * bs : 0;
+    be->n_visit = nb > 0 ? (nb - 1) * be->m_visit + (len_last + sr - 1) / sr : 0;
+  }
   // Event-dense windows accumulate IL in a corner-split float4 image (1 vector reduction per event,
   // 4x the image bytes); sparse windows on a big panorama keep float planes (4 reductions per event).
   be->use_quad = (2 * n_eff >= be->A);
@@ -170,6 +182,7 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
   }
   if ((size_t)w->n_knots > be->knots_cap) {
     cudaFree(be->d_knots0); cudaFree(be->d_knots); cudaFree(be->d_x); cudaFree(be->d_grad);
+    cudaFree(be->d_seg_lo); cudaFree(be->d_seg_hi); be->d_seg_lo = be->d_seg_hi = nullptr;
     if (be->h_x) cudaFreeHost(be->h_x);
     if (be->h_grad) cudaFreeHost(be->h_grad);
     be->h_x = be->h_grad = nullptr; be->knots_cap = 0;
@@ -178,6 +191,8 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
     CMAXB_TRY(dev_alloc(&be->d_knots, K));
     CMAXB_TRY(dev_alloc(&be->d_x, 3 * K));
     CMAXB_TRY(dev_alloc(&be->d_grad, 3 * K));
+    CMAXB_TRY(dev_alloc(&be->d_seg_lo, K));
+    CMAXB_TRY(dev_alloc(&be->d_seg_hi, K));
     CMAXB_CUDA_TRY(cudaMallocHost((void**)&be->h_x, sizeof(double) * 3 * K));
     CMAXB_CUDA_TRY(cudaMallocHost((void**)&be->h_grad, sizeof(double) * 3 * K));
     be->knots_cap = K;
@@ -212,6 +227,14 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
     }
     CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_flags, be->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
     CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+    if (!(*be->h_flags & 4) && nb > 0) {   // segment indices are valid: bounding batch run of every segment
+      CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_seg_lo, 0x7f, sizeof(int) * be->n_knots, s));
+      CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_seg_hi, 0, sizeof(int) * be->n_knots, s));
+      CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+        be_segment_ranges_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(be->d_bt, nb, be->d_seg_lo, be->d_seg_hi);
+      }));
+      CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+    }
     if (*be->h_flags & 2) return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor");
     if (*be->h_flags & 4) return set_error(CMAXB_ERR_SPLINE_RANGE, "batch time outside the spline's valid range");
   } else {
@@ -248,9 +271,26 @@ static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
   return CMAXB_OK;
 }
 
-static int be_run_scatter(cmaxb_be* be, bool allow_quad) {
+static unsigned be_event_grid(const cmaxb_be* be) {
+  long long blocks = (be->n_visit + kBeThreads - 1) / kBeThreads;
+  const long long cap = 148LL * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false) {
   cudaStream_t s = be->stream;
   const bool quad = allow_quad && be->use_quad;
+  if (want_cache && (size_t)be->n_visit > be->cache_cap) {
+    cudaFree(be->d_ccell); cudaFree(be->d_ca); cudaFree(be->d_cb);
+    be->d_ccell = nullptr; be->d_ca = nullptr; be->d_cb = nullptr; be->cache_cap = 0;
+    CMAXB_TRY(dev_alloc(&be->d_ccell, (size_t)be->n_visit));
+    CMAXB_TRY(dev_alloc(&be->d_ca, (size_t)be->n_visit));
+    CMAXB_TRY(dev_alloc(&be->d_cb, (size_t)be->n_visit));
+    be->cache_cap = (size_t)be->n_visit;
+  }
+  const BeCache cache{be->d_ccell, be->d_ca, be->d_cb};
   be->il_is_quad = quad;
   CMAXB_TRY(be->prof.run(CMAXB_K_ZERO, s, false, [&] {
     if (quad) cudaMemsetAsync(be->d_ilq, 0, sizeof(float4) * be->A, s);
@@ -262,8 +302,14 @@ static int be_run_scatter(cmaxb_be* be, bool allow_quad) {
   if (be->nb > 0) {
     const BeGeom g = be_geom(be);
     CMAXB_TRY(be->prof.run(CMAXB_K_BE_SCATTER, s, true, [&] {
-      if (quad) be_scatter_kernel<2><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, nullptr, be->d_ilq);
-      else be_scatter_kernel<0><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_il_old, be->d_il_new, nullptr);
+      const unsigned grid = be_event_grid(be);
+      if (quad) {
+        if (want_cache) be_scatter_kernel<2, true><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, nullptr, nullptr, be->d_ilq, cache);
+        else be_scatter_kernel<2, false><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, nullptr, nullptr, be->d_ilq, cache);
+      } else {
+        if (want_cache) be_scatter_kernel<0, true><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, be->d_il_old, be->d_il_new, nullptr, cache);
+        else be_scatter_kernel<0, false><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, be->d_il_old, be->d_il_new, nullptr, cache);
+      }
     }));
   }
   // first evaluation of a window with alpha unspecified: updateAlpha            (:201-210)
@@ -359,10 +405,11 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
   CMAXB_CUDA_TRY(cudaSetDevice(be->device));
   const bool want_grad = grad != nullptr;
   cudaStream_t s = be->stream;
-  CMAXB_TRY(be_run_poses(be, x, n, want_grad));
-  CMAXB_TRY(be_run_scatter(be, true));
-  CMAXB_TRY(be_run_image(be, be->taps));
   const int P = 3 * be->n_opt;
+  const bool adjoint_grad = want_grad && P > 0 && be->cfg.grad_mode == CMAXB_GRAD_ADJOINT;
+  CMAXB_TRY(be_run_poses(be, x, n, want_grad));
+  CMAXB_TRY(be_run_scatter(be, true, adjoint_grad));
+  CMAXB_TRY(be_run_image(be, be->taps));
   if (want_grad && P > 0) {
     const int W = be->cfg.pano_width, H = be->cfg.pano_height;
     if (be->cfg.grad_mode == CMAXB_GRAD_ADJOINT) {
@@ -375,20 +422,21 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
       if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("adjoint_blur launch: ") + cudaGetErrorString(le));
       if (be->nb > 0) {
         const BeGeom g = be_geom(be);
+        const BeCache cache{be->d_ccell, be->d_ca, be->d_cb};
         CMAXB_TRY(be->prof.run(CMAXB_K_BE_GATHER, s, true, [&] {
           if (be->N == 2) {
-            if (quad) be_gather_kernel<2, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, be->d_GQ, be->d_wgrad);
-            else be_gather_kernel<2, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, nullptr, be->d_wgrad);
+            if (quad) be_gather_kernel<2, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, be->d_GQ, cache, be->d_wgrad);
+            else be_gather_kernel<2, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, nullptr, cache, be->d_wgrad);
           } else {
-            if (quad) be_gather_kernel<4, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, be->d_GQ, be->d_wgrad);
-            else be_gather_kernel<4, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, nullptr, be->d_wgrad);
+            if (quad) be_gather_kernel<4, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, be->d_GQ, cache, be->d_wgrad);
+            else be_gather_kernel<4, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, nullptr, cache, be->d_wgrad);
           }
         }));
       }
       const double inv_np = 1.0 / ((double)W * (double)H);
       CMAXB_TRY(be->prof.run(CMAXB_K_BE_GRAD_REDUCE, s, true, [&] {
-        if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
-        else be_grad_reduce_kernel<4><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+        if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+        else be_grad_reduce_kernel<4><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
       }));
     } else {
       CMAXB_TRY(be_run_bands(be, true));

@@ -40,6 +40,17 @@ struct BeGeom {
   double fx, fy, cx, cy;   // equirectangular focal lengths / centre      (equirectangular_camera.h:11-16,64-67)
   uint32_t tnext_sec, tnext_nsec;
   int n_fixed, Nk;
+  // enumeration of the events the reference loop visits (stride sample_rate inside each batch, :262):
+  // visited event j lives in batch b = min(j / m, nb-1) at offset (j - b*m) * sample_rate
+  int m;                   // visited events per full batch = ceil(batch_size / sample_rate)
+  long long n_visit;       // total visited events
+};
+
+// per visited event, written by the gradient scatter pass and consumed by the gather pass
+struct BeCache {
+  int* cell;               // yy*W+xx or -1
+  float4* a;               // (dx, dy, dd00, dd01)
+  float4* b;               // (dd02, dd10, dd11, dd12)
 };
 
 // t_mid of each batch -> (s, u); flags |= 4 when outside the spline (BASALT_ASSERT, so3_spline.h:221-230)
@@ -170,37 +181,45 @@ __device__ __forceinline__ BeWarp be_warp(const BeGeom& g, const double* R, uint
 constexpr int kBeThreads = 256;
 constexpr int kBeWarps = kBeThreads / 32;
 
-// value scatter.  MODE 0: IL_old_ / IL_new_ as two float planes (what updateIG needs).
+// value scatter, one THREAD per visited event (full lane efficiency; the batch pose is read through
+// L1, where the ~100 consecutive threads of a batch hit the same 72 bytes).
+// MODE 0: IL_old_ / IL_new_ as two float planes (what updateIG needs).
 // MODE 2: IL = old + new as ONE corner-split float4 image, one vector reduction per event (the cost
 // evaluation only ever uses the sum, event_pano_warper.cpp:199).
-template <int MODE>
+// CACHE: also compute the 2x3 Jacobian factor and store (cell, dx, dy, dd) for the gather pass.
+template <int MODE, bool CACHE>
 __global__ void __launch_bounds__(kBeThreads)
 be_scatter_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict__ il_old, float* __restrict__ il_new,
-                  float4* __restrict__ il_quad) {
-  const int lane = threadIdx.x & 31;
-  const long long wstride = (long long)gridDim.x * kBeWarps;
-  for (long long b = blockIdx.x * (long long)kBeWarps + (threadIdx.x >> 5); b < g.nb; b += wstride) {
-    const long long beg = b * g.batch_size;
-    long long end = beg + g.batch_size;
-    if (end > g.n_eff || g.n_eff - beg <= g.batch_size) end = g.n_eff;
+                  float4* __restrict__ il_quad, BeCache cache) {
+  const long long stride = (long long)gridDim.x * kBeThreads;
+  for (long long j = blockIdx.x * (long long)kBeThreads + threadIdx.x; j < g.n_visit; j += stride) {
+    long long b = j / g.m;
+    if (b > g.nb - 1) b = g.nb - 1;
+    const long long i = b * g.batch_size + (j - b * g.m) * g.sample_rate;
+    if (i >= g.n_eff) continue;   // never true by construction of n_visit; kept as a guard
     double R[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = __ldg(&poses[b].R[i]);
-    for (long long i = beg + (long long)lane * g.sample_rate; i < end; i += 32LL * g.sample_rate) {
-      const uint4 e = load_event(g.ev, i);
-      const BeWarp w = be_warp<false>(g, R, e);
-      if (!w.in) continue;
-      const float dx = w.dx, dy = w.dy;
-      const long long p = (long long)w.yy * g.W + w.xx;
-      if (MODE == 2) {
-        atomicAdd(il_quad + p, make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy));
-      } else {
-        float* il = w.is_old ? il_old : il_new;
-        atomicAdd(il + p, (1.f - dx) * (1.f - dy));
-        atomicAdd(il + p + 1, dx * (1.f - dy));
-        atomicAdd(il + p + g.W, (1.f - dx) * dy);
-        atomicAdd(il + p + g.W + 1, dx * dy);
+    for (int q = 0; q < 9; ++q) R[q] = __ldg(&poses[b].R[q]);
+    const uint4 e = load_event(g.ev, i);
+    const BeWarp w = be_warp<CACHE>(g, R, e);
+    if (CACHE) {
+      cache.cell[j] = w.in ? w.yy * g.W + w.xx : -1;
+      if (w.in) {
+        cache.a[j] = make_float4(w.dx, w.dy, w.dd[0][0], w.dd[0][1]);
+        cache.b[j] = make_float4(w.dd[0][2], w.dd[1][0], w.dd[1][1], w.dd[1][2]);
       }
+    }
+    if (!w.in) continue;
+    const float dx = w.dx, dy = w.dy;
+    const long long p = (long long)w.yy * g.W + w.xx;
+    if (MODE == 2) {
+      atomicAdd(il_quad + p, make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy));
+    } else {
+      float* il = w.is_old ? il_old : il_new;
+      atomicAdd(il + p, (1.f - dx) * (1.f - dy));
+      atomicAdd(il + p + 1, dx * (1.f - dy));
+      atomicAdd(il + p + g.W, (1.f - dx) * dy);
+      atomicAdd(il + p + g.W + 1, dx * dy);
     }
   }
 }
@@ -269,38 +288,37 @@ __global__ void be_cells_kernel(BeGeom g, const BePose* __restrict__ poses, long
 // jac = dd * Jk, the contribution to g_j is  (a*dd[0,:] + b*dd[1,:]) . Jk[:, j]  with
 // a = sum_c s_c G(c), b = sum_c t_c G(c).  The bracket is summed over the batch first (3 numbers),
 // then multiplied by the batch's Jk once: wgrad[b][c] = V_b . Jk[:, c].
+// One WARP per batch; the per-event geometry is NOT recomputed: (cell, dx, dy, dd) come from the
+// cache the gradient scatter pass wrote (36 bytes per event, streamed once).
 template <int N, bool QUAD>
 __global__ void __launch_bounds__(kBeThreads)
 be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __restrict__ G, const float4* __restrict__ GQ,
-                 double* __restrict__ wgrad) {
+                 BeCache cache, double* __restrict__ wgrad) {
   const int lane = threadIdx.x & 31;
   const long long wstride = (long long)gridDim.x * kBeWarps;
   for (long long b = blockIdx.x * (long long)kBeWarps + (threadIdx.x >> 5); b < g.nb; b += wstride) {
-    const long long beg = b * g.batch_size;
-    long long end = beg + g.batch_size;
-    if (end > g.n_eff || g.n_eff - beg <= g.batch_size) end = g.n_eff;
-    double R[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = __ldg(&poses[b].R[i]);
+    const long long j0 = b * g.m;
+    long long j1 = j0 + g.m;
+    if (b == g.nb - 1 || j1 > g.n_visit) j1 = g.n_visit;
     double v0 = 0, v1 = 0, v2 = 0;
-    for (long long i = beg + (long long)lane * g.sample_rate; i < end; i += 32LL * g.sample_rate) {
-      const uint4 e = load_event(g.ev, i);
-      const BeWarp w = be_warp<true>(g, R, e);
-      if (!w.in) continue;
+    for (long long j = j0 + lane; j < j1; j += 32) {
+      const int cell = __ldg(cache.cell + j);
+      if (cell < 0) continue;
+      const float4 ca = __ldg(cache.a + j), cb = __ldg(cache.b + j);
       double g00, g01, g10, g11;
       if (QUAD) {
-        const float4 q = __ldg(GQ + (long long)w.yy * g.W + w.xx);
+        const float4 q = __ldg(GQ + cell);
         g00 = q.x; g01 = q.y; g10 = q.z; g11 = q.w;
       } else {
-        const float* p = G + (long long)w.yy * g.W + w.xx;
+        const float* p = G + cell;
         g00 = __ldg(p); g01 = __ldg(p + 1); g10 = __ldg(p + g.W); g11 = __ldg(p + g.W + 1);
       }
-      const double dx = w.dx, dy = w.dy;
+      const double dx = ca.x, dy = ca.y;
       const double a = (1.0 - dy) * (g01 - g00) + dy * (g11 - g10);
       const double bb = (1.0 - dx) * (g10 - g00) + dx * (g11 - g01);
-      v0 += a * (double)w.dd[0][0] + bb * (double)w.dd[1][0];
-      v1 += a * (double)w.dd[0][1] + bb * (double)w.dd[1][1];
-      v2 += a * (double)w.dd[0][2] + bb * (double)w.dd[1][2];
+      v0 += a * (double)ca.z + bb * (double)cb.y;
+      v1 += a * (double)ca.w + bb * (double)cb.z;
+      v2 += a * (double)cb.x + bb * (double)cb.w;
     }
     v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
     if (lane < 3 * N) {
@@ -310,18 +328,33 @@ be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __rest
   }
 }
 
+// Batches of spline segment s form a contiguous run when the events are time-sorted; record the
+// bounding run [lo, hi) of every segment once per window (correct for unsorted input too: the
+// reduction re-checks idx inside the run).
+__global__ void be_segment_ranges_kernel(const BeBatchTime* __restrict__ bt, long long nb, int* __restrict__ seg_lo,
+                                         int* __restrict__ seg_hi) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int s = (int)bt[b].s;
+  atomicMin(seg_lo + s, (int)b);
+  atomicMax(seg_hi + s, (int)b + 1);
+}
+
 // g[3*kk + c] = (1/Np) * sum over batches touching knot (kk + n_fixed) of wgrad[b][3*(knot-idx_b)+c].
 // One CTA per optimised knot; fixed summation order (deterministic).
 template <int N>
 __global__ void __launch_bounds__(256)
-be_grad_reduce_kernel(const int* __restrict__ idx, const double* __restrict__ wgrad, long long nb, int n_fixed,
-                      double inv_np, double* __restrict__ grad) {
+be_grad_reduce_kernel(const int* __restrict__ idx, const int* __restrict__ seg_lo, const int* __restrict__ seg_hi,
+                      const double* __restrict__ wgrad, long long nb, int n_fixed, double inv_np, double* __restrict__ grad) {
   __shared__ double s_red[8 * 3];
   const int knot = blockIdx.x + n_fixed;
   double a[3] = {0.0, 0.0, 0.0};
-  for (long long b = threadIdx.x; b < nb; b += blockDim.x) {
-    const int rel = knot - __ldg(idx + b);
-    if (rel >= 0 && rel < N) {
+  for (int rel = 0; rel < N; ++rel) {
+    const int s = knot - rel;               // batches of segment s touch knots s .. s+N-1
+    if (s < 0) continue;
+    const int lo = seg_lo[s], hi = seg_hi[s];
+    for (long long b = lo + (long long)threadIdx.x; b < hi; b += blockDim.x) {
+      if (__ldg(idx + b) != s) continue;
       const double* w = wgrad + b * (3 * N) + 3 * rel;
       a[0] += w[0]; a[1] += w[1]; a[2] += w[2];
     }

@@ -43,6 +43,7 @@ struct cmaxb_fe {
   unsigned long long* h_phase = nullptr; unsigned long long* d_phase = nullptr;   // mapped: phase boundary timestamps
   unsigned long long* h_done = nullptr; unsigned long long* d_done = nullptr;     // mapped: completion sequence number
   unsigned long long seq = 0;
+  double* d_mirror = nullptr;   // caller-owned device buffer [kmax][4] (cmaxb_fe_set_result_mirror)
   bool force_multi_kernel = false;   // CMAXB_FE_MULTI_KERNEL=1: stand-alone kernels (profiling / A-B comparison)
   int last_k = 0; bool last_grad = false; bool pending = false;
   KernelProfiler prof;
@@ -312,6 +313,7 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
     p.part_img = fe->d_part_img + (long long)c0 * kMegaMaxCtas * 2;
     p.part_ev = fe->d_part_ev + (long long)c0 * kMegaMaxCtas * 3;
     p.result = fe->d_mega_result + 4 * c0;
+    p.mirror = fe->d_mirror ? fe->d_mirror + 4 * c0 : nullptr;
     p.done_flag = fe->d_done;
     p.seq = ++fe->seq;
     p.phase_ns = fe->prof.enabled ? fe->d_phase : nullptr;
@@ -480,6 +482,12 @@ extern "C" int cmaxb_fe_profile(cmaxb_fe* fe, int enable) {
   if (!fe) return set_error(CMAXB_ERR_INVALID, "null argument");
   fe->prof.enabled = enable != 0;
   fe->prof.reset();
+  return CMAXB_OK;
+}
+extern "C" int cmaxb_fe_set_result_mirror(cmaxb_fe* fe, double* device_ptr) {
+  if (!fe) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream)); fe->pending = false; }
+  fe->d_mirror = device_ptr;
   return CMAXB_OK;
 }
 extern "C" int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10) {

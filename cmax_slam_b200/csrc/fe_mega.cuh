@@ -37,6 +37,7 @@ struct FeMegaParams {
   double* part_img;           // [k][kMegaMaxCtas][2]
   double* part_ev;            // [k][kMegaMaxCtas][3]
   double* result;             // [k][4] mapped pinned host memory (device pointer)
+  double* mirror;             // optional [k][4] DEVICE copy of the results (feeds an NCCL collective without a host hop)
   unsigned long long* done_flag; // mapped host word: receives `seq` after the results are visible to the host
   unsigned long long seq;
   unsigned long long* phase_ns; // optional [8]: %globaltimer of CTA 0 at every phase boundary (mapped host memory)
@@ -339,6 +340,10 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
         contrast = sd * sd;
       }
       p.result[4 * h] = contrast;
+      if (p.mirror) {
+        p.mirror[4 * h] = contrast;
+        if (!p.want_grad) { p.mirror[4 * h + 1] = 0.0; p.mirror[4 * h + 2] = 0.0; p.mirror[4 * h + 3] = 0.0; }
+      }
     }
   }
   __syncthreads();
@@ -372,6 +377,7 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
       block_sum<3>(t, s_red);
       if (threadIdx.x == 0) {
         p.result[4 * h + 1] = t[0] / Np; p.result[4 * h + 2] = t[1] / Np; p.result[4 * h + 3] = t[2] / Np;
+        if (p.mirror) { p.mirror[4 * h + 1] = t[0] / Np; p.mirror[4 * h + 2] = t[1] / Np; p.mirror[4 * h + 3] = t[2] / Np; }
       }
     }
     CMAXB_PHASE_MARK(9);

@@ -28,12 +28,14 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 // ---- pixel sources ------------------------------------------------------------------------------
 struct SrcPlane {            // one float plane per hypothesis
+  static constexpr bool kQuad = false;
   const float* base; long long stride_h;
   __device__ __forceinline__ float load(int h, int x, int y, int W) const {
     return base[h * stride_h + (long long)y * W + x];
   }
 };
 struct SrcPlane4 {           // interleaved (I, D0, D1, D2)
+  static constexpr bool kQuad = false;
   const float4* base; long long stride_h;
   __device__ __forceinline__ float4 load(int h, int x, int y, int W) const {
     return base[h * stride_h + (long long)y * W + x];
@@ -45,7 +47,10 @@ struct SrcPlane4 {           // interleaved (I, D0, D1, D2)
 // scalar ones (the scatter is bound by L2 reduction operations, not bytes).  The image proper is
 // re-assembled here, at load time, in a fixed order.
 struct SrcQuad {
+  static constexpr bool kQuad = true;
   const float4* base; long long stride_h;
+  __device__ __forceinline__ float4 cell(int h, int x, int y, int W) const { return __ldcg(base + h * stride_h + (long long)y * W + x); }
+  __device__ __forceinline__ float finish(float v, int, int, int) const { return v; }
   // __ldcg (L2-coherent) rather than the read-only path: in the fused evaluation kernel the image
   // was written by other SMs earlier in the SAME launch.
   __device__ __forceinline__ float load(int h, int x, int y, int W) const {
@@ -61,13 +66,19 @@ struct SrcQuad {
 };
 // back-end: I = IL + alpha * IGp with IL held as a quad image
 struct SrcBeQuad {
+  static constexpr bool kQuad = true;
   SrcQuad il; const float* igp; float alpha;
+  __device__ __forceinline__ float4 cell(int h, int x, int y, int W) const { return il.cell(h, x, y, W); }
+  __device__ __forceinline__ float finish(float v, int x, int y, int W) const {
+    return igp ? igp[(long long)y * W + x] * alpha + v : v;
+  }
   __device__ __forceinline__ float load(int h, int x, int y, int W) const {
     const float v = il.load(h, x, y, W);
     return igp ? igp[(long long)y * W + x] * alpha + v : v;
   }
 };
 struct SrcBeI {              // I = IL_old + IL_new + alpha * IGp     (event_pano_warper.cpp:199,213)
+  static constexpr bool kQuad = false;
   const float* il_old; const float* il_new; const float* igp; float alpha;
   __device__ __forceinline__ float load(int, int x, int y, int W) const {
     const long long i = (long long)y * W + x;
@@ -89,7 +100,7 @@ __device__ __forceinline__ float4 pfma(float w, float4 a, float4 s) {
 }
 __device__ __forceinline__ float4 padd(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-constexpr int kMaxImgCtas = 148 * 4;   // persistent CTAs per image plane (4 resident per SM)
+constexpr int kMaxImgCtas = 148 * 16;  // CTAs per image plane (larger images: each CTA strides over several tiles)
 
 struct ReduceOut {
   double* partials;     // [n_planes][kMaxImgCtas][kNAcc]  per-CTA sums (plain stores, no atomics)
@@ -136,7 +147,11 @@ blur_reduce_kernel(Src src, int W, int H, Taps taps, typename PixT<C>::type* out
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int r = (R >= 0) ? R : taps.r;
   const int IW = kTW + 2 * r, IH = kTH + 2 * r;
-  Pix* s_in = reinterpret_cast<Pix*>(smem_raw);
+  // quad sources: the cells of the tile (+halo+1) are staged once as float4 (one 16-byte request per
+  // cell, cells outside the image as zero) and the pixels are assembled from shared memory
+  const int QW = IW + 1, QH = IH + 1;
+  float4* s_q = reinterpret_cast<float4*>(smem_raw);
+  Pix* s_in = reinterpret_cast<Pix*>(smem_raw + (Src::kQuad ? sizeof(float4) * QW * QH : 0));
   Pix* s_tmp = s_in + IW * IH;
   double* s_red = reinterpret_cast<double*>(s_tmp + IH * kTW);
 
@@ -151,11 +166,39 @@ blur_reduce_kernel(Src src, int W, int H, Taps taps, typename PixT<C>::type* out
   for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
     const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * kTH;
     __syncthreads();   // previous tile's column pass is done with s_tmp / s_in
-    for (int i = tid; i < IW * IH; i += kImgThreads) {
-      const int ly = i / IW, lx = i - ly * IW;
-      const int gx = reflect101(min(tx0 + lx - r, W + r), W);
-      const int gy = reflect101(min(ty0 + ly - r, H + r), H);
-      s_in[i] = src.load(h, gx, gy, W);
+    if constexpr (Src::kQuad) {
+      const int qx0 = tx0 - r - 1, qy0 = ty0 - r - 1;
+      for (int i = tid; i < QW * QH; i += kImgThreads) {
+        const int ly = i / QW, lx = i - ly * QW;
+        const int gx = qx0 + lx, gy = qy0 + ly;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = src.cell(h, gx, gy, W);
+        s_q[i] = v;
+      }
+      __syncthreads();
+      for (int i = tid; i < IW * IH; i += kImgThreads) {
+        const int ly = i / IW, lx = i - ly * IW;
+        const int gx = reflect101(min(tx0 + lx - r, W + r), W);
+        const int gy = reflect101(min(ty0 + ly - r, H + r), H);
+        const int cx = gx - qx0, cy = gy - qy0;
+        float v = 0.f;
+        if (cx >= 1 && cy >= 1 && cx < QW && cy < QH) {
+          const float4* c = s_q + cy * QW + cx;
+          v = c[0].x;
+          v += c[-1].y;
+          v += c[-QW].z;
+          v += c[-QW - 1].w;
+          v = src.finish(v, gx, gy, W);
+        }
+        s_in[i] = v;
+      }
+    } else {
+      for (int i = tid; i < IW * IH; i += kImgThreads) {
+        const int ly = i / IW, lx = i - ly * IW;
+        const int gx = reflect101(min(tx0 + lx - r, W + r), W);
+        const int gy = reflect101(min(ty0 + ly - r, H + r), H);
+        s_in[i] = src.load(h, gx, gy, W);
+      }
     }
     __syncthreads();
     // row pass: s = w0*x0; s = fma(w_j, x_j, s)
@@ -238,10 +281,11 @@ blur_reduce_kernel(Src src, int W, int H, Taps taps, typename PixT<C>::type* out
 }
 
 template <int C>
-inline size_t blur_smem_bytes(int r) {
+inline size_t blur_smem_bytes(int r, bool quad = false) {
   const size_t pix = (C == 1) ? sizeof(float) : sizeof(float4);
   const int IW = kTW + 2 * r, IH = kTH + 2 * r;
-  return pix * ((size_t)IW * IH + (size_t)IH * kTW) + sizeof(double) * (kImgThreads / 32) * kNAcc;
+  return pix * ((size_t)IW * IH + (size_t)IH * kTW) + sizeof(double) * (kImgThreads / 32) * kNAcc +
+         (quad ? sizeof(float4) * (size_t)(IW + 1) * (IH + 1) : 0);
 }
 
 inline dim3 image_grid(int W, int H, int planes) { return dim3((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, planes); }
@@ -257,7 +301,7 @@ inline cudaError_t launch_blur_reduce_r(cudaStream_t s, int planes, const Src& s
                                         typename PixT<C>::type* out, long long out_stride_h, const ReduceOut& ro, int measure,
                                         float4* zero_ptr, long long zero_stride_h) {
   auto kern = blur_reduce_kernel<C, Src, WRITE_OUT, R>;
-  const size_t smem = blur_smem_bytes<C>(taps.r);
+  const size_t smem = blur_smem_bytes<C>(taps.r, Src::kQuad);
   static size_t configured[64] = {};   // per device: the attribute belongs to the device's context
   int dev = 0;
   cudaGetDevice(&dev);
@@ -288,12 +332,12 @@ inline cudaError_t launch_blur_reduce(cudaStream_t s, int planes, const Src& src
 // global_focus_funcs.cpp:39-43 (the mean(blur(D_j)) term multiplies sum(2(I-mu)) == 0).
 // QUAD_OUT: G is written as one float4 per CELL, (G(y,x), G(y,x+1), G(y+1,x), G(y+1,x+1)), so the
 // gather needs a single 16-byte load per event instead of two sector requests.
-template <bool QUAD_OUT>
+template <bool QUAD_OUT, int R = -1>
 __global__ void __launch_bounds__(kImgThreads)
 adjoint_blur_kernel(const float* __restrict__ blurred, long long stride_h, int W, int H, Taps taps,
                     const double* __restrict__ mean, int measure, float* __restrict__ G, float4* __restrict__ GQ) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int r = taps.r;
+  const int r = (R >= 0) ? R : taps.r;
   const int IW = kTW + 1 + 2 * r, IH = kTH + 1 + 2 * r;   // one extra row/column for the quad packing
   constexpr int OW = kTW + 1, OH = kTH + 1;
   float* s_in = reinterpret_cast<float*>(smem_raw);
@@ -320,6 +364,7 @@ adjoint_blur_kernel(const float* __restrict__ blurred, long long stride_h, int W
     const float* row = s_in + ly * IW;     // row[j] holds z0 at x = tx0 - r + j
     float s = 0.f;
     if (q < W) {
+#pragma unroll
       for (int d = -r; d <= r; ++d) s = fmaf(taps.w[r + d], row[lx + r + d], s);
       if (q >= 1 && q <= r)
         for (int d = q; d <= r; ++d) s = fmaf(taps.w[r + d], row[(-q + d) - tx0 + r], s);
@@ -335,6 +380,7 @@ adjoint_blur_kernel(const float* __restrict__ blurred, long long stride_h, int W
     float s = 0.f;
     if (gx < W && q < H) {
       const float* col = s_tmp + lx;       // col[j*OW] holds the row at y = ty0 - r + j
+#pragma unroll
       for (int d = -r; d <= r; ++d) s = fmaf(taps.w[r + d], col[(ly + r + d) * OW], s);
       if (q >= 1 && q <= r)
         for (int d = q; d <= r; ++d) s = fmaf(taps.w[r + d], col[((-q + d) - ty0 + r) * OW], s);
@@ -358,10 +404,19 @@ inline size_t adjoint_smem_bytes(int r) {
   const int IW = kTW + 1 + 2 * r, IH = kTH + 1 + 2 * r;
   return sizeof(float) * ((size_t)IW * IH + (size_t)IH * (kTW + 1) + (size_t)(kTH + 1) * (kTW + 1));
 }
+template <bool QUAD_OUT, int R>
+inline cudaError_t launch_adjoint_blur_r(cudaStream_t s, int planes, const float* blurred, long long stride_h, int W, int H,
+                                         const Taps& taps, const double* mean, int measure, float* G, float4* GQ);
 template <bool QUAD_OUT>
 inline cudaError_t launch_adjoint_blur(cudaStream_t s, int planes, const float* blurred, long long stride_h, int W, int H,
                                        const Taps& taps, const double* mean, int measure, float* G, float4* GQ) {
-  auto kern = adjoint_blur_kernel<QUAD_OUT>;
+  if (taps.r == 4) return launch_adjoint_blur_r<QUAD_OUT, 4>(s, planes, blurred, stride_h, W, H, taps, mean, measure, G, GQ);
+  return launch_adjoint_blur_r<QUAD_OUT, -1>(s, planes, blurred, stride_h, W, H, taps, mean, measure, G, GQ);
+}
+template <bool QUAD_OUT, int R>
+inline cudaError_t launch_adjoint_blur_r(cudaStream_t s, int planes, const float* blurred, long long stride_h, int W, int H,
+                                         const Taps& taps, const double* mean, int measure, float* G, float4* GQ) {
+  auto kern = adjoint_blur_kernel<QUAD_OUT, R>;
   const size_t smem = adjoint_smem_bytes(taps.r);
   static size_t configured[64] = {};   // per device: the attribute belongs to the device's context
   int dev = 0;

@@ -85,6 +85,11 @@ class AngVelEstimatorCMax:
         _capi.check(self._L.cmaxb_fe_eval_fetch(self._h, _capi.dptr(self._res_c), _capi.dptr(self._res_g)))
         return self._res_c[: self._k].copy(), self._res_g[: self._k].copy()
 
+    def set_result_mirror(self, device_ptr):
+        """device_ptr: address of a device buffer of max_hypotheses*4 float64 (e.g. tensor.data_ptr()) that also
+        receives every evaluation's (contrast, g0, g1, g2) rows -- input of the multi-GPU collective."""
+        _capi.check(self._L.cmaxb_fe_set_result_mirror(self._h, C.c_void_p(device_ptr) if device_ptr else None))
+
     # -- reference-named entry points ------------------------------------------------------------
     def computeImageOfWarpedEvents(self, ang_vel, with_deriv=False, blurred=True):
         """IWE (H,W) float32 [and derivative image (H,W,3)] as the reference function fills them."""

@@ -97,6 +97,11 @@ int cmaxb_fe_eval_batch(cmaxb_fe* fe, const double* omegas, int k, double* contr
 int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, int want_grad);
 int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grads3k);
 
+/* Optional: a caller-owned DEVICE buffer of max_hypotheses*4 doubles that also receives (contrast, g0, g1, g2)
+ * of every evaluation, so that a collective (NCCL all-gather / all-reduce of the per-hypothesis rows,
+ * SURVEY section 8e) can consume the results on the handle's stream without a host round trip.  NULL = off. */
+int cmaxb_fe_set_result_mirror(cmaxb_fe* fe, double* device_ptr);
+
 /* IWE for display / parity (publishEventImage, ang_vel_estimator.cpp:203-233).  blurred=0: raw
  * accumulator; 1: after the Gaussian blur.  out: height*width floats. */
 int cmaxb_fe_get_iwe(cmaxb_fe* fe, const double omega[3], int blurred, float* out);
