@@ -36,7 +36,7 @@ struct cmaxb_fe {
   double* d_acc = nullptr; unsigned int* d_ticket = nullptr; unsigned int* d_ticket2 = nullptr;
   double* d_gacc = nullptr; double* d_result = nullptr; double* d_mean = nullptr; double* h_result = nullptr;
   // fused (single cooperative kernel) evaluation
-  int mega_grid = 0; bool mega_ok = false;
+  int mega_grid = 0; int mega_th = 16; bool mega_ok = false;
   double* d_part_img = nullptr; double* d_part_ev = nullptr;
   double* h_mega_result = nullptr; double* d_mega_result = nullptr;   // mapped pinned memory
   bool last_mega = false;
@@ -130,7 +130,7 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, fe->device);
     int nsm = 0;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, fe->device);
-    const size_t smem = mega_smem_bytes(fe->taps.r);
+    const size_t smem = mega_smem_bytes(fe->taps.r);   // sized for the tallest tile
     int occ = 0;
     cudaError_t e1 = cudaFuncSetAttribute(fe_eval_megakernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaError_t e2 = cudaFuncSetAttribute(fe_eval_megakernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -141,6 +141,7 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
       int grid = occ * nsm;
       if (grid > kMegaMaxCtas) grid = kMegaMaxCtas;
       fe->mega_grid = grid;
+      fe->mega_th = mega_tile_height(cfg->width, cfg->height, grid);
       const size_t kk = (size_t)fe->kmax;
       bool okm = dev_alloc(&fe->d_part_img, kk * kMegaMaxCtas * 2) == CMAXB_OK && dev_alloc(&fe->d_part_ev, kk * kMegaMaxCtas * 3) == CMAXB_OK;
       okm = okm && cudaHostAlloc((void**)&fe->h_mega_result, sizeof(double) * 4 * kk, cudaHostAllocMapped) == cudaSuccess;
@@ -303,7 +304,7 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
     const int kc = (k - c0 < kMegaMaxHyp) ? k - c0 : kMegaMaxHyp;
     FeMegaParams p;
     p.g = fe_geom(fe);
-    p.k = kc; p.want_grad = want_grad; p.measure = fe->cfg.contrast_measure; p.taps = fe->taps;
+    p.k = kc; p.th = fe->mega_th; p.want_grad = want_grad; p.measure = fe->cfg.contrast_measure; p.taps = fe->taps;
     for (int i = 0; i < 3 * kc; ++i) p.omegas[i] = omegas[3 * c0 + i];
     p.quad = fe->d_quad[cur] + (long long)c0 * fe->A;
     p.quad_next = clear_next ? fe->d_quad[oth] + (long long)c0 * fe->A : nullptr;
@@ -312,6 +313,8 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
     p.A = fe->A;
     p.part_img = fe->d_part_img + (long long)c0 * kMegaMaxCtas * 2;
     p.part_ev = fe->d_part_ev + (long long)c0 * kMegaMaxCtas * 3;
+    p.ticket = fe->d_ticket;
+    p.contrast_dev = fe->d_mean + c0;   // d_mean is unused by the fused path: reuse it as the contrast scratch
     p.result = fe->d_mega_result + 4 * c0;
     p.mirror = fe->d_mirror ? fe->d_mirror + 4 * c0 : nullptr;
     p.done_flag = fe->d_done;

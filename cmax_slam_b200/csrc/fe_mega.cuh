@@ -25,6 +25,7 @@ constexpr int kMegaMaxCtas = 148 * 8;
 struct FeMegaParams {
   FeGeom g;
   int k;                      // hypotheses in this launch
+  int th;                     // image tile height (rows), chosen so that #tiles <= #CTAs: one tile per CTA per phase
   int want_grad;
   int measure;
   Taps taps;
@@ -36,6 +37,8 @@ struct FeMegaParams {
   long long A;
   double* part_img;           // [k][kMegaMaxCtas][2]
   double* part_ev;            // [k][kMegaMaxCtas][3]
+  unsigned int* ticket;       // arrival counter for the final reduction (re-armed by the kernel)
+  double* contrast_dev;       // [k] device scratch: contrast of a gradient evaluation until the last CTA publishes it
   double* result;             // [k][4] mapped pinned host memory (device pointer)
   double* mirror;             // optional [k][4] DEVICE copy of the results (feeds an NCCL collective without a host hop)
   unsigned long long* done_flag; // mapped host word: receives `seq` after the results are visible to the host
@@ -49,6 +52,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 #define CMAXB_PHASE_MARK(idx) do { if (p.phase_ns && blockIdx.x == 0 && threadIdx.x == 0) p.phase_ns[idx] = global_timer_ns(); } while (0)
+#define CMAXB_PHASE_MARK_ANY(idx) do { if (p.phase_ns && threadIdx.x == 0) p.phase_ns[idx] = global_timer_ns(); } while (0)
 
 constexpr int kEvUnroll = 4;
 
@@ -103,20 +107,21 @@ template <int R>
 __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned char* smem_raw, bool write_out) {
   const int W = p.g.W, H = p.g.H;
   const int r = (R >= 0) ? R : p.taps.r;
-  const int IW = kTW + 2 * r, IH = kTH + 2 * r;
+  const int TH = p.th;
+  const int IW = kTW + 2 * r, IH = TH + 2 * r;
   const int QW = IW + 1, QH = IH + 1;
   float4* s_q = reinterpret_cast<float4*>(smem_raw);          // [QH][QW] cells at image coords (tx0-r-1.., ty0-r-1..)
   float* s_in = reinterpret_cast<float*>(s_q + QW * QH);      // [IH][IW]
   float* s_tmp = s_in + IW * IH;                              // [IH][kTW]
   double* s_red = reinterpret_cast<double*>(s_tmp + IH * kTW);
   const int tid = threadIdx.x;
-  const int ntx = (W + kTW - 1) / kTW, nty = (H + kTH - 1) / kTH;
+  const int ntx = (W + kTW - 1) / kTW, nty = (H + TH - 1) / TH;
   const float4* quad = p.quad + h * p.A;
   float* out = p.blurred + h * p.A;
   float4* zero_ptr = p.quad_next ? p.quad_next + h * p.A : nullptr;
   double a[2] = {0.0, 0.0};
   for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
-    const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * kTH;
+    const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * TH;
     const int qx0 = tx0 - r - 1, qy0 = ty0 - r - 1;
     __syncthreads();
     for (int i = tid; i < QW * QH; i += kMegaThreads) {
@@ -153,7 +158,7 @@ __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned
     }
     __syncthreads();
     const int lx = tid & (kTW - 1);
-    for (int ly = tid / kTW; ly < kTH; ly += kMegaThreads / kTW) {
+    for (int ly = tid / kTW; ly < TH; ly += kMegaThreads / kTW) {
       const int gx = tx0 + lx, gy = ty0 + ly;
       if (gx < W && gy < H) {
         const float* c = s_tmp + (ly + r) * kTW + lx;
@@ -193,8 +198,10 @@ template <int R>
 __device__ __forceinline__ void mega_adjoint(const FeMegaParams& p, int h, double mean, unsigned char* smem_raw) {
   const int W = p.g.W, H = p.g.H;
   const int r = (R >= 0) ? R : p.taps.r;
-  const int IW = kTW + 1 + 2 * r, IH = kTH + 1 + 2 * r;
-  constexpr int OW = kTW + 1, OH = kTH + 1;
+  const int TH = p.th;
+  const int IW = kTW + 1 + 2 * r, IH = TH + 1 + 2 * r;
+  constexpr int OW = kTW + 1;
+  const int OH = TH + 1;
   float* s_in = reinterpret_cast<float*>(smem_raw);
   float* s_tmp = s_in + IW * IH;
   float* s_g = s_tmp + IH * OW;
@@ -203,9 +210,9 @@ __device__ __forceinline__ void mega_adjoint(const FeMegaParams& p, int h, doubl
   const float b2 = (p.measure == CMAXB_CONTRAST_MEAN_SQUARE) ? 0.0f : (float)(-2.0 * mean);
   const float* img = p.blurred + h * p.A;
   float4* GQ = p.GQ + h * p.A;
-  const int ntx = (W + kTW - 1) / kTW, nty = (H + kTH - 1) / kTH;
+  const int ntx = (W + kTW - 1) / kTW, nty = (H + TH - 1) / TH;
   for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
-    const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * kTH;
+    const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * TH;
     __syncthreads();
     for (int i = tid; i < IW * IH; i += kMegaThreads) {
       const int ly = i / IW, lx = i - ly * IW;
@@ -247,7 +254,7 @@ __device__ __forceinline__ void mega_adjoint(const FeMegaParams& p, int h, doubl
       s_g[i] = s;
     }
     __syncthreads();
-    for (int i = tid; i < kTW * kTH; i += kMegaThreads) {
+    for (int i = tid; i < kTW * TH; i += kMegaThreads) {
       const int ly = i / kTW, lx = i & (kTW - 1);
       const int gx = tx0 + lx, gy = ty0 + ly;
       if (gx < W && gy < H) {
@@ -339,10 +346,11 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
         const double sd = sqrt(var);
         contrast = sd * sd;
       }
-      p.result[4 * h] = contrast;
-      if (p.mirror) {
-        p.mirror[4 * h] = contrast;
-        if (!p.want_grad) { p.mirror[4 * h + 1] = 0.0; p.mirror[4 * h + 2] = 0.0; p.mirror[4 * h + 3] = 0.0; }
+      if (p.want_grad) {
+        p.contrast_dev[h] = contrast;   // published to the host by the last CTA, together with the gradient
+      } else {
+        p.result[4 * h] = contrast;
+        if (p.mirror) { p.mirror[4 * h] = contrast; p.mirror[4 * h + 1] = 0.0; p.mirror[4 * h + 2] = 0.0; p.mirror[4 * h + 3] = 0.0; }
       }
     }
   }
@@ -364,9 +372,17 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
     mega_gather(p, h, s_red);
   }
   CMAXB_PHASE_MARK(7);
-  grid.sync();
+  // no fourth grid barrier: the last CTA to publish its gather record (atomic ticket) does the final sum
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
   CMAXB_PHASE_MARK(8);
-  if (blockIdx.x == 0) {
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x == 0) *p.ticket = 0u;
     for (int h = 0; h < p.k; ++h) {
       const double* all = p.part_ev + (long long)h * kMegaMaxCtas * 3;
       double t[3] = {0.0, 0.0, 0.0};
@@ -376,11 +392,13 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
       __syncthreads();
       block_sum<3>(t, s_red);
       if (threadIdx.x == 0) {
+        const double c = __ldcg(p.contrast_dev + h);
+        p.result[4 * h] = c;
         p.result[4 * h + 1] = t[0] / Np; p.result[4 * h + 2] = t[1] / Np; p.result[4 * h + 3] = t[2] / Np;
-        if (p.mirror) { p.mirror[4 * h + 1] = t[0] / Np; p.mirror[4 * h + 2] = t[1] / Np; p.mirror[4 * h + 3] = t[2] / Np; }
+        if (p.mirror) { p.mirror[4 * h] = c; p.mirror[4 * h + 1] = t[0] / Np; p.mirror[4 * h + 2] = t[1] / Np; p.mirror[4 * h + 3] = t[2] / Np; }
       }
     }
-    CMAXB_PHASE_MARK(9);
+    CMAXB_PHASE_MARK_ANY(9);
     if (threadIdx.x == 0) {
       __threadfence_system();
       *reinterpret_cast<volatile unsigned long long*>(p.done_flag) = p.seq;
@@ -388,12 +406,24 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
   }
 }
 
-inline size_t mega_smem_bytes(int r) {
-  const int IW = kTW + 2 * r, IH = kTH + 2 * r;
+constexpr int kMegaMaxTH = 32;
+inline size_t mega_smem_bytes(int r, int th = kMegaMaxTH) {
+  const int IW = kTW + 2 * r, IH = th + 2 * r;
   const size_t a = sizeof(float4) * (size_t)(IW + 1) * (IH + 1) + sizeof(float) * ((size_t)IW * IH + (size_t)IH * kTW) +
                    sizeof(double) * (kMegaThreads / 32) * kNAcc;
-  const size_t b = adjoint_smem_bytes(r);
+  const int JW = kTW + 1 + 2 * r, JH = th + 1 + 2 * r;
+  const size_t b = sizeof(float) * ((size_t)JW * JH + (size_t)JH * (kTW + 1) + (size_t)(th + 1) * (kTW + 1));
   return a > b ? a : b;
+}
+// tile height such that one hypothesis plane has at most `grid` tiles (each CTA: one tile per phase)
+inline int mega_tile_height(int W, int H, int grid) {
+  const int ntx = (W + kTW - 1) / kTW;
+  int rows_of_tiles = grid / ntx;
+  if (rows_of_tiles < 1) rows_of_tiles = 1;
+  int th = (H + rows_of_tiles - 1) / rows_of_tiles;
+  if (th < 8) th = 8;
+  if (th > kMegaMaxTH) th = kMegaMaxTH;
+  return th;
 }
 
 }  // namespace cmaxb
