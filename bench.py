@@ -34,6 +34,24 @@ METRIC = "warped-events/sec (1M ev, 640x480 IWE, contrast+grad eval)"
 UNIT = "events/s"
 
 
+def ncu_traffic_bytes(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu --set full
+    summary of this round (profiles/); None when there is no capture for that kernel."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*.txt")), reverse=True):
+        txt = open(path).read()
+        for blk in txt.split("---"):
+            if kernel not in blk:
+                continue
+            rd = re.search(r"dram__bytes_read\.sum = ([0-9.]+) (\w+)", blk)
+            wr = re.search(r"dram__bytes_write\.sum = ([0-9.]+) (\w+)", blk)
+            if rd and wr:
+                mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                return float(rd.group(1)) * mul[rd.group(2)] + float(wr.group(1)) * mul[wr.group(2)], os.path.basename(path)
+    return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -282,6 +300,8 @@ def run_ours(args, rank, world, local_rank):
             "fe_scatter": 16 * n_ev + 24 * A + 16 * A,           # DENSE: events + LUT + (I,dI) accumulator
             "blur_reduce": 16 * A,
         }.get(dom, 0)
+        ncu_name = {"fe_eval_fused": "fe_eval_megakernel", "fe_scatter": "fe_scatter_kernel", "blur_reduce": "blur_reduce_kernel"}.get(dom, dom)
+        traffic, traffic_src = ncu_traffic_bytes(ncu_name)
         dur_s = kern[dom]["avg_us"] * 1e-6
         achieved = alg / dur_s / 1e9 if dur_s > 0 else 0.0
         step_us_kernels = sum(v["avg_us"] * v["launches"] for v in per_kernel.values()) / max(1, min(K, 200))
@@ -301,7 +321,10 @@ def run_ours(args, rank, world, local_rank):
                     "path": "cmaxb_fe_set_packet(pinned host events) + cmaxb_fe_eval through the C ABI"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "note": "the packet (35 MB) is L2 resident across evaluations: DRAM traffic is ~0 in steady state; "
+                                 "ncu's figure is a cold-cache replay.  The binding resources are L2 request rate / latency and "
+                                 "f64 issue (DESIGN.md section 4), so the HBM fraction is reported, not padded.",
                          "algorithmic_bytes_per_launch": alg, "avg_launch_us": kern[dom]["avg_us"],
                          "kernel_share_of_step": kern[dom]["avg_us"] * kern[dom]["launches"] / max(1, min(K, 200)) / step_us_kernels,
                          "per_kernel": per_kernel},

@@ -50,7 +50,7 @@ class BeWindow(C.Structure):
 EXPORTS = [
     "cmaxb_fe_create", "cmaxb_fe_destroy", "cmaxb_fe_set_packet", "cmaxb_fe_eval", "cmaxb_fe_eval_batch",
     "cmaxb_fe_eval_launch", "cmaxb_fe_eval_fetch", "cmaxb_fe_set_result_mirror", "cmaxb_fe_get_iwe", "cmaxb_fe_get_deriv", "cmaxb_fe_get_cells",
-    "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_get_alpha",
+    "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_eval_begin", "cmaxb_be_il_plane", "cmaxb_be_eval_end", "cmaxb_be_get_alpha",
     "cmaxb_be_get_il", "cmaxb_be_get_iwe", "cmaxb_be_get_bands", "cmaxb_be_get_cells", "cmaxb_be_get_poses",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
     "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_fe_phase_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
@@ -94,6 +94,9 @@ def lib():
     L.cmaxb_be_set_window.argtypes = [vp, C.POINTER(BeWindow)]
     L.cmaxb_be_eval.argtypes = [vp, dp, C.c_int, dp, dp]
     L.cmaxb_be_get_alpha.argtypes = [vp, dp]
+    L.cmaxb_be_eval_begin.argtypes = [vp, dp, C.c_int, C.c_int]
+    L.cmaxb_be_il_plane.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.cmaxb_be_eval_end.argtypes = [vp, dp, dp]
     L.cmaxb_be_get_il.argtypes = [vp, dp, C.c_int, vp, vp]
     L.cmaxb_be_get_iwe.argtypes = [vp, dp, C.c_int, C.c_int, vp]
     L.cmaxb_be_get_bands.argtypes = [vp, dp, C.c_int, C.c_int, vp]

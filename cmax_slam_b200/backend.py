@@ -78,6 +78,36 @@ class EventWarperCMax:
                                           _capi.dptr(g) if want_grad else None))
         return c.value, (g[: self.n_params] if want_grad else None)
 
+    # -- event-sharded evaluation (one window split by time across GPUs) -------------------------------
+    def eval_begin(self, x=None, want_grad=True):
+        """Poses + scatter of this rank's events; IL assembled into the plane returned by il_plane()."""
+        xx, n = self._x(x)
+        _capi.check(self._L.cmaxb_be_eval_begin(self._h, None if xx is None else _capi.dptr(xx), n, int(want_grad)))
+        self._split_grad = bool(want_grad)
+
+    def il_plane(self):
+        """(device pointer, element count) of the float32 IL plane to all-reduce across ranks."""
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        _capi.check(self._L.cmaxb_be_il_plane(self._h, C.byref(ptr), C.byref(cnt)))
+        return ptr.value, cnt.value
+
+    def il_plane_tensor(self):
+        """The IL plane as a torch CUDA tensor VIEW of the library's buffer (for torch.distributed collectives)."""
+        import torch
+        ptr, cnt = self.il_plane()
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (cnt,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_View(), device="cuda")
+
+    def eval_end(self):
+        """(contrast, this rank's PARTIAL gradient or None) after the caller summed the IL planes."""
+        c = C.c_double()
+        g = np.zeros(max(self.n_params, 1))
+        _capi.check(self._L.cmaxb_be_eval_end(self._h, C.byref(c), _capi.dptr(g) if self._split_grad else None))
+        return c.value, (g[: self.n_params] if self._split_grad else None)
+
     @property
     def alpha(self):
         a = C.c_double()

@@ -28,6 +28,8 @@ struct cmaxb_be {
   float* d_il_old = nullptr; float* d_il_new = nullptr; float* d_blur = nullptr; float* d_G = nullptr;
   float4* d_ilq = nullptr; float4* d_GQ = nullptr;   // corner-split accumulator / adjoint image (event-dense windows)
   bool use_quad = false; bool il_is_quad = false;
+  float* d_il_plane = nullptr; bool il_is_plane = false;   // assembled IL (event-sharded evaluation)
+  bool split_pending = false; bool split_grad = false;
   int* d_ccell = nullptr; float4* d_ca = nullptr; float4* d_cb = nullptr; size_t cache_cap = 0;   // per-event gather cache
   long long n_visit = 0; int m_visit = 1;
   float* d_bands = nullptr; float* d_bands_blur = nullptr; size_t bands_cap = 0;
@@ -125,7 +127,7 @@ extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
   cudaFree(be->d_seg_lo); cudaFree(be->d_seg_hi);
   cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
   cudaFree(be->d_bands); cudaFree(be->d_bands_blur); cudaFree(be->d_ilq); cudaFree(be->d_GQ);
-  cudaFree(be->d_ccell); cudaFree(be->d_ca); cudaFree(be->d_cb);
+  cudaFree(be->d_ccell); cudaFree(be->d_ca); cudaFree(be->d_cb); cudaFree(be->d_il_plane);
   cudaFree(be->d_acc); cudaFree(be->d_ticket); cudaFree(be->d_result); cudaFree(be->d_mean);
   cudaFree(be->d_bacc); cudaFree(be->d_bticket); cudaFree(be->d_bresult); cudaFree(be->d_bmean);
   cudaFree(be->d_alpha_sums); cudaFree(be->d_flags); cudaFree(be->d_cells);
@@ -271,6 +273,22 @@ static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
   return CMAXB_OK;
 }
 
+// updateAlpha (event_pano_warper.cpp:134-165) from the current IL; il_old may be an assembled plane (il_new = null)
+static int be_run_alpha(cmaxb_be* be, const float* il_old, const float* il_new, const float4* il_quad) {
+  cudaStream_t s = be->stream;
+  CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_alpha_sums, 0, sizeof(double) * 8, s));
+  CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+    be_alpha_sums_kernel<<<148 * 4, 256, 0, s>>>(be->d_igp, il_old, il_new, il_quad, be->cfg.pano_width, be->A, be->d_alpha_sums);
+  }));
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_alpha_sums, be->d_alpha_sums, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  const double* v = be->h_alpha_sums;
+  if (v[4] < 1.0) be->alpha = 0.0;                                              // countNonZero(IGp_) < 1
+  else be->alpha = (v[3] / v[2]) / (v[1] / v[0]);
+  be->alpha_pending = false;
+  return CMAXB_OK;
+}
+
 static unsigned be_event_grid(const cmaxb_be* be) {
   long long blocks = (be->n_visit + kBeThreads - 1) / kBeThreads;
   const long long cap = 148LL * 16;
@@ -279,7 +297,7 @@ static unsigned be_event_grid(const cmaxb_be* be) {
   return (unsigned)blocks;
 }
 
-static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false) {
+static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false, bool defer_alpha = false) {
   cudaStream_t s = be->stream;
   const bool quad = allow_quad && be->use_quad;
   if (want_cache && (size_t)be->n_visit > be->cache_cap) {
@@ -313,21 +331,10 @@ static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false
     }));
   }
   // first evaluation of a window with alpha unspecified: updateAlpha            (:201-210)
-  if (be->alpha_pending) {
-    CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_alpha_sums, 0, sizeof(double) * 8, s));
-    CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
-      be_alpha_sums_kernel<<<148 * 4, 256, 0, s>>>(be->d_igp, be->d_il_old, be->d_il_new, quad ? be->d_ilq : nullptr,
-                                                   be->cfg.pano_width, be->A, be->d_alpha_sums);
-    }));
-    CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_alpha_sums, be->d_alpha_sums, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
-    CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
-    const double* v = be->h_alpha_sums;
-    if (v[4] < 1.0) be->alpha = 0.0;                                              // countNonZero(IGp_) < 1
-    else be->alpha = (v[3] / v[2]) / (v[1] / v[0]);
-    be->alpha_pending = false;
-  }
+  if (be->alpha_pending && !defer_alpha) CMAXB_TRY(be_run_alpha(be, be->d_il_old, be->d_il_new, quad ? be->d_ilq : nullptr));
   return CMAXB_OK;
 }
+
 
 // blur(I) + contrast; leaves the blurred image in d_blur and its mean in d_mean
 static int be_run_image(cmaxb_be* be, const Taps& taps) {
@@ -337,7 +344,10 @@ static int be_run_image(cmaxb_be* be, const Taps& taps) {
   const float* igp = be->have_igp ? be->d_igp : nullptr;
   cudaError_t le = cudaSuccess;
   CMAXB_TRY(be->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
-    if (be->il_is_quad) {
+    if (be->il_is_plane) {
+      const SrcBePlane src{be->d_il_plane, igp, (float)be->alpha};
+      le = launch_blur_reduce<1, SrcBePlane, true>(s, 1, src, W, H, taps, be->d_blur, 0, ro, be->cfg.contrast_measure);
+    } else if (be->il_is_quad) {
       const SrcBeQuad src{SrcQuad{be->d_ilq, 0}, igp, (float)be->alpha};
       le = launch_blur_reduce<1, SrcBeQuad, true>(s, 1, src, W, H, taps, be->d_blur, 0, ro, be->cfg.contrast_measure);
     } else {
@@ -399,16 +409,10 @@ static int be_run_bands(cmaxb_be* be, bool blur) {
   return CMAXB_OK;
 }
 
-extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contrast, double* grad) {
-  if (!be || !contrast) return set_error(CMAXB_ERR_INVALID, "null argument");
-  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window: call cmaxb_be_set_window first");
-  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
-  const bool want_grad = grad != nullptr;
+// image -> contrast (+ gradient) on the current IL (quad / planes / assembled plane); results to the host
+static int be_finish_eval(cmaxb_be* be, bool want_grad, double* contrast, double* grad) {
   cudaStream_t s = be->stream;
   const int P = 3 * be->n_opt;
-  const bool adjoint_grad = want_grad && P > 0 && be->cfg.grad_mode == CMAXB_GRAD_ADJOINT;
-  CMAXB_TRY(be_run_poses(be, x, n, want_grad));
-  CMAXB_TRY(be_run_scatter(be, true, adjoint_grad));
   CMAXB_TRY(be_run_image(be, be->taps));
   if (want_grad && P > 0) {
     const int W = be->cfg.pano_width, H = be->cfg.pano_height;
@@ -449,8 +453,68 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
   CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_result, be->d_result, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
   CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
   *contrast = be->h_result[0];
-  if (want_grad) for (int i = 0; i < P; ++i) grad[i] = be->h_grad[i];
+  if (want_grad && grad) for (int i = 0; i < P; ++i) grad[i] = be->h_grad[i];
   return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contrast, double* grad) {
+  if (!be || !contrast) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window: call cmaxb_be_set_window first");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  const bool want_grad = grad != nullptr;
+  const int P = 3 * be->n_opt;
+  const bool adjoint_grad = want_grad && P > 0 && be->cfg.grad_mode == CMAXB_GRAD_ADJOINT;
+  be->split_pending = false;
+  CMAXB_TRY(be_run_poses(be, x, n, want_grad));
+  CMAXB_TRY(be_run_scatter(be, true, adjoint_grad));
+  return be_finish_eval(be, want_grad, contrast, grad);
+}
+
+// ---- event-sharded evaluation: one window split by TIME across GPUs ----------------
+// begin : poses + scatter of THIS rank's events, IL assembled into one float plane
+// (caller): all-reduce (SUM) of that plane across ranks, on the handle's stream
+// end   : blur + variance on the summed plane (identical on every rank), adjoint image, gather over this
+//         rank's events -> contrast and this rank's PARTIAL gradient (caller sums the partials)
+extern "C" int cmaxb_be_eval_begin(cmaxb_be* be, const double* x, int n, int want_grad) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window: call cmaxb_be_set_window first");
+  if (want_grad && be->cfg.grad_mode != CMAXB_GRAD_ADJOINT) return set_error(CMAXB_ERR_INVALID, "event-sharded evaluation needs CMAXB_GRAD_ADJOINT");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  const int P = 3 * be->n_opt;
+  const bool g = want_grad && P > 0;
+  if (!be->d_il_plane) CMAXB_TRY(dev_alloc(&be->d_il_plane, (size_t)be->A));
+  CMAXB_TRY(be_run_poses(be, x, n, want_grad != 0));
+  CMAXB_TRY(be_run_scatter(be, true, g, /*defer_alpha=*/true));
+  cudaStream_t s = be->stream;
+  CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+    be_assemble_il_kernel<<<148 * 8, 256, 0, s>>>(be->d_il_old, be->d_il_new, be->il_is_quad ? be->d_ilq : nullptr,
+                                                 be->cfg.pano_width, be->A, be->d_il_plane);
+  }));
+  be->il_is_plane = true;
+  be->split_pending = true; be->split_grad = want_grad != 0;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_il_plane(cmaxb_be* be, float** device_ptr, size_t* count) {
+  if (!be || !device_ptr || !count) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->d_il_plane) {
+    CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+    CMAXB_TRY(dev_alloc(&be->d_il_plane, (size_t)be->A));
+  }
+  *device_ptr = be->d_il_plane;
+  *count = (size_t)be->A;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_eval_end(cmaxb_be* be, double* contrast, double* grad_partial) {
+  if (!be || !contrast) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->split_pending) return set_error(CMAXB_ERR_STATE, "cmaxb_be_eval_end without cmaxb_be_eval_begin");
+  if (grad_partial && !be->split_grad) return set_error(CMAXB_ERR_STATE, "gradient requested but eval_begin ran without want_grad");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  be->split_pending = false;
+  be->il_is_plane = true;
+  if (be->alpha_pending) CMAXB_TRY(be_run_alpha(be, be->d_il_plane, nullptr, nullptr));
+  return be_finish_eval(be, grad_partial != nullptr, contrast, grad_partial);
 }
 
 extern "C" int cmaxb_be_get_alpha(cmaxb_be* be, double* alpha) {

@@ -396,6 +396,25 @@ be_band_reduce_kernel(const float* __restrict__ I, const float* __restrict__ ban
   }
 }
 
+// IL as one float plane (from the corner-split accumulator or from IL_old + IL_new): the buffer that is
+// summed across GPUs when one window is sharded by time.
+__global__ void __launch_bounds__(256)
+be_assemble_il_kernel(const float* __restrict__ il_old, const float* __restrict__ il_new, const float4* __restrict__ il_quad,
+                      int W, long long A, float* __restrict__ plane) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A; i += (long long)gridDim.x * blockDim.x) {
+    float l;
+    if (il_quad) {
+      const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+      l = il_quad[i].x;
+      if (x > 0) l += il_quad[i - 1].y;
+      if (y > 0) { l += il_quad[i - W].z; if (x > 0) l += il_quad[i - W - 1].w; }
+    } else {
+      l = il_old[i] + il_new[i];
+    }
+    plane[i] = l;
+  }
+}
+
 // updateAlpha sums (event_pano_warper.cpp:134-165): out[0..4] = sum(1-exp(-IGp)), sum(IGp),
 // sum(1-exp(-IL)), sum(IL), countNonZero(IGp); IL = IL_old + IL_new.
 // il_quad != nullptr: IL is re-assembled from the corner-split accumulator.
@@ -413,7 +432,7 @@ be_alpha_sums_kernel(const float* __restrict__ igp, const float* __restrict__ il
       if (x > 0) l += il_quad[i - 1].y;
       if (y > 0) { l += il_quad[i - W].z; if (x > 0) l += il_quad[i - W - 1].w; }
     } else {
-      l = il_old[i] + il_new[i];
+      l = il_new ? il_old[i] + il_new[i] : il_old[i];
     }
     v[0] += (double)(1.f - expf(-1.0f * a));
     v[1] += (double)a;

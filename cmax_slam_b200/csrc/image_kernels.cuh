@@ -87,6 +87,16 @@ struct SrcBeI {              // I = IL_old + IL_new + alpha * IGp     (event_pan
   }
 };
 
+struct SrcBePlane {          // I = IL + alpha * IGp with IL already assembled (and summed across ranks) as a float plane
+  static constexpr bool kQuad = false;
+  const float* il; const float* igp; float alpha;
+  __device__ __forceinline__ float load(int, int x, int y, int W) const {
+    const long long i = (long long)y * W + x;
+    const float v = il[i];
+    return igp ? igp[i] * alpha + v : v;
+  }
+};
+
 template <int C> struct PixT;
 template <> struct PixT<1> { using type = float; };
 template <> struct PixT<4> { using type = float4; };

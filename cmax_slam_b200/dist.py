@@ -42,3 +42,59 @@ def sharded_eval(evaluate, omegas, want_grad=True, group=None, device=None):
         dist.all_reduce(buf, group=group)  # zero-padded rows: SUM == gather
         rows = buf.cpu().numpy()
     return rows[:, 0].copy(), (rows[:, 1:].copy() if want_grad else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# One big back-end window sharded by TIME across ranks (SURVEY.md section 8e, BASELINE config C5)
+# ------------------------------------------------------------------------------------------------
+def time_slab(n_events, batch_size, rank, world):
+    """[begin, end) of the events owned by `rank`.  Slabs are contiguous in time (events are time-sorted) and
+    cut at multiples of batch_size, so that every rank forms exactly the batches (and batch mid-times) of the
+    un-sharded evaluation; the tail -- including the reference's never-visited trailing single event
+    (event_pano_warper.cpp:188-196) -- stays with the last rank."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    nb = (n_events + batch_size - 1) // batch_size
+    per = (nb + world - 1) // world
+    b0 = min(rank * per, nb)
+    b1 = min((rank + 1) * per, nb)
+    beg = min(b0 * batch_size, n_events)
+    end = n_events if rank == world - 1 else min(b1 * batch_size, n_events)
+    if rank == world - 1 and b0 >= nb:
+        beg = n_events
+    return beg, max(beg, end)
+
+
+class ShardedEventWarper:
+    """Event-sharded contrast functor: rank r holds the events of its time slab and all knots.
+    eval(x) = begin (local scatter) -> all-reduce SUM of the un-blurred IL plane (image sized, NCCL over NVLink)
+    -> end (blur, variance -- identical on every rank --, adjoint, gather over own events) -> all-reduce SUM
+    of the partial gradients (3*K_opt doubles).  Results are identical on all ranks."""
+
+    def __init__(self, warper, group=None):
+        self.w = warper
+        self.group = group
+
+    def set_window(self, events, knots_xyzw, t0_ns, dt_ns, n_fixed, t_next_win_beg, IGp=None, alpha=float("nan"),
+                   batch_size=100):
+        import torch.distributed as dist
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        beg, end = time_slab(len(events), batch_size, rank, world)
+        self.slab = (beg, end)
+        self.w.set_window(events[beg:end], knots_xyzw, t0_ns, dt_ns, n_fixed, t_next_win_beg, IGp, alpha)
+
+    def eval(self, x=None, want_grad=True):
+        import torch
+        import torch.distributed as dist
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        self.w.eval_begin(x, want_grad)
+        if multi:
+            plane = self.w.il_plane_tensor()
+            dist.all_reduce(plane, group=self.group)          # the path's one real exchange step
+        c, g = self.w.eval_end()
+        if multi and want_grad and g is not None and len(g):
+            gt = torch.from_numpy(g).to(plane.device)
+            dist.all_reduce(gt, group=self.group)
+            g = gt.cpu().numpy()
+        return c, g

@@ -151,6 +151,19 @@ int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w);
  * grad: same length or NULL (value only). */
 int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contrast, double* grad);
 int cmaxb_be_get_alpha(cmaxb_be* be, double* alpha);
+
+/* Event-sharded evaluation: ONE window split by time across GPUs (BASELINE config C5).  Every
+ * rank holds a batch-aligned time slab of the window's events and ALL knots.  Variance is non-linear in the
+ * image, so the partial images must be summed before mean / variance:
+ *   cmaxb_be_eval_begin : spline poses + scatter of this rank's events; IL assembled into one float plane
+ *   (caller)            : all-reduce SUM of cmaxb_be_il_plane() across ranks (NCCL) on the handle's stream
+ *   cmaxb_be_eval_end   : blur + contrast on the summed plane (identical on all ranks), adjoint image, gather
+ *                         over this rank's events -> contrast and this rank's PARTIAL gradient; the caller
+ *                         sums the partial gradients (all-reduce of 3*K_opt doubles).
+ * With one rank (no exchange) begin + end == cmaxb_be_eval.  Needs CMAXB_GRAD_ADJOINT for gradients. */
+int cmaxb_be_eval_begin(cmaxb_be* be, const double* x, int n, int want_grad);
+int cmaxb_be_il_plane(cmaxb_be* be, float** device_ptr, size_t* count);
+int cmaxb_be_eval_end(cmaxb_be* be, double* contrast, double* grad_partial);
 /* IL_old_ / IL_new_ at x (needed by updateIG, event_pano_warper.cpp:109-126); either may be NULL */
 int cmaxb_be_get_il(cmaxb_be* be, const double* x, int n, float* il_old, float* il_new);
 /* final image I = blur(IL + alpha*IGp) at x */

@@ -152,3 +152,16 @@ def test_product_exp_log_jacobians_vs_real_sophus(so3h, golden):
         assert np.abs(lg - g["log_exp_w"][i]).max() < 1e-15
         so3h.so3h_jac(_d(w), _d(a), _d(b))
         assert np.abs(a - g["Jl"][i]).max() < 1e-14 and np.abs(b - g["Jlinv"][i]).max() < 1e-14
+
+
+def test_time_slabs_are_batch_aligned_and_cover_the_window():
+    """Event sharding of one back-end window: contiguous slabs cut at batch boundaries."""
+    from cmax_slam_b200.dist import time_slab
+    for n, bs, world in [(1001, 100, 2), (1000, 100, 3), (50, 100, 4), (0, 100, 2), (12345, 64, 8), (401, 100, 2)]:
+        sl = [time_slab(n, bs, r, world) for r in range(world)]
+        assert sl[0][0] == 0 and sl[-1][1] == n
+        assert all(sl[i][1] == sl[i + 1][0] for i in range(world - 1))
+        assert all(b % bs == 0 or b == n for b, _ in sl)
+        # the reference's trailing single-event batch can only ever sit in the LAST slab
+        for b, e in sl[:-1]:
+            assert (e - b) % bs == 0 or e == n      # a ragged slab is always the global tail
