@@ -3,6 +3,7 @@
 #include "fe_kernels.cuh"
 #include "image_kernels.cuh"
 #include "fe_mega.cuh"
+#include "fe_binning.cuh"
 
 using namespace cmaxb;
 
@@ -22,6 +23,8 @@ struct cmaxb_fe {
   double4* d_lut = nullptr;
   uint4* d_ev = nullptr; size_t ev_cap = 0;
   double* d_dt = nullptr; size_t dt_cap = 0;
+  uint2* d_bev = nullptr; size_t bev_cap = 0; bool have_bins = false; bool use_bins = true;   // spatially binned copy of the packet
+  unsigned int* d_tile_count = nullptr; unsigned int* d_tile_cursor = nullptr; int ntiles = 0, ntx = 0;
   long long n = 0, nb = 0;
   bool have_packet = false;
   int* d_flags = nullptr; int* h_flags = nullptr;
@@ -51,7 +54,7 @@ struct cmaxb_fe {
 
 static FeGeom fe_geom(const cmaxb_fe* fe) {
   FeGeom g;
-  g.ev = fe->d_ev; g.n = fe->n; g.batch_size = fe->cfg.batch_size; g.dt_tab = fe->d_dt; g.lut = fe->d_lut;
+  g.ev = fe->d_ev; g.bev = nullptr; g.n = fe->n; g.batch_size = fe->cfg.batch_size; g.dt_tab = fe->d_dt; g.lut = fe->d_lut;
   g.W = fe->cfg.width; g.H = fe->cfg.height;
   g.fx = fe->cfg.fx; g.fy = fe->cfg.fy; g.cx = fe->cfg.cx; g.cy = fe->cfg.cy;
   return g;
@@ -78,6 +81,8 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   {
     const char* mk = getenv("CMAXB_FE_MULTI_KERNEL");
     fe->force_multi_kernel = mk && mk[0] == '1';
+    const char* nb = getenv("CMAXB_FE_NO_BINNING");   // A/B switch: evaluate the packet in arrival (time) order
+    fe->use_bins = !(nb && nb[0] == '1');
   }
   int rc = make_taps(cfg->blur_sigma, &fe->taps);
   if (rc != CMAXB_OK) { delete fe; return rc; }
@@ -167,6 +172,7 @@ extern "C" void cmaxb_fe_destroy(cmaxb_fe* fe) {
   cudaSetDevice(fe->device);
   if (fe->stream) cudaStreamSynchronize(fe->stream);
   cudaFree(fe->d_lut); cudaFree(fe->d_ev); cudaFree(fe->d_dt); cudaFree(fe->d_flags);
+  cudaFree(fe->d_bev); cudaFree(fe->d_tile_count); cudaFree(fe->d_tile_cursor);
   cudaFree(fe->d_quad[0]); cudaFree(fe->d_quad[1]); cudaFree(fe->d_blur1); cudaFree(fe->d_GQ); cudaFree(fe->d_img4); cudaFree(fe->d_blur4);
   cudaFree(fe->d_cells); cudaFree(fe->d_omegas); cudaFree(fe->d_acc); cudaFree(fe->d_ticket); cudaFree(fe->d_ticket2);
   cudaFree(fe->d_gacc); cudaFree(fe->d_result); cudaFree(fe->d_mean);
@@ -212,6 +218,34 @@ extern "C" int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size
     CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
       fe_batch_dt_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ev, nn, ibs, t_ref_sec, dt, nb, flags);
     }));
+    // one-time spatial binning of the packet (reused by every evaluation until the next set_packet)
+    fe->have_bins = false;
+    fe->ntx = (W + kBinTile - 1) / kBinTile;
+    fe->ntiles = fe->ntx * ((H + kBinTile - 1) / kBinTile);
+    if (fe->use_bins && fe->ntiles <= kBinMaxTiles && nn < (1LL << 32)) {
+      if (n > fe->bev_cap) {
+        cudaFree(fe->d_bev); fe->d_bev = nullptr; fe->bev_cap = 0;
+        CMAXB_TRY(dev_alloc(&fe->d_bev, n));
+        fe->bev_cap = n;
+      }
+      if (!fe->d_tile_count) {
+        CMAXB_TRY(dev_alloc(&fe->d_tile_count, (size_t)kBinMaxTiles));
+        CMAXB_TRY(dev_alloc(&fe->d_tile_cursor, (size_t)kBinMaxTiles));
+      }
+      const int ntiles = fe->ntiles, ntx = fe->ntx;
+      const unsigned nchunks = (unsigned)((nn + kBinChunk - 1) / kBinChunk);
+      CMAXB_CUDA_TRY(cudaMemsetAsync(fe->d_tile_count, 0, sizeof(unsigned int) * ntiles, s));
+      CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
+        fe_bin_count_kernel<<<nchunks, kBinThreads, sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, fe->d_tile_count);
+      }));
+      CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
+        fe_bin_scan_kernel<<<1, 1024, 0, s>>>(fe->d_tile_count, ntiles, fe->d_tile_cursor);
+      }));
+      CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
+        fe_bin_scatter_kernel<<<nchunks, kBinThreads, 2 * sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, ibs, fe->d_tile_cursor, fe->d_bev);
+      }));
+      fe->have_bins = true;
+    }
     CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->h_flags, fe->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
     CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
     if (*fe->h_flags & 2) return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor");
@@ -304,6 +338,7 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
     const int kc = (k - c0 < kMegaMaxHyp) ? k - c0 : kMegaMaxHyp;
     FeMegaParams p;
     p.g = fe_geom(fe);
+    p.g.bev = fe->have_bins ? fe->d_bev : nullptr;   // the fused kernel walks the tile-binned copy of the packet
     p.k = kc; p.th = fe->mega_th; p.want_grad = want_grad; p.measure = fe->cfg.contrast_measure; p.taps = fe->taps;
     for (int i = 0; i < 3 * kc; ++i) p.omegas[i] = omegas[3 * c0 + i];
     p.quad = fe->d_quad[cur] + (long long)c0 * fe->A;

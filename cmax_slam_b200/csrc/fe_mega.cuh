@@ -58,26 +58,36 @@ constexpr int kEvUnroll = 4;
 
 __device__ __forceinline__ void mega_scatter(const FeMegaParams& p) {
   const FeGeom& g = p.g;
-  const long long stride = (long long)gridDim.x * kMegaThreads;
-  const long long i0 = blockIdx.x * (long long)kMegaThreads + threadIdx.x;
-  // kEvUnroll events per iteration: all event records, dt entries and LUT sectors are requested
-  // before the first dependent use (the loop is latency-bound on L2, not throughput-bound)
-  for (long long i = i0; i < g.n; i += kEvUnroll * stride) {
+  // every CTA owns one contiguous run of the (tile-binned) packet, so that the LUT / accumulator lines of
+  // a source tile stay in its SM's L1; kEvUnroll events per thread-iteration, all event records, dt
+  // entries and LUT sectors requested before the first dependent use
+  const long long chunk = (g.n + gridDim.x - 1) / gridDim.x;
+  const long long c_beg = blockIdx.x * chunk;
+  const long long c_end = (c_beg + chunk < g.n) ? c_beg + chunk : g.n;
+  constexpr long long stride = kMegaThreads;
+  for (long long i = c_beg + threadIdx.x; i < c_end; i += kEvUnroll * stride) {
     uint4 e[kEvUnroll];
     double dt[kEvUnroll];
     double2 bxy[kEvUnroll];
     double bz[kEvUnroll];
     bool ok[kEvUnroll];
+    unsigned int bidx[kEvUnroll];
 #pragma unroll
     for (int u = 0; u < kEvUnroll; ++u) {
       const long long j = i + u * stride;
-      ok[u] = j < g.n;
-      e[u] = load_event(g.ev, ok[u] ? j : i);
+      ok[u] = j < c_end;
+      const long long jj = ok[u] ? j : i;
+      if (g.bev) {
+        const uint2 r = __ldg(g.bev + jj);
+        e[u].x = r.x; bidx[u] = r.y;
+      } else {
+        e[u] = load_event(g.ev, jj);
+        bidx[u] = (unsigned)jj / (unsigned)g.batch_size;
+      }
     }
 #pragma unroll
     for (int u = 0; u < kEvUnroll; ++u) {
-      const long long j = ok[u] ? i + u * stride : i;
-      dt[u] = __ldg(g.dt_tab + (unsigned)j / (unsigned)g.batch_size);
+      dt[u] = __ldg(g.dt_tab + bidx[u]);
       const int ex = e[u].x & 0xffff, ey = e[u].x >> 16;
       const double2* lp = reinterpret_cast<const double2*>(g.lut + (ey * g.W + ex));
       bxy[u] = __ldg(lp);
@@ -124,12 +134,26 @@ __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned
     const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * TH;
     const int qx0 = tx0 - r - 1, qy0 = ty0 - r - 1;
     __syncthreads();
-    for (int i = tid; i < QW * QH; i += kMegaThreads) {
-      const int ly = i / QW, lx = i - ly * QW;
-      const int gx = qx0 + lx, gy = qy0 + ly;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = __ldcg(quad + (long long)gy * W + gx);
-      s_q[i] = v;
+    // all of a thread's cell requests are issued back to back (registers), then stored: one L2 round trip
+    // per tile instead of one per cell
+    constexpr int kCellsPerThread = 6;   // >= ceil((kTW+2*16+1)*(kMegaMaxTH+... )) is not needed: loop below handles the rest
+    for (int base = 0; base < QW * QH; base += kCellsPerThread * kMegaThreads) {
+      float4 v[kCellsPerThread];
+#pragma unroll
+      for (int u = 0; u < kCellsPerThread; ++u) {
+        const int i = base + u * kMegaThreads + tid;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < QW * QH) {
+          const int ly = i / QW, lx = i - ly * QW;
+          const int gx = qx0 + lx, gy = qy0 + ly;
+          if (gx >= 0 && gx < W && gy >= 0 && gy < H) v[u] = __ldcg(quad + (long long)gy * W + gx);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kCellsPerThread; ++u) {
+        const int i = base + u * kMegaThreads + tid;
+        if (i < QW * QH) s_q[i] = v[u];
+      }
     }
     __syncthreads();
     for (int i = tid; i < IW * IH; i += kMegaThreads) {
@@ -214,12 +238,26 @@ __device__ __forceinline__ void mega_adjoint(const FeMegaParams& p, int h, doubl
   for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
     const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * TH;
     __syncthreads();
-    for (int i = tid; i < IW * IH; i += kMegaThreads) {
-      const int ly = i / IW, lx = i - ly * IW;
-      const int gx = tx0 + lx - r, gy = ty0 + ly - r;
-      float z = 0.f;
-      if (gx >= 0 && gx < W && gy >= 0 && gy < H) z = __ldcg(img + (long long)gy * W + gx) * a2 + b2;
-      s_in[i] = z;
+    constexpr int kPixPerThread = 6;
+    for (int base = 0; base < IW * IH; base += kPixPerThread * kMegaThreads) {
+      float z[kPixPerThread];
+      bool inside[kPixPerThread];
+#pragma unroll
+      for (int u = 0; u < kPixPerThread; ++u) {
+        const int i = base + u * kMegaThreads + tid;
+        z[u] = 0.f; inside[u] = false;
+        if (i < IW * IH) {
+          const int ly = i / IW, lx = i - ly * IW;
+          const int gx = tx0 + lx - r, gy = ty0 + ly - r;
+          inside[u] = gx >= 0 && gx < W && gy >= 0 && gy < H;
+          if (inside[u]) z[u] = __ldcg(img + (long long)gy * W + gx);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kPixPerThread; ++u) {
+        const int i = base + u * kMegaThreads + tid;
+        if (i < IW * IH) s_in[i] = inside[u] ? z[u] * a2 + b2 : 0.f;     // img_zeromean (f32), zero outside the image
+      }
     }
     __syncthreads();
     for (int i = tid; i < IH * OW; i += kMegaThreads) {
@@ -271,19 +309,28 @@ __device__ __forceinline__ void mega_gather(const FeMegaParams& p, int h, double
   const float4* GQh = p.GQ + h * p.A;
   double acc[3] = {0.0, 0.0, 0.0};
   constexpr int U = 2;
-  const long long stride = (long long)gridDim.x * kMegaThreads;
-  for (long long i = blockIdx.x * (long long)kMegaThreads + threadIdx.x; i < g.n; i += U * stride) {
-    uint4 e[U]; double dt[U]; double2 bxy[U]; double bz[U]; bool ok[U];
+  const long long chunk = (g.n + gridDim.x - 1) / gridDim.x;
+  const long long c_beg = blockIdx.x * chunk;
+  const long long c_end = (c_beg + chunk < g.n) ? c_beg + chunk : g.n;
+  constexpr long long stride = kMegaThreads;
+  for (long long i = c_beg + threadIdx.x; i < c_end; i += U * stride) {
+    uint4 e[U]; double dt[U]; double2 bxy[U]; double bz[U]; bool ok[U]; unsigned int bidx[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long j = i + u * stride;
-      ok[u] = j < g.n;
-      e[u] = load_event(g.ev, ok[u] ? j : i);
+      ok[u] = j < c_end;
+      const long long jj = ok[u] ? j : i;
+      if (g.bev) {
+        const uint2 r = __ldg(g.bev + jj);
+        e[u].x = r.x; bidx[u] = r.y;
+      } else {
+        e[u] = load_event(g.ev, jj);
+        bidx[u] = (unsigned)jj / (unsigned)g.batch_size;
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long j = ok[u] ? i + u * stride : i;
-      dt[u] = __ldg(g.dt_tab + (unsigned)j / (unsigned)g.batch_size);
+      dt[u] = __ldg(g.dt_tab + bidx[u]);
       const int ex = e[u].x & 0xffff, ey = e[u].x >> 16;
       const double2* lp = reinterpret_cast<const double2*>(g.lut + (ey * g.W + ex));
       bxy[u] = __ldg(lp);
@@ -383,21 +430,23 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
   if (s_last) {
     __threadfence();
     if (threadIdx.x == 0) *p.ticket = 0u;
-    for (int h = 0; h < p.k; ++h) {
+    // one WARP per hypothesis: lanes add the per-CTA records in a fixed order, lane 0 publishes
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int h = wid; h < p.k; h += kMegaThreads / 32) {
       const double* all = p.part_ev + (long long)h * kMegaMaxCtas * 3;
-      double t[3] = {0.0, 0.0, 0.0};
-      for (int c = threadIdx.x; c < (int)gridDim.x; c += kMegaThreads) {
-        t[0] += __ldcg(all + 3 * c); t[1] += __ldcg(all + 3 * c + 1); t[2] += __ldcg(all + 3 * c + 2);
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+      for (int c = lane; c < (int)gridDim.x; c += 32) {
+        t0 += __ldcg(all + 3 * c); t1 += __ldcg(all + 3 * c + 1); t2 += __ldcg(all + 3 * c + 2);
       }
-      __syncthreads();
-      block_sum<3>(t, s_red);
-      if (threadIdx.x == 0) {
+      t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
+      if (lane == 0) {
         const double c = __ldcg(p.contrast_dev + h);
         p.result[4 * h] = c;
-        p.result[4 * h + 1] = t[0] / Np; p.result[4 * h + 2] = t[1] / Np; p.result[4 * h + 3] = t[2] / Np;
-        if (p.mirror) { p.mirror[4 * h] = c; p.mirror[4 * h + 1] = t[0] / Np; p.mirror[4 * h + 2] = t[1] / Np; p.mirror[4 * h + 3] = t[2] / Np; }
+        p.result[4 * h + 1] = t0 / Np; p.result[4 * h + 2] = t1 / Np; p.result[4 * h + 3] = t2 / Np;
+        if (p.mirror) { p.mirror[4 * h] = c; p.mirror[4 * h + 1] = t0 / Np; p.mirror[4 * h + 2] = t1 / Np; p.mirror[4 * h + 3] = t2 / Np; }
       }
     }
+    __syncthreads();
     CMAXB_PHASE_MARK_ANY(9);
     if (threadIdx.x == 0) {
       __threadfence_system();
