@@ -531,6 +531,11 @@ extern "C" int cmaxb_fe_set_result_mirror(cmaxb_fe* fe, double* device_ptr) {
 extern "C" int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10) {
   if (!fe || !us10) return set_error(CMAXB_ERR_INVALID, "null argument");
   CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+  if (getenv("CMAXB_DEBUG_STAGES")) {   // developer aid: blur-stage stamps of CTA 0 (slots 10..15)
+    std::fprintf(stderr, "blur stages (us from entry):");
+    for (int i = 10; i < 16; ++i) std::fprintf(stderr, " %.2f", (double)(fe->h_phase[i] - fe->h_phase[0]) * 1e-3);
+    std::fprintf(stderr, "\n");
+  }
   for (int i = 0; i < 10; ++i)
     us10[i] = (fe->h_phase && fe->h_phase[i] && fe->h_phase[0]) ? (double)(fe->h_phase[i] - fe->h_phase[0]) * 1e-3 : -1.0;
   return CMAXB_OK;

@@ -134,6 +134,7 @@ __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned
     const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * TH;
     const int qx0 = tx0 - r - 1, qy0 = ty0 - r - 1;
     __syncthreads();
+    CMAXB_PHASE_MARK(10);
     // all of a thread's cell requests are issued back to back (registers), then stored: one L2 round trip
     // per tile instead of one per cell
     constexpr int kCellsPerThread = 6;   // >= ceil((kTW+2*16+1)*(kMegaMaxTH+... )) is not needed: loop below handles the rest
@@ -156,6 +157,7 @@ __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned
       }
     }
     __syncthreads();
+    CMAXB_PHASE_MARK(11);
     for (int i = tid; i < IW * IH; i += kMegaThreads) {
       const int ly = i / IW, lx = i - ly * IW;
       const int gx = reflect101(min(tx0 + lx - r, W + r), W);
@@ -172,6 +174,7 @@ __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned
       s_in[i] = v;
     }
     __syncthreads();
+    CMAXB_PHASE_MARK(12);
     for (int i = tid; i < IH * kTW; i += kMegaThreads) {
       const int ly = i / kTW, lx = i - ly * kTW;
       const float* q = s_in + ly * IW + lx;
@@ -181,6 +184,7 @@ __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned
       s_tmp[i] = s;
     }
     __syncthreads();
+    CMAXB_PHASE_MARK(13);
     const int lx = tid & (kTW - 1);
     for (int ly = tid / kTW; ly < TH; ly += kMegaThreads / kTW) {
       const int gx = tx0 + lx, gy = ty0 + ly;
@@ -196,11 +200,13 @@ __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned
       }
     }
   }
+  CMAXB_PHASE_MARK(14);
   block_sum<2>(a, s_red);
   if (tid == 0) {
     double* part = p.part_img + ((long long)h * kMegaMaxCtas + blockIdx.x) * 2;
     part[0] = a[0]; part[1] = a[1];
   }
+  CMAXB_PHASE_MARK(15);
 }
 
 // every CTA adds the per-CTA records of hypothesis h in the same fixed order -> identical S1, S2
@@ -435,8 +441,17 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
     for (int h = wid; h < p.k; h += kMegaThreads / 32) {
       const double* all = p.part_ev + (long long)h * kMegaMaxCtas * 3;
       double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-      for (int c = lane; c < (int)gridDim.x; c += 32) {
-        t0 += __ldcg(all + 3 * c); t1 += __ldcg(all + 3 * c + 1); t2 += __ldcg(all + 3 * c + 2);
+      constexpr int kRecUnroll = 8;    // 24 independent loads in flight per lane (the loop is one L2 round trip per step)
+      for (int c0 = lane; c0 < (int)gridDim.x; c0 += 32 * kRecUnroll) {
+        double v[kRecUnroll][3];
+#pragma unroll
+        for (int u = 0; u < kRecUnroll; ++u) {
+          const int c = c0 + 32 * u;
+          const bool ok = c < (int)gridDim.x;
+          v[u][0] = ok ? __ldcg(all + 3 * c) : 0.0; v[u][1] = ok ? __ldcg(all + 3 * c + 1) : 0.0; v[u][2] = ok ? __ldcg(all + 3 * c + 2) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kRecUnroll; ++u) { t0 += v[u][0]; t1 += v[u][1]; t2 += v[u][2]; }
       }
       t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
       if (lane == 0) {
