@@ -128,6 +128,7 @@ extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
   cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
   cudaFree(be->d_bands); cudaFree(be->d_bands_blur); cudaFree(be->d_ilq); cudaFree(be->d_GQ);
   cudaFree(be->d_ccell); cudaFree(be->d_ca); cudaFree(be->d_cb); cudaFree(be->d_il_plane);
+
   cudaFree(be->d_acc); cudaFree(be->d_ticket); cudaFree(be->d_result); cudaFree(be->d_mean);
   cudaFree(be->d_bacc); cudaFree(be->d_bticket); cudaFree(be->d_bresult); cudaFree(be->d_bmean);
   cudaFree(be->d_alpha_sums); cudaFree(be->d_flags); cudaFree(be->d_cells);
@@ -260,14 +261,11 @@ static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
   cudaStream_t s = be->stream;
   for (int i = 0; i < 3 * be->n_opt; ++i) be->h_x[i] = x ? x[i] : 0.0;
   if (be->n_opt > 0) CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_x, be->h_x, sizeof(double) * 3 * be->n_opt, cudaMemcpyHostToDevice, s));
-  CMAXB_TRY(be->prof.run(CMAXB_K_BE_POSES, s, true, [&] {
-    be_update_knots_kernel<<<(be->n_knots + 127) / 128, 128, 0, s>>>(be->d_knots0, be->d_x, be->n_knots, be->n_fixed, be->d_knots);
-  }));
   if (be->nb > 0) {
     const unsigned grid = (unsigned)((be->nb + 127) / 128);
     CMAXB_TRY(be->prof.run(CMAXB_K_BE_POSES, s, true, [&] {
-      if (be->N == 2) be_pose_kernel<2><<<grid, 128, 0, s>>>(be->d_knots, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx);
-      else be_pose_kernel<4><<<grid, 128, 0, s>>>(be->d_knots, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx);
+      if (be->N == 2) be_pose_kernel<2><<<grid, 128, 0, s>>>(be->d_knots0, be->d_x, be->n_fixed, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx);
+      else be_pose_kernel<4><<<grid, 128, 0, s>>>(be->d_knots0, be->d_x, be->n_fixed, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx);
     }));
   }
   return CMAXB_OK;

@@ -78,31 +78,26 @@ __global__ void be_batch_time_kernel(const uint4* __restrict__ ev, long long n, 
   out[b] = bt;
 }
 
-// temp trajectory: K_i <- exp(x_i) * K_i for the optimised knots
-// (CopyAndIncrementalUpdate / incrementalUpdate, trajectory.cpp:221-263,491-522)
-__global__ void be_update_knots_kernel(const Quat* __restrict__ knots0, const double* __restrict__ x, int n_knots,
-                                       int n_fixed, Quat* __restrict__ knots) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_knots) return;
-  Quat q = knots0[i];
-  if (i >= n_fixed) {
-    const int j = i - n_fixed;
-    Vec3 d; d.x = x[3 * j]; d.y = x[3 * j + 1]; d.z = x[3 * j + 2];
-    q = quat_mul(so3_exp(d), q);
-  }
-  knots[i] = q;
-}
-
+// one batch: K_i <- exp(x_i) K_i for the N knots of its segment (incrementalUpdate, trajectory.cpp:221-238,
+// 491-499), then So3Spline<N>::evaluate (+ f32 knot Jacobians).  knots0: the window's knots; x: 3*n_opt increments.
 template <int N>
-__global__ void be_pose_kernel(const Quat* __restrict__ knots, const BeBatchTime* __restrict__ bt, long long nb,
-                               int want_grad, BePose* __restrict__ poses, int* __restrict__ idx_out) {
-  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  const BeBatchTime t = bt[b];
+__device__ __forceinline__ void be_pose_one(const Quat* __restrict__ knots0, const double* __restrict__ x, int n_fixed,
+                                            BeBatchTime t, int want_grad, BePose* __restrict__ p, int* __restrict__ idx_out) {
+  Quat loc[N];
+  const int s = (int)t.s;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    Quat q = knots0[s + i];
+    if (s + i >= n_fixed) {
+      const int j = s + i - n_fixed;
+      Vec3 d; d.x = x[3 * j]; d.y = x[3 * j + 1]; d.z = x[3 * j + 2];
+      q = quat_mul(so3_exp(d), q);
+    }
+    loc[i] = q;
+  }
   Mat3 J[N];
-  const Quat q = so3_spline_eval<N>(knots, (int)t.s, t.u, want_grad ? J : nullptr);
+  const Quat q = so3_spline_eval<N>(loc, 0, t.u, want_grad ? J : nullptr);
   const Mat3 R = quat_to_mat(q);
-  BePose* p = poses + b;
 #pragma unroll
   for (int i = 0; i < 9; ++i) p->R[i] = R.m[i];
   if (want_grad) {
@@ -111,9 +106,18 @@ __global__ void be_pose_kernel(const Quat* __restrict__ knots, const BeBatchTime
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) p->Jk[r * (3 * N) + 3 * k + c] = (float)J[k].m[r * 3 + c];
   }
-  p->idx_cp_beg = (int)t.s;
+  p->idx_cp_beg = s;
   p->valid = 1;
-  idx_out[b] = (int)t.s;     // packed copy for the per-knot reduction (coalesced scan)
+  *idx_out = s;     // packed copy for the per-knot reduction (coalesced scan)
+}
+
+template <int N>
+__global__ void be_pose_kernel(const Quat* __restrict__ knots0, const double* __restrict__ x, int n_fixed,
+                               const BeBatchTime* __restrict__ bt, long long nb, int want_grad, BePose* __restrict__ poses,
+                               int* __restrict__ idx_out) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  be_pose_one<N>(knots0, x, n_fixed, bt[b], want_grad, poses + b, idx_out + b);
 }
 
 struct BeWarp {
@@ -188,18 +192,17 @@ constexpr int kBeWarps = kBeThreads / 32;
 // evaluation only ever uses the sum, event_pano_warper.cpp:199).
 // CACHE: also compute the 2x3 Jacobian factor and store (cell, dx, dy, dd) for the gather pass.
 template <int MODE, bool CACHE>
-__global__ void __launch_bounds__(kBeThreads)
-be_scatter_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict__ il_old, float* __restrict__ il_new,
-                  float4* __restrict__ il_quad, BeCache cache) {
-  const long long stride = (long long)gridDim.x * kBeThreads;
-  for (long long j = blockIdx.x * (long long)kBeThreads + threadIdx.x; j < g.n_visit; j += stride) {
+__device__ __forceinline__ void be_scatter_range(const BeGeom& g, const BePose* __restrict__ poses, float* __restrict__ il_old,
+                                                 float* __restrict__ il_new, float4* __restrict__ il_quad, const BeCache& cache,
+                                                 long long j0, long long stride) {
+  for (long long j = j0; j < g.n_visit; j += stride) {
     long long b = j / g.m;
     if (b > g.nb - 1) b = g.nb - 1;
     const long long i = b * g.batch_size + (j - b * g.m) * g.sample_rate;
     if (i >= g.n_eff) continue;   // never true by construction of n_visit; kept as a guard
     double R[9];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) R[q] = __ldg(&poses[b].R[q]);
+    for (int q = 0; q < 9; ++q) R[q] = __ldcg(&poses[b].R[q]);
     const uint4 e = load_event(g.ev, i);
     const BeWarp w = be_warp<CACHE>(g, R, e);
     if (CACHE) {
@@ -222,6 +225,14 @@ be_scatter_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict_
       atomicAdd(il + p + g.W + 1, dx * dy);
     }
   }
+}
+
+template <int MODE, bool CACHE>
+__global__ void __launch_bounds__(kBeThreads)
+be_scatter_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict__ il_old, float* __restrict__ il_new,
+                  float4* __restrict__ il_quad, BeCache cache) {
+  be_scatter_range<MODE, CACHE>(g, poses, il_old, il_new, il_quad, cache, blockIdx.x * (long long)kBeThreads + threadIdx.x,
+                                (long long)gridDim.x * kBeThreads);
 }
 
 // dense derivative bands (reference-faithful DENSE mode / parity): planar bands[P][A]
@@ -291,27 +302,26 @@ __global__ void be_cells_kernel(BeGeom g, const BePose* __restrict__ poses, long
 // One WARP per batch; the per-event geometry is NOT recomputed: (cell, dx, dy, dd) come from the
 // cache the gradient scatter pass wrote (36 bytes per event, streamed once).
 template <int N, bool QUAD>
-__global__ void __launch_bounds__(kBeThreads)
-be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __restrict__ G, const float4* __restrict__ GQ,
-                 BeCache cache, double* __restrict__ wgrad) {
+__device__ __forceinline__ void be_gather_range(const BeGeom& g, const BePose* __restrict__ poses, const float* __restrict__ G,
+                                                const float4* __restrict__ GQ, const BeCache& cache, double* __restrict__ wgrad,
+                                                long long b0, long long wstride) {
   const int lane = threadIdx.x & 31;
-  const long long wstride = (long long)gridDim.x * kBeWarps;
-  for (long long b = blockIdx.x * (long long)kBeWarps + (threadIdx.x >> 5); b < g.nb; b += wstride) {
+  for (long long b = b0; b < g.nb; b += wstride) {
     const long long j0 = b * g.m;
     long long j1 = j0 + g.m;
     if (b == g.nb - 1 || j1 > g.n_visit) j1 = g.n_visit;
     double v0 = 0, v1 = 0, v2 = 0;
     for (long long j = j0 + lane; j < j1; j += 32) {
-      const int cell = __ldg(cache.cell + j);
+      const int cell = __ldcg(cache.cell + j);
       if (cell < 0) continue;
-      const float4 ca = __ldg(cache.a + j), cb = __ldg(cache.b + j);
+      const float4 ca = __ldcg(cache.a + j), cb = __ldcg(cache.b + j);
       double g00, g01, g10, g11;
       if (QUAD) {
-        const float4 q = __ldg(GQ + cell);
+        const float4 q = __ldcg(GQ + cell);
         g00 = q.x; g01 = q.y; g10 = q.z; g11 = q.w;
       } else {
         const float* p = G + cell;
-        g00 = __ldg(p); g01 = __ldg(p + 1); g10 = __ldg(p + g.W); g11 = __ldg(p + g.W + 1);
+        g00 = __ldcg(p); g01 = __ldcg(p + 1); g10 = __ldcg(p + g.W); g11 = __ldcg(p + g.W + 1);
       }
       const double dx = ca.x, dy = ca.y;
       const double a = (1.0 - dy) * (g01 - g00) + dy * (g11 - g10);
@@ -323,9 +333,17 @@ be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __rest
     v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
     if (lane < 3 * N) {
       const float* Jk = poses[b].Jk;
-      wgrad[b * (3 * N) + lane] = v0 * (double)Jk[lane] + v1 * (double)Jk[3 * N + lane] + v2 * (double)Jk[6 * N + lane];
+      wgrad[b * (3 * N) + lane] = v0 * (double)__ldcg(Jk + lane) + v1 * (double)__ldcg(Jk + 3 * N + lane) + v2 * (double)__ldcg(Jk + 6 * N + lane);
     }
   }
+}
+
+template <int N, bool QUAD>
+__global__ void __launch_bounds__(kBeThreads)
+be_gather_kernel(BeGeom g, const BePose* __restrict__ poses, const float* __restrict__ G, const float4* __restrict__ GQ,
+                 BeCache cache, double* __restrict__ wgrad) {
+  be_gather_range<N, QUAD>(g, poses, G, GQ, cache, wgrad, blockIdx.x * (long long)kBeWarps + (threadIdx.x >> 5),
+                           (long long)gridDim.x * kBeWarps);
 }
 
 // Batches of spline segment s form a contiguous run when the events are time-sorted; record the
@@ -343,32 +361,40 @@ __global__ void be_segment_ranges_kernel(const BeBatchTime* __restrict__ bt, lon
 // g[3*kk + c] = (1/Np) * sum over batches touching knot (kk + n_fixed) of wgrad[b][3*(knot-idx_b)+c].
 // One CTA per optimised knot; fixed summation order (deterministic).
 template <int N>
-__global__ void __launch_bounds__(256)
-be_grad_reduce_kernel(const int* __restrict__ idx, const int* __restrict__ seg_lo, const int* __restrict__ seg_hi,
-                      const double* __restrict__ wgrad, long long nb, int n_fixed, double inv_np, double* __restrict__ grad) {
-  __shared__ double s_red[8 * 3];
-  const int knot = blockIdx.x + n_fixed;
+__device__ __forceinline__ void be_grad_reduce_knot(int kk, const int* __restrict__ idx, const int* __restrict__ seg_lo,
+                                                    const int* __restrict__ seg_hi, const double* __restrict__ wgrad, int n_fixed,
+                                                    double inv_np, double* __restrict__ grad, double* s_red /*[8*3]*/) {
+  const int knot = kk + n_fixed;
   double a[3] = {0.0, 0.0, 0.0};
   for (int rel = 0; rel < N; ++rel) {
     const int s = knot - rel;               // batches of segment s touch knots s .. s+N-1
     if (s < 0) continue;
     const int lo = seg_lo[s], hi = seg_hi[s];
     for (long long b = lo + (long long)threadIdx.x; b < hi; b += blockDim.x) {
-      if (__ldg(idx + b) != s) continue;
+      if (__ldcg(idx + b) != s) continue;
       const double* w = wgrad + b * (3 * N) + 3 * rel;
-      a[0] += w[0]; a[1] += w[1]; a[2] += w[2];
+      a[0] += __ldcg(w); a[1] += __ldcg(w + 1); a[2] += __ldcg(w + 2);
     }
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < 3; ++c) a[c] = warp_sum(a[c]);
+  __syncthreads();
   if (lane == 0) { s_red[wid * 3] = a[0]; s_red[wid * 3 + 1] = a[1]; s_red[wid * 3 + 2] = a[2]; }
   __syncthreads();
   if (threadIdx.x < 3) {
     double s = 0;
-    for (int w = 0; w < 8; ++w) s += s_red[w * 3 + threadIdx.x];
-    grad[3 * blockIdx.x + threadIdx.x] = s * inv_np;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += s_red[w * 3 + threadIdx.x];
+    grad[3 * kk + threadIdx.x] = s * inv_np;
   }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256)
+be_grad_reduce_kernel(const int* __restrict__ idx, const int* __restrict__ seg_lo, const int* __restrict__ seg_hi,
+                      const double* __restrict__ wgrad, long long nb, int n_fixed, double inv_np, double* __restrict__ grad) {
+  __shared__ double s_red[8 * 3];
+  be_grad_reduce_knot<N>(blockIdx.x, idx, seg_lo, seg_hi, wgrad, n_fixed, inv_np, grad, s_red);
 }
 
 // DENSE mode: reduce blurred bands against the blurred image.

@@ -12,15 +12,13 @@
 #include <cooperative_groups.h>
 
 #include "fe_kernels.cuh"
-#include "image_kernels.cuh"
+#include "tile_phases.cuh"
 
 namespace cmaxb {
 
 namespace cg = cooperative_groups;
 
-constexpr int kMegaThreads = 256;
 constexpr int kMegaMaxHyp = 32;       // hypotheses per launch (kernel-parameter space)
-constexpr int kMegaMaxCtas = 148 * 8;
 
 struct FeMegaParams {
   FeGeom g;
@@ -46,11 +44,6 @@ struct FeMegaParams {
   unsigned long long* phase_ns; // optional [8]: %globaltimer of CTA 0 at every phase boundary (mapped host memory)
 };
 
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
 #define CMAXB_PHASE_MARK(idx) do { if (p.phase_ns && blockIdx.x == 0 && threadIdx.x == 0) p.phase_ns[idx] = global_timer_ns(); } while (0)
 #define CMAXB_PHASE_MARK_ANY(idx) do { if (p.phase_ns && threadIdx.x == 0) p.phase_ns[idx] = global_timer_ns(); } while (0)
 
@@ -109,204 +102,22 @@ __device__ __forceinline__ void mega_scatter(const FeMegaParams& p) {
   }
 }
 
-// blur + S1,S2 partial sums of hypothesis h; clears the same tiles of the next accumulator.
-// The quad cells of the tile (+halo+1) are staged ONCE in shared memory as float4 (one 16-byte L2
-// request per cell, all requests of a thread issued back to back), cells outside the image staged as
-// zero, and the image pixels -- including the BORDER_REFLECT_101 halo -- are assembled from there.
+// image phases: thin wrappers over tile_phases.cuh
 template <int R>
 __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned char* smem_raw, bool write_out) {
-  const int W = p.g.W, H = p.g.H;
-  const int r = (R >= 0) ? R : p.taps.r;
-  const int TH = p.th;
-  const int IW = kTW + 2 * r, IH = TH + 2 * r;
-  const int QW = IW + 1, QH = IH + 1;
-  float4* s_q = reinterpret_cast<float4*>(smem_raw);          // [QH][QW] cells at image coords (tx0-r-1.., ty0-r-1..)
-  float* s_in = reinterpret_cast<float*>(s_q + QW * QH);      // [IH][IW]
-  float* s_tmp = s_in + IW * IH;                              // [IH][kTW]
-  double* s_red = reinterpret_cast<double*>(s_tmp + IH * kTW);
-  const int tid = threadIdx.x;
-  const int ntx = (W + kTW - 1) / kTW, nty = (H + TH - 1) / TH;
-  const float4* quad = p.quad + h * p.A;
-  float* out = p.blurred + h * p.A;
-  float4* zero_ptr = p.quad_next ? p.quad_next + h * p.A : nullptr;
-  double a[2] = {0.0, 0.0};
-  for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
-    const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * TH;
-    const int qx0 = tx0 - r - 1, qy0 = ty0 - r - 1;
-    __syncthreads();
-    CMAXB_PHASE_MARK(10);
-    // all of a thread's cell requests are issued back to back (registers), then stored: one L2 round trip
-    // per tile instead of one per cell
-    constexpr int kCellsPerThread = 6;   // >= ceil((kTW+2*16+1)*(kMegaMaxTH+... )) is not needed: loop below handles the rest
-    for (int base = 0; base < QW * QH; base += kCellsPerThread * kMegaThreads) {
-      float4 v[kCellsPerThread];
-#pragma unroll
-      for (int u = 0; u < kCellsPerThread; ++u) {
-        const int i = base + u * kMegaThreads + tid;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < QW * QH) {
-          const int ly = i / QW, lx = i - ly * QW;
-          const int gx = qx0 + lx, gy = qy0 + ly;
-          if (gx >= 0 && gx < W && gy >= 0 && gy < H) v[u] = __ldcg(quad + (long long)gy * W + gx);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kCellsPerThread; ++u) {
-        const int i = base + u * kMegaThreads + tid;
-        if (i < QW * QH) s_q[i] = v[u];
-      }
-    }
-    __syncthreads();
-    CMAXB_PHASE_MARK(11);
-    for (int i = tid; i < IW * IH; i += kMegaThreads) {
-      const int ly = i / IW, lx = i - ly * IW;
-      const int gx = reflect101(min(tx0 + lx - r, W + r), W);
-      const int gy = reflect101(min(ty0 + ly - r, H + r), H);
-      const int cx = gx - qx0, cy = gy - qy0;                 // >= 1 by construction
-      float v = 0.f;
-      if (cx >= 1 && cy >= 1 && cx < QW && cy < QH) {          // always true for pixels that feed a valid output
-        const float4* c = s_q + cy * QW + cx;
-        v = c[0].x;
-        v += c[-1].y;
-        v += c[-QW].z;
-        v += c[-QW - 1].w;
-      }
-      s_in[i] = v;
-    }
-    __syncthreads();
-    CMAXB_PHASE_MARK(12);
-    for (int i = tid; i < IH * kTW; i += kMegaThreads) {
-      const int ly = i / kTW, lx = i - ly * kTW;
-      const float* q = s_in + ly * IW + lx;
-      float s = p.taps.w[0] * q[0];
-#pragma unroll
-      for (int j = 1; j <= 2 * r; ++j) s = fmaf(p.taps.w[j], q[j], s);
-      s_tmp[i] = s;
-    }
-    __syncthreads();
-    CMAXB_PHASE_MARK(13);
-    const int lx = tid & (kTW - 1);
-    for (int ly = tid / kTW; ly < TH; ly += kMegaThreads / kTW) {
-      const int gx = tx0 + lx, gy = ty0 + ly;
-      if (gx < W && gy < H) {
-        const float* c = s_tmp + (ly + r) * kTW + lx;
-        float s = p.taps.w[r] * c[0];
-#pragma unroll
-        for (int j = 1; j <= r; ++j) s = fmaf(p.taps.w[r + j], c[j * kTW] + c[-j * kTW], s);
-        if (write_out) out[(long long)gy * W + gx] = s;
-        const double v = (double)s;
-        a[0] += v; a[1] += v * v;
-        if (zero_ptr) zero_ptr[(long long)gy * W + gx] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  }
-  CMAXB_PHASE_MARK(14);
-  block_sum<2>(a, s_red);
-  if (tid == 0) {
-    double* part = p.part_img + ((long long)h * kMegaMaxCtas + blockIdx.x) * 2;
-    part[0] = a[0]; part[1] = a[1];
-  }
-  CMAXB_PHASE_MARK(15);
+  const TileCtx c{p.g.W, p.g.H, p.th, p.taps};
+  const MQuad src{p.quad + h * p.A, nullptr, 0.f};
+  tile_blur_phase<R>(c, src, write_out ? p.blurred + h * p.A : nullptr, p.quad_next ? p.quad_next + h * p.A : nullptr,
+                     p.part_img + (long long)h * kMegaMaxCtas * 2, smem_raw);
 }
-
-// every CTA adds the per-CTA records of hypothesis h in the same fixed order -> identical S1, S2
 __device__ __forceinline__ void mega_image_sums(const FeMegaParams& p, int h, double* s_red, double* S1, double* S2) {
-  const double* all = p.part_img + (long long)h * kMegaMaxCtas * 2;
-  double t[2] = {0.0, 0.0};
-  for (int c = threadIdx.x; c < (int)gridDim.x; c += kMegaThreads) {
-    t[0] += __ldcg(all + 2 * c); t[1] += __ldcg(all + 2 * c + 1);
-  }
-  block_sum<2>(t, s_red);
-  __shared__ double s_bc[2];
-  if (threadIdx.x == 0) { s_bc[0] = t[0]; s_bc[1] = t[1]; }
-  __syncthreads();
-  *S1 = s_bc[0]; *S2 = s_bc[1];
-  __syncthreads();
+  tile_sum_partials(p.part_img + (long long)h * kMegaMaxCtas * 2, s_red, S1, S2);
 }
-
 template <int R>
 __device__ __forceinline__ void mega_adjoint(const FeMegaParams& p, int h, double mean, unsigned char* smem_raw) {
-  const int W = p.g.W, H = p.g.H;
-  const int r = (R >= 0) ? R : p.taps.r;
-  const int TH = p.th;
-  const int IW = kTW + 1 + 2 * r, IH = TH + 1 + 2 * r;
-  constexpr int OW = kTW + 1;
-  const int OH = TH + 1;
-  float* s_in = reinterpret_cast<float*>(smem_raw);
-  float* s_tmp = s_in + IW * IH;
-  float* s_g = s_tmp + IH * OW;
-  const int tid = threadIdx.x;
-  const float a2 = 2.0f;
+  const TileCtx c{p.g.W, p.g.H, p.th, p.taps};
   const float b2 = (p.measure == CMAXB_CONTRAST_MEAN_SQUARE) ? 0.0f : (float)(-2.0 * mean);
-  const float* img = p.blurred + h * p.A;
-  float4* GQ = p.GQ + h * p.A;
-  const int ntx = (W + kTW - 1) / kTW, nty = (H + TH - 1) / TH;
-  for (int tile = blockIdx.x; tile < ntx * nty; tile += gridDim.x) {
-    const int tx0 = (tile % ntx) * kTW, ty0 = (tile / ntx) * TH;
-    __syncthreads();
-    constexpr int kPixPerThread = 6;
-    for (int base = 0; base < IW * IH; base += kPixPerThread * kMegaThreads) {
-      float z[kPixPerThread];
-      bool inside[kPixPerThread];
-#pragma unroll
-      for (int u = 0; u < kPixPerThread; ++u) {
-        const int i = base + u * kMegaThreads + tid;
-        z[u] = 0.f; inside[u] = false;
-        if (i < IW * IH) {
-          const int ly = i / IW, lx = i - ly * IW;
-          const int gx = tx0 + lx - r, gy = ty0 + ly - r;
-          inside[u] = gx >= 0 && gx < W && gy >= 0 && gy < H;
-          if (inside[u]) z[u] = __ldcg(img + (long long)gy * W + gx);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kPixPerThread; ++u) {
-        const int i = base + u * kMegaThreads + tid;
-        if (i < IW * IH) s_in[i] = inside[u] ? z[u] * a2 + b2 : 0.f;     // img_zeromean (f32), zero outside the image
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < IH * OW; i += kMegaThreads) {
-      const int ly = i / OW, lx = i - ly * OW;
-      const int q = tx0 + lx;
-      const float* row = s_in + ly * IW;
-      float s = 0.f;
-      if (q < W) {
-#pragma unroll
-        for (int d = -r; d <= r; ++d) s = fmaf(p.taps.w[r + d], row[lx + r + d], s);
-        if (q >= 1 && q <= r)
-          for (int d = q; d <= r; ++d) s = fmaf(p.taps.w[r + d], row[(-q + d) - tx0 + r], s);
-        if (q <= W - 2 && q >= W - 1 - r)
-          for (int d = -r; d <= q - (W - 1); ++d) s = fmaf(p.taps.w[r + d], row[(2 * (W - 1) - q + d) - tx0 + r], s);
-      }
-      s_tmp[i] = s;
-    }
-    __syncthreads();
-    for (int i = tid; i < OH * OW; i += kMegaThreads) {
-      const int ly = i / OW, lx = i - ly * OW;
-      const int gx = tx0 + lx, q = ty0 + ly;
-      float s = 0.f;
-      if (gx < W && q < H) {
-        const float* col = s_tmp + lx;
-#pragma unroll
-        for (int d = -r; d <= r; ++d) s = fmaf(p.taps.w[r + d], col[(ly + r + d) * OW], s);
-        if (q >= 1 && q <= r)
-          for (int d = q; d <= r; ++d) s = fmaf(p.taps.w[r + d], col[((-q + d) - ty0 + r) * OW], s);
-        if (q <= H - 2 && q >= H - 1 - r)
-          for (int d = -r; d <= q - (H - 1); ++d) s = fmaf(p.taps.w[r + d], col[((2 * (H - 1) - q + d) - ty0 + r) * OW], s);
-      }
-      s_g[i] = s;
-    }
-    __syncthreads();
-    for (int i = tid; i < kTW * TH; i += kMegaThreads) {
-      const int ly = i / kTW, lx = i & (kTW - 1);
-      const int gx = tx0 + lx, gy = ty0 + ly;
-      if (gx < W && gy < H) {
-        const float* q = s_g + ly * OW + lx;
-        GQ[(long long)gy * W + gx] = make_float4(q[0], q[1], q[OW], q[OW + 1]);
-      }
-    }
-  }
+  tile_adjoint_phase<R>(c, p.blurred + h * p.A, 2.0f, b2, nullptr, p.GQ + h * p.A, smem_raw);
 }
 
 __device__ __forceinline__ void mega_gather(const FeMegaParams& p, int h, double* s_red) {
@@ -470,24 +281,7 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
   }
 }
 
-constexpr int kMegaMaxTH = 32;
-inline size_t mega_smem_bytes(int r, int th = kMegaMaxTH) {
-  const int IW = kTW + 2 * r, IH = th + 2 * r;
-  const size_t a = sizeof(float4) * (size_t)(IW + 1) * (IH + 1) + sizeof(float) * ((size_t)IW * IH + (size_t)IH * kTW) +
-                   sizeof(double) * (kMegaThreads / 32) * kNAcc;
-  const int JW = kTW + 1 + 2 * r, JH = th + 1 + 2 * r;
-  const size_t b = sizeof(float) * ((size_t)JW * JH + (size_t)JH * (kTW + 1) + (size_t)(th + 1) * (kTW + 1));
-  return a > b ? a : b;
-}
-// tile height such that one hypothesis plane has at most `grid` tiles (each CTA: one tile per phase)
-inline int mega_tile_height(int W, int H, int grid) {
-  const int ntx = (W + kTW - 1) / kTW;
-  int rows_of_tiles = grid / ntx;
-  if (rows_of_tiles < 1) rows_of_tiles = 1;
-  int th = (H + rows_of_tiles - 1) / rows_of_tiles;
-  if (th < 8) th = 8;
-  if (th > kMegaMaxTH) th = kMegaMaxTH;
-  return th;
-}
+inline size_t mega_smem_bytes(int r, int th = kMegaMaxTH) { return tile_smem_bytes(r, th); }
+inline int mega_tile_height(int W, int H, int grid) { return tile_height_for_grid(W, H, grid); }
 
 }  // namespace cmaxb
