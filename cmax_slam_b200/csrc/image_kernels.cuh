@@ -49,8 +49,10 @@ struct SrcPlane4 {           // interleaved (I, D0, D1, D2)
 struct SrcQuad {
   static constexpr bool kQuad = true;
   const float4* base; long long stride_h;
+  static constexpr bool kExtra = false;
   __device__ __forceinline__ float4 cell(int h, int x, int y, int W) const { return __ldcg(base + h * stride_h + (long long)y * W + x); }
-  __device__ __forceinline__ float finish(float v, int, int, int) const { return v; }
+  __device__ __forceinline__ float extra(int, int, int) const { return 0.f; }
+  __device__ __forceinline__ float combine(float, float v) const { return v; }
   // __ldcg (L2-coherent) rather than the read-only path: in the fused evaluation kernel the image
   // was written by other SMs earlier in the SAME launch.
   __device__ __forceinline__ float load(int h, int x, int y, int W) const {
@@ -68,10 +70,10 @@ struct SrcQuad {
 struct SrcBeQuad {
   static constexpr bool kQuad = true;
   SrcQuad il; const float* igp; float alpha;
+  static constexpr bool kExtra = true;   // + alpha * IGp: fetched with the cells (batched), combined at assembly
   __device__ __forceinline__ float4 cell(int h, int x, int y, int W) const { return il.cell(h, x, y, W); }
-  __device__ __forceinline__ float finish(float v, int x, int y, int W) const {
-    return igp ? igp[(long long)y * W + x] * alpha + v : v;
-  }
+  __device__ __forceinline__ float extra(int x, int y, int W) const { return igp ? __ldg(igp + (long long)y * W + x) : 0.f; }
+  __device__ __forceinline__ float combine(float e, float v) const { return igp ? e * alpha + v : v; }
   __device__ __forceinline__ float load(int h, int x, int y, int W) const {
     const float v = il.load(h, x, y, W);
     return igp ? igp[(long long)y * W + x] * alpha + v : v;
@@ -178,12 +180,45 @@ blur_reduce_kernel(Src src, int W, int H, Taps taps, typename PixT<C>::type* out
     __syncthreads();   // previous tile's column pass is done with s_tmp / s_in
     if constexpr (Src::kQuad) {
       const int qx0 = tx0 - r - 1, qy0 = ty0 - r - 1;
-      for (int i = tid; i < QW * QH; i += kImgThreads) {
-        const int ly = i / QW, lx = i - ly * QW;
-        const int gx = qx0 + lx, gy = qy0 + ly;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = src.cell(h, gx, gy, W);
-        s_q[i] = v;
+      // all of a thread's requests (cells, and the IGp pixels of the back-end) are issued back to back and
+      // only then stored: one L2 round trip per tile instead of one per element
+      constexpr int kPerThread = 6;
+      for (int base = 0; base < QW * QH; base += kPerThread * kImgThreads) {
+        float4 v[kPerThread];
+#pragma unroll
+        for (int u = 0; u < kPerThread; ++u) {
+          const int i = base + u * kImgThreads + tid;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < QW * QH) {
+            const int ly = i / QW, lx = i - ly * QW;
+            const int gx = qx0 + lx, gy = qy0 + ly;
+            if (gx >= 0 && gx < W && gy >= 0 && gy < H) v[u] = src.cell(h, gx, gy, W);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kPerThread; ++u) {
+          const int i = base + u * kImgThreads + tid;
+          if (i < QW * QH) s_q[i] = v[u];
+        }
+      }
+      if constexpr (Src::kExtra) {
+        for (int base = 0; base < IW * IH; base += kPerThread * kImgThreads) {
+          float e[kPerThread];
+#pragma unroll
+          for (int u = 0; u < kPerThread; ++u) {
+            const int i = base + u * kImgThreads + tid;
+            e[u] = 0.f;
+            if (i < IW * IH) {
+              const int ly = i / IW, lx = i - ly * IW;
+              e[u] = src.extra(reflect101(min(tx0 + lx - r, W + r), W), reflect101(min(ty0 + ly - r, H + r), H), W);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kPerThread; ++u) {
+            const int i = base + u * kImgThreads + tid;
+            if (i < IW * IH) s_in[i] = e[u];
+          }
+        }
       }
       __syncthreads();
       for (int i = tid; i < IW * IH; i += kImgThreads) {
@@ -198,7 +233,7 @@ blur_reduce_kernel(Src src, int W, int H, Taps taps, typename PixT<C>::type* out
           v += c[-1].y;
           v += c[-QW].z;
           v += c[-QW - 1].w;
-          v = src.finish(v, gx, gy, W);
+          if constexpr (Src::kExtra) v = src.combine(s_in[i], v);
         }
         s_in[i] = v;
       }
