@@ -40,6 +40,16 @@ class BeCfg(C.Structure):
                 ("stream", C.c_void_p)]
 
 
+class OptParams(C.Structure):
+    _fields_ = [("initial_step", C.c_double), ("line_tol", C.c_double), ("max_iterations", C.c_int32),
+                ("epsabs_grad", C.c_double), ("tolfun", C.c_double)]
+
+
+class OptResult(C.Structure):
+    _fields_ = [("cost_initial", C.c_double), ("cost_final", C.c_double), ("iterations", C.c_int32),
+                ("f_evals", C.c_int32), ("g_evals", C.c_int32), ("stop_reason", C.c_int32)]
+
+
 class BeWindow(C.Structure):
     _fields_ = [("events", C.c_void_p), ("n_events", C.c_size_t), ("knots_xyzw", C.c_void_p),
                 ("n_knots", C.c_int32), ("t0_ns", C.c_int64), ("dt_ns", C.c_int64), ("n_fixed", C.c_int32),
@@ -52,6 +62,7 @@ EXPORTS = [
     "cmaxb_fe_eval_launch", "cmaxb_fe_eval_fetch", "cmaxb_fe_set_result_mirror", "cmaxb_fe_get_iwe", "cmaxb_fe_get_deriv", "cmaxb_fe_get_cells",
     "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_eval_begin", "cmaxb_be_il_plane", "cmaxb_be_eval_end", "cmaxb_be_get_alpha",
     "cmaxb_be_get_il", "cmaxb_be_get_iwe", "cmaxb_be_get_bands", "cmaxb_be_get_cells", "cmaxb_be_get_poses",
+    "cmaxb_fe_optimize", "cmaxb_be_optimize",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
     "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_fe_phase_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
 ]
@@ -79,6 +90,8 @@ def lib():
     L.cmaxb_fe_get_iwe.argtypes = [vp, dp, C.c_int, vp]
     L.cmaxb_fe_get_deriv.argtypes = [vp, dp, C.c_int, vp]
     L.cmaxb_fe_get_cells.argtypes = [vp, dp, vp]
+    L.cmaxb_fe_optimize.argtypes = [vp, dp, C.POINTER(OptParams), dp, C.POINTER(OptResult)]
+    L.cmaxb_be_optimize.argtypes = [vp, dp, C.c_int, C.POINTER(OptParams), dp, C.POINTER(OptResult)]
     L.cmaxb_last_error.restype = C.c_char_p
     L.cmaxb_launch_count.restype = C.c_uint64
     L.cmaxb_kernel_name.restype = C.c_char_p

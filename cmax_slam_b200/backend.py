@@ -108,6 +108,17 @@ class EventWarperCMax:
         _capi.check(self._L.cmaxb_be_eval_end(self._h, C.byref(c), _capi.dptr(g) if self._split_grad else None))
         return c.value, (g[: self.n_params] if self._split_grad else None)
 
+    def setupProblemAndOptimize(self, x0=None, params=None):
+        """PoseGraphOptimizer::setupProblemAndOptimize_gsl (global_optim_contrast_gsl.cpp:15-145) without GSL.
+        Returns (x_opt, stats dict); the caller applies x_opt with incrementalUpdate (trajectory.cpp:221-238)."""
+        n = self.n_params
+        xs = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).reshape(n)
+        out = np.zeros(max(n, 1))
+        res = _capi.OptResult()
+        prm = None if params is None else C.byref(_capi.OptParams(*params))
+        _capi.check(self._L.cmaxb_be_optimize(self._h, None if xs is None else _capi.dptr(xs), n, prm, _capi.dptr(out), C.byref(res)))
+        return out[:n], {k: getattr(res, k) for k, _ in _capi.OptResult._fields_}
+
     @property
     def alpha(self):
         a = C.c_double()

@@ -90,6 +90,16 @@ class AngVelEstimatorCMax:
         receives every evaluation's (contrast, g0, g1, g2) rows -- input of the multi-GPU collective."""
         _capi.check(self._L.cmaxb_fe_set_result_mirror(self._h, C.c_void_p(device_ptr) if device_ptr else None))
 
+    def setupProblemAndOptimize(self, ang_vel0, params=None):
+        """AngVelEstimator::setupProblemAndOptimize_gsl (local_optim_contrast_gsl.cpp:74-233) without GSL:
+        Fletcher-Reeves CG with the reference's constants.  Returns (ang_vel, stats dict)."""
+        om = np.ascontiguousarray(ang_vel0, dtype=np.float64).reshape(3)
+        out = np.zeros(3)
+        res = _capi.OptResult()
+        prm = None if params is None else C.byref(_capi.OptParams(*params))
+        _capi.check(self._L.cmaxb_fe_optimize(self._h, _capi.dptr(om), prm, _capi.dptr(out), C.byref(res)))
+        return out, {k: getattr(res, k) for k, _ in _capi.OptResult._fields_}
+
     # -- reference-named entry points ------------------------------------------------------------
     def computeImageOfWarpedEvents(self, ang_vel, with_deriv=False, blurred=True):
         """IWE (H,W) float32 [and derivative image (H,W,3)] as the reference function fills them."""

@@ -177,6 +177,30 @@ int cmaxb_be_get_cells(cmaxb_be* be, const double* x, int n, int32_t* out);
 int cmaxb_be_get_poses(cmaxb_be* be, const double* x, int n, int64_t* n_batches, double* R9,
                        float* Jk, int32_t* idx_cp_beg, int64_t capacity);
 
+/* ------------------------------------------------------------------ optimiser loop ------- */
+/* the reference's solve loops (GSL Fletcher-Reeves conjugate gradient with the
+ * reference's constants and stopping rules; local_optim_contrast_gsl.cpp:74-233,
+ * global_optim_contrast_gsl.cpp:15-145) on top of the evaluation entry points, so a whole packet / window
+ * solve needs neither GSL nor per-evaluation glue.  GSL's algorithm is restated (conjugate_fr.c,
+ * directional_minimize.c); cost = -contrast.  params == NULL selects the reference's constants. */
+typedef struct cmaxb_opt_params {
+  double initial_step;   /* 0.1 */
+  double line_tol;       /* FE 0.05, BE 0.1 */
+  int32_t max_iterations;/* 50 */
+  double epsabs_grad;    /* FE 1e-3, BE 1e-4 */
+  double tolfun;         /* 1e-4 */
+} cmaxb_opt_params;
+typedef struct cmaxb_opt_result {
+  double cost_initial, cost_final;   /* -contrast */
+  int32_t iterations, f_evals, g_evals;
+  int32_t stop_reason;               /* 0 iteration limit, 1 cost stagnation, 2 gradient norm, 3 no progress */
+} cmaxb_opt_result;
+int cmaxb_fe_optimize(cmaxb_fe* fe, const double omega0[3], const cmaxb_opt_params* params, double omega_out[3],
+                      cmaxb_opt_result* result);
+/* x0 == NULL: start from zero increments (global_optim_contrast_gsl.cpp:36-37) */
+int cmaxb_be_optimize(cmaxb_be* be, const double* x0, int n, const cmaxb_opt_params* params, double* x_out,
+                      cmaxb_opt_result* result);
+
 /* ------------------------------------------------------------------ diagnostics ---------- */
 const char* cmaxb_last_error(void);
 int cmaxb_version(void);
