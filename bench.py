@@ -215,10 +215,6 @@ def run_ours(args, rank, world, local_rank):
         c, g = fe.eval_fetch()
         return c[0], g[0]
 
-    def step_e2e():
-        fe.set_packet(ev_host, pkt.t_ref_sec)  # H2D of the packet from pinned memory + validation
-        return step_resident()
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -271,10 +267,53 @@ def run_ours(args, rank, world, local_rank):
     value = world * n_ev / (ms_per_step * 1e-3)
     # same loop without the L2 flush (the optimiser's real regime: ~100-300 evals per packet, L2 warm)
     warm_ms, _, _, _ = timed(step_resident, K, 3, False)
-    # end to end through the C ABI with host buffers
+    # End to end through the C ABI with HOST buffers: every step uploads its 16 MB packet from pinned host memory
+    # (cmaxb_fe_set_packet_async: H2D copy + validation + batch table + binning), evaluates contrast + gradient and
+    # reads the result back.  Two handles on two streams are used alternately so that the upload of step i+1 overlaps
+    # the evaluation of step i (what a front-end thread does with the next packet); everything -- copies, L2 flush,
+    # kernels, collective -- is inside the timed span [start event, end event].
+    stream2 = torch.cuda.Stream(device=dev)
+    fe2 = AngVelEstimatorCMax(pkt.width, pkt.height, pkt.K, pkt.lut, blur_sigma=pkt.blur_sigma,
+                              event_batch_size=pkt.batch_size, grad_mode=grad_mode, device=local_rank,
+                              stream=stream2.cuda_stream)
+    mine2 = torch.zeros(4, dtype=torch.float64, device=dev)
+    if world > 1:
+        fe2.set_result_mirror(mine2.data_ptr())
+    lanes = [(fe, stream, mine), (fe2, stream2, mine2)]
+
+    def e2e_run(steps, warmup):
+        total = steps + warmup
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        lanes[0][0].set_packet(ev_host, pkt.t_ref_sec, wait=False)
+        for i in range(total):
+            cur, nxt = lanes[i % 2], lanes[(i + 1) % 2]
+            if i == warmup:
+                barrier()
+                t0.record(cur[1])
+            if i + 1 < total:
+                nxt[0].set_packet(ev_host, pkt.t_ref_sec, wait=False)      # upload of the NEXT step's packet
+            with torch.cuda.stream(cur[1]):
+                flush.fill_(float(i))                                        # L2 flush, inside the timed span
+                cur[0].eval_launch(omega[None, :], True)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered.view(-1), cur[2])
+                cur[0].eval_fetch()
+            if i == total - 1:
+                t1.record(cur[1])
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     e2e_steps = max(10, min(K, 200))
-    e2e_ms, _, _, _ = timed(step_e2e, e2e_steps, 3, True)
+    e2e_ms = e2e_run(e2e_steps, 3)
     e2e_value = world * n_ev / (e2e_ms / e2e_steps * 1e-3)
+    torch.cuda.set_stream(stream)
+    fe.set_packet(ev_host, pkt.t_ref_sec)      # back to the resident packet for the profiled pass
 
     # per-kernel device times (CUDA events on the launching stream, library profiler), rank 0
     fe.profile(True)
@@ -318,7 +357,8 @@ def run_ours(args, rank, world, local_rank):
                         "note": "no L2 flush between iterations (optimiser regime)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_ev + 24, "d2h_bytes_per_step": 32 + 4,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "path": "cmaxb_fe_set_packet(pinned host events) + cmaxb_fe_eval through the C ABI"},
+                    "path": "cmaxb_fe_set_packet_async(pinned host events) + cmaxb_fe_eval through the C ABI; uploads double-buffered "
+                            "(two handles / streams), L2 flush inside the timed span"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -336,6 +376,7 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
         print(json.dumps(line), flush=True)
     fe.close()
+    fe2.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

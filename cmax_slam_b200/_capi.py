@@ -58,10 +58,12 @@ class BeWindow(C.Structure):
 
 # every symbol include/cmax_b200.h declares
 EXPORTS = [
-    "cmaxb_fe_create", "cmaxb_fe_destroy", "cmaxb_fe_set_packet", "cmaxb_fe_eval", "cmaxb_fe_eval_batch",
+    "cmaxb_fe_create", "cmaxb_fe_destroy", "cmaxb_fe_set_packet", "cmaxb_fe_set_packet_async", "cmaxb_fe_eval", "cmaxb_fe_eval_batch",
     "cmaxb_fe_eval_launch", "cmaxb_fe_eval_fetch", "cmaxb_fe_set_result_mirror", "cmaxb_fe_get_iwe", "cmaxb_fe_get_deriv", "cmaxb_fe_get_cells",
     "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_eval_begin", "cmaxb_be_il_plane", "cmaxb_be_eval_end", "cmaxb_be_get_alpha",
     "cmaxb_be_get_il", "cmaxb_be_get_iwe", "cmaxb_be_get_bands", "cmaxb_be_get_cells", "cmaxb_be_get_poses",
+    "cmaxb_be_map_reset", "cmaxb_be_map_set", "cmaxb_be_map_get", "cmaxb_be_map_use_as_igp", "cmaxb_be_map_update",
+    "cmaxb_be_map_mark_fov",
     "cmaxb_fe_optimize", "cmaxb_be_optimize",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
     "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_fe_phase_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
@@ -82,6 +84,7 @@ def lib():
     L.cmaxb_fe_destroy.argtypes = [vp]
     L.cmaxb_fe_destroy.restype = None
     L.cmaxb_fe_set_packet.argtypes = [vp, vp, C.c_size_t, C.c_double]
+    L.cmaxb_fe_set_packet_async.argtypes = [vp, vp, C.c_size_t, C.c_double]
     L.cmaxb_fe_eval.argtypes = [vp, dp, dp, dp]
     L.cmaxb_fe_eval_batch.argtypes = [vp, dp, C.c_int, dp, dp]
     L.cmaxb_fe_eval_launch.argtypes = [vp, dp, C.c_int, C.c_int]
@@ -90,6 +93,12 @@ def lib():
     L.cmaxb_fe_get_iwe.argtypes = [vp, dp, C.c_int, vp]
     L.cmaxb_fe_get_deriv.argtypes = [vp, dp, C.c_int, vp]
     L.cmaxb_fe_get_cells.argtypes = [vp, dp, vp]
+    L.cmaxb_be_map_reset.argtypes = [vp]
+    L.cmaxb_be_map_set.argtypes = [vp, vp, vp]
+    L.cmaxb_be_map_get.argtypes = [vp, vp, vp]
+    L.cmaxb_be_map_use_as_igp.argtypes = [vp, C.c_double]
+    L.cmaxb_be_map_update.argtypes = [vp, dp, C.c_int, C.c_int]
+    L.cmaxb_be_map_mark_fov.argtypes = [vp, dp, C.c_int, C.c_int]
     L.cmaxb_fe_optimize.argtypes = [vp, dp, C.POINTER(OptParams), dp, C.POINTER(OptResult)]
     L.cmaxb_be_optimize.argtypes = [vp, dp, C.c_int, C.POINTER(OptParams), dp, C.POINTER(OptResult)]
     L.cmaxb_last_error.restype = C.c_char_p

@@ -108,6 +108,35 @@ class EventWarperCMax:
         _capi.check(self._L.cmaxb_be_eval_end(self._h, C.byref(c), _capi.dptr(g) if self._split_grad else None))
         return c.value, (g[: self.n_params] if self._split_grad else None)
 
+    # -- device-resident global map (event_pano_warper.cpp:81-132) --------------------------------------------
+    def resetIG(self):
+        _capi.check(self._L.cmaxb_be_map_reset(self._h))
+
+    def setMap(self, IG=None, visit_counts=None):
+        ig = None if IG is None else np.ascontiguousarray(IG, dtype=np.float32)
+        vc = None if visit_counts is None else np.ascontiguousarray(visit_counts, dtype=np.uint8)
+        _capi.check(self._L.cmaxb_be_map_set(self._h, None if ig is None else C.c_void_p(ig.ctypes.data),
+                                             None if vc is None else C.c_void_p(vc.ctypes.data)))
+
+    def getIG(self):
+        """(IG_ float32 pano, IG_update_times_map_ uint8 pano)"""
+        ig = np.empty((self.pano_height, self.pano_width), np.float32)
+        vc = np.empty((self.pano_height, self.pano_width), np.uint8)
+        _capi.check(self._L.cmaxb_be_map_get(self._h, C.c_void_p(ig.ctypes.data), C.c_void_p(vc.ctypes.data)))
+        return ig, vc
+
+    def updateIGp(self, alpha=float("nan")):
+        """IGp <- IG on the device (after set_window); alpha NaN => updateAlpha on the first evaluation."""
+        _capi.check(self._L.cmaxb_be_map_use_as_igp(self._h, float(alpha)))
+
+    def updateIG(self, x_opt=None, max_update_times=10):
+        xx, n = self._x(x_opt)
+        _capi.check(self._L.cmaxb_be_map_update(self._h, None if xx is None else _capi.dptr(xx), n, int(max_update_times)))
+
+    def setUpdateTimesIG(self, rots_xyzw, radius=3):
+        q = np.ascontiguousarray(rots_xyzw, dtype=np.float64).reshape(-1, 4)
+        _capi.check(self._L.cmaxb_be_map_mark_fov(self._h, _capi.dptr(q), q.shape[0], int(radius)))
+
     def setupProblemAndOptimize(self, x0=None, params=None):
         """PoseGraphOptimizer::setupProblemAndOptimize_gsl (global_optim_contrast_gsl.cpp:15-145) without GSL.
         Returns (x_opt, stats dict); the caller applies x_opt with incrementalUpdate (trajectory.cpp:221-238)."""

@@ -30,6 +30,8 @@ struct cmaxb_be {
   bool use_quad = false; bool il_is_quad = false;
   float* d_il_plane = nullptr; bool il_is_plane = false;   // assembled IL (event-sharded evaluation)
   bool split_pending = false; bool split_grad = false;
+  // device-resident global map (IG_, IG_update_times_map_)
+  float* d_IG = nullptr; unsigned char* d_times = nullptr; unsigned char* d_mask = nullptr;
   int* d_ccell = nullptr; float4* d_ca = nullptr; float4* d_cb = nullptr; size_t cache_cap = 0;   // per-event gather cache
   long long n_visit = 0; int m_visit = 1;
   float* d_bands = nullptr; float* d_bands_blur = nullptr; size_t bands_cap = 0;
@@ -128,6 +130,7 @@ extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
   cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
   cudaFree(be->d_bands); cudaFree(be->d_bands_blur); cudaFree(be->d_ilq); cudaFree(be->d_GQ);
   cudaFree(be->d_ccell); cudaFree(be->d_ca); cudaFree(be->d_cb); cudaFree(be->d_il_plane);
+  cudaFree(be->d_IG); cudaFree(be->d_times); cudaFree(be->d_mask);
 
   cudaFree(be->d_acc); cudaFree(be->d_ticket); cudaFree(be->d_result); cudaFree(be->d_mean);
   cudaFree(be->d_bacc); cudaFree(be->d_bticket); cudaFree(be->d_bresult); cudaFree(be->d_bmean);
@@ -600,6 +603,96 @@ extern "C" int cmaxb_be_get_poses(cmaxb_be* be, const double* x, int n, int64_t*
     if (Jk) for (int i = 0; i < nj; ++i) Jk[nj * b + i] = h[b].Jk[i];
     if (idx_cp_beg) idx_cp_beg[b] = h[b].idx_cp_beg;
   }
+  return CMAXB_OK;
+}
+
+// ---- device-resident global map: IG_ and IG_update_times_map_ stay in HBM between windows -------------------
+static int be_map_ensure(cmaxb_be* be) {
+  if (be->d_IG) return CMAXB_OK;
+  CMAXB_TRY(dev_alloc(&be->d_IG, (size_t)be->A));
+  CMAXB_TRY(dev_alloc(&be->d_times, (size_t)be->A));
+  CMAXB_TRY(dev_alloc(&be->d_mask, (size_t)be->A));
+  CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_IG, 0, sizeof(float) * be->A, be->stream));
+  CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_times, 0, (size_t)be->A, be->stream));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_map_reset(cmaxb_be* be) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_map_ensure(be));
+  CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_IG, 0, sizeof(float) * be->A, be->stream));
+  CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_times, 0, (size_t)be->A, be->stream));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(be->stream));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_map_set(cmaxb_be* be, const float* IG, const uint8_t* times) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_map_ensure(be));
+  if (IG) CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_IG, IG, sizeof(float) * be->A, cudaMemcpyHostToDevice, be->stream));
+  if (times) CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_times, times, (size_t)be->A, cudaMemcpyHostToDevice, be->stream));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(be->stream));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_map_get(cmaxb_be* be, float* IG, uint8_t* times) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_map_ensure(be));
+  if (IG) CMAXB_CUDA_TRY(cudaMemcpyAsync(IG, be->d_IG, sizeof(float) * be->A, cudaMemcpyDeviceToHost, be->stream));
+  if (times) CMAXB_CUDA_TRY(cudaMemcpyAsync(times, be->d_times, (size_t)be->A, cudaMemcpyDeviceToHost, be->stream));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(be->stream));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_map_use_as_igp(cmaxb_be* be, double alpha) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window: call cmaxb_be_set_window first");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_map_ensure(be));
+  // updateIGp: IGp <- IG (event_pano_warper.cpp:128-132), device to device
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_igp, be->d_IG, sizeof(float) * be->A, cudaMemcpyDeviceToDevice, be->stream));
+  be->have_igp = true;
+  if (std::isnan(alpha)) { be->alpha = 0.0; be->alpha_pending = true; }
+  else { be->alpha = alpha; be->alpha_pending = false; }
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_map_update(cmaxb_be* be, const double* x, int n, int max_update_times) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window: call cmaxb_be_set_window first");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_map_ensure(be));
+  // IL_old_ at the optimum, then updateIG (event_pano_warper.cpp:109-126)
+  CMAXB_TRY(be_run_poses(be, x, n, false));
+  CMAXB_TRY(be_run_scatter(be, false, false, /*defer_alpha=*/true));
+  cudaStream_t s = be->stream;
+  CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+    be_update_ig_kernel<<<148 * 8, 256, 0, s>>>(be->d_IG, be->d_il_old, be->d_times, max_update_times, be->A);
+  }));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_map_mark_fov(cmaxb_be* be, const double* rot_xyzw, int m, int radius) {
+  if (!be || (!rot_xyzw && m > 0) || radius < 0) return set_error(CMAXB_ERR_INVALID, "bad argument");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_map_ensure(be));
+  cudaStream_t s = be->stream;
+  const BeGeom g = be_geom(be);
+  for (int i = 0; i < m; ++i) {   // one setUpdateTimesIG(rot_check, radius) per pose (pose_graph_optimizer.cpp:325-337)
+    Quat q; q.x = rot_xyzw[4 * i]; q.y = rot_xyzw[4 * i + 1]; q.z = rot_xyzw[4 * i + 2]; q.w = rot_xyzw[4 * i + 3];
+    CMAXB_CUDA_TRY(cudaMemsetAsync(be->d_mask, 0, (size_t)be->A, s));
+    CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+      be_fov_mask_kernel<<<(unsigned)((be->SA + 255) / 256), 256, 0, s>>>(g, q, radius, be->d_mask);
+    }));
+    CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+      be_times_add_kernel<<<148 * 8, 256, 0, s>>>(be->d_times, be->d_mask, be->A);
+    }));
+  }
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
   return CMAXB_OK;
 }
 

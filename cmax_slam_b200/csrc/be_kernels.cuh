@@ -422,6 +422,47 @@ be_band_reduce_kernel(const float* __restrict__ I, const float* __restrict__ ban
   }
 }
 
+// ---- global-map upkeep (event_pano_warper.cpp:81-132) ---------------------------
+// EventWarper::setUpdateTimesIG(rot, radius): rasterise the sensor's field of view at pose `rot` into a 0/1 mask
+// (every sensor pixel warped with warpEventToMap, dilated by `radius`, including the reference's
+// `0 <= y_mask + j` bound), one thread per sensor pixel.  Stores of 1 are idempotent: no atomics.
+__global__ void __launch_bounds__(256)
+be_fov_mask_kernel(BeGeom g, Quat rot, int radius, unsigned char* __restrict__ mask) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)g.SW * g.SH) return;
+  const Mat3 Rm = quat_to_mat(rot);
+  const double2* lp = reinterpret_cast<const double2*>(g.lut + i);
+  const double2 bxy = __ldg(lp);
+  const double bz = __ldg(reinterpret_cast<const double*>(lp + 1));
+  const double wx = Rm.m[0] * bxy.x + Rm.m[1] * bxy.y + Rm.m[2] * bz;
+  const double wy = Rm.m[3] * bxy.x + Rm.m[4] * bxy.y + Rm.m[5] * bz;
+  const double wz = Rm.m[6] * bxy.x + Rm.m[7] * bxy.y + Rm.m[8] * bz;
+  const double phi = atan2(wx, wz);
+  const double theta = asin(wy / sqrt(wx * wx + wy * wy + wz * wz));
+  const double px = g.cx + phi * g.fx, py = g.cy + theta * g.fy;
+  if (!(fabs(px) < 2e9 && fabs(py) < 2e9)) return;
+  const int ic = (int)px, ir = (int)py;                                   // (:91)
+  for (int a = -radius; a <= radius; ++a)
+    for (int j = -radius; j <= radius; ++j) {
+      const int x_mask = ic + a, y_mask = ir + j;
+      if (0 <= y_mask + j && y_mask >= 0 && y_mask < g.H && 0 <= x_mask && x_mask < g.W)   // (:97; y_mask >= 0 guards the store)
+        mask[(long long)y_mask * g.W + x_mask] = 1;
+    }
+}
+// cv::add(IG_update_times_map_, mask, IG_update_times_map_) on CV_8U saturates            (:106)
+__global__ void be_times_add_kernel(unsigned char* __restrict__ times, const unsigned char* __restrict__ mask, long long A) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)times[i] + (int)mask[i];
+    times[i] = (unsigned char)(v > 255 ? 255 : v);
+  }
+}
+// EventWarper::updateIG: IG += IL_old where the pixel has been visited at most max_update_times times   (:109-126)
+__global__ void be_update_ig_kernel(float* __restrict__ IG, const float* __restrict__ il_old, const unsigned char* __restrict__ times,
+                                    int max_update_times, long long A) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A; i += (long long)gridDim.x * blockDim.x)
+    if ((int)times[i] <= max_update_times) IG[i] += il_old[i];
+}
+
 // IL as one float plane (from the corner-split accumulator or from IL_old + IL_new): the buffer that is
 // summed across GPUs when one window is sharded by time.
 __global__ void __launch_bounds__(256)

@@ -26,7 +26,7 @@ struct cmaxb_fe {
   uint2* d_bev = nullptr; size_t bev_cap = 0; bool have_bins = false; bool use_bins = true;   // spatially binned copy of the packet
   unsigned int* d_tile_count = nullptr; unsigned int* d_tile_cursor = nullptr; int ntiles = 0, ntx = 0;
   long long n = 0, nb = 0;
-  bool have_packet = false;
+  bool have_packet = false; bool flags_pending = false;
   int* d_flags = nullptr; int* h_flags = nullptr;
   // value accumulators: two corner-split ("quad") images used alternately; the blur kernel of one
   // evaluation clears the image the next evaluation scatters into (no memset in steady state)
@@ -188,7 +188,16 @@ extern "C" void cmaxb_fe_destroy(cmaxb_fe* fe) {
   delete fe;
 }
 
-extern "C" int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec) {
+static int fe_check_packet_flags(cmaxb_fe* fe) {
+  // validation result of an asynchronous set_packet (its D2H copy precedes every later operation on the stream)
+  if (!fe->flags_pending) return CMAXB_OK;
+  fe->flags_pending = false;
+  if (*fe->h_flags & 2) { fe->have_packet = false; return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor"); }
+  if (*fe->h_flags & 1) { fe->have_packet = false; return set_error(CMAXB_ERR_TIME_ORDER, "Events must span a non-negative time interval"); }
+  return CMAXB_OK;
+}
+
+static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec, bool wait) {
   if (!fe || (!events && n > 0)) return set_error(CMAXB_ERR_INVALID, "null argument");
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
   if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream)); fe->pending = false; }
@@ -247,12 +256,23 @@ extern "C" int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size
       fe->have_bins = true;
     }
     CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->h_flags, fe->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
-    if (*fe->h_flags & 2) return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor");
-    if (*fe->h_flags & 1) return set_error(CMAXB_ERR_TIME_ORDER, "Events must span a non-negative time interval");
+    fe->flags_pending = true;
+    fe->have_packet = true;
+    if (wait) {
+      CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+      return fe_check_packet_flags(fe);
+    }
+    return CMAXB_OK;
   }
   fe->have_packet = true;
   return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec) {
+  return fe_set_packet_impl(fe, events, n, t_ref_sec, true);
+}
+extern "C" int cmaxb_fe_set_packet_async(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec) {
+  return fe_set_packet_impl(fe, events, n, t_ref_sec, false);
 }
 
 static int fe_upload_omegas(cmaxb_fe* fe, const double* omegas, int k) {
@@ -436,6 +456,7 @@ extern "C" int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grad
     CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
   }
   fe->pending = false;
+  CMAXB_TRY(fe_check_packet_flags(fe));
   const double* res = fe->last_mega ? fe->h_mega_result : fe->h_result;
   for (int h = 0; h < fe->last_k; ++h) {
     contrasts[h] = res[4 * h];
@@ -531,11 +552,6 @@ extern "C" int cmaxb_fe_set_result_mirror(cmaxb_fe* fe, double* device_ptr) {
 extern "C" int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10) {
   if (!fe || !us10) return set_error(CMAXB_ERR_INVALID, "null argument");
   CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
-  if (getenv("CMAXB_DEBUG_STAGES")) {   // developer aid: blur-stage stamps of CTA 0 (slots 10..15)
-    std::fprintf(stderr, "blur stages (us from entry):");
-    for (int i = 10; i < 16; ++i) std::fprintf(stderr, " %.2f", (double)(fe->h_phase[i] - fe->h_phase[0]) * 1e-3);
-    std::fprintf(stderr, "\n");
-  }
   for (int i = 0; i < 10; ++i)
     us10[i] = (fe->h_phase && fe->h_phase[i] && fe->h_phase[0]) ? (double)(fe->h_phase[i] - fe->h_phase[0]) * 1e-3 : -1.0;
   return CMAXB_OK;

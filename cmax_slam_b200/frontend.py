@@ -44,9 +44,10 @@ class AngVelEstimatorCMax:
     __del__ = close
 
     # -- packet ---------------------------------------------------------------------------------
-    def set_packet(self, events, t_ref_sec):
+    def set_packet(self, events, t_ref_sec, wait=True):
         """events: numpy structured array with the 16-byte dvs_msgs::Event layout (synth.EVENT_DTYPE)
-        or a (ptr, n) tuple of pinned host memory; t_ref_sec = time_packet_.toSec()."""
+        or a (ptr, n) tuple of pinned host memory; t_ref_sec = time_packet_.toSec().  wait=False queues the
+        upload and returns (the validation verdict comes with the next evaluation)."""
         if isinstance(events, tuple):
             ptr, n = events
         else:
@@ -55,7 +56,8 @@ class AngVelEstimatorCMax:
                 raise ValueError("events must be 16-byte dvs_msgs::Event records")
             self._ev_keep = ev
             ptr, n = ev.ctypes.data, len(ev)
-        _capi.check(self._L.cmaxb_fe_set_packet(self._h, C.c_void_p(ptr), n, float(t_ref_sec)))
+        fn = self._L.cmaxb_fe_set_packet if wait else self._L.cmaxb_fe_set_packet_async
+        _capi.check(fn(self._h, C.c_void_p(ptr), n, float(t_ref_sec)))
         self.n_events = n
 
     # -- cost ------------------------------------------------------------------------------------

@@ -84,6 +84,11 @@ void cmaxb_fe_destroy(cmaxb_fe* fe);
  * and its reference time time_packet_.toSec().  `events` is host memory (pinned memory makes
  * the copy asynchronous).  Validates pixel range and batch time order. */
 int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec);
+/* Same, but returns as soon as the copy and the preparation kernels are queued on the handle's stream (events
+ * must stay valid -- pinned -- until the next call that waits).  The validation verdict is delivered by the next
+ * cmaxb_fe_eval / cmaxb_fe_eval_fetch.  Lets the upload of packet i+1 (on another handle / stream) overlap the
+ * evaluations of packet i. */
+int cmaxb_fe_set_packet_async(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec);
 
 /* One cost evaluation = computeImageOfWarpedEvents + computeContrast.  grad3 == NULL => value
  * only (the local_contrast_f path, local_optim_contrast_gsl.cpp:58-63). */
@@ -176,6 +181,23 @@ int cmaxb_be_get_cells(cmaxb_be* be, const double* x, int n, int32_t* out);
  * idx_cp_beg.  Parity / debugging of the device So3Spline. Arrays sized n_batches. */
 int cmaxb_be_get_poses(cmaxb_be* be, const double* x, int n, int64_t* n_batches, double* R9,
                        float* Jk, int32_t* idx_cp_beg, int64_t capacity);
+
+/* ------------------------------------------------------------------ global map upkeep ---- */
+/* IG_ and IG_update_times_map_ (event_pano_warper.h) kept in HBM between windows, so a
+ * window neither uploads a panorama (IGp) nor downloads IL_old:
+ *   cmaxb_be_map_reset      resetIG + zero visit counts                      event_pano_warper.h:56, .cpp:21-28
+ *   cmaxb_be_map_set / _get host <-> device copy of IG (pano floats) and the visit counts (pano bytes); NULL = skip
+ *   cmaxb_be_map_use_as_igp after set_window: IGp <- IG on the device (updateIGp, .cpp:128-132); alpha as in
+ *                           cmaxb_be_window.alpha (NaN => updateAlpha on the first evaluation)
+ *   cmaxb_be_map_update     IG += IL_old(x) where visits <= max_update_times (updateIG, .cpp:109-126)
+ *   cmaxb_be_map_mark_fov   setUpdateTimesIG(rot, radius) for m poses (x,y,z,w): sensor FOV raster dilated by
+ *                           radius, added (saturating) to the visit counts   (.cpp:81-107, pose_graph_optimizer.cpp:325-337) */
+int cmaxb_be_map_reset(cmaxb_be* be);
+int cmaxb_be_map_set(cmaxb_be* be, const float* IG, const uint8_t* visit_counts);
+int cmaxb_be_map_get(cmaxb_be* be, float* IG, uint8_t* visit_counts);
+int cmaxb_be_map_use_as_igp(cmaxb_be* be, double alpha);
+int cmaxb_be_map_update(cmaxb_be* be, const double* x, int n, int max_update_times);
+int cmaxb_be_map_mark_fov(cmaxb_be* be, const double* rot_xyzw, int m, int radius);
 
 /* ------------------------------------------------------------------ optimiser loop ------- */
 /* the reference's solve loops (GSL Fletcher-Reeves conjugate gradient with the

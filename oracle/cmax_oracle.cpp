@@ -745,6 +745,41 @@ extern "C" int orc_be_eval(const orc_be_args* a, const double* x, int want_grad,
   return 0;
 }
 
+// EventWarper::setUpdateTimesIG(rot, radius) (event_pano_warper.cpp:81-107) with warpEventToMap (:37-54)
+extern "C" void orc_set_update_times(const double* lut_xyz, int SW, int SH, int PW, int PH, const double rot_xyzw[4],
+                                     int radius, uint8_t* times) {
+  std::vector<uint8_t> mask((size_t)PW * PH, 0);
+  const M3 R = qmat(Quat{rot_xyzw[0], rot_xyzw[1], rot_xyzw[2], rot_xyzw[3]});
+  const double cxp = (double)PW / 2.0, cyp = (double)PH / 2.0;
+  const double fx = double((PW / 360.0) * 180.0 / M_PI), fy = double((PH / 180.0) * 180.0 / M_PI);
+  for (int x = 0; x < SW; ++x)
+    for (int y = 0; y < SH; ++y) {
+      const double* b = lut_xyz + 3 * ((size_t)y * SW + x);
+      const double wx = R(0, 0) * b[0] + R(0, 1) * b[1] + R(0, 2) * b[2];
+      const double wy = R(1, 0) * b[0] + R(1, 1) * b[1] + R(1, 2) * b[2];
+      const double wz = R(2, 0) * b[0] + R(2, 1) * b[1] + R(2, 2) * b[2];
+      const double phi = std::atan2(wx, wz);
+      const double theta = std::asin(wy / std::sqrt(wx * wx + wy * wy + wz * wz));
+      const double px = cxp + phi * fx, py = cyp + theta * fy;
+      const int ic = (int)px, ir = (int)py;                                          // :91
+      for (int i = -radius; i <= radius; i++)
+        for (int j = -radius; j <= radius; j++) {
+          const int x_mask = ic + i, y_mask = ir + j;
+          // :97 as written (`0 <= y_mask+j`); y_mask >= 0 added: Mat::at with a negative row is out of bounds
+          if (0 <= y_mask + j && y_mask >= 0 && y_mask < PH && 0 <= x_mask && x_mask < PW) mask[(size_t)y_mask * PW + x_mask] = 1;
+        }
+    }
+  for (size_t i = 0; i < mask.size(); ++i) {                                          // cv::add on CV_8U saturates (:106)
+    const int v = (int)times[i] + (int)mask[i];
+    times[i] = (uint8_t)(v > 255 ? 255 : v);
+  }
+}
+// EventWarper::updateIG (event_pano_warper.cpp:109-126)
+extern "C" void orc_update_ig(float* IG, const float* il_old, const uint8_t* times, int max_update_times, int64_t n) {
+  for (int64_t i = 0; i < n; ++i)
+    if ((int)times[i] <= max_update_times) IG[i] += il_old[i];
+}
+
 // ================================================================================================
 // Building blocks for the pinning tests
 // ================================================================================================

@@ -98,6 +98,11 @@ int orc_be_eval(const orc_be_args* a, const double* x, int want_grad, orc_be_out
 /* EventWarper::updateAlpha (event_pano_warper.cpp:134-165) */
 double orc_update_alpha(const float* IGp, const float* IL, int64_t n_px);
 
+/* map upkeep: EventWarper::setUpdateTimesIG (event_pano_warper.cpp:81-107), updateIG (:109-126) */
+void orc_set_update_times(const double* lut_xyz, int SW, int SH, int PW, int PH, const double rot_xyzw[4], int radius,
+                          uint8_t* times);
+void orc_update_ig(float* IG, const float* il_old, const uint8_t* times, int max_update_times, int64_t n);
+
 /* building blocks exposed for pinning tests */
 int orc_gaussian_kernel(double sigma, float* taps /* >= 64 */);                 /* returns ksize */
 void orc_gaussian_blur(const float* src, float* dst, int W, int H, int C, double sigma);

@@ -254,6 +254,28 @@ def ref_spline_eval(order, knots, t0_ns, dt_ns, t_ns, want_J=True):
     return _spline_eval(ref().ref_so3_spline_eval, order, knots, t0_ns, dt_ns, t_ns, want_J)
 
 
+def set_update_times(lut, SW, SH, PW, PH, rot_xyzw, radius, times):
+    """in place on `times` (uint8 [PH,PW])"""
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    q = np.ascontiguousarray(rot_xyzw, dtype=np.float64)
+    assert times.dtype == np.uint8 and times.flags.c_contiguous
+    L = lib()
+    L.orc_set_update_times.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_void_p]
+    L.orc_set_update_times.restype = None
+    L.orc_set_update_times(_d(lut), SW, SH, PW, PH, _d(q), int(radius), times.ctypes.data)
+
+
+def update_ig(IG, il_old, times, max_update_times):
+    """in place on IG (float32)"""
+    assert IG.dtype == np.float32 and IG.flags.c_contiguous
+    il = np.ascontiguousarray(il_old, dtype=np.float32)
+    t = np.ascontiguousarray(times, dtype=np.uint8)
+    L = lib()
+    L.orc_update_ig.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64]
+    L.orc_update_ig.restype = None
+    L.orc_update_ig(IG.ctypes.data, il.ctypes.data, t.ctypes.data, int(max_update_times), IG.size)
+
+
 def update_alpha(IGp, IL):
     a = np.ascontiguousarray(IGp, dtype=np.float32)
     b = np.ascontiguousarray(IL, dtype=np.float32)
