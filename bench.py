@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
                     for bit, nm in names.items():
                         if r & bit and nm != "gpu_idle":
                             self.reasons.add(nm)
-                time.sleep(0.02)
+                time.sleep(0.004)
         except Exception as e:  # NVML missing: report that, never fake
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -290,6 +290,7 @@ def run_ours(args, rank, world, local_rank):
             cur, nxt = lanes[i % 2], lanes[(i + 1) % 2]
             if i == warmup:
                 barrier()
+                sampler.active = True
                 t0.record(cur[1])
             if i + 1 < total:
                 nxt[0].set_packet(ev_host, pkt.t_ref_sec, wait=False)      # upload of the NEXT step's packet
@@ -302,6 +303,7 @@ def run_ours(args, rank, world, local_rank):
             if i == total - 1:
                 t1.record(cur[1])
         barrier()
+        sampler.active = False
         ms = t0.elapsed_time(t1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)

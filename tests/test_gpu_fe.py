@@ -199,3 +199,44 @@ def test_native_library_is_what_ran():
     fe.close()
     assert _capi.launch_count() - n0 >= 3      # validate + batch-dt kernels + the fused evaluation kernel
     assert "libcmax_b200.so" in open("/proc/self/maps").read()
+
+
+def test_fe_more_hypotheses_than_one_launch_holds(oracle):
+    """k = 40 > 32 hypotheses: the fused kernel is launched in chunks; rows must line up with the single evaluations."""
+    pk = synth.fe_config("C1", scale=0.1)
+    fe = _mk(pk, max_hypotheses=40)
+    oms = synth.fe_hypotheses(pk, 40, sigma=0.3)
+    c, g = fe.eval_batch(oms, True)
+    a = oracle.fe_args(pk.events, pk.t_ref_sec, pk.lut, pk.width, pk.height, pk.K)
+    co, go = oracle.fe_eval_batch(a, oms, True, n_threads=8)
+    assert np.abs(c - co).max() <= RTOL * np.abs(co).max()
+    assert np.abs(g - go).max() <= RTOL * np.abs(go).max()
+    cv, _ = fe.eval_batch(oms[:33], False)
+    assert np.abs(cv - co[:33]).max() <= RTOL * np.abs(co).max()
+    fe.close()
+
+
+def test_fe_async_packet_upload_and_deferred_verdict(oracle):
+    """cmaxb_fe_set_packet_async: evaluation right after the queued upload; a bad packet is reported by the
+    next evaluation instead of by set_packet."""
+    from cmax_slam_b200._capi import CmaxbError
+    pk = synth.fe_config("C1", scale=0.1)
+    fe = _mk(pk)
+    om = pk.omega_true + 0.1
+    a = oracle.fe_args(pk.events, pk.t_ref_sec, pk.lut, pk.width, pk.height, pk.K)
+    ro = oracle.fe_eval(a, om, True)
+    fe.set_packet(pk.events, pk.t_ref_sec, wait=False)
+    c, g = fe.eval(om, True)
+    assert abs(c - ro["contrast"]) <= RTOL * ro["contrast"] and np.abs(g - ro["grad"]).max() <= RTOL * np.abs(ro["grad"]).max()
+    bad = pk.events.copy(); bad["x"][11] = pk.width
+    fe.set_packet(bad, pk.t_ref_sec, wait=False)            # accepted: nothing has been checked yet
+    with pytest.raises(CmaxbError) as e:
+        fe.eval(om, True)
+    assert e.value.code == -3
+    with pytest.raises(CmaxbError) as e:                     # the packet is now marked unusable
+        fe.eval(om, True)
+    assert e.value.code == -6
+    fe.set_packet(pk.events, pk.t_ref_sec)
+    c2, _ = fe.eval(om, False)
+    assert abs(c2 - ro["contrast"]) <= RTOL * ro["contrast"]
+    fe.close()
