@@ -208,12 +208,28 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         fe.set_result_mirror(mine.data_ptr())
 
-    def step_resident():
+    use_p2p = world > 1 and args.collective == "p2p"
+    if use_p2p:
+        # fused compute + all-gather: the evaluation kernel stores its row into every peer's exchange buffer over
+        # NVLink (CUDA IPC mappings) and returns the rows of all ranks -- no separate collective launch
+        fe.exchange_connect(gathered_dev_ptr=gathered.data_ptr())
+        fe.set_result_mirror(None)
+
+    def launch_step():
         fe.eval_launch(omega[None, :], True)
-        if world > 1:
+        if world > 1 and not use_p2p:
             dist.all_gather_into_tensor(gathered.view(-1), mine)
+
+    def fetch_step():
+        if use_p2p:
+            rows = fe.eval_fetch_all()
+            return rows[rank, 0, 0], rows[rank, 0, 1:]
         c, g = fe.eval_fetch()
         return c[0], g[0]
+
+    def step_resident():
+        launch_step()
+        return fetch_step()
 
     def barrier():
         if world > 1:
@@ -223,21 +239,33 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    def timed(step_fn, steps, warmup, do_flush):
+    def timed(steps, warmup, do_flush, depth):
+        """K steps, each bracketed by CUDA events on the launching stream.  depth = evaluations queued on the
+        stream before the oldest result is read back (1: the host waits for every result before the next launch
+        -- the latency of one GSL callback; >= 2: consecutive evaluations run back to back on the device, the
+        host reads result i while evaluation i+1 runs -- throughput).  Every result is fetched inside the region."""
         for _ in range(warmup):
-            step_fn()
+            step_resident()
         barrier()
         ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         launches0 = _capi.launch_count()
         sampler.active = True
         wall0 = time.perf_counter()
+        outstanding = 0
         for i in range(steps):
             if do_flush:
                 flush.fill_(float(i))     # evict L2 between timed iterations (outside the event pair)
             ev0[i].record(stream)
-            step_fn()
+            launch_step()
             ev1[i].record(stream)
+            outstanding += 1
+            if outstanding >= depth:
+                fetch_step()
+                outstanding -= 1
+        while outstanding:
+            fetch_step()
+            outstanding -= 1
         barrier()
         wall = time.perf_counter() - wall0
         sampler.active = False
@@ -254,19 +282,36 @@ def run_ours(args, rank, world, local_rank):
         return total_ms, launches, wall, ms
 
     # sanity: the collective really delivers every rank's row
-    c_chk, g_chk = step_resident()
-    barrier()
-    if world > 1:
-        rows = gathered.cpu().numpy()
-        assert abs(rows[rank, 0] - c_chk) <= 1e-12 * abs(c_chk) and np.allclose(rows[rank, 1:], g_chk, rtol=1e-12), "mirror row != fetched result"
+    if use_p2p:
+        launch_step()
+        rows = fe.eval_fetch_all()[:, 0, :]
+        barrier()
+        assert np.array_equal(rows, gathered.cpu().numpy()), "device copy of the gathered rows != host copy"
         assert np.all(rows[:, 0] > 0), "a rank's row is missing from the gathered buffer"
+        # every rank re-evaluates its right neighbour's hypothesis (again a symmetric, exchanged launch) and
+        # compares with the row the neighbour delivered
+        nb = (rank + 1) % world
+        fe.eval_launch(oms[nb][None, :], True)
+        rows_b = fe.eval_fetch_all()[:, 0, :]
+        assert np.allclose(rows[nb], rows_b[rank], rtol=1e-6, atol=1e-9 * abs(rows[nb, 0])), "exchanged row != local re-evaluation"
+        barrier()
+    else:
+        c_chk, g_chk = step_resident()
+        barrier()
+        if world > 1:
+            rows = gathered.cpu().numpy()
+            assert abs(rows[rank, 0] - c_chk) <= 1e-12 * abs(c_chk) and np.allclose(rows[rank, 1:], g_chk, rtol=1e-12), "mirror row != fetched result"
+            assert np.all(rows[:, 0] > 0), "a rank's row is missing from the gathered buffer"
 
     K, Wm = args.steps, args.warmup
-    total_ms, launches, wall, ms = timed(step_resident, K, Wm, True)
+    depth = max(1, min(args.depth, 4))
+    total_ms, launches, wall, ms = timed(K, Wm, True, depth)
     ms_per_step = total_ms / K
     value = world * n_ev / (ms_per_step * 1e-3)
     # same loop without the L2 flush (the optimiser's real regime: ~100-300 evals per packet, L2 warm)
-    warm_ms, _, _, _ = timed(step_resident, K, 3, False)
+    warm_ms, _, _, _ = timed(K, 3, False, depth)
+    # latency of ONE synchronous evaluation (launch -> result on the host before the next launch), L2 warm
+    lat_ms, _, _, _ = timed(K, 3, False, 1)
     # End to end through the C ABI with HOST buffers: every step uploads its 16 MB packet from pinned host memory
     # (cmaxb_fe_set_packet_async: H2D copy + validation + batch table + binning), evaluates contrast + gradient and
     # reads the result back.  Two handles on two streams are used alternately so that the upload of step i+1 overlaps
@@ -277,7 +322,10 @@ def run_ours(args, rank, world, local_rank):
                               event_batch_size=pkt.batch_size, grad_mode=grad_mode, device=local_rank,
                               stream=stream2.cuda_stream)
     mine2 = torch.zeros(4, dtype=torch.float64, device=dev)
-    if world > 1:
+    gathered2 = torch.zeros(max(world, 1), 4, dtype=torch.float64, device=dev)
+    if use_p2p:
+        fe2.exchange_connect(gathered_dev_ptr=gathered2.data_ptr())
+    elif world > 1:
         fe2.set_result_mirror(mine2.data_ptr())
     lanes = [(fe, stream, mine), (fe2, stream2, mine2)]
 
@@ -297,9 +345,12 @@ def run_ours(args, rank, world, local_rank):
             with torch.cuda.stream(cur[1]):
                 flush.fill_(float(i))                                        # L2 flush, inside the timed span
                 cur[0].eval_launch(omega[None, :], True)
-                if world > 1:
-                    dist.all_gather_into_tensor(gathered.view(-1), cur[2])
-                cur[0].eval_fetch()
+                if use_p2p:
+                    cur[0].eval_fetch_all()
+                else:
+                    if world > 1:
+                        dist.all_gather_into_tensor(gathered.view(-1), cur[2])
+                    cur[0].eval_fetch()
             if i == total - 1:
                 t1.record(cur[1])
         barrier()
@@ -354,9 +405,16 @@ def run_ours(args, rank, world, local_rank):
                        "events": n_ev, "image": [W, H], "batch_size": pkt.batch_size, "blur_sigma": pkt.blur_sigma,
                        "grad_mode": args.grad_mode, "l2": "flushed between timed iterations (256 MiB fill)",
                        "parallelism": f"hypothesis-sharded x{world}" if world > 1 else "single GPU",
-                       "collective": "1 NCCL all-gather of the [N,4] f64 result rows per step, device-resident" if world > 1 else "none"},
+                       "pipeline_depth": depth,
+                       "collective": ("none" if world == 1 else
+                                      "fused in the evaluation kernel: peer-to-peer stores of the [k,4] f64 rows into every rank's exchange buffer "
+                                      "over NVLink (CUDA IPC) + flag wait, one launch per step" if use_p2p else
+                                      "1 NCCL all-gather of the [N,4] f64 result rows per step, device-resident")},
             "l2_warm": {"ms_per_step": warm_ms / K, "value": world * n_ev / (warm_ms / K * 1e-3),
                         "note": "no L2 flush between iterations (optimiser regime)"},
+            "latency": {"us_per_eval": lat_ms / K * 1e3, "value": world * n_ev / (lat_ms / K * 1e-3),
+                        "note": "one synchronous contrast+gradient evaluation (the GSL callback): launch, wait for the result on the host, "
+                                "then the next launch; L2 warm"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_ev + 24, "d2h_bytes_per_step": 32 + 4,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "path": "cmaxb_fe_set_packet_async(pinned host events) + cmaxb_fe_eval through the C ABI; uploads double-buffered "
@@ -391,6 +449,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grad-mode", default="adjoint", choices=["dense", "adjoint"])
+    ap.add_argument("--depth", type=int, default=2, help="evaluations queued on the stream before the oldest result is read (1 = synchronous)")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N>1: fused in-kernel exchange over peer memory, or a separate NCCL all-gather")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

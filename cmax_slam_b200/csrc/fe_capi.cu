@@ -5,7 +5,17 @@
 #include "fe_mega.cuh"
 #include "fe_binning.cuh"
 
+#include <deque>
+
 using namespace cmaxb;
+
+// evaluations that may be queued on the stream before the oldest is fetched (results live in a ring of
+// mapped host slots, so the host never has to drain the stream between launches)
+constexpr int kFeRing = 4;
+
+struct FeInflight {
+  int k; bool grad; bool mega; int slot; unsigned long long seq; bool xchg;
+};
 
 namespace cmaxb {
 thread_local std::string g_last_error;
@@ -49,6 +59,17 @@ struct cmaxb_fe {
   double* d_mirror = nullptr;   // caller-owned device buffer [kmax][4] (cmaxb_fe_set_result_mirror)
   bool force_multi_kernel = false;   // CMAXB_FE_MULTI_KERNEL=1: stand-alone kernels (profiling / A-B comparison)
   int last_k = 0; bool last_grad = false; bool pending = false;
+  std::deque<FeInflight> inflight;   // launched, not yet fetched (FIFO)
+  int ring_next = 0;
+  bool gather_f32 = true;            // CMAXB_FE_GATHER_F64=1 selects the all-f64 gather
+  // fused result exchange over peer memory (cmaxb_fe_exchange_*)
+  int x_world = 0, x_rank = 0; bool x_on = false;
+  double* x_local = nullptr; size_t x_bytes = 0;
+  double* x_peer[kXMaxWorld] = {};
+  double* x_all_dev = nullptr;
+  double* h_xall = nullptr; double* d_xall = nullptr;        // mapped: [kFeRing][world][kmax][4]
+  unsigned int* h_xerr = nullptr; unsigned int* d_xerr = nullptr;
+  unsigned long long x_seq = 0;
   KernelProfiler prof;
 };
 
@@ -83,6 +104,8 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
     fe->force_multi_kernel = mk && mk[0] == '1';
     const char* nb = getenv("CMAXB_FE_NO_BINNING");   // A/B switch: evaluate the packet in arrival (time) order
     fe->use_bins = !(nb && nb[0] == '1');
+    const char* g64 = getenv("CMAXB_FE_GATHER_F64");  // A/B switch: Jacobian chain of the gather pass in f64
+    fe->gather_f32 = !(g64 && g64[0] == '1');
   }
   int rc = make_taps(cfg->blur_sigma, &fe->taps);
   if (rc != CMAXB_OK) { delete fe; return rc; }
@@ -149,7 +172,7 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
       fe->mega_th = mega_tile_height(cfg->width, cfg->height, grid);
       const size_t kk = (size_t)fe->kmax;
       bool okm = dev_alloc(&fe->d_part_img, kk * kMegaMaxCtas * 2) == CMAXB_OK && dev_alloc(&fe->d_part_ev, kk * kMegaMaxCtas * 3) == CMAXB_OK;
-      okm = okm && cudaHostAlloc((void**)&fe->h_mega_result, sizeof(double) * 4 * kk, cudaHostAllocMapped) == cudaSuccess;
+      okm = okm && cudaHostAlloc((void**)&fe->h_mega_result, sizeof(double) * 4 * kk * kFeRing, cudaHostAllocMapped) == cudaSuccess;
       okm = okm && cudaHostGetDevicePointer((void**)&fe->d_mega_result, fe->h_mega_result, 0) == cudaSuccess;
       okm = okm && cudaHostAlloc((void**)&fe->h_done, sizeof(unsigned long long) * 8, cudaHostAllocMapped) == cudaSuccess;
       okm = okm && cudaHostGetDevicePointer((void**)&fe->d_done, fe->h_done, 0) == cudaSuccess;
@@ -183,6 +206,11 @@ extern "C" void cmaxb_fe_destroy(cmaxb_fe* fe) {
   if (fe->h_phase) cudaFreeHost(fe->h_phase);
   if (fe->h_done) cudaFreeHost(fe->h_done);
   cudaFree(fe->d_part_img); cudaFree(fe->d_part_ev);
+  for (int r = 0; r < fe->x_world; ++r)
+    if (r != fe->x_rank && fe->x_peer[r]) cudaIpcCloseMemHandle(fe->x_peer[r]);
+  cudaFree(fe->x_local);
+  if (fe->h_xall) cudaFreeHost(fe->h_xall);
+  if (fe->h_xerr) cudaFreeHost(fe->h_xerr);
   fe->prof.destroy();
   if (fe->own_stream && fe->stream) cudaStreamDestroy(fe->stream);
   delete fe;
@@ -342,11 +370,23 @@ static int fe_run_scatter_dense(cmaxb_fe* fe, int k) {
   return CMAXB_OK;
 }
 
+// Wait until the stream is idle.  Evaluations already launched stay fetchable (their rows sit in the mapped ring).
+static int fe_drain_stream(cmaxb_fe* fe) {
+  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream)); fe->pending = false; }
+  return CMAXB_OK;
+}
+
 // One cooperative launch per <= kMegaMaxHyp hypotheses; omegas travel as kernel parameters and the
-// results land in mapped pinned memory.
+// results land in a ring slot of mapped pinned memory (up to kFeRing launches may be outstanding).
 static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int want_grad) {
   cudaStream_t s = fe->stream;
-  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(s)); fe->pending = false; }
+  if ((int)fe->inflight.size() >= kFeRing)
+    return set_error(CMAXB_ERR_STATE, "too many outstanding evaluations: call cmaxb_fe_eval_fetch first");
+  if (!fe->inflight.empty() && !fe->inflight.back().mega) CMAXB_TRY(fe_drain_stream(fe));
+  if (fe->x_on && k > kMegaMaxHyp)
+    return set_error(CMAXB_ERR_INVALID, "result exchange supports at most 32 hypotheses per launch");
+  const int slot = fe->ring_next;
+  fe->ring_next = (fe->ring_next + 1) % kFeRing;
   const int cur = fe->quad_cur, oth = cur ^ 1;
   if (fe->quad_dirty[cur] > 0) {
     const int planes = fe->quad_dirty[cur];
@@ -369,12 +409,22 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
     p.part_img = fe->d_part_img + (long long)c0 * kMegaMaxCtas * 2;
     p.part_ev = fe->d_part_ev + (long long)c0 * kMegaMaxCtas * 3;
     p.ticket = fe->d_ticket;
-    p.contrast_dev = fe->d_mean + c0;   // d_mean is unused by the fused path: reuse it as the contrast scratch
-    p.result = fe->d_mega_result + 4 * c0;
+    p.contrast_dev = fe->d_mean + c0;
+    p.result = fe->d_mega_result + ((long long)slot * fe->kmax + c0) * 4;
     p.mirror = fe->d_mirror ? fe->d_mirror + 4 * c0 : nullptr;
     p.done_flag = fe->d_done;
     p.seq = ++fe->seq;
     p.phase_ns = fe->prof.enabled ? fe->d_phase : nullptr;
+    p.gather_f32 = fe->gather_f32 ? 1 : 0;
+    std::memset(&p.x, 0, sizeof(p.x));
+    if (fe->x_on) {
+      p.x.world = fe->x_world; p.x.rank = fe->x_rank; p.x.kmax = fe->kmax;
+      p.x.seq = ++fe->x_seq;
+      for (int r = 0; r < fe->x_world; ++r) p.x.peer[r] = fe->x_peer[r];
+      p.x.all_host = fe->d_xall + (long long)slot * fe->x_world * fe->kmax * 4;
+      p.x.all_dev = fe->x_all_dev;
+      p.x.err = fe->d_xerr;
+    }
     if (fe->prof.enabled) for (int i = 0; i < 16; ++i) fe->h_phase[i] = 0;
     void* args[] = {&p};
     const size_t smem = mega_smem_bytes(fe->taps.r);
@@ -389,6 +439,7 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
   if (clear_next) fe->quad_dirty[oth] = 0;
   if (fe->n > 0) fe->quad_dirty[cur] = k;
   fe->quad_cur = oth;
+  fe->inflight.push_back(FeInflight{k, want_grad != 0, true, slot, fe->seq, fe->x_on});
   fe->last_k = k; fe->last_grad = want_grad != 0; fe->pending = true; fe->last_mega = true;
   return CMAXB_OK;
 }
@@ -400,6 +451,9 @@ extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, i
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
   if (!(want_grad && fe->cfg.grad_mode == CMAXB_GRAD_DENSE) && !fe->force_multi_kernel)
     return fe_eval_launch_fused(fe, omegas, k, want_grad);
+  // multi-kernel pipeline (DENSE gradients, A/B runs): one evaluation outstanding at a time
+  if (!fe->inflight.empty())
+    return set_error(CMAXB_ERR_STATE, "multi-kernel evaluation: fetch the outstanding evaluation first");
   CMAXB_TRY(fe_upload_omegas(fe, omegas, k));
   fe->last_mega = false;
   cudaStream_t s = fe->stream;
@@ -430,43 +484,129 @@ extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, i
     }
   }
   CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->h_result, fe->d_result, sizeof(double) * 4 * k, cudaMemcpyDeviceToHost, s));
+  fe->inflight.push_back(FeInflight{k, want_grad != 0, false, 0, 0ull, false});
   fe->last_k = k; fe->last_grad = want_grad != 0; fe->pending = true;
   return CMAXB_OK;
 }
 
-extern "C" int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grads3k) {
-  if (!fe || !contrasts) return set_error(CMAXB_ERR_INVALID, "null argument");
-  if (fe->last_k <= 0) return set_error(CMAXB_ERR_STATE, "no evaluation launched");
-  if (fe->last_mega && fe->pending) {
+// waits for the OLDEST outstanding launch and pops it; *out = its record
+static int fe_wait_oldest(cmaxb_fe* fe, FeInflight* out) {
+  if (fe->inflight.empty()) return set_error(CMAXB_ERR_STATE, "no evaluation launched");
+  const FeInflight f = fe->inflight.front();
+  if (f.mega) {
     // The fused kernel publishes its results in mapped pinned memory and then stores its sequence
-    // number: spin on that word (~1 us) instead of paying the driver's stream-synchronise latency;
-    // check the stream now and then so that a faulted kernel cannot hang the caller.
+    // number (monotonic): spin on that word (~1 us) instead of paying the driver's stream-synchronise
+    // latency; check the stream now and then so that a faulted kernel cannot hang the caller.
     volatile unsigned long long* done = fe->h_done;
     unsigned long long spins = 0;
-    while (*done != fe->seq) {
+    while (*done < f.seq) {
       if ((++spins & 0x3fff) == 0) {
         cudaError_t q = cudaStreamQuery(fe->stream);
         if (q == cudaSuccess) break;                       // finished (flag write raced the query) or faulted
-        if (q != cudaErrorNotReady) return set_error(CMAXB_ERR_CUDA, std::string("fused evaluation kernel: ") + cudaGetErrorString(q));
+        if (q != cudaErrorNotReady) { fe->inflight.clear(); return set_error(CMAXB_ERR_CUDA, std::string("fused evaluation kernel: ") + cudaGetErrorString(q)); }
       }
     }
-    if (*done != fe->seq) CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
-    if (*done != fe->seq) return set_error(CMAXB_ERR_CUDA, "fused evaluation kernel finished without publishing its result");
+    if (*done < f.seq) CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+    if (*done < f.seq) { fe->inflight.clear(); return set_error(CMAXB_ERR_CUDA, "fused evaluation kernel finished without publishing its result"); }
   } else {
     CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
   }
-  fe->pending = false;
-  CMAXB_TRY(fe_check_packet_flags(fe));
-  const double* res = fe->last_mega ? fe->h_mega_result : fe->h_result;
-  for (int h = 0; h < fe->last_k; ++h) {
+  fe->inflight.pop_front();
+  if (fe->inflight.empty() && (!f.mega || *fe->h_done >= fe->seq)) fe->pending = false;   // nothing of ours is left on the stream
+  *out = f;
+  return fe_check_packet_flags(fe);
+}
+
+extern "C" int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grads3k) {
+  if (!fe || !contrasts) return set_error(CMAXB_ERR_INVALID, "null argument");
+  FeInflight f;
+  CMAXB_TRY(fe_wait_oldest(fe, &f));
+  if (f.xchg && *fe->h_xerr) return set_error(CMAXB_ERR_CUDA, "result exchange: a peer's rows did not arrive (timeout)");
+  const double* res = f.mega ? fe->h_mega_result + (long long)f.slot * fe->kmax * 4 : fe->h_result;
+  for (int h = 0; h < f.k; ++h) {
     contrasts[h] = res[4 * h];
-    if (grads3k && fe->last_grad)
+    if (grads3k && f.grad)
       for (int c = 0; c < 3; ++c) grads3k[3 * h + c] = res[4 * h + 1 + c];
   }
   return CMAXB_OK;
 }
 
+// ---- fused result exchange over peer memory -----------------------------------------------------------
+extern "C" int cmaxb_fe_exchange_init(cmaxb_fe* fe, int world, int rank, void* handle64_out) {
+  if (!fe || !handle64_out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (world < 1 || world > kXMaxWorld || rank < 0 || rank >= world) return set_error(CMAXB_ERR_INVALID, "bad world / rank (at most 8 ranks)");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  CMAXB_TRY(fe_drain_stream(fe));
+  if (fe->x_local) return set_error(CMAXB_ERR_STATE, "exchange already initialised");
+  const size_t need = sizeof(double) * 2 * (size_t)world * fe->kmax * 4 + sizeof(unsigned long long) * world;
+  size_t bytes = (size_t)2 << 20;            // a whole 2 MiB block: the IPC handle exports nothing else
+  while (bytes < need) bytes <<= 1;
+  CMAXB_CUDA_TRY(cudaMalloc((void**)&fe->x_local, bytes));
+  CMAXB_CUDA_TRY(cudaMemset(fe->x_local, 0, bytes));
+  CMAXB_CUDA_TRY(cudaDeviceSynchronize());
+  fe->x_bytes = bytes;
+  cudaIpcMemHandle_t h;
+  CMAXB_CUDA_TRY(cudaIpcGetMemHandle(&h, fe->x_local));
+  std::memcpy(handle64_out, &h, 64);
+  fe->x_world = world; fe->x_rank = rank;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_exchange_connect(cmaxb_fe* fe, const void* handles, double* gathered_dev) {
+  if (!fe || !handles) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!fe->x_local) return set_error(CMAXB_ERR_STATE, "call cmaxb_fe_exchange_init first");
+  CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  CMAXB_TRY(fe_drain_stream(fe));
+  for (int r = 0; r < fe->x_world; ++r) {
+    if (r == fe->x_rank) { fe->x_peer[r] = fe->x_local; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* ptr = nullptr;
+    CMAXB_CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    fe->x_peer[r] = (double*)ptr;
+  }
+  if (!fe->h_xall) {
+    CMAXB_CUDA_TRY(cudaHostAlloc((void**)&fe->h_xall, sizeof(double) * 4 * (size_t)fe->kmax * fe->x_world * kFeRing, cudaHostAllocMapped));
+    CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&fe->d_xall, fe->h_xall, 0));
+    CMAXB_CUDA_TRY(cudaHostAlloc((void**)&fe->h_xerr, sizeof(unsigned int) * 4, cudaHostAllocMapped));
+    CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&fe->d_xerr, fe->h_xerr, 0));
+    fe->h_xerr[0] = 0;
+  }
+  fe->x_all_dev = gathered_dev;
+  fe->x_seq = 0;
+  fe->x_on = fe->x_world > 1;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_exchange_close(cmaxb_fe* fe) {
+  if (!fe) return set_error(CMAXB_ERR_INVALID, "null argument");
+  cudaSetDevice(fe->device);
+  if (fe->stream) cudaStreamSynchronize(fe->stream);
+  fe->pending = false;
+  fe->x_on = false;
+  for (int r = 0; r < fe->x_world; ++r) {
+    if (r != fe->x_rank && fe->x_peer[r]) cudaIpcCloseMemHandle(fe->x_peer[r]);
+    fe->x_peer[r] = nullptr;
+  }
+  // the local buffer stays allocated until destroy: a peer may still have it mapped
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_eval_fetch_all(cmaxb_fe* fe, double* rows) {
+  if (!fe || !rows) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (fe->inflight.empty()) return set_error(CMAXB_ERR_STATE, "no evaluation launched");
+  if (!fe->inflight.front().xchg) return set_error(CMAXB_ERR_STATE, "the oldest evaluation was launched without a result exchange");
+  FeInflight f;
+  CMAXB_TRY(fe_wait_oldest(fe, &f));
+  if (*fe->h_xerr) return set_error(CMAXB_ERR_CUDA, "result exchange: a peer's rows did not arrive (timeout)");
+  const double* all = fe->h_xall + (long long)f.slot * fe->x_world * fe->kmax * 4;
+  std::memcpy(rows, all, sizeof(double) * 4 * (size_t)f.k * fe->x_world);
+  return CMAXB_OK;
+}
+
 extern "C" int cmaxb_fe_eval_batch(cmaxb_fe* fe, const double* omegas, int k, double* contrasts, double* grads3k) {
+  if (fe && !fe->inflight.empty()) return set_error(CMAXB_ERR_STATE, "outstanding cmaxb_fe_eval_launch calls: fetch them first");
   CMAXB_TRY(cmaxb_fe_eval_launch(fe, omegas, k, grads3k != nullptr));
   return cmaxb_fe_eval_fetch(fe, contrasts, grads3k);
 }

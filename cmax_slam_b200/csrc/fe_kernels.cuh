@@ -30,7 +30,11 @@ struct FeWarp {
 
 // One event, one hypothesis.  No FMA contraction (see common.cuh).
 // (bx,by,bz) = bearing vector of the event's pixel, already loaded.
-template <bool GRAD>
+// GRAD: 0 = cell + bilinear fractions only; 1 = Jacobian rows evaluated in f64 and rounded to f32 exactly as
+// the reference does (:110-135,157-160); 2 = the same chain evaluated in f32 from the f64 projection (the
+// rows differ from GRAD 1 by <= a few f32 ulps; used by the adjoint gather, whose sum is accumulated in f64
+// and checked to 1e-5 of the gradient -- it halves the pass's f64 instruction count).
+template <int GRAD>
 __device__ __forceinline__ FeWarp fe_warp_b(const FeGeom& g, double bx, double by, double bz, double dt, double ox, double oy, double oz) {
   FeWarp o;
   // delta_rot = ang_vel * dt ; p' = p + delta_rot x p                     (:76,101)
@@ -56,7 +60,20 @@ __device__ __forceinline__ FeWarp fe_warp_b(const FeGeom& g, double bx, double b
       o.dy = (float)(py - (double)yy);
     }
   }
-  if (GRAD) {
+  if (GRAD == 2) {
+    const float fu = (float)u, fv = (float)v, finv = (float)inv;
+    const float ndt = -(float)dt;
+    const float mx = ndt * (float)bx, my = ndt * (float)by, mz = ndt * (float)bz;
+    const float a02 = -fu * finv, a12 = -fv * finv;
+    const float ffx = (float)g.fx, ffy = (float)g.fy;
+    o.r0[0] = ffx * (a02 * (-my));
+    o.r0[1] = ffx * (finv * (-mz) + a02 * mx);
+    o.r0[2] = ffx * (finv * my);
+    o.r1[0] = ffy * (finv * mz + a12 * (-my));
+    o.r1[1] = ffy * (a12 * mx);
+    o.r1[2] = ffy * (finv * (-mx));
+  }
+  if (GRAD == 1) {
     // M = cross2Matrix((-dt)*p)                                           (:110)
     const double ndt = -dt;
     const double mx = ndt * bx, my = ndt * by, mz = ndt * bz;
@@ -75,7 +92,7 @@ __device__ __forceinline__ FeWarp fe_warp_b(const FeGeom& g, double bx, double b
   return o;
 }
 
-template <bool GRAD>
+template <int GRAD>
 __device__ __forceinline__ FeWarp fe_warp(const FeGeom& g, uint4 e, double dt, double ox, double oy, double oz) {
   const int ex = e.x & 0xffff, ey = e.x >> 16;
   const double2* lp = reinterpret_cast<const double2*>(g.lut + (ey * g.W + ex));
@@ -116,7 +133,7 @@ fe_scatter_kernel(FeGeom g, const double* __restrict__ omegas, float* __restrict
   for (long long i = blockIdx.x * (long long)kFeThreads + threadIdx.x; i < g.n; i += stride) {
     const uint4 e = load_event(g.ev, i);
     const double dt = __ldg(g.dt_tab + i / g.batch_size);
-    const FeWarp w = fe_warp<MODE == 1>(g, e, dt, ox, oy, oz);
+    const FeWarp w = fe_warp<(MODE == 1) ? 1 : 0>(g, e, dt, ox, oy, oz);
     if (!w.in) continue;
     const float dx = w.dx, dy = w.dy;
     const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy);
@@ -154,7 +171,7 @@ __global__ void fe_cells_kernel(FeGeom g, const double* __restrict__ omegas, int
   if (i >= g.n) return;
   const uint4 e = load_event(g.ev, i);
   const double dt = g.dt_tab[i / g.batch_size];
-  const FeWarp w = fe_warp<false>(g, e, dt, omegas[0], omegas[1], omegas[2]);
+  const FeWarp w = fe_warp<0>(g, e, dt, omegas[0], omegas[1], omegas[2]);
   cells[i] = w.in ? w.yy * g.W + w.xx : -1;
 }
 
@@ -178,7 +195,7 @@ fe_gather_kernel(FeGeom g, const double* __restrict__ omegas, const float* __res
   for (long long i = blockIdx.x * (long long)kFeThreads + threadIdx.x; i < g.n; i += stride) {
     const uint4 e = load_event(g.ev, i);
     const double dt = __ldg(g.dt_tab + i / g.batch_size);
-    const FeWarp w = fe_warp<true>(g, e, dt, ox, oy, oz);
+    const FeWarp w = fe_warp<1>(g, e, dt, ox, oy, oz);
     if (!w.in) continue;
     double g00, g01, g10, g11;
     if (QUAD) {

@@ -20,6 +20,72 @@ namespace cg = cooperative_groups;
 
 constexpr int kMegaMaxHyp = 32;       // hypotheses per launch (kernel-parameter space)
 
+// ---- fused result exchange ---------------------------------------------------------------------------------
+// Multi-GPU hypothesis sharding: every rank evaluates its own hypotheses of the replicated
+// packet and all ranks need all (contrast, g) rows.  Instead of a separate NCCL all-gather after the kernel, the
+// CTA that publishes the result also stores its rows straight into every peer's exchange buffer (peer-to-peer
+// stores over NVLink / NVSwitch, buffers opened with CUDA IPC), releases a per-rank sequence flag, waits for the
+// peers' flags and copies the gathered rows to mapped host memory -- compute + collective in ONE launch.
+// Exchange buffer of a rank (doubles): rows[2][world][kmax][4] (double-buffered by the parity of the sequence
+// number: a rank can run at most one evaluation ahead of a peer that has not yet read its rows) followed by
+// flags[world] (u64, monotonic).
+constexpr int kXMaxWorld = 8;
+constexpr unsigned long long kXTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;   // a dead peer must not hang the GPU
+
+struct FeXchgParams {
+  int world, rank, kmax;
+  unsigned long long seq;           // exchange sequence number of this launch (same on all ranks)
+  double* peer[kXMaxWorld];         // exchange buffer of every rank as mapped into THIS process (peer[rank] = own)
+  double* all_host;                 // mapped host memory [world][k][4]: gathered rows of this launch
+  double* all_dev;                  // optional device copy [world][k][4] (caller owned)
+  unsigned int* err;                // mapped host word, set to 1 when a peer's flag does not arrive in time
+};
+
+__device__ __forceinline__ double* xchg_rows(const FeXchgParams& x, double* base, int par, int r) {
+  return base + ((long long)(par * x.world + r) * x.kmax) * 4;
+}
+__device__ __forceinline__ unsigned long long* xchg_flags(const FeXchgParams& x, double* base) {
+  return reinterpret_cast<unsigned long long*>(base + (long long)2 * x.world * x.kmax * 4);
+}
+
+// Called by ALL threads of ONE CTA.  s_rows[k*4] (shared memory) = this rank's rows of the launch.
+__device__ __forceinline__ void mega_exchange(const FeXchgParams& x, int k, const double* s_rows) {
+  const int par = (int)(x.seq & 1ull);
+  const int nv = k * 4;
+  __syncthreads();
+  // 1. own rows -> every rank's buffer (own copy included)
+  for (int i = threadIdx.x; i < x.world * nv; i += blockDim.x) {
+    const int r = i / nv, j = i - r * nv;
+    *reinterpret_cast<volatile double*>(xchg_rows(x, x.peer[r], par, x.rank) + j) = s_rows[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < x.world) {
+    // 2. release: flags[rank] = seq in every rank's buffer
+    unsigned long long* fr = xchg_flags(x, x.peer[threadIdx.x]) + x.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fr), "l"(x.seq) : "memory");
+    // 3. acquire: rank threadIdx.x's flag in OUR buffer
+    const unsigned long long* fa = xchg_flags(x, x.peer[x.rank]) + threadIdx.x;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(fa) : "memory");
+      if (v >= x.seq) break;
+      if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > kXTimeoutNs) { *x.err = 1u; break; }
+    }
+  }
+  __syncthreads();
+  // 4. gathered rows -> mapped host memory (+ device copy)
+  for (int i = threadIdx.x; i < x.world * nv; i += blockDim.x) {
+    const int r = i / nv, j = i - r * nv;
+    const double v = *reinterpret_cast<const volatile double*>(xchg_rows(x, x.peer[x.rank], par, r) + j);
+    x.all_host[i] = v;
+    if (x.all_dev) x.all_dev[i] = v;
+  }
+  __syncthreads();
+}
+
 struct FeMegaParams {
   FeGeom g;
   int k;                      // hypotheses in this launch
@@ -42,6 +108,8 @@ struct FeMegaParams {
   unsigned long long* done_flag; // mapped host word: receives `seq` after the results are visible to the host
   unsigned long long seq;
   unsigned long long* phase_ns; // optional [8]: %globaltimer of CTA 0 at every phase boundary (mapped host memory)
+  int gather_f32;             // 1: Jacobian rows and bilinear adjoint of the gather pass in f32 (f64 accumulation)
+  FeXchgParams x;             // in-kernel all-gather of the result rows over peer memory (x.world <= 1: off)
 };
 
 #define CMAXB_PHASE_MARK(idx) do { if (p.phase_ns && blockIdx.x == 0 && threadIdx.x == 0) p.phase_ns[idx] = global_timer_ns(); } while (0)
@@ -91,7 +159,7 @@ __device__ __forceinline__ void mega_scatter(const FeMegaParams& p) {
       float4* q = p.quad + h * p.A;
 #pragma unroll
       for (int u = 0; u < kEvUnroll; ++u) {
-        const FeWarp w = fe_warp_b<false>(g, bxy[u].x, bxy[u].y, bz[u], dt[u], ox, oy, oz);
+        const FeWarp w = fe_warp_b<0>(g, bxy[u].x, bxy[u].y, bz[u], dt[u], ox, oy, oz);
         if (ok[u] && w.in) {
           const float dx = w.dx, dy = w.dy;
           atomicAdd(q + (long long)w.yy * g.W + w.xx,
@@ -120,6 +188,7 @@ __device__ __forceinline__ void mega_adjoint(const FeMegaParams& p, int h, doubl
   tile_adjoint_phase<R>(c, p.blurred + h * p.A, 2.0f, b2, nullptr, p.GQ + h * p.A, smem_raw);
 }
 
+template <bool F32>
 __device__ __forceinline__ void mega_gather(const FeMegaParams& p, int h, double* s_red) {
   const FeGeom& g = p.g;
   const double ox = p.omegas[3 * h], oy = p.omegas[3 * h + 1], oz = p.omegas[3 * h + 2];
@@ -157,12 +226,20 @@ __device__ __forceinline__ void mega_gather(const FeMegaParams& p, int h, double
     float4 q[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      w[u] = fe_warp_b<true>(g, bxy[u].x, bxy[u].y, bz[u], dt[u], ox, oy, oz);
+      w[u] = fe_warp_b<F32 ? 2 : 1>(g, bxy[u].x, bxy[u].y, bz[u], dt[u], ox, oy, oz);
       q[u] = (ok[u] && w[u].in) ? __ldcg(GQh + (long long)w[u].yy * g.W + w[u].xx) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (!(ok[u] && w[u].in)) continue;
+      if (F32) {
+        const float dx = w[u].dx, dy = w[u].dy;
+        const float a = (1.f - dy) * (q[u].y - q[u].x) + dy * (q[u].w - q[u].z);
+        const float b = (1.f - dx) * (q[u].z - q[u].x) + dx * (q[u].w - q[u].y);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += (double)(w[u].r0[c] * a + w[u].r1[c] * b);
+        continue;
+      }
       const double g00 = q[u].x, g01 = q[u].y, g10 = q[u].z, g11 = q[u].w;
       const double dx = w[u].dx, dy = w[u].dy;
       const double a = (1.0 - dy) * (g01 - g00) + dy * (g11 - g10);
@@ -178,12 +255,30 @@ __device__ __forceinline__ void mega_gather(const FeMegaParams& p, int h, double
   }
 }
 
+// rows of this launch (shared memory, [k][4]) -> mapped host result (+ device mirror) (+ exchange with the
+// peers), then the completion word the host spins on.  Called by all threads of ONE CTA.
+__device__ __forceinline__ void mega_publish(const FeMegaParams& p, const double* s_rows) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * p.k; i += kMegaThreads) {
+    const double v = s_rows[i];
+    p.result[i] = v;
+    if (p.mirror) p.mirror[i] = v;
+  }
+  if (p.x.world > 1) mega_exchange(p.x, p.k, s_rows);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(p.done_flag) = p.seq;
+  }
+}
+
 template <int R>
 __global__ void __launch_bounds__(kMegaThreads)
 fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[(kMegaThreads / 32) * 3];
   __shared__ double s_mean[kMegaMaxHyp];
+  __shared__ double s_rows[kMegaMaxHyp * 4];
   cg::grid_group grid = cg::this_grid();
   const double Np = (double)p.g.W * (double)p.g.H;
 
@@ -200,8 +295,8 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
     double S1, S2;
     mega_image_sums(p, h, s_red, &S1, &S2);
     const double mean = S1 / Np;
-    if (threadIdx.x == 0) s_mean[h] = mean;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      s_mean[h] = mean;
       double contrast;
       if (p.measure == CMAXB_CONTRAST_MEAN_SQUARE) contrast = S2 / Np;
       else {
@@ -210,21 +305,14 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
         const double sd = sqrt(var);
         contrast = sd * sd;
       }
-      if (p.want_grad) {
-        p.contrast_dev[h] = contrast;   // published to the host by the last CTA, together with the gradient
-      } else {
-        p.result[4 * h] = contrast;
-        if (p.mirror) { p.mirror[4 * h] = contrast; p.mirror[4 * h + 1] = 0.0; p.mirror[4 * h + 2] = 0.0; p.mirror[4 * h + 3] = 0.0; }
-      }
+      // every CTA holds the identical value (fixed-order sums); the publishing CTA uses its own copy
+      s_rows[4 * h] = contrast; s_rows[4 * h + 1] = 0.0; s_rows[4 * h + 2] = 0.0; s_rows[4 * h + 3] = 0.0;
     }
   }
   __syncthreads();
   if (!p.want_grad) {
     CMAXB_PHASE_MARK(5);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(p.done_flag) = p.seq;
-    }
+    if (blockIdx.x == 0) mega_publish(p, s_rows);
     return;
   }
   for (int h = 0; h < p.k; ++h) mega_adjoint<R>(p, h, s_mean[h], smem_raw);
@@ -233,7 +321,8 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
   CMAXB_PHASE_MARK(6);
   for (int h = 0; h < p.k; ++h) {
     __syncthreads();
-    mega_gather(p, h, s_red);
+    if (p.gather_f32) mega_gather<true>(p, h, s_red);
+    else mega_gather<false>(p, h, s_red);
   }
   CMAXB_PHASE_MARK(7);
   // no fourth grid barrier: the last CTA to publish its gather record (atomic ticket) does the final sum
@@ -247,37 +336,51 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
   if (s_last) {
     __threadfence();
     if (threadIdx.x == 0) *p.ticket = 0u;
-    // one WARP per hypothesis: lanes add the per-CTA records in a fixed order, lane 0 publishes
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int h = wid; h < p.k; h += kMegaThreads / 32) {
-      const double* all = p.part_ev + (long long)h * kMegaMaxCtas * 3;
-      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-      constexpr int kRecUnroll = 8;    // 24 independent loads in flight per lane (the loop is one L2 round trip per step)
-      for (int c0 = lane; c0 < (int)gridDim.x; c0 += 32 * kRecUnroll) {
-        double v[kRecUnroll][3];
+    if (p.k <= 4) {
+      // few hypotheses: the whole CTA adds the per-CTA records of one hypothesis (all loads of a thread in
+      // flight at once: one L2 round trip), fixed order
+      constexpr int kRec = (kMegaMaxCtas + kMegaThreads - 1) / kMegaThreads;
+      for (int h = 0; h < p.k; ++h) {
+        const double* all = p.part_ev + (long long)h * kMegaMaxCtas * 3;
+        double v[kRec][3];
 #pragma unroll
-        for (int u = 0; u < kRecUnroll; ++u) {
-          const int c = c0 + 32 * u;
+        for (int u = 0; u < kRec; ++u) {
+          const int c = threadIdx.x + u * kMegaThreads;
           const bool ok = c < (int)gridDim.x;
           v[u][0] = ok ? __ldcg(all + 3 * c) : 0.0; v[u][1] = ok ? __ldcg(all + 3 * c + 1) : 0.0; v[u][2] = ok ? __ldcg(all + 3 * c + 2) : 0.0;
         }
+        double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int u = 0; u < kRecUnroll; ++u) { t0 += v[u][0]; t1 += v[u][1]; t2 += v[u][2]; }
+        for (int u = 0; u < kRec; ++u) { t[0] += v[u][0]; t[1] += v[u][1]; t[2] += v[u][2]; }
+        __syncthreads();
+        block_sum<3>(t, s_red);
+        if (threadIdx.x == 0) { s_rows[4 * h + 1] = t[0] / Np; s_rows[4 * h + 2] = t[1] / Np; s_rows[4 * h + 3] = t[2] / Np; }
       }
-      t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
-      if (lane == 0) {
-        const double c = __ldcg(p.contrast_dev + h);
-        p.result[4 * h] = c;
-        p.result[4 * h + 1] = t0 / Np; p.result[4 * h + 2] = t1 / Np; p.result[4 * h + 3] = t2 / Np;
-        if (p.mirror) { p.mirror[4 * h] = c; p.mirror[4 * h + 1] = t0 / Np; p.mirror[4 * h + 2] = t1 / Np; p.mirror[4 * h + 3] = t2 / Np; }
+    } else {
+      // one WARP per hypothesis: lanes add the per-CTA records in a fixed order
+      for (int h = wid; h < p.k; h += kMegaThreads / 32) {
+        const double* all = p.part_ev + (long long)h * kMegaMaxCtas * 3;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        constexpr int kRecUnroll = 8;    // 24 independent loads in flight per lane (the loop is one L2 round trip per step)
+        for (int c0 = lane; c0 < (int)gridDim.x; c0 += 32 * kRecUnroll) {
+          double v[kRecUnroll][3];
+#pragma unroll
+          for (int u = 0; u < kRecUnroll; ++u) {
+            const int c = c0 + 32 * u;
+            const bool ok = c < (int)gridDim.x;
+            v[u][0] = ok ? __ldcg(all + 3 * c) : 0.0; v[u][1] = ok ? __ldcg(all + 3 * c + 1) : 0.0; v[u][2] = ok ? __ldcg(all + 3 * c + 2) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < kRecUnroll; ++u) { t0 += v[u][0]; t1 += v[u][1]; t2 += v[u][2]; }
+        }
+        t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
+        if (lane == 0) { s_rows[4 * h + 1] = t0 / Np; s_rows[4 * h + 2] = t1 / Np; s_rows[4 * h + 3] = t2 / Np; }
       }
     }
     __syncthreads();
     CMAXB_PHASE_MARK_ANY(9);
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(p.done_flag) = p.seq;
-    }
+    mega_publish(p, s_rows);
   }
 }
 

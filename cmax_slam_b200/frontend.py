@@ -35,6 +35,8 @@ class AngVelEstimatorCMax:
         self._res_c = np.zeros(self.max_hypotheses)
         self._res_g = np.zeros((self.max_hypotheses, 3))
         self._om = np.zeros((self.max_hypotheses, 3))
+        self._ks = []
+        self._xworld = 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -78,14 +80,45 @@ class AngVelEstimatorCMax:
         return c, (g if want_grad else None)
 
     def eval_launch(self, ang_vels, want_grad=True):
+        """Queue one evaluation (up to 4 may be outstanding); results come back in launch order from eval_fetch."""
         om = np.ascontiguousarray(ang_vels, dtype=np.float64).reshape(-1, 3)
-        self._k = om.shape[0]
-        self._om[: self._k] = om
-        _capi.check(self._L.cmaxb_fe_eval_launch(self._h, _capi.dptr(self._om), self._k, int(want_grad)))
+        k = om.shape[0]
+        self._om[:k] = om
+        _capi.check(self._L.cmaxb_fe_eval_launch(self._h, _capi.dptr(self._om), k, int(want_grad)))
+        self._ks.append(k)
 
     def eval_fetch(self):
+        k = self._ks[0] if self._ks else 0
         _capi.check(self._L.cmaxb_fe_eval_fetch(self._h, _capi.dptr(self._res_c), _capi.dptr(self._res_g)))
-        return self._res_c[: self._k].copy(), self._res_g[: self._k].copy()
+        self._ks.pop(0)
+        return self._res_c[:k].copy(), self._res_g[:k].copy()
+
+    # -- fused multi-GPU result exchange (peer-to-peer stores from the evaluation kernel) ----------
+    def exchange_connect(self, group=None, gathered_dev_ptr=None):
+        """Collective over `group` (torch.distributed, any backend: only the 64-byte IPC handles travel
+        through it).  Afterwards every rank must issue the same sequence of eval_launch calls."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        h = C.create_string_buffer(64)
+        _capi.check(self._L.cmaxb_fe_exchange_init(self._h, world, rank, h))
+        handles = [None] * world
+        dist.all_gather_object(handles, h.raw, group=group)
+        blob = b"".join(handles)
+        _capi.check(self._L.cmaxb_fe_exchange_connect(self._h, blob, C.c_void_p(gathered_dev_ptr) if gathered_dev_ptr else None))
+        self._xworld = world
+        dist.barrier(group)
+
+    def exchange_close(self):
+        _capi.check(self._L.cmaxb_fe_exchange_close(self._h))
+        self._xworld = 0
+
+    def eval_fetch_all(self):
+        """Rows (contrast, g0, g1, g2) of ALL ranks for the oldest outstanding launch: array [world, k, 4]."""
+        k = self._ks[0] if self._ks else 0
+        rows = np.zeros((self._xworld, max(k, 1), 4))
+        _capi.check(self._L.cmaxb_fe_eval_fetch_all(self._h, _capi.dptr(rows)))
+        self._ks.pop(0)
+        return rows
 
     def set_result_mirror(self, device_ptr):
         """device_ptr: address of a device buffer of max_hypotheses*4 float64 (e.g. tensor.data_ptr()) that also

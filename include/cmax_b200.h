@@ -97,10 +97,32 @@ int cmaxb_fe_eval(cmaxb_fe* fe, const double omega[3], double* contrast, double*
 /* k hypotheses on the resident packet in one pass over the events (BASELINE config C3). */
 int cmaxb_fe_eval_batch(cmaxb_fe* fe, const double* omegas, int k, double* contrasts, double* grads3k);
 
-/* Asynchronous pair used by the multi-GPU driver and the benchmark: launch returns as soon as
- * the work is queued on the stream; fetch waits and returns the results of the last launch. */
+/* Asynchronous pair used by the multi-GPU driver, batched line searches and the benchmark: launch returns as
+ * soon as the work is queued on the stream; fetch waits for the OLDEST outstanding launch and returns its
+ * results (FIFO).  Up to CMAXB_FE_MAX_OUTSTANDING launches may be queued before the first fetch (each has its
+ * own result slot in mapped host memory), so consecutive evaluations run back to back on the device with no
+ * host round trip between them; one more launch returns CMAXB_ERR_STATE. */
+#define CMAXB_FE_MAX_OUTSTANDING 4
 int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, int want_grad);
 int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grads3k);
+
+/* Fused result exchange for hypothesis sharding across GPUs (BASELINE config C3): one process
+ * per GPU, every rank holds the packet and evaluates its own hypotheses.  After connect, the evaluation kernel
+ * itself stores its (contrast, g0, g1, g2) rows into every peer's exchange buffer (peer-to-peer stores over
+ * NVLink / NVSwitch through CUDA IPC mappings), signals a per-rank sequence flag, waits for the peers' flags and
+ * hands the rows of ALL ranks to the host -- the all-gather the reference-side driver would otherwise issue as
+ * a separate NCCL collective happens inside the one launch.
+ *   cmaxb_fe_exchange_init    allocates this rank's exchange buffer; handle64_out receives its 64-byte
+ *                             cudaIpcMemHandle_t, which the caller distributes to all ranks (any transport)
+ *   cmaxb_fe_exchange_connect handles = world x 64 bytes in rank order; gathered_dev (optional, caller-owned
+ *                             device buffer of world*k*4 doubles) also receives the gathered rows
+ *   cmaxb_fe_eval_fetch_all   like cmaxb_fe_eval_fetch, but returns rows[world][k][4] of all ranks
+ * Contract: after connect every rank must issue the same sequence of cmaxb_fe_eval_launch calls (same k,
+ * k <= 32); a peer that does not show up within 10 s makes the fetch fail with CMAXB_ERR_CUDA instead of hanging. */
+int cmaxb_fe_exchange_init(cmaxb_fe* fe, int world, int rank, void* handle64_out);
+int cmaxb_fe_exchange_connect(cmaxb_fe* fe, const void* handles, double* gathered_dev);
+int cmaxb_fe_exchange_close(cmaxb_fe* fe);
+int cmaxb_fe_eval_fetch_all(cmaxb_fe* fe, double* rows);
 
 /* Optional: a caller-owned DEVICE buffer of max_hypotheses*4 doubles that also receives (contrast, g0, g1, g2)
  * of every evaluation, so that a collective (NCCL all-gather / all-reduce of the per-hypothesis rows,
