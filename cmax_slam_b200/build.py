@@ -33,9 +33,28 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
+def build_variant(name, defines, verbose=False):
+    """A/B build with extra -D flags into scratch/variants/libcmax_b200_<name>.so (select it at run time with
+    CMAXB_LIB_PATH=<path>); tuning aid, never the shipped library."""
+    out_dir = os.path.join(os.path.dirname(_HERE), "scratch", "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libcmax_b200_{name}.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", out] + sources()
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    subprocess.check_call(cmd, env=env)
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into cmax_slam_b200/libcmax_b200.so.  nvcc cross-compiles
     without a GPU.  Returns the library path."""
+    override = os.environ.get("CMAXB_LIB_PATH")
+    if override:
+        if not os.path.exists(override):
+            raise RuntimeError(f"CMAXB_LIB_PATH={override} does not exist")
+        return override
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -52,4 +71,8 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if not a.startswith("-")], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
