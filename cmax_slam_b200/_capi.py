@@ -50,6 +50,10 @@ class OptResult(C.Structure):
                 ("f_evals", C.c_int32), ("g_evals", C.c_int32), ("stop_reason", C.c_int32)]
 
 
+class Stamp(C.Structure):
+    _fields_ = [("sec", C.c_uint32), ("nsec", C.c_uint32)]
+
+
 class BeWindow(C.Structure):
     _fields_ = [("events", C.c_void_p), ("n_events", C.c_size_t), ("knots_xyzw", C.c_void_p),
                 ("n_knots", C.c_int32), ("t0_ns", C.c_int64), ("dt_ns", C.c_int64), ("n_fixed", C.c_int32),
@@ -66,6 +70,8 @@ EXPORTS = [
     "cmaxb_be_map_reset", "cmaxb_be_map_set", "cmaxb_be_map_get", "cmaxb_be_map_use_as_igp", "cmaxb_be_map_update",
     "cmaxb_be_map_mark_fov",
     "cmaxb_fe_optimize", "cmaxb_be_optimize",
+    "cmaxb_traj_integrate_ang_vel", "cmaxb_traj_num_ctrl_poses", "cmaxb_traj_fit_ctrl_poses", "cmaxb_traj_evaluate",
+    "cmaxb_traj_incremental_update",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
     "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_fe_phase_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
 ]
@@ -106,6 +112,12 @@ def lib():
     L.cmaxb_be_map_mark_fov.argtypes = [vp, dp, C.c_int, C.c_int]
     L.cmaxb_fe_optimize.argtypes = [vp, dp, C.POINTER(OptParams), dp, C.POINTER(OptResult)]
     L.cmaxb_be_optimize.argtypes = [vp, dp, C.c_int, C.POINTER(OptParams), dp, C.POINTER(OptResult)]
+    sp = C.POINTER(Stamp)
+    L.cmaxb_traj_integrate_ang_vel.argtypes = [Stamp, dp, sp, dp, C.c_int, sp, dp, C.c_int, sp, dp, C.POINTER(C.c_int)]
+    L.cmaxb_traj_num_ctrl_poses.argtypes = [C.c_int, Stamp, Stamp, C.c_double]
+    L.cmaxb_traj_fit_ctrl_poses.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, sp, dp, C.c_int, dp]
+    L.cmaxb_traj_evaluate.argtypes = [C.c_int, dp, C.c_int, C.c_int64, C.c_int64, Stamp, dp]
+    L.cmaxb_traj_incremental_update.argtypes = [dp, C.c_int, C.c_int, dp]
     L.cmaxb_last_error.restype = C.c_char_p
     L.cmaxb_launch_count.restype = C.c_uint64
     L.cmaxb_kernel_name.restype = C.c_char_p

@@ -245,6 +245,36 @@ int cmaxb_fe_optimize(cmaxb_fe* fe, const double omega0[3], const cmaxb_opt_para
 int cmaxb_be_optimize(cmaxb_be* be, const double* x0, int n, const cmaxb_opt_params* params, double* x_out,
                       cmaxb_opt_result* result);
 
+/* ------------------------------------------------------------------ trajectory initialisation ---- */
+/* the step between the front-end's angular velocities and the back-end window solve.
+ * Host C++ inside the library (a few dozen poses, one small dense least-squares system) so that a whole window
+ * -- initialise, solve, update the map -- runs behind this ABI.  Rotations are unit quaternions (x, y, z, w). */
+typedef struct cmaxb_stamp { uint32_t sec, nsec; } cmaxb_stamp;   /* ros::Time */
+
+/* PoseGraphOptimizer::integrateAngVel (pose_graph_optimizer.cpp:191-222): trapezoid integration of the m angular
+ * velocities (strictly increasing stamps) from pose_latest_; entries not newer than ang_vel_prev_ are skipped
+ * unless first_time_window.  ang_vel_prev_t / ang_vel_prev are updated in place (state carried across windows).
+ * pose_*_out: capacity m; *n_out = poses produced. */
+int cmaxb_traj_integrate_ang_vel(cmaxb_stamp pose_latest_t, const double pose_latest_xyzw[4],
+                                 cmaxb_stamp* ang_vel_prev_t, double ang_vel_prev[3], int first_time_window,
+                                 const cmaxb_stamp* t, const double* ang_vel, int m,
+                                 cmaxb_stamp* pose_t_out, double* pose_xyzw_out, int* n_out);
+/* number of control poses generateCtrlPoses fits for [t_beg, t_end]: round(span / dt_knots) + 1 (order 2) or + 3
+ * (order 4)   (trajectory.cpp:203-212, 479-489).  Negative = error. */
+int cmaxb_traj_num_ctrl_poses(int spline_order, cmaxb_stamp t_beg, cmaxb_stamp t_end, double dt_knots);
+/* Linear/CubicTrajectory::fitCtrlPoses (trajectory.cpp:112-186, 357-463): lift the poses to the tangent space at
+ * the first pose, solve the B-spline collocation system N P = D in the least-squares sense (full-pivoting
+ * Householder QR, as Eigen::FullPivHouseholderQR), retract.  ctrl_xyzw_out: num_cps quaternions. */
+int cmaxb_traj_fit_ctrl_poses(int spline_order, double dt_knots, double t_beg_sec, int num_cps,
+                              const cmaxb_stamp* pose_t, const double* pose_xyzw, int n_poses, double* ctrl_xyzw_out);
+/* Trajectory::evaluate(t), value only (pose_latest_ update pose_graph_optimizer.cpp:316-317, setUpdateTimesIG
+ * :325-337).  t0_ns / dt_ns as in cmaxb_be_window. */
+int cmaxb_traj_evaluate(int spline_order, const double* knots_xyzw, int n_knots, int64_t t0_ns, int64_t dt_ns,
+                        cmaxb_stamp t, double out_xyzw[4]);
+/* Trajectory::incrementalUpdate: knots[i] <- exp(x[i - idx_beg]) * knots[i], i >= idx_beg (trajectory.cpp:221-238,
+ * 491-499) -- applies the optimiser's result to the trajectory. */
+int cmaxb_traj_incremental_update(double* knots_xyzw, int n_knots, int idx_beg, const double* x);
+
 /* ------------------------------------------------------------------ diagnostics ---------- */
 const char* cmaxb_last_error(void);
 int cmaxb_version(void);

@@ -110,6 +110,12 @@ def ref():
         L.ref_so3_log.argtypes = [_dp, _dp]
         L.ref_knot_update.argtypes = [_dp, _dp, _dp]
         L.ref_left_jacobians.argtypes = [_dp, _dp, _dp]
+        if hasattr(L, "ref_fit_ctrl_poses"):
+            _up = C.POINTER(C.c_uint32)
+            L.ref_fit_ctrl_poses.restype = C.c_int
+            L.ref_fit_ctrl_poses.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, _up, _dp, C.c_int, _dp]
+            L.ref_integrate_ang_vel.restype = C.c_int
+            L.ref_integrate_ang_vel.argtypes = [_up, _dp, _up, _dp, C.c_int, _up, _dp, C.c_int, _up, _dp]
         _ref = L
     return _ref
 
@@ -280,3 +286,33 @@ def update_alpha(IGp, IL):
     a = np.ascontiguousarray(IGp, dtype=np.float32)
     b = np.ascontiguousarray(IL, dtype=np.float32)
     return lib().orc_update_alpha(a.ctypes.data_as(_fp), b.ctypes.data_as(_fp), a.size)
+
+
+# ---- trajectory initialisation against the real Eigen / Sophus code (oracle/_ref) -------------------------------
+def ref_fit_ctrl_poses(order, dt_knots, t_beg, num_cps, stamps, poses_xyzw):
+    """stamps: (n,2) uint32 (sec, nsec); poses: (n,4).  Returns (num_cps,4) or raises."""
+    L = ref()
+    st = np.ascontiguousarray(stamps, dtype=np.uint32)
+    q = np.ascontiguousarray(poses_xyzw, dtype=np.float64)
+    out = np.zeros((num_cps, 4))
+    rc = L.ref_fit_ctrl_poses(order, float(dt_knots), float(t_beg), int(num_cps), st.ctypes.data_as(C.POINTER(C.c_uint32)), _d(q), len(q), _d(out))
+    if rc != 0:
+        raise ValueError(f"ref_fit_ctrl_poses rc={rc}")
+    return out
+
+
+def ref_integrate_ang_vel(latest_stamp, latest_xyzw, prev_stamp, prev_w, first, stamps, w):
+    """Returns (pose_stamps (n,2), poses (n,4), new prev_stamp, new prev_w)."""
+    L = ref()
+    up = C.POINTER(C.c_uint32)
+    ls = np.ascontiguousarray(latest_stamp, dtype=np.uint32)
+    lq = np.ascontiguousarray(latest_xyzw, dtype=np.float64)
+    ps = np.array(prev_stamp, dtype=np.uint32)
+    pw = np.array(prev_w, dtype=np.float64)
+    st = np.ascontiguousarray(stamps, dtype=np.uint32).reshape(-1, 2)
+    ww = np.ascontiguousarray(w, dtype=np.float64).reshape(-1, 3)
+    os_ = np.zeros((len(st), 2), np.uint32)
+    oq = np.zeros((len(st), 4))
+    n = L.ref_integrate_ang_vel(ls.ctypes.data_as(up), _d(lq), ps.ctypes.data_as(up), _d(pw), int(first), st.ctypes.data_as(up), _d(ww), len(st),
+                                os_.ctypes.data_as(up), _d(oq))
+    return os_[:n], oq[:n], ps, pw

@@ -68,3 +68,85 @@ extern "C" void ref_left_jacobians(const double phi[3], double Jl[9], double Jli
   Sophus::leftJacobianInvSO3(p, b);
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { Jl[r * 3 + c] = a(r, c); Jlinv[r * 3 + c] = b(r, c); }
 }
+
+/* ---- trajectory initialisation ---------------------------------------------------
+ * The first-party functions (src/backend/trajectory.cpp, pose_graph_optimizer.cpp) need ROS/OpenCV/glog and do
+ * not compile here; the functions below restate their control flow line by line around the REAL third-party
+ * calls they make -- Sophus::SO3d exp / log / inverse / operator* and Eigen::FullPivHouseholderQR::solve
+ * (Eigen 3.3.9, vendored by the reference) -- so the product's own QR and SO(3) code is pinned against them. */
+#include <Eigen/Dense>
+#include <cmath>
+#include <vector>
+
+static double ref_stamp_diff(uint32_t as, uint32_t an, uint32_t bs, uint32_t bn) {   /* (a - b).toSec(), ros::Duration normalisation */
+  long long s = (long long)as - (long long)bs, ns = (long long)an - (long long)bn;
+  if (ns < 0) { ns += 1000000000ll; --s; }
+  return (double)(int)s + 1e-9 * (double)(int)ns;
+}
+
+/* Linear/CubicTrajectory::fitCtrlPoses, trajectory.cpp:112-186 / 357-463.  stamps: n x (sec, nsec). */
+extern "C" int ref_fit_ctrl_poses(int order, double dt_knots, double t_beg, int num_cps, const uint32_t* stamps,
+                                  const double* poses_xyzw, int n, double* ctrl_xyzw) {
+  if (n < num_cps) return -1;
+  auto so3 = [](const double* q) { return Sophus::SO3d(Eigen::Quaterniond(q[3], q[0], q[1], q[2])); };
+  Sophus::SO3d offset = so3(poses_xyzw);
+  Sophus::SO3d offset_inv = offset.inverse();
+  Eigen::MatrixXd N = Eigen::MatrixXd::Zero(n, num_cps);
+  Eigen::VectorXd Dx(n), Dy(n), Dz(n);
+  Eigen::Matrix2d M2 = (Eigen::MatrixXd(2, 2) << 1.0, 0.0, -1.0, 1.0).finished();
+  Eigen::Matrix4d M4 = (Eigen::MatrixXd(4, 4) << 1. / 6, 2. / 3, 1. / 6, 0.0, -0.5, 0.0, 0.5, 0.0, 0.5, -1.0, 0.5, 0.0, -1. / 6, 0.5, -0.5, 1. / 6).finished();
+  for (int idx = 0; idx < n; ++idx) {
+    Sophus::SO3d drot = offset_inv * so3(poses_xyzw + 4 * idx);
+    double t = (double)stamps[2 * idx] + 1e-9 * (double)stamps[2 * idx + 1];
+    int t_i = std::floor((t - t_beg) / dt_knots);
+    double u = (t - (t_i * dt_knots + t_beg)) / dt_knots;
+    if (t_i < 0 || t_i + order > num_cps) return -2;
+    if (order == 2) {
+      Eigen::Matrix<double, 1, 2> U;
+      for (int i = 0; i < 2; i++) U(i) = std::pow(u, i);
+      Eigen::Matrix<double, 1, 2> N_idx = U * M2;
+      for (int j = 0; j < 2; j++) N(idx, t_i + j) = N_idx(j);
+    } else {
+      Eigen::Matrix<double, 1, 4> U;
+      for (int i = 0; i < 4; i++) U(i) = std::pow(u, i);
+      Eigen::Matrix<double, 1, 4> N_idx = U * M4;
+      for (int j = 0; j < 4; j++) N(idx, t_i + j) = N_idx(j);
+    }
+    Eigen::Vector3d rv = drot.log();
+    Dx(idx) = rv(0); Dy(idx) = rv(1); Dz(idx) = rv(2);
+  }
+  Eigen::VectorXd Px = N.fullPivHouseholderQr().solve(Dx);
+  Eigen::VectorXd Py = N.fullPivHouseholderQr().solve(Dy);
+  Eigen::VectorXd Pz = N.fullPivHouseholderQr().solve(Dz);
+  for (int i = 0; i < num_cps; ++i) {
+    Sophus::SO3d cp = offset * Sophus::SO3d::exp(Eigen::Vector3d(Px(i), Py(i), Pz(i)));
+    ctrl_xyzw[4 * i] = cp.unit_quaternion().x(); ctrl_xyzw[4 * i + 1] = cp.unit_quaternion().y();
+    ctrl_xyzw[4 * i + 2] = cp.unit_quaternion().z(); ctrl_xyzw[4 * i + 3] = cp.unit_quaternion().w();
+  }
+  return 0;
+}
+
+/* PoseGraphOptimizer::integrateAngVel, pose_graph_optimizer.cpp:191-222.  state = (prev sec, prev nsec) + prev w. */
+extern "C" int ref_integrate_ang_vel(const uint32_t latest_stamp[2], const double latest_xyzw[4], uint32_t prev_stamp[2],
+                                     double prev_w[3], int first_time_window, const uint32_t* stamps, const double* w, int m,
+                                     uint32_t* out_stamps, double* out_xyzw) {
+  Sophus::SO3d cur(Eigen::Quaterniond(latest_xyzw[3], latest_xyzw[0], latest_xyzw[1], latest_xyzw[2]));
+  uint32_t cs = latest_stamp[0], cn = latest_stamp[1];
+  int n = 0;
+  for (int i = 0; i < m; ++i) {
+    const uint32_t s = stamps[2 * i], ns = stamps[2 * i + 1];
+    const bool newer = s > prev_stamp[0] || (s == prev_stamp[0] && ns > prev_stamp[1]);
+    if (!newer && !first_time_window) continue;
+    const double dt = ref_stamp_diff(s, ns, cs, cn);
+    Eigen::Vector3d drotv = dt * ((Eigen::Vector3d(prev_w[0], prev_w[1], prev_w[2]) + Eigen::Vector3d(w[3 * i], w[3 * i + 1], w[3 * i + 2])) / 2.0);
+    cs = s; cn = ns;
+    cur = cur * Sophus::SO3d::exp(drotv);
+    out_stamps[2 * n] = s; out_stamps[2 * n + 1] = ns;
+    out_xyzw[4 * n] = cur.unit_quaternion().x(); out_xyzw[4 * n + 1] = cur.unit_quaternion().y();
+    out_xyzw[4 * n + 2] = cur.unit_quaternion().z(); out_xyzw[4 * n + 3] = cur.unit_quaternion().w();
+    ++n;
+    prev_stamp[0] = s; prev_stamp[1] = ns;
+    prev_w[0] = w[3 * i]; prev_w[1] = w[3 * i + 1]; prev_w[2] = w[3 * i + 2];
+  }
+  return n;
+}

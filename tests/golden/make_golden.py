@@ -132,7 +132,67 @@ def golden_be():
     np.savez_compressed(os.path.join(OUT, "be_oracle.npz"), **d)
 
 
+def _rand_walk_poses(rng, n, t0, span, sigma):
+    """n poses on a random SO(3) walk at sorted stamps in [t0, t0 + span] (ns-integral)."""
+    ts = np.sort(rng.uniform(t0, t0 + span, n))
+    stamps = np.array([[int(np.floor(t)), int(round((t - np.floor(t)) * 1e9)) % 1000000000] for t in ts], dtype=np.uint32)
+    L = O.ref()
+    q = np.zeros((n, 4)); q[0] = [0, 0, 0, 1]
+    cur = np.array([0.0, 0.0, 0.0, 1.0])
+    # start from a non-trivial rotation
+    e = np.zeros(4); L.ref_so3_exp(O._d(np.array([0.3, -0.2, 0.5])), O._d(e)); cur = e.copy(); q[0] = cur
+    for i in range(1, n):
+        out = np.zeros(4)
+        L.ref_knot_update(O._d(rng.normal(0, sigma, 3)), O._d(cur), O._d(out))
+        cur = out; q[i] = cur
+    return stamps, q
+
+
+def golden_traj():
+    """Trajectory initialisation through the REAL Eigen FullPivHouseholderQR / Sophus code
+    of the reference (oracle/_ref): control-pose fits (linear, cubic; well- and ill-posed) and the angular-velocity
+    integration."""
+    assert O.have_ref()
+    rng = np.random.default_rng(17)
+    d = {}
+    cases = []
+    # (order, dt_knots, span, n_poses, sigma)
+    for ci, (order, dtk, span, n, sig) in enumerate([(2, 0.1, 0.5, 40, 0.02), (4, 0.1, 0.5, 40, 0.02), (2, 0.05, 0.2, 9, 0.05),
+                                                     (4, 0.05, 0.2, 9, 0.05), (4, 0.1, 1.0, 200, 0.01), (2, 0.02, 0.2, 14, 0.03)]):
+        t0 = 1.6e9 + 37.123456789 + ci
+        stamps, q = _rand_walk_poses(rng, n, t0 + 1e-4, span - 2e-4, sig)
+        num = int(round(span / dtk)) + (3 if order == 4 else 1)
+        ctrl = O.ref_fit_ctrl_poses(order, dtk, t0, num, stamps, q)
+        d[f"fit{ci}_in"] = np.array([order, dtk, t0, num])
+        d[f"fit{ci}_stamps"] = stamps; d[f"fit{ci}_poses"] = q; d[f"fit{ci}_ctrl"] = ctrl
+        cases.append(ci)
+    # rank-deficient system: all poses inside the first knot interval of a 6-control-pose linear fit
+    stamps, q = _rand_walk_poses(rng, 12, 100.0 + 1e-3, 0.09, 0.02)
+    d["fitdef_in"] = np.array([2, 0.1, 100.0, 6]); d["fitdef_stamps"] = stamps; d["fitdef_poses"] = q
+    d["fitdef_ctrl"] = O.ref_fit_ctrl_poses(2, 0.1, 100.0, 6, stamps, q)
+    d["n_fit"] = np.array(len(cases))
+    # integration: first window (nothing skipped) and a later window with stale entries
+    for ci, first in enumerate((1, 0)):
+        m = 30
+        ts = np.sort(rng.uniform(50.0, 50.6, m))
+        stamps = np.array([[int(np.floor(t)), int((t - np.floor(t)) * 1e9)] for t in ts], dtype=np.uint32)
+        w = rng.normal(0, 1.5, (m, 3))
+        latest_stamp = np.array([49, 999000000], np.uint32)
+        latest_q = np.array([0.1, -0.2, 0.05, 0.0]); latest_q[3] = np.sqrt(1 - (latest_q[:3] ** 2).sum())
+        prev_stamp = stamps[4].copy() if not first else np.array([49, 990000000], np.uint32)
+        prev_w = rng.normal(0, 1.0, 3)
+        os_, oq, ps, pw = O.ref_integrate_ang_vel(latest_stamp, latest_q, prev_stamp, prev_w, first, stamps, w)
+        d[f"int{ci}_stamps"] = stamps; d[f"int{ci}_w"] = w; d[f"int{ci}_latest_stamp"] = latest_stamp; d[f"int{ci}_latest_q"] = latest_q
+        d[f"int{ci}_prev_stamp"] = prev_stamp; d[f"int{ci}_prev_w"] = prev_w; d[f"int{ci}_first"] = np.array(first)
+        d[f"int{ci}_out_stamps"] = os_; d[f"int{ci}_out_q"] = oq; d[f"int{ci}_new_prev_stamp"] = ps; d[f"int{ci}_new_prev_w"] = pw
+    np.savez_compressed(os.path.join(OUT, "traj_ref.npz"), **d)
+
+
 if __name__ == "__main__":
+    if "--only-traj" in sys.argv:
+        golden_traj()
+        sys.exit(0)
+    golden_traj()
     golden_blur()
     golden_spline()
     golden_fe()
