@@ -61,8 +61,7 @@ struct cmaxb_fe {
   int last_k = 0; bool last_grad = false; bool pending = false;
   std::deque<FeInflight> inflight;   // launched, not yet fetched (FIFO)
   int ring_next = 0;
-  bool gather_f32 = false;           // CMAXB_FE_GATHER_F32=1: Jacobian chain of the gather in f32 (measured: no faster; kept for A/B)
-  float tx_lo[kMaxRadius + 2] = {}, tx_hi[kMaxRadius + 2] = {}, ty_lo[kMaxRadius + 2] = {}, ty_hi[kMaxRadius + 2] = {};   // T = B^T(1) near the borders
+  bool gather_f32 = false;           // CMAXB_FE_GATHER_F32=1: Jacobian chain of the gather in f32 (measured 1.5 % faster; default = the reference's f64 chain)
   // fused result exchange over peer memory (cmaxb_fe_exchange_*)
   int x_world = 0, x_rank = 0; bool x_on = false;
   double* x_local = nullptr; size_t x_bytes = 0;
@@ -73,33 +72,6 @@ struct cmaxb_fe {
   unsigned long long x_seq = 0;
   KernelProfiler prof;
 };
-
-// T = B^T(1) along one axis of length len (B = the Gaussian with BORDER_REFLECT_101): T[q] = sum over output
-// pixels p and taps d with reflect101(p + d) == q of w[d].  1 in the interior; lo[x] = T[x], hi[x] = T[len-1-x]
-// for x <= r+1.
-static void adjoint_of_ones(const Taps& taps, int len, float* lo, float* hi) {
-  const int r = taps.r;
-  std::vector<double> T((size_t)len, 0.0);
-  auto refl = [len](int q) { if (q < 0) q = -q; if (q >= len) q = 2 * (len - 1) - q; return q; };
-  auto add_from = [&](int p) {
-    for (int d = -r; d <= r; ++d) {
-      const int q = refl(p + d);
-      if (q >= 0 && q < len) T[(size_t)q] += (double)taps.w[r + d];
-    }
-  };
-  // only pixels within 2r+2 of a border can touch the border entries we keep; the others are 1 by symmetry
-  const int span = 2 * r + 3;
-  if (len <= 2 * span) { for (int p = 0; p < len; ++p) add_from(p); }
-  else {
-    for (int p = 0; p < span; ++p) add_from(p);
-    for (int p = len - span; p < len; ++p) add_from(p);
-  }
-  for (int x = 0; x <= r + 1; ++x) {
-    lo[x] = (x < len) ? (float)T[(size_t)x] : 1.0f;
-    hi[x] = (len - 1 - x >= 0) ? (float)T[(size_t)(len - 1 - x)] : 1.0f;
-  }
-  hi[r + 1] = lo[r + 1];   // both are the interior value (the sum of the taps)
-}
 
 static FeGeom fe_geom(const cmaxb_fe* fe) {
   FeGeom g;
@@ -138,8 +110,6 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   int rc = make_taps(cfg->blur_sigma, &fe->taps);
   if (rc != CMAXB_OK) { delete fe; return rc; }
   if (fe->taps.r + 2 > cfg->width || fe->taps.r + 2 > cfg->height) { delete fe; return set_error(CMAXB_ERR_INVALID, "image smaller than the blur kernel"); }
-  adjoint_of_ones(fe->taps, cfg->width, fe->tx_lo, fe->tx_hi);
-  adjoint_of_ones(fe->taps, cfg->height, fe->ty_lo, fe->ty_hi);
   auto fail = [&](int code) { cmaxb_fe_destroy(fe); return code; };
   if (cfg->stream) fe->stream = (cudaStream_t)cfg->stream;
   else {
@@ -201,7 +171,7 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
       fe->mega_grid = grid;
       fe->mega_th = mega_tile_height(cfg->width, cfg->height, grid);
       const size_t kk = (size_t)fe->kmax;
-      bool okm = dev_alloc(&fe->d_part_img, kk * kMegaMaxCtas * 2) == CMAXB_OK && dev_alloc(&fe->d_part_ev, kk * kMegaMaxCtas * 6) == CMAXB_OK;
+      bool okm = dev_alloc(&fe->d_part_img, kk * kMegaMaxCtas * 2) == CMAXB_OK && dev_alloc(&fe->d_part_ev, kk * kMegaMaxCtas * 3) == CMAXB_OK;
       okm = okm && cudaHostAlloc((void**)&fe->h_mega_result, sizeof(double) * 4 * kk * kFeRing, cudaHostAllocMapped) == cudaSuccess;
       okm = okm && cudaHostGetDevicePointer((void**)&fe->d_mega_result, fe->h_mega_result, 0) == cudaSuccess;
       okm = okm && cudaHostAlloc((void**)&fe->h_done, sizeof(unsigned long long) * 8, cudaHostAllocMapped) == cudaSuccess;
@@ -437,7 +407,7 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
     p.GQ = fe->d_GQ + (long long)c0 * fe->A;
     p.A = fe->A;
     p.part_img = fe->d_part_img + (long long)c0 * kMegaMaxCtas * 2;
-    p.part_ev = fe->d_part_ev + (long long)c0 * kMegaMaxCtas * 6;
+    p.part_ev = fe->d_part_ev + (long long)c0 * kMegaMaxCtas * 3;
     p.ticket = fe->d_ticket;
     p.contrast_dev = fe->d_mean + c0;
     p.result = fe->d_mega_result + ((long long)slot * fe->kmax + c0) * 4;
@@ -446,8 +416,6 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
     p.seq = ++fe->seq;
     p.phase_ns = fe->prof.enabled ? fe->d_phase : nullptr;
     p.gather_f32 = fe->gather_f32 ? 1 : 0;
-    std::memcpy(p.tx_lo, fe->tx_lo, sizeof(p.tx_lo)); std::memcpy(p.tx_hi, fe->tx_hi, sizeof(p.tx_hi));
-    std::memcpy(p.ty_lo, fe->ty_lo, sizeof(p.ty_lo)); std::memcpy(p.ty_hi, fe->ty_hi, sizeof(p.ty_hi));
     std::memset(&p.x, 0, sizeof(p.x));
     if (fe->x_on) {
       p.x.world = fe->x_world; p.x.rank = fe->x_rank; p.x.kmax = fe->kmax;

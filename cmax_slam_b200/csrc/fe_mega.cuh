@@ -100,9 +100,7 @@ struct FeMegaParams {
   float4* GQ;                 // [k][A]
   long long A;
   double* part_img;           // [k][kMegaMaxCtas][2]
-  double* part_ev;            // [k][kMegaMaxCtas][6]: gather sums against B^T(2 I) and against T = B^T(1)
-  float tx_lo[kMaxRadius + 2], tx_hi[kMaxRadius + 2];   // T is separable: Tx(x) for x <= r+1 / for W-1-x <= r+1 (1 elsewhere)
-  float ty_lo[kMaxRadius + 2], ty_hi[kMaxRadius + 2];
+  double* part_ev;            // [k][kMegaMaxCtas][3]
   unsigned int* ticket;       // arrival counter for the final reduction (re-armed by the kernel)
   double* contrast_dev;       // [k] device scratch: contrast of a gradient evaluation until the last CTA publishes it
   double* result;             // [k][4] mapped pinned host memory (device pointer)
@@ -117,16 +115,7 @@ struct FeMegaParams {
 #define CMAXB_PHASE_MARK(idx) do { if (p.phase_ns && blockIdx.x == 0 && threadIdx.x == 0) p.phase_ns[idx] = global_timer_ns(); } while (0)
 #define CMAXB_PHASE_MARK_ANY(idx) do { if (p.phase_ns && threadIdx.x == 0) p.phase_ns[idx] = global_timer_ns(); } while (0)
 
-#ifndef CMAXB_EV_UNROLL
-#define CMAXB_EV_UNROLL 4
-#endif
-#ifndef CMAXB_MEGA_MIN_CTAS
-#define CMAXB_MEGA_MIN_CTAS 3
-#endif
-#ifndef CMAXB_GATHER_UNROLL
-#define CMAXB_GATHER_UNROLL 2
-#endif
-constexpr int kEvUnroll = CMAXB_EV_UNROLL;   // compile-time tuning knobs (A/B builds: cmax_slam_b200/build.py --variant)
+constexpr int kEvUnroll = 4;
 
 __device__ __forceinline__ void mega_scatter(const FeMegaParams& p) {
   const FeGeom& g = p.g;
@@ -192,18 +181,11 @@ __device__ __forceinline__ void mega_blur(const FeMegaParams& p, int h, unsigned
 __device__ __forceinline__ void mega_image_sums(const FeMegaParams& p, int h, double* s_red, double* S1, double* S2) {
   tile_sum_partials(p.part_img + (long long)h * kMegaMaxCtas * 2, s_red, S1, S2);
 }
-// The adjoint image is built WITHOUT the mean: blur is linear, so B^T(2(I - mu)) = B^T(2 I) - 2 mu T with
-// T = B^T(1) a fixed separable image that equals 1 except within r pixels of the border.  The bilinear
-// derivative weights of an event sum to zero, so the -2 mu T term only contributes for events next to the
-// border; the gather accumulates it separately (acc[3..5]) and the final reduction combines the two once mu
-// is known.  No CTA needs mu before the end: the all-CTA sum of the image partials and one phase are gone.
 template <int R>
-__device__ __forceinline__ void mega_adjoint(const FeMegaParams& p, int h, unsigned char* smem_raw) {
+__device__ __forceinline__ void mega_adjoint(const FeMegaParams& p, int h, double mean, unsigned char* smem_raw) {
   const TileCtx c{p.g.W, p.g.H, p.th, p.taps};
-  tile_adjoint_phase<R>(c, p.blurred + h * p.A, 2.0f, 0.0f, nullptr, p.GQ + h * p.A, smem_raw);
-}
-__device__ __forceinline__ float mega_T(const float* lo, const float* hi, int x, int len, int r) {
-  return (x <= r + 1) ? lo[x] : ((len - 1 - x <= r + 1) ? hi[len - 1 - x] : lo[r + 1]);   // lo[r+1] = interior value (sum of the taps)
+  const float b2 = (p.measure == CMAXB_CONTRAST_MEAN_SQUARE) ? 0.0f : (float)(-2.0 * mean);
+  tile_adjoint_phase<R>(c, p.blurred + h * p.A, 2.0f, b2, nullptr, p.GQ + h * p.A, smem_raw);
 }
 
 template <bool F32>
@@ -211,10 +193,8 @@ __device__ __forceinline__ void mega_gather(const FeMegaParams& p, int h, double
   const FeGeom& g = p.g;
   const double ox = p.omegas[3 * h], oy = p.omegas[3 * h + 1], oz = p.omegas[3 * h + 2];
   const float4* GQh = p.GQ + h * p.A;
-  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  const int rr = p.taps.r;
-  const bool want_T = p.measure != CMAXB_CONTRAST_MEAN_SQUARE;
-  constexpr int U = CMAXB_GATHER_UNROLL;
+  double acc[3] = {0.0, 0.0, 0.0};
+  constexpr int U = 2;
   const long long chunk = (g.n + gridDim.x - 1) / gridDim.x;
   const long long c_beg = blockIdx.x * chunk;
   const long long c_end = (c_beg + chunk < g.n) ? c_beg + chunk : g.n;
@@ -252,16 +232,6 @@ __device__ __forceinline__ void mega_gather(const FeMegaParams& p, int h, double
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (!(ok[u] && w[u].in)) continue;
-      if (want_T && (w[u].xx <= rr || w[u].xx + 1 >= g.W - 1 - rr || w[u].yy <= rr || w[u].yy + 1 >= g.H - 1 - rr)) {
-        // border event: its share of sum_c dw_c * T(c)
-        const double tx0 = mega_T(p.tx_lo, p.tx_hi, w[u].xx, g.W, rr), tx1 = mega_T(p.tx_lo, p.tx_hi, w[u].xx + 1, g.W, rr);
-        const double ty0 = mega_T(p.ty_lo, p.ty_hi, w[u].yy, g.H, rr), ty1 = mega_T(p.ty_lo, p.ty_hi, w[u].yy + 1, g.H, rr);
-        const double dx = w[u].dx, dy = w[u].dy;
-        const double aT = (tx1 - tx0) * ((1.0 - dy) * ty0 + dy * ty1);
-        const double bT = (ty1 - ty0) * ((1.0 - dx) * tx0 + dx * tx1);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[3 + c] += (double)w[u].r0[c] * aT + (double)w[u].r1[c] * bT;
-      }
       if (F32) {
         const float dx = w[u].dx, dy = w[u].dy;
         const float a = (1.f - dy) * (q[u].y - q[u].x) + dy * (q[u].w - q[u].z);
@@ -278,32 +248,11 @@ __device__ __forceinline__ void mega_gather(const FeMegaParams& p, int h, double
       for (int c = 0; c < 3; ++c) acc[c] += (double)w[u].r0[c] * a + (double)w[u].r1[c] * b;
     }
   }
-  block_sum<6>(acc, s_red);
+  block_sum<3>(acc, s_red);
   if (threadIdx.x == 0) {
-    double* part = p.part_ev + ((long long)h * kMegaMaxCtas + blockIdx.x) * 6;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) part[c] = acc[c];
+    double* part = p.part_ev + ((long long)h * kMegaMaxCtas + blockIdx.x) * 3;
+    part[0] = acc[0]; part[1] = acc[1]; part[2] = acc[2];
   }
-}
-
-// Fixed-order sum of the per-CTA records rec[n][NV] by ALL threads of one CTA (every load of a thread is in
-// flight at once: one L2 round trip); result valid in thread 0.
-template <int NV>
-__device__ __forceinline__ void mega_sum_records(const double* __restrict__ rec, int n, double* s_red, double (&t)[NV]) {
-#pragma unroll
-  for (int j = 0; j < NV; ++j) t[j] = 0.0;
-  for (int c0 = threadIdx.x; c0 < n; c0 += 2 * kMegaThreads) {    // two records (2 NV loads) in flight per thread
-    const int c1 = c0 + kMegaThreads;
-    double v0[NV], v1[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) v0[j] = __ldcg(rec + (long long)NV * c0 + j);
-#pragma unroll
-    for (int j = 0; j < NV; ++j) v1[j] = (c1 < n) ? __ldcg(rec + (long long)NV * c1 + j) : 0.0;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) { t[j] += v0[j]; t[j] += v1[j]; }
-  }
-  __syncthreads();
-  block_sum<NV>(t, s_red);
 }
 
 // rows of this launch (shared memory, [k][4]) -> mapped host result (+ device mirror) (+ exchange with the
@@ -324,12 +273,12 @@ __device__ __forceinline__ void mega_publish(const FeMegaParams& p, const double
 }
 
 template <int R>
-__global__ void __launch_bounds__(kMegaThreads, CMAXB_MEGA_MIN_CTAS)
+__global__ void __launch_bounds__(kMegaThreads)
 fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double s_red[(kMegaThreads / 32) * 6];
+  __shared__ double s_red[(kMegaThreads / 32) * 3];
+  __shared__ double s_mean[kMegaMaxHyp];
   __shared__ double s_rows[kMegaMaxHyp * 4];
-  __shared__ bool s_last;
   cg::grid_group grid = cg::this_grid();
   const double Np = (double)p.g.W * (double)p.g.H;
 
@@ -340,55 +289,99 @@ fe_eval_megakernel(const __grid_constant__ FeMegaParams p) {
   CMAXB_PHASE_MARK(2);
   for (int h = 0; h < p.k; ++h) mega_blur<R>(p, h, smem_raw, p.want_grad != 0);
   CMAXB_PHASE_MARK(3);
-  if (p.want_grad) {
-    grid.sync();
-    CMAXB_PHASE_MARK(4);
-    for (int h = 0; h < p.k; ++h) mega_adjoint<R>(p, h, smem_raw);
-    CMAXB_PHASE_MARK(5);
-    grid.sync();
-    CMAXB_PHASE_MARK(6);
-    for (int h = 0; h < p.k; ++h) {
-      __syncthreads();
-      if (p.gather_f32) mega_gather<true>(p, h, s_red);
-      else mega_gather<false>(p, h, s_red);
+  grid.sync();
+  CMAXB_PHASE_MARK(4);
+  for (int h = 0; h < p.k; ++h) {
+    double S1, S2;
+    mega_image_sums(p, h, s_red, &S1, &S2);
+    const double mean = S1 / Np;
+    if (threadIdx.x == 0) {
+      s_mean[h] = mean;
+      double contrast;
+      if (p.measure == CMAXB_CONTRAST_MEAN_SQUARE) contrast = S2 / Np;
+      else {
+        double var = S2 / Np - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double sd = sqrt(var);
+        contrast = sd * sd;
+      }
+      // every CTA holds the identical value (fixed-order sums); the publishing CTA uses its own copy
+      s_rows[4 * h] = contrast; s_rows[4 * h + 1] = 0.0; s_rows[4 * h + 2] = 0.0; s_rows[4 * h + 3] = 0.0;
     }
-    CMAXB_PHASE_MARK(7);
   }
-  // no further grid barrier: the last CTA to publish its records (atomic ticket) does the final sums --
-  // image sums S1, S2 -> mean, contrast; gather sums -> gradient -- in a fixed order
   __syncthreads();
+  if (!p.want_grad) {
+    CMAXB_PHASE_MARK(5);
+    if (blockIdx.x == 0) mega_publish(p, s_rows);
+    return;
+  }
+  for (int h = 0; h < p.k; ++h) mega_adjoint<R>(p, h, s_mean[h], smem_raw);
+  CMAXB_PHASE_MARK(5);
+  grid.sync();
+  CMAXB_PHASE_MARK(6);
+  for (int h = 0; h < p.k; ++h) {
+    __syncthreads();
+    if (p.gather_f32) mega_gather<true>(p, h, s_red);
+    else mega_gather<false>(p, h, s_red);
+  }
+  CMAXB_PHASE_MARK(7);
+  // no fourth grid barrier: the last CTA to publish its gather record (atomic ticket) does the final sum
+  __shared__ bool s_last;
   if (threadIdx.x == 0) {
     __threadfence();
     s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
   CMAXB_PHASE_MARK(8);
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x == 0) *p.ticket = 0u;
-  for (int h = 0; h < p.k; ++h) {
-    double S[2];
-    mega_sum_records<2>(p.part_img + (long long)h * kMegaMaxCtas * 2, (int)gridDim.x, s_red, S);
-    double mean = 0.0;
-    if (threadIdx.x == 0) {
-      mean = S[0] / Np;
-      s_rows[4 * h] = contrast_from_sums(S[0], S[1], Np, p.measure);
-      s_rows[4 * h + 1] = 0.0; s_rows[4 * h + 2] = 0.0; s_rows[4 * h + 3] = 0.0;
-    }
-    if (p.want_grad) {
-      double t[6];
-      __syncthreads();
-      mega_sum_records<6>(p.part_ev + (long long)h * kMegaMaxCtas * 6, (int)gridDim.x, s_red, t);
-      if (threadIdx.x == 0) {
-        const double m2 = (p.measure == CMAXB_CONTRAST_MEAN_SQUARE) ? 0.0 : 2.0 * mean;
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x == 0) *p.ticket = 0u;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (p.k <= 4) {
+      // few hypotheses: the whole CTA adds the per-CTA records of one hypothesis (all loads of a thread in
+      // flight at once: one L2 round trip), fixed order
+      constexpr int kRec = (kMegaMaxCtas + kMegaThreads - 1) / kMegaThreads;
+      for (int h = 0; h < p.k; ++h) {
+        const double* all = p.part_ev + (long long)h * kMegaMaxCtas * 3;
+        double v[kRec][3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) s_rows[4 * h + 1 + c] = (t[c] - m2 * t[3 + c]) / Np;
+        for (int u = 0; u < kRec; ++u) {
+          const int c = threadIdx.x + u * kMegaThreads;
+          const bool ok = c < (int)gridDim.x;
+          v[u][0] = ok ? __ldcg(all + 3 * c) : 0.0; v[u][1] = ok ? __ldcg(all + 3 * c + 1) : 0.0; v[u][2] = ok ? __ldcg(all + 3 * c + 2) : 0.0;
+        }
+        double t[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < kRec; ++u) { t[0] += v[u][0]; t[1] += v[u][1]; t[2] += v[u][2]; }
+        __syncthreads();
+        block_sum<3>(t, s_red);
+        if (threadIdx.x == 0) { s_rows[4 * h + 1] = t[0] / Np; s_rows[4 * h + 2] = t[1] / Np; s_rows[4 * h + 3] = t[2] / Np; }
+      }
+    } else {
+      // one WARP per hypothesis: lanes add the per-CTA records in a fixed order
+      for (int h = wid; h < p.k; h += kMegaThreads / 32) {
+        const double* all = p.part_ev + (long long)h * kMegaMaxCtas * 3;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        constexpr int kRecUnroll = 8;    // 24 independent loads in flight per lane (the loop is one L2 round trip per step)
+        for (int c0 = lane; c0 < (int)gridDim.x; c0 += 32 * kRecUnroll) {
+          double v[kRecUnroll][3];
+#pragma unroll
+          for (int u = 0; u < kRecUnroll; ++u) {
+            const int c = c0 + 32 * u;
+            const bool ok = c < (int)gridDim.x;
+            v[u][0] = ok ? __ldcg(all + 3 * c) : 0.0; v[u][1] = ok ? __ldcg(all + 3 * c + 1) : 0.0; v[u][2] = ok ? __ldcg(all + 3 * c + 2) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < kRecUnroll; ++u) { t0 += v[u][0]; t1 += v[u][1]; t2 += v[u][2]; }
+        }
+        t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
+        if (lane == 0) { s_rows[4 * h + 1] = t0 / Np; s_rows[4 * h + 2] = t1 / Np; s_rows[4 * h + 3] = t2 / Np; }
       }
     }
     __syncthreads();
+    CMAXB_PHASE_MARK_ANY(9);
+    mega_publish(p, s_rows);
   }
-  CMAXB_PHASE_MARK_ANY(9);
-  mega_publish(p, s_rows);
 }
 
 inline size_t mega_smem_bytes(int r, int th = kMegaMaxTH) { return tile_smem_bytes(r, th); }

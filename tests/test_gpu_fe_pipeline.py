@@ -85,7 +85,7 @@ np.save(sys.argv[2], np.concatenate([c, g.ravel(), [c1], g1]))
 
 
 def test_gather_f32_and_f64_both_meet_the_bar(oracle, tmp_path):
-    """The gather's Jacobian chain in f32 (default) and in f64 (CMAXB_FE_GATHER_F64=1) against the oracle; the
+    """The gather's Jacobian chain in f64 (default) and in f32 (CMAXB_FE_GATHER_F32=1) against the oracle; the
     true angular velocity (gradient near its zero crossing) is among the hypotheses."""
     pk = synth.fe_config("C1", scale=0.5)
     oms = np.concatenate([synth.fe_hypotheses(pk, 5, sigma=0.4), pk.omega_true[None, :]])
@@ -94,7 +94,7 @@ def test_gather_f32_and_f64_both_meet_the_bar(oracle, tmp_path):
     script = tmp_path / "g.py"
     script.write_text(_GATHER_WORKER)
     out = {}
-    for tag, env in (("f32", {}), ("f64", {"CMAXB_FE_GATHER_F64": "1"})):
+    for tag, env in (("f64", {}), ("f32", {"CMAXB_FE_GATHER_F32": "1"})):
         path = tmp_path / f"{tag}.npy"
         r = subprocess.run([sys.executable, str(script), ROOT, str(path)], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
