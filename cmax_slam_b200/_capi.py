@@ -54,6 +54,19 @@ class Stamp(C.Structure):
     _fields_ = [("sec", C.c_uint32), ("nsec", C.c_uint32)]
 
 
+class PgoCfg(C.Structure):
+    _fields_ = [("spline_order", C.c_int32), ("dt_knots", C.c_double), ("time_window_size", C.c_double),
+                ("sliding_window_stride", C.c_double), ("y_angle_deg", C.c_double), ("max_update_times", C.c_int32),
+                ("min_num_ev_per_win", C.c_double), ("use_opt_params", C.c_int32), ("opt_params", OptParams)]
+
+
+class PgoReport(C.Structure):
+    _fields_ = [("window", C.c_int32), ("t_win_beg", Stamp), ("t_win_end", Stamp), ("n_ang_vel", C.c_int32),
+                ("n_frontend_poses", C.c_int32), ("n_ctrl_poses", C.c_int32), ("idx_cp_traj_beg", C.c_int32),
+                ("idx_cp_opt_beg", C.c_int32), ("num_cp_opt", C.c_int32), ("optimized", C.c_int32), ("opt", OptResult),
+                ("alpha", C.c_double), ("n_fov_marks", C.c_int32), ("pose_latest_t", Stamp), ("pose_latest_xyzw", C.c_double * 4)]
+
+
 class BeWindow(C.Structure):
     _fields_ = [("events", C.c_void_p), ("n_events", C.c_size_t), ("knots_xyzw", C.c_void_p),
                 ("n_knots", C.c_int32), ("t0_ns", C.c_int64), ("dt_ns", C.c_int64), ("n_fixed", C.c_int32),
@@ -72,6 +85,8 @@ EXPORTS = [
     "cmaxb_fe_optimize", "cmaxb_be_optimize",
     "cmaxb_traj_integrate_ang_vel", "cmaxb_traj_num_ctrl_poses", "cmaxb_traj_fit_ctrl_poses", "cmaxb_traj_evaluate",
     "cmaxb_traj_incremental_update",
+    "cmaxb_pgo_create", "cmaxb_pgo_destroy", "cmaxb_pgo_push_ang_vel", "cmaxb_pgo_window", "cmaxb_pgo_process_window",
+    "cmaxb_pgo_get_ctrl_poses", "cmaxb_be_last_eval_x",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
     "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_fe_phase_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
 ]
@@ -118,6 +133,14 @@ def lib():
     L.cmaxb_traj_fit_ctrl_poses.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, sp, dp, C.c_int, dp]
     L.cmaxb_traj_evaluate.argtypes = [C.c_int, dp, C.c_int, C.c_int64, C.c_int64, Stamp, dp]
     L.cmaxb_traj_incremental_update.argtypes = [dp, C.c_int, C.c_int, dp]
+    L.cmaxb_pgo_create.argtypes = [C.POINTER(PgoCfg), vp, C.POINTER(vp)]
+    L.cmaxb_pgo_destroy.argtypes = [vp]
+    L.cmaxb_pgo_destroy.restype = None
+    L.cmaxb_pgo_push_ang_vel.argtypes = [vp, Stamp, dp]
+    L.cmaxb_pgo_window.argtypes = [vp, sp, sp, C.POINTER(C.c_int)]
+    L.cmaxb_pgo_process_window.argtypes = [vp, vp, C.c_size_t, C.POINTER(PgoReport)]
+    L.cmaxb_pgo_get_ctrl_poses.argtypes = [vp, dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.cmaxb_be_last_eval_x.argtypes = [vp, dp, C.c_int]
     L.cmaxb_last_error.restype = C.c_char_p
     L.cmaxb_launch_count.restype = C.c_uint64
     L.cmaxb_kernel_name.restype = C.c_char_p

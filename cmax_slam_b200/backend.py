@@ -219,3 +219,56 @@ def global_contrast_f(v, warper):
 
 def global_contrast_df(v, warper):
     return global_contrast_fdf(v, warper, want_df=True)[1]
+
+
+class PoseGraphOptimizerCMax:
+    """Host-side mirror of PoseGraphOptimizer's window pipeline (src/backend/pose_graph_optimizer.cpp:72-354) over the
+    C ABI (cmaxb_pgo_*): pushAngVel / isReadyFrontendPoses / processTimeWindow (+ getAngVelSubset, integrateAngVel,
+    setUpdateTimesIG, slideWindow).  `warper` is an EventWarperCMax whose spline order matches."""
+
+    def __init__(self, warper, spline_order, dt_knots, time_window_size, sliding_window_stride, y_angle_deg=0.0,
+                 max_update_times=255, min_num_ev_per_win=0.0, opt_params=None):
+        self._L = _capi.lib()
+        self.warper = warper
+        cfg = _capi.PgoCfg(int(spline_order), float(dt_knots), float(time_window_size), float(sliding_window_stride),
+                           float(y_angle_deg), int(max_update_times), float(min_num_ev_per_win),
+                           0 if opt_params is None else 1, _capi.OptParams(*(opt_params or (0.1, 0.1, 50, 1e-4, 1e-4))))
+        h = C.c_void_p()
+        _capi.check(self._L.cmaxb_pgo_create(C.byref(cfg), warper._h if warper is not None else None, C.byref(h)))
+        self._p = h
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._L.cmaxb_pgo_destroy(self._p)
+            self._p = None
+
+    __del__ = close
+
+    def pushAngVel(self, ts, ang_vel):
+        w = np.ascontiguousarray(ang_vel, dtype=np.float64).reshape(3)
+        _capi.check(self._L.cmaxb_pgo_push_ang_vel(self._p, _capi.Stamp(int(ts[0]), int(ts[1])), _capi.dptr(w)))
+
+    def window(self):
+        """((sec, nsec) t_win_beg, (sec, nsec) t_win_end, ang_vel_ready)"""
+        a, b, r = _capi.Stamp(), _capi.Stamp(), C.c_int(0)
+        _capi.check(self._L.cmaxb_pgo_window(self._p, C.byref(a), C.byref(b), C.byref(r)))
+        return (a.sec, a.nsec), (b.sec, b.nsec), bool(r.value)
+
+    def processTimeWindow(self, events):
+        ev = np.ascontiguousarray(events)
+        rep = _capi.PgoReport()
+        _capi.check(self._L.cmaxb_pgo_process_window(self._p, C.c_void_p(ev.ctypes.data), len(ev), C.byref(rep)))
+        out = {k: getattr(rep, k) for k in ("window", "n_ang_vel", "n_frontend_poses", "n_ctrl_poses", "idx_cp_traj_beg",
+                                            "idx_cp_opt_beg", "num_cp_opt", "optimized", "alpha", "n_fov_marks")}
+        out["opt"] = {k: getattr(rep.opt, k) for k, _ in _capi.OptResult._fields_}
+        out["pose_latest"] = ((rep.pose_latest_t.sec, rep.pose_latest_t.nsec), np.array(rep.pose_latest_xyzw[:]))
+        out["t_win"] = ((rep.t_win_beg.sec, rep.t_win_beg.nsec), (rep.t_win_end.sec, rep.t_win_end.nsec))
+        return out
+
+    def ctrl_poses(self):
+        n, t0, dt = C.c_int(0), C.c_int64(0), C.c_int64(0)
+        _capi.check(self._L.cmaxb_pgo_get_ctrl_poses(self._p, None, 0, C.byref(n), C.byref(t0), C.byref(dt)))
+        q = np.zeros((n.value, 4))
+        if n.value:
+            _capi.check(self._L.cmaxb_pgo_get_ctrl_poses(self._p, _capi.dptr(q), n.value, C.byref(n), C.byref(t0), C.byref(dt)))
+        return q, t0.value, dt.value

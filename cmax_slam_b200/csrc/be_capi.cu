@@ -42,6 +42,7 @@ struct cmaxb_be {
   int* d_flags = nullptr; int* h_flags = nullptr;
   int* d_cells = nullptr; size_t cells_cap = 0;
   bool have_window = false;
+  std::vector<double> last_x;   // parameter vector of the most recent cmaxb_be_eval (the reference's IL_old_ / IL_new_ members hold THAT evaluation's images)
   KernelProfiler prof;
 };
 
@@ -153,6 +154,7 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
   cudaStream_t s = be->stream;
   CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
   be->have_window = false;
+  be->last_x.clear();
   const long long n = (long long)w->n_events, bs = be->cfg.batch_size;
   // the reference loop `for (beg = begin; beg < end-1; beg += bs)` never visits a trailing batch
   // of exactly one event (event_pano_warper.cpp:188-196)
@@ -468,7 +470,15 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
   be->split_pending = false;
   CMAXB_TRY(be_run_poses(be, x, n, want_grad));
   CMAXB_TRY(be_run_scatter(be, true, adjoint_grad));
+  if (x && n > 0) be->last_x.assign(x, x + n); else be->last_x.assign((size_t)(n > 0 ? n : 0), 0.0);
   return be_finish_eval(be, want_grad, contrast, grad);
+}
+
+extern "C" int cmaxb_be_last_eval_x(cmaxb_be* be, double* x, int n) {
+  if (!be || (!x && n > 0)) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if ((int)be->last_x.size() != n) return set_error(CMAXB_ERR_STATE, "no evaluation with that many parameters since set_window");
+  for (int i = 0; i < n; ++i) x[i] = be->last_x[(size_t)i];
+  return CMAXB_OK;
 }
 
 // ---- event-sharded evaluation: one window split by TIME across GPUs ----------------

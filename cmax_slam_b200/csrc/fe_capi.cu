@@ -64,8 +64,8 @@ struct cmaxb_fe {
   bool gather_f32 = false;           // CMAXB_FE_GATHER_F32=1: Jacobian chain of the gather in f32 (measured 1.5 % faster; default = the reference's f64 chain)
   // fused result exchange over peer memory (cmaxb_fe_exchange_*)
   int x_world = 0, x_rank = 0; bool x_on = false;
-  double* x_local = nullptr; size_t x_bytes = 0;
-  double* x_peer[kXMaxWorld] = {};
+  ulonglong2* x_local = nullptr; size_t x_bytes = 0;
+  ulonglong2* x_peer[kXMaxWorld] = {};
   double* x_all_dev = nullptr;
   double* h_xall = nullptr; double* d_xall = nullptr;        // mapped: [kFeRing][world][kmax][4]
   unsigned int* h_xerr = nullptr; unsigned int* d_xerr = nullptr;
@@ -539,7 +539,7 @@ extern "C" int cmaxb_fe_exchange_init(cmaxb_fe* fe, int world, int rank, void* h
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
   CMAXB_TRY(fe_drain_stream(fe));
   if (fe->x_local) return set_error(CMAXB_ERR_STATE, "exchange already initialised");
-  const size_t need = sizeof(double) * 2 * (size_t)world * fe->kmax * 4 + sizeof(unsigned long long) * world;
+  const size_t need = sizeof(ulonglong2) * 2 * (size_t)world * fe->kmax * 4;
   size_t bytes = (size_t)2 << 20;            // a whole 2 MiB block: the IPC handle exports nothing else
   while (bytes < need) bytes <<= 1;
   CMAXB_CUDA_TRY(cudaMalloc((void**)&fe->x_local, bytes));
@@ -564,7 +564,7 @@ extern "C" int cmaxb_fe_exchange_connect(cmaxb_fe* fe, const void* handles, doub
     std::memcpy(&h, (const char*)handles + 64 * r, 64);
     void* ptr = nullptr;
     CMAXB_CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    fe->x_peer[r] = (double*)ptr;
+    fe->x_peer[r] = (ulonglong2*)ptr;
   }
   if (!fe->h_xall) {
     CMAXB_CUDA_TRY(cudaHostAlloc((void**)&fe->h_xall, sizeof(double) * 4 * (size_t)fe->kmax * fe->x_world * kFeRing, cudaHostAllocMapped));
@@ -574,7 +574,6 @@ extern "C" int cmaxb_fe_exchange_connect(cmaxb_fe* fe, const void* handles, doub
     fe->h_xerr[0] = 0;
   }
   fe->x_all_dev = gathered_dev;
-  fe->x_seq = 0;
   fe->x_on = fe->x_world > 1;
   return CMAXB_OK;
 }

@@ -24,28 +24,27 @@ constexpr int kMegaMaxHyp = 32;       // hypotheses per launch (kernel-parameter
 // Multi-GPU hypothesis sharding: every rank evaluates its own hypotheses of the replicated
 // packet and all ranks need all (contrast, g) rows.  Instead of a separate NCCL all-gather after the kernel, the
 // CTA that publishes the result also stores its rows straight into every peer's exchange buffer (peer-to-peer
-// stores over NVLink / NVSwitch, buffers opened with CUDA IPC), releases a per-rank sequence flag, waits for the
-// peers' flags and copies the gathered rows to mapped host memory -- compute + collective in ONE launch.
-// Exchange buffer of a rank (doubles): rows[2][world][kmax][4] (double-buffered by the parity of the sequence
-// number: a rank can run at most one evaluation ahead of a peer that has not yet read its rows) followed by
-// flags[world] (u64, monotonic).
+// stores over NVLink / NVSwitch, buffers opened with CUDA IPC), waits for the peers' rows and copies the
+// gathered rows to mapped host memory -- compute + collective in ONE launch.
+// Wire format ("low latency": data and flag travel together, no fence, no separate flag round trip): every
+// double is sent as ONE 16-byte store {value bits, sequence number}; the receiver spins on the slot until the
+// tag equals the sequence number of the launch.  Exchange buffer of a rank: slots[2][world][kmax][4] x 16 B,
+// double-buffered by the parity of the sequence number (a rank can run at most one evaluation ahead of a peer
+// that has not yet read its rows, because its own next kernel waits for that peer's rows of the same number).
 constexpr int kXMaxWorld = 8;
 constexpr unsigned long long kXTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;   // a dead peer must not hang the GPU
 
 struct FeXchgParams {
   int world, rank, kmax;
-  unsigned long long seq;           // exchange sequence number of this launch (same on all ranks)
-  double* peer[kXMaxWorld];         // exchange buffer of every rank as mapped into THIS process (peer[rank] = own)
+  unsigned long long seq;           // exchange sequence number of this launch (same on all ranks), >= 1
+  ulonglong2* peer[kXMaxWorld];     // exchange buffer of every rank as mapped into THIS process (peer[rank] = own)
   double* all_host;                 // mapped host memory [world][k][4]: gathered rows of this launch
   double* all_dev;                  // optional device copy [world][k][4] (caller owned)
-  unsigned int* err;                // mapped host word, set to 1 when a peer's flag does not arrive in time
+  unsigned int* err;                // mapped host word, set to 1 when a peer's rows do not arrive in time
 };
 
-__device__ __forceinline__ double* xchg_rows(const FeXchgParams& x, double* base, int par, int r) {
+__device__ __forceinline__ ulonglong2* xchg_slots(const FeXchgParams& x, ulonglong2* base, int par, int r) {
   return base + ((long long)(par * x.world + r) * x.kmax) * 4;
-}
-__device__ __forceinline__ unsigned long long* xchg_flags(const FeXchgParams& x, double* base) {
-  return reinterpret_cast<unsigned long long*>(base + (long long)2 * x.world * x.kmax * 4);
 }
 
 // Called by ALL threads of ONE CTA.  s_rows[k*4] (shared memory) = this rank's rows of the launch.
@@ -53,33 +52,26 @@ __device__ __forceinline__ void mega_exchange(const FeXchgParams& x, int k, cons
   const int par = (int)(x.seq & 1ull);
   const int nv = k * 4;
   __syncthreads();
-  // 1. own rows -> every rank's buffer (own copy included)
+  // 1. own rows -> every rank's buffer (own copy included), one tagged 16-byte store per value
   for (int i = threadIdx.x; i < x.world * nv; i += blockDim.x) {
     const int r = i / nv, j = i - r * nv;
-    *reinterpret_cast<volatile double*>(xchg_rows(x, x.peer[r], par, x.rank) + j) = s_rows[j];
+    ulonglong2* dst = xchg_slots(x, x.peer[r], par, x.rank) + j;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(s_rows[j]);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(bits), "l"(x.seq) : "memory");
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < x.world) {
-    // 2. release: flags[rank] = seq in every rank's buffer
-    unsigned long long* fr = xchg_flags(x, x.peer[threadIdx.x]) + x.rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fr), "l"(x.seq) : "memory");
-    // 3. acquire: rank threadIdx.x's flag in OUR buffer
-    const unsigned long long* fa = xchg_flags(x, x.peer[x.rank]) + threadIdx.x;
+  // 2. every rank's rows out of OUR buffer -> mapped host memory (+ device copy); spin until the tag arrives
+  for (int i = threadIdx.x; i < x.world * nv; i += blockDim.x) {
+    const int r = i / nv, j = i - r * nv;
+    const ulonglong2* src = xchg_slots(x, x.peer[x.rank], par, r) + j;
     const unsigned long long t0 = global_timer_ns();
+    unsigned long long bits = 0, tag = 0;
     unsigned int spins = 0;
     for (;;) {
-      unsigned long long v;
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(fa) : "memory");
-      if (v >= x.seq) break;
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tag) : "l"(src) : "memory");
+      if (tag == x.seq) break;
       if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > kXTimeoutNs) { *x.err = 1u; break; }
     }
-  }
-  __syncthreads();
-  // 4. gathered rows -> mapped host memory (+ device copy)
-  for (int i = threadIdx.x; i < x.world * nv; i += blockDim.x) {
-    const int r = i / nv, j = i - r * nv;
-    const double v = *reinterpret_cast<const volatile double*>(xchg_rows(x, x.peer[x.rank], par, r) + j);
+    const double v = __longlong_as_double((long long)bits);
     x.all_host[i] = v;
     if (x.all_dev) x.all_dev[i] = v;
   }

@@ -178,6 +178,10 @@ int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w);
  * grad: same length or NULL (value only). */
 int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contrast, double* grad);
 int cmaxb_be_get_alpha(cmaxb_be* be, double* alpha);
+/* parameter vector of the most recent cmaxb_be_eval since set_window.  The reference's updateIG consumes the
+ * IL_old_ image left behind by the LAST cost evaluation of the solve (event_pano_warper.cpp:109-126), which is
+ * not necessarily the optimum the solver returns; this is how a caller reproduces that. */
+int cmaxb_be_last_eval_x(cmaxb_be* be, double* x, int n);
 
 /* Event-sharded evaluation: ONE window split by time across GPUs (BASELINE config C5).  Every
  * rank holds a batch-aligned time slab of the window's events and ALL knots.  Variance is non-linear in the
@@ -274,6 +278,48 @@ int cmaxb_traj_evaluate(int spline_order, const double* knots_xyzw, int n_knots,
 /* Trajectory::incrementalUpdate: knots[i] <- exp(x[i - idx_beg]) * knots[i], i >= idx_beg (trajectory.cpp:221-238,
  * 491-499) -- applies the optimiser's result to the trajectory. */
 int cmaxb_traj_incremental_update(double* knots_xyzw, int n_knots, int idx_beg, const double* x);
+
+/* ------------------------------------------------------------------ back-end window pipeline ---- */
+/* Everything PoseGraphOptimizer does for one sliding time window (pose_graph_optimizer.cpp:72-354), as host C++
+ * over a cmaxb_be handle: the caller pushes the front-end's angular velocities and hands over the events of the
+ * current window; the library integrates them, fits and appends the new control poses, freezes / slides the
+ * control-pose indices, solves the window (Fletcher-Reeves over cmaxb_be_eval, x0 = 0), applies the increments,
+ * updates the panoramic map and its visit counts ON THE DEVICE and prepares the next window.  Replaces, in
+ * src/backend/pose_graph_optimizer.cpp: pushAngVel, getAngVelSubset, integrateAngVel, processTimeWindow,
+ * setUpdateTimesIG, slideWindow (+ setupProblemAndOptimize_gsl).  The event cut for [t_win_beg, t_win_end) is
+ * the caller's (cmaxb_stream_*, or the reference's own getEventSubset). */
+typedef struct cmaxb_pgo cmaxb_pgo;
+typedef struct cmaxb_pgo_cfg {
+  int32_t spline_order;            /* 2 (traj_opt.spline_degree 1) or 4 (degree 3); must match the cmaxb_be handle */
+  double dt_knots;                 /* traj_opt.dt_knots */
+  double time_window_size;         /* sliding_window_opt.time_window_size (s) */
+  double sliding_window_stride;    /* sliding_window_opt.sliding_window_stride (s) */
+  double y_angle_deg;              /* map_opt.Y_angle: initial pose = rotation about Y (pose_graph_optimizer.cpp:99-103) */
+  int32_t max_update_times;        /* map_opt.max_update_times (updateIG gate) */
+  double min_num_ev_per_win;       /* min_num_ev_per_win_ (pose_graph_optimizer.cpp:64-67): fewer events => no solve */
+  int32_t use_opt_params;          /* 0: the reference's constants (step 0.1, tol 0.1, 50 iterations, 1e-4, 1e-4) */
+  cmaxb_opt_params opt_params;
+} cmaxb_pgo_cfg;
+typedef struct cmaxb_pgo_report {
+  int32_t window;                  /* count_window_ of the processed window */
+  cmaxb_stamp t_win_beg, t_win_end;
+  int32_t n_ang_vel, n_frontend_poses;
+  int32_t n_ctrl_poses, idx_cp_traj_beg, idx_cp_opt_beg, num_cp_opt;
+  int32_t optimized;               /* 0: too few events, camera assumed still */
+  cmaxb_opt_result opt;
+  double alpha;
+  int32_t n_fov_marks;
+  cmaxb_stamp pose_latest_t; double pose_latest_xyzw[4];
+} cmaxb_pgo_report;
+int cmaxb_pgo_create(const cmaxb_pgo_cfg* cfg, cmaxb_be* be /* borrowed; NULL = trajectory bookkeeping only, no solve */, cmaxb_pgo** out);
+void cmaxb_pgo_destroy(cmaxb_pgo* pgo);
+int cmaxb_pgo_push_ang_vel(cmaxb_pgo* pgo, cmaxb_stamp ts, const double ang_vel[3]);
+/* current window cursors; *ang_vel_ready = the latest angular velocity lies beyond t_win_end (isReadyFrontendPoses) */
+int cmaxb_pgo_window(cmaxb_pgo* pgo, cmaxb_stamp* t_win_beg, cmaxb_stamp* t_win_end, int* ang_vel_ready);
+/* getAngVelSubset + processTimeWindow + slideWindow on the given event subset (host memory) */
+int cmaxb_pgo_process_window(cmaxb_pgo* pgo, const cmaxb_event* events, size_t n_events, cmaxb_pgo_report* report);
+/* all control poses so far (x,y,z,w) and the spline's time origin / knot spacing; xyzw may be NULL to query *n */
+int cmaxb_pgo_get_ctrl_poses(cmaxb_pgo* pgo, double* xyzw, int capacity, int* n, int64_t* t0_ns, int64_t* dt_ns);
 
 /* ------------------------------------------------------------------ diagnostics ---------- */
 const char* cmaxb_last_error(void);

@@ -1,0 +1,126 @@
+"""Back-end window pipeline (cmaxb_pgo_*, csrc/pgo.cu) against the independent Python restatement composed from the
+oracle's pieces (oracle/pgo_py.py: real Sophus/Eigen for integration + fit, CPU oracle cost, restated GSL loop, oracle
+map upkeep).  CPU: the trajectory bookkeeping without a solve (no device needed).  GPU: three sliding windows solved
+on the device."""
+import numpy as np
+import pytest
+
+from cmax_slam_b200 import synth
+
+K_T = (60.0, 61.0, 31.5, 23.5)
+ORDER_CASES = [2, 4]
+
+
+def _qdist(a, b):
+    a, b = np.atleast_2d(a), np.atleast_2d(b)
+    c = np.minimum(np.linalg.norm(a - b, axis=1), np.linalg.norm(a + b, axis=1))
+    return float((4 * np.arcsin(np.clip(c / 2, 0, 1))).max())
+
+
+def _scenario(order, n_events=30000, seed=23):
+    """A 14-knot synthetic rotation (0.65 s) observed by a 64x48 sensor, the true body angular velocity sampled every
+    10 ms (+ noise) as the front-end would deliver it."""
+    w = synth.make_be_window(n_events, 14 + (order - 2), 128, 64, seed, order=2, sensor=(64, 48), K4=K_T, n_landmarks=400, n_fixed=1,
+                             knot_sigma=0.03)
+    rng = np.random.default_rng(seed + 1)
+    t0 = w.t0_ns
+    stamps, ws = [], []
+    for k in range(64):
+        t_ns = t0 + 5_000_000 + k * 10_000_000
+        seg = min((t_ns - t0) // w.dt_ns, len(w.knots_xyzw) - 2)
+        d = synth._qlog(synth._qmul(synth._qconj(w.knots_xyzw[seg][None, :]), w.knots_xyzw[seg + 1][None, :]))[0]
+        stamps.append((t_ns // 1_000_000_000, t_ns % 1_000_000_000))
+        ws.append(d / (w.dt_ns * 1e-9) + rng.normal(0, 0.05, 3))
+    ev_t = w.events["sec"].astype(np.int64) * 1_000_000_000 + w.events["nsec"].astype(np.int64)
+    return w, stamps, np.array(ws), ev_t
+
+
+def _cut(w, ev_t, tb, te):
+    lo = np.searchsorted(ev_t, tb[0] * 1_000_000_000 + tb[1], side="left")
+    hi = np.searchsorted(ev_t, te[0] * 1_000_000_000 + te[1], side="left")
+    return w.events[lo:hi]
+
+
+@pytest.mark.parametrize("order", ORDER_CASES)
+def test_bookkeeping_without_solve_matches_restatement(oracle, order):
+    """be = NULL: integrate, fit, append, freeze / slide indices, latest pose -- host code only."""
+    if not oracle.have_ref() or not hasattr(oracle.ref(), "ref_fit_ctrl_poses"):
+        pytest.skip("oracle/_ref (real Eigen / Sophus) not available")
+    from cmax_slam_b200.backend import PoseGraphOptimizerCMax
+    from oracle.pgo_py import PipelineOracle
+    w, stamps, ws, ev_t = _scenario(order)
+    pgo = PoseGraphOptimizerCMax(None, order, 0.05, 0.2, 0.1, y_angle_deg=10.0)
+    ref = PipelineOracle(w.lut, 64, 48, 128, 64, order, 0.05, 0.2, 0.1, y_angle_deg=10.0, min_num_ev=1e18)
+    for s, v in zip(stamps, ws):
+        pgo.pushAngVel(s, v)
+        ref.push(s, v)
+    pgo.pushAngVel(stamps[3], [9, 9, 9])                      # duplicate stamp: std::map::insert keeps the first
+    for win in range(4):
+        tb, te, ready = pgo.window()
+        assert ready and tb == ref.t_win_beg and te == ref.t_win_end
+        rep = pgo.processTimeWindow(_cut(w, ev_t, tb, te))
+        rr = ref.process(_cut(w, ev_t, tb, te))
+        for k in ("n_ctrl_poses", "idx_cp_traj_beg", "idx_cp_opt_beg", "num_cp_opt", "optimized"):
+            assert rep[k] == rr[k], (win, k, rep[k], rr[k])
+        assert rep["pose_latest"][0] == rr["pose_latest"][0]
+        assert _qdist(rep["pose_latest"][1], rr["pose_latest"][1]) <= 1e-9
+        q, t0_ns, dt_ns = pgo.ctrl_poses()
+        assert (t0_ns, dt_ns) == (ref.traj_t_beg_ns, ref.traj_dt_ns)
+        assert q.shape == ref.knots.shape and _qdist(q, ref.knots) <= 1e-8, (win, _qdist(q, ref.knots))
+    # expected index pattern of the reference: window k starts at control pose k * cp_stride (= 2)
+    assert rep["idx_cp_traj_beg"] == 6 and rep["window"] == 3
+    pgo.close()
+
+
+def test_not_ready_and_state_errors():
+    from cmax_slam_b200._capi import CmaxbError
+    from cmax_slam_b200.backend import PoseGraphOptimizerCMax
+    pgo = PoseGraphOptimizerCMax(None, 2, 0.05, 0.2, 0.1)
+    with pytest.raises(CmaxbError) as e:
+        pgo.window()
+    assert e.value.code == -6
+    pgo.pushAngVel((100, 0), [0, 0, 1.0])
+    pgo.pushAngVel((100, 100_000_000), [0, 0, 1.0])
+    tb, te, ready = pgo.window()
+    assert tb == (100, 0) and te == (100, 200_000_000) and not ready
+    with pytest.raises(CmaxbError):                           # too few front-end poses to fit 5 control poses (CHECK_GE)
+        pgo.processTimeWindow(np.zeros(0, synth.EVENT_DTYPE))
+    with pytest.raises(CmaxbError):
+        PoseGraphOptimizerCMax(None, 3, 0.05, 0.2, 0.1)
+    pgo.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ORDER_CASES)
+def test_three_windows_on_device_match_restatement(oracle, order):
+    from cmax_slam_b200.backend import EventWarperCMax, PoseGraphOptimizerCMax
+    from oracle.pgo_py import PipelineOracle
+    w, stamps, ws, ev_t = _scenario(order)
+    be = EventWarperCMax(64, 48, w.lut, 128, 64, spline_order=order)
+    be.resetIG()
+    pgo = PoseGraphOptimizerCMax(be, order, 0.05, 0.2, 0.1, max_update_times=20, min_num_ev_per_win=100)
+    ref = PipelineOracle(w.lut, 64, 48, 128, 64, order, 0.05, 0.2, 0.1, max_update_times=20, min_num_ev=100)
+    for s, v in zip(stamps, ws):
+        pgo.pushAngVel(s, v)
+        ref.push(s, v)
+    for win in range(3):
+        tb, te, ready = pgo.window()
+        assert ready
+        ev = _cut(w, ev_t, tb, te)
+        rep = pgo.processTimeWindow(ev)
+        rr = ref.process(ev)
+        for k in ("n_ctrl_poses", "idx_cp_traj_beg", "idx_cp_opt_beg", "num_cp_opt", "optimized", "n_fov_marks"):
+            assert rep[k] == rr[k], (win, k, rep[k], rr[k])
+        assert rep["optimized"] == 1
+        assert abs(rep["alpha"] - rr["alpha"]) <= 1e-3 * max(1e-6, abs(rr["alpha"])) + 1e-9, (win, rep["alpha"], rr["alpha"])
+        # a line search is a chain of comparisons: the OUTCOME is compared, as in tests/test_optim.py
+        assert rep["opt"]["cost_final"] < rep["opt"]["cost_initial"]
+        assert abs(rep["opt"]["cost_final"] - rr["opt"]["cost_final"]) <= 2e-3 * abs(rr["opt"]["cost_final"]), (win, rep["opt"], rr["opt"])
+        q, _, _ = pgo.ctrl_poses()
+        assert _qdist(q, ref.knots) <= 5e-3, (win, _qdist(q, ref.knots))
+        assert _qdist(rep["pose_latest"][1], rr["pose_latest"][1]) <= 5e-3
+        IG, times = be.getIG()
+        assert abs(float(IG.sum()) - float(ref.IG.sum())) <= 0.02 * float(ref.IG.sum()) + 1.0
+        assert abs(int(times.astype(np.int64).sum()) - int(ref.times.astype(np.int64).sum())) <= 0.05 * int(ref.times.astype(np.int64).sum()) + 10
+    pgo.close()
+    be.close()
