@@ -54,6 +54,10 @@ class Stamp(C.Structure):
     _fields_ = [("sec", C.c_uint32), ("nsec", C.c_uint32)]
 
 
+class StreamCfg(C.Structure):
+    _fields_ = [("dt_ang_vel", C.c_double), ("num_events_per_packet", C.c_int32), ("event_sample_rate", C.c_int32)]
+
+
 class PgoCfg(C.Structure):
     _fields_ = [("spline_order", C.c_int32), ("dt_knots", C.c_double), ("time_window_size", C.c_double),
                 ("sliding_window_stride", C.c_double), ("y_angle_deg", C.c_double), ("max_update_times", C.c_int32),
@@ -85,6 +89,8 @@ EXPORTS = [
     "cmaxb_fe_optimize", "cmaxb_be_optimize",
     "cmaxb_traj_integrate_ang_vel", "cmaxb_traj_num_ctrl_poses", "cmaxb_traj_fit_ctrl_poses", "cmaxb_traj_evaluate",
     "cmaxb_traj_incremental_update",
+    "cmaxb_stream_create", "cmaxb_stream_destroy", "cmaxb_stream_push", "cmaxb_stream_next_packet", "cmaxb_stream_window_events",
+    "cmaxb_stream_state",
     "cmaxb_pgo_create", "cmaxb_pgo_destroy", "cmaxb_pgo_push_ang_vel", "cmaxb_pgo_window", "cmaxb_pgo_process_window",
     "cmaxb_pgo_get_ctrl_poses", "cmaxb_be_last_eval_x",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
@@ -133,6 +139,13 @@ def lib():
     L.cmaxb_traj_fit_ctrl_poses.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, sp, dp, C.c_int, dp]
     L.cmaxb_traj_evaluate.argtypes = [C.c_int, dp, C.c_int, C.c_int64, C.c_int64, Stamp, dp]
     L.cmaxb_traj_incremental_update.argtypes = [dp, C.c_int, C.c_int, dp]
+    L.cmaxb_stream_create.argtypes = [C.POINTER(StreamCfg), C.POINTER(vp)]
+    L.cmaxb_stream_destroy.argtypes = [vp]
+    L.cmaxb_stream_destroy.restype = None
+    L.cmaxb_stream_push.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_int)]
+    L.cmaxb_stream_next_packet.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), sp, C.POINTER(C.c_int)]
+    L.cmaxb_stream_window_events.argtypes = [vp, Stamp, Stamp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.cmaxb_stream_state.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), sp]
     L.cmaxb_pgo_create.argtypes = [C.POINTER(PgoCfg), vp, C.POINTER(vp)]
     L.cmaxb_pgo_destroy.argtypes = [vp]
     L.cmaxb_pgo_destroy.restype = None

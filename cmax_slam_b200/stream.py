@@ -1,0 +1,64 @@
+"""Host-side mirror of the reference's event ingestion over the C ABI.
+
+Reference surface mirrored:
+  CMaxSLAM::eventsCallback                       src/cmax_slam.cpp:147-161
+  AngVelEstimator::pushEvent / getEventSubset / deleteOldEvents / slideWindow
+                                                 src/frontend/ang_vel_estimator.cpp:68-183
+  PoseGraphOptimizer::getEventSubset             src/backend/pose_graph_optimizer.cpp:133-166
+The bookkeeping is host C++ inside libcmax_b200.so (csrc/stream.cu); packets / windows come back as numpy views of
+the library's pinned staging buffers (valid until the call after next)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .synth import EVENT_DTYPE
+
+
+class EventStream:
+    def __init__(self, dt_ang_vel, num_events_per_packet, event_sample_rate=1):
+        self._L = _capi.lib()
+        cfg = _capi.StreamCfg(float(dt_ang_vel), int(num_events_per_packet), int(event_sample_rate))
+        h = C.c_void_p()
+        _capi.check(self._L.cmaxb_stream_create(C.byref(cfg), C.byref(h)))
+        self._s = h
+
+    def close(self):
+        if getattr(self, "_s", None):
+            self._L.cmaxb_stream_destroy(self._s)
+            self._s = None
+
+    __del__ = close
+
+    def eventsCallback(self, msg_events):
+        """One dvs_msgs::EventArray (16-byte records).  Returns the number of complete packets waiting."""
+        ev = np.ascontiguousarray(msg_events)
+        k = C.c_int(0)
+        _capi.check(self._L.cmaxb_stream_push(self._s, C.c_void_p(ev.ctypes.data), len(ev), C.byref(k)))
+        return k.value
+
+    def _view(self, ptr, n):
+        if not n:
+            return np.zeros(0, EVENT_DTYPE)
+        buf = (C.c_uint8 * (16 * n)).from_address(ptr)
+        return np.frombuffer(buf, dtype=EVENT_DTYPE)
+
+    def next_packet(self):
+        """None, or (events view, (sec, nsec) time_packet, span_too_long)."""
+        p, n, t, f = C.c_void_p(), C.c_size_t(0), _capi.Stamp(), C.c_int(0)
+        rc = self._L.cmaxb_stream_next_packet(self._s, C.byref(p), C.byref(n), C.byref(t), C.byref(f))
+        if rc == 1:
+            return None
+        _capi.check(rc)
+        return self._view(p.value, n.value), (t.sec, t.nsec), bool(f.value)
+
+    def window_events(self, t_beg, t_end):
+        p, n = C.c_void_p(), C.c_size_t(0)
+        _capi.check(self._L.cmaxb_stream_window_events(self._s, _capi.Stamp(int(t_beg[0]), int(t_beg[1])),
+                                                       _capi.Stamp(int(t_end[0]), int(t_end[1])), C.byref(p), C.byref(n)))
+        return self._view(p.value, n.value)
+
+    def state(self):
+        a, b, c, t = C.c_int64(0), C.c_int64(0), C.c_int64(0), _capi.Stamp()
+        _capi.check(self._L.cmaxb_stream_state(self._s, C.byref(a), C.byref(b), C.byref(c), C.byref(t)))
+        return {"n_stored": a.value, "n_subsets_pending": b.value, "n_ts_map": c.value, "time_packet": (t.sec, t.nsec)}

@@ -279,6 +279,34 @@ int cmaxb_traj_evaluate(int spline_order, const double* knots_xyzw, int n_knots,
  * 491-499) -- applies the optimiser's result to the trajectory. */
 int cmaxb_traj_incremental_update(double* knots_xyzw, int n_knots, int idx_beg, const double* x);
 
+/* ------------------------------------------------------------------ event ingestion / staging ---- */
+/* the event store both ends share, the front-end's packet cutter and the back-end's
+ * window cutter (host C++).  Packets / windows are handed out in PINNED host buffers (when a CUDA device is present),
+ * so cmaxb_fe_set_packet_async / cmaxb_be_set_window move them by DMA while the previous packet is evaluated; the
+ * per-packet spatial binning and validation happen on the device inside set_packet.  Replaces
+ * CMaxSLAM::eventsCallback (src/cmax_slam.cpp:147-161), AngVelEstimator::pushEvent / getEventSubset /
+ * deleteOldEvents / slideWindow (src/frontend/ang_vel_estimator.cpp:68-183) and PoseGraphOptimizer::getEventSubset
+ * (src/backend/pose_graph_optimizer.cpp:133-166). */
+typedef struct cmaxb_stream cmaxb_stream;
+typedef struct cmaxb_stream_cfg {
+  double dt_ang_vel;              /* params.dt_ang_vel: one packet (one angular velocity) per dt */
+  int32_t num_events_per_packet;  /* params.num_events_per_packet */
+  int32_t event_sample_rate;      /* front_end_params_.warp_opt.event_sample_rate: stride over each incoming message */
+} cmaxb_stream_cfg;
+int cmaxb_stream_create(const cmaxb_stream_cfg* cfg, cmaxb_stream** out);
+void cmaxb_stream_destroy(cmaxb_stream* s);
+/* one dvs_msgs::EventArray; *packets_ready = packets whose trailing half has arrived */
+int cmaxb_stream_push(cmaxb_stream* s, const cmaxb_event* msg_events, size_t n, int* packets_ready);
+/* oldest complete packet: event_subset_ (valid until the call after next), time_packet_, and whether its time
+ * span exceeds 10 dt_ang_vel (the reference then assumes zero angular velocity).  Returns 1 when none is ready. */
+int cmaxb_stream_next_packet(cmaxb_stream* s, const cmaxb_event** events, size_t* n, cmaxb_stamp* time_packet,
+                             int* span_too_long);
+/* events of the back-end window [t_beg, t_end) by the reference's coarse-to-fine search (packet-level look-up table,
+ * then 100-event strides back from the end); consumes the look-up entries and deletes the events no end needs any
+ * more.  CMAXB_ERR_STATE when the store does not cover the window yet. */
+int cmaxb_stream_window_events(cmaxb_stream* s, cmaxb_stamp t_beg, cmaxb_stamp t_end, const cmaxb_event** events, size_t* n);
+int cmaxb_stream_state(cmaxb_stream* s, int64_t* n_stored, int64_t* n_subsets_pending, int64_t* n_ts_map, cmaxb_stamp* time_packet);
+
 /* ------------------------------------------------------------------ back-end window pipeline ---- */
 /* Everything PoseGraphOptimizer does for one sliding time window (pose_graph_optimizer.cpp:72-354), as host C++
  * over a cmaxb_be handle: the caller pushes the front-end's angular velocities and hands over the events of the
