@@ -54,6 +54,11 @@ class Stamp(C.Structure):
     _fields_ = [("sec", C.c_uint32), ("nsec", C.c_uint32)]
 
 
+class CameraInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("K", C.c_double * 9), ("D", C.c_double * 12), ("n_D", C.c_int32),
+                ("R", C.c_double * 9), ("P", C.c_double * 12)]
+
+
 class StreamCfg(C.Structure):
     _fields_ = [("dt_ang_vel", C.c_double), ("num_events_per_packet", C.c_int32), ("event_sample_rate", C.c_int32)]
 
@@ -89,6 +94,7 @@ EXPORTS = [
     "cmaxb_fe_optimize", "cmaxb_be_optimize",
     "cmaxb_traj_integrate_ang_vel", "cmaxb_traj_num_ctrl_poses", "cmaxb_traj_fit_ctrl_poses", "cmaxb_traj_evaluate",
     "cmaxb_traj_incremental_update",
+    "cmaxb_precompute_bearing_vectors",
     "cmaxb_stream_create", "cmaxb_stream_destroy", "cmaxb_stream_push", "cmaxb_stream_next_packet", "cmaxb_stream_window_events",
     "cmaxb_stream_state",
     "cmaxb_pgo_create", "cmaxb_pgo_destroy", "cmaxb_pgo_push_ang_vel", "cmaxb_pgo_window", "cmaxb_pgo_process_window",
@@ -139,6 +145,7 @@ def lib():
     L.cmaxb_traj_fit_ctrl_poses.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, sp, dp, C.c_int, dp]
     L.cmaxb_traj_evaluate.argtypes = [C.c_int, dp, C.c_int, C.c_int64, C.c_int64, Stamp, dp]
     L.cmaxb_traj_incremental_update.argtypes = [dp, C.c_int, C.c_int, dp]
+    L.cmaxb_precompute_bearing_vectors.argtypes = [C.POINTER(CameraInfo), C.c_int, dp]
     L.cmaxb_stream_create.argtypes = [C.POINTER(StreamCfg), C.POINTER(vp)]
     L.cmaxb_stream_destroy.argtypes = [vp]
     L.cmaxb_stream_destroy.restype = None

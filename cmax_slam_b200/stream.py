@@ -62,3 +62,20 @@ class EventStream:
         a, b, c, t = C.c_int64(0), C.c_int64(0), C.c_int64(0), _capi.Stamp()
         _capi.check(self._L.cmaxb_stream_state(self._s, C.byref(a), C.byref(b), C.byref(c), C.byref(t)))
         return {"n_stored": a.value, "n_subsets_pending": b.value, "n_ts_map": c.value, "time_packet": (t.sec, t.nsec)}
+
+
+def precompute_bearing_vectors(width, height, K, D, R=None, P=None, device=0):
+    """CMaxSLAM::precomputeBearingVectors (src/cmax_slam.cpp:106-120) on the device: (H*W, 3) float64."""
+    K = np.asarray(K, dtype=np.float64).reshape(3, 3)
+    D = np.asarray(D, dtype=np.float64).reshape(-1)
+    R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64).reshape(3, 3)
+    P = np.hstack([K, np.zeros((3, 1))]) if P is None else np.asarray(P, dtype=np.float64).reshape(3, 4)
+    info = _capi.CameraInfo()
+    info.width, info.height, info.n_D = int(width), int(height), len(D)
+    info.K[:] = K.ravel().tolist()
+    info.D[:] = (D.tolist() + [0.0] * 12)[:12]
+    info.R[:] = R.ravel().tolist()
+    info.P[:] = P.ravel().tolist()
+    out = np.zeros((width * height, 3))
+    _capi.check(_capi.lib().cmaxb_precompute_bearing_vectors(C.byref(info), int(device), _capi.dptr(out)))
+    return out

@@ -279,6 +279,22 @@ int cmaxb_traj_evaluate(int spline_order, const double* knots_xyzw, int n_knots,
  * 491-499) -- applies the optimiser's result to the trajectory. */
 int cmaxb_traj_incremental_update(double* knots_xyzw, int n_knots, int idx_beg, const double* x);
 
+/* ------------------------------------------------------------------ bearing-vector LUT ---------- */
+/* CMaxSLAM::precomputeBearingVectors (src/cmax_slam.cpp:106-120): for every sensor pixel,
+ * cam.projectPixelTo3dRay(cam.rectifyPoint(pixel)) with image_geometry::PinholeCameraModel semantics (float32 round
+ * trip through cv::undistortPoints with 5 iterations when any distortion coefficient is non-zero; ray from the
+ * projection matrix P).  One thread per pixel on the device; lut_xyz receives width*height*3 doubles, the input of
+ * cmaxb_fe_cfg.lut_xyz / cmaxb_be_cfg.lut_xyz.  Fields = sensor_msgs::CameraInfo (no binning / ROI). */
+typedef struct cmaxb_camera_info {
+  int32_t width, height;
+  double K[9];      /* row-major 3x3 */
+  double D[12];     /* k1 k2 p1 p2 k3 [k4 k5 k6 [s1 s2 s3 s4]] (plumb_bob: 5, rational_polynomial: 8) */
+  int32_t n_D;
+  double R[9];      /* rectification rotation */
+  double P[12];     /* row-major 3x4 projection matrix */
+} cmaxb_camera_info;
+int cmaxb_precompute_bearing_vectors(const cmaxb_camera_info* info, int device, double* lut_xyz);
+
 /* ------------------------------------------------------------------ event ingestion / staging ---- */
 /* the event store both ends share, the front-end's packet cutter and the back-end's
  * window cutter (host C++).  Packets / windows are handed out in PINNED host buffers (when a CUDA device is present),

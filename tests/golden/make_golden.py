@@ -188,10 +188,42 @@ def golden_traj():
     np.savez_compressed(os.path.join(OUT, "traj_ref.npz"), **d)
 
 
+def golden_lut():
+    """cv2.undistortPoints (4.13) on every pixel of small sensors with DAVIS-like calibrations: pins the bearing-vector
+    LUT restatement (oracle/lut_py.py) and the device kernel (csrc/camera.cu)."""
+    import cv2
+    d = {"cv2_version": np.array(cv2.__version__)}
+    cams = {
+        # DAVIS240C-like plumb_bob calibration, identity rectification, P = [K | 0]
+        "a": dict(W=240, H=180, K=[199.09, 0, 132.19, 0, 198.83, 110.71, 0, 0, 1], D=[-0.368, 0.150, -0.0003, -0.0002, 0.0],
+                  R=np.eye(3).ravel(), P=[199.09, 0, 132.19, 0, 0, 198.83, 110.71, 0, 0, 0, 1, 0]),
+        # rectified stereo-style: rotated R, new projection with a baseline term, 8-coefficient rational model
+        "b": dict(W=96, H=64, K=[80.5, 0, 47.2, 0, 81.1, 31.7, 0, 0, 1], D=[0.12, -0.25, 0.001, -0.002, 0.05, 0.01, -0.02, 0.003],
+                  R=cv2.Rodrigues(np.array([0.01, -0.02, 0.005]))[0].ravel(), P=[78.0, 0, 48.0, -3.9, 0, 78.0, 32.0, 0, 0, 0, 1, 0]),
+    }
+    for name, c in cams.items():
+        W, H = c["W"], c["H"]
+        K = np.array(c["K"], float).reshape(3, 3); D = np.array(c["D"], float)
+        R = np.array(c["R"], float).reshape(3, 3); P = np.array(c["P"], float).reshape(3, 4)
+        ys, xs = np.mgrid[0:H, 0:W]
+        pts = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.float32).reshape(-1, 1, 2)
+        # one point per call, as rectifyPoint does (1x1 CV_32FC2 Mat), would be 43200 calls; a single N x 1 call runs the same scalar code
+        rect = cv2.undistortPoints(pts, K, D, R=R, P=P).reshape(-1, 2)
+        for k in ("K", "D", "R", "P"):
+            d[f"{name}_{k}"] = np.array(c[k], float)
+        d[f"{name}_WH"] = np.array([W, H])
+        d[f"{name}_rect"] = rect.astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "lut_cv2.npz"), **d)
+
+
 if __name__ == "__main__":
     if "--only-traj" in sys.argv:
         golden_traj()
         sys.exit(0)
+    if "--only-lut" in sys.argv:
+        golden_lut()
+        sys.exit(0)
+    golden_lut()
     golden_traj()
     golden_blur()
     golden_spline()
