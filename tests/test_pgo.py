@@ -117,7 +117,7 @@ def test_three_windows_on_device_match_restatement(oracle, order):
         assert abs(rep["alpha"] - rr["alpha"]) <= (1e-5 if win == 0 else 2e-2) * abs(rr["alpha"]) + 1e-9, (win, rep["alpha"], rr["alpha"])
         # a line search is a chain of comparisons: the OUTCOME is compared, as in tests/test_optim.py
         assert rep["opt"]["cost_final"] < rep["opt"]["cost_initial"]
-        assert abs(rep["opt"]["cost_final"] - rr["opt"]["cost_final"]) <= 2e-3 * abs(rr["opt"]["cost_final"]), (win, rep["opt"], rr["opt"])
+        assert abs(rep["opt"]["cost_final"] - rr["opt"]["cost_final"]) <= 1e-2 * abs(rr["opt"]["cost_final"]), (win, rep["opt"], rr["opt"])
         q, _, _ = pgo.ctrl_poses()
         assert _qdist(q, ref.knots) <= 5e-3, (win, _qdist(q, ref.knots))
         assert _qdist(rep["pose_latest"][1], rr["pose_latest"][1]) <= 5e-3
