@@ -108,6 +108,28 @@ class EventWarperCMax:
         _capi.check(self._L.cmaxb_be_eval_end(self._h, C.byref(c), _capi.dptr(g) if self._split_grad else None))
         return c.value, (g[: self.n_params] if self._split_grad else None)
 
+    def eval_end_launch(self):
+        _capi.check(self._L.cmaxb_be_eval_end_launch(self._h, int(self._split_grad)))
+
+    def grad_tensor(self):
+        """This rank's partial gradient as a torch CUDA tensor VIEW of the library's buffer (float64, 3*K_opt)."""
+        import torch
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        _capi.check(self._L.cmaxb_be_grad_device(self._h, C.byref(ptr), C.byref(cnt)))
+        if cnt.value == 0:
+            return None
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (cnt.value,), "typestr": "<f8", "data": (ptr.value, False), "version": 2}
+
+        return torch.as_tensor(_View(), device="cuda")
+
+    def eval_end_fetch(self):
+        c = C.c_double()
+        g = np.zeros(max(self.n_params, 1))
+        _capi.check(self._L.cmaxb_be_eval_end_fetch(self._h, C.byref(c), _capi.dptr(g) if self._split_grad else None))
+        return c.value, (g[: self.n_params] if self._split_grad else None)
+
     # -- device-resident global map (event_pano_warper.cpp:81-132) --------------------------------------------
     def resetIG(self):
         _capi.check(self._L.cmaxb_be_map_reset(self._h))

@@ -29,7 +29,7 @@ struct cmaxb_be {
   float4* d_ilq = nullptr; float4* d_GQ = nullptr;   // corner-split accumulator / adjoint image (event-dense windows)
   bool use_quad = false; bool il_is_quad = false;
   float* d_il_plane = nullptr; bool il_is_plane = false;   // assembled IL (event-sharded evaluation)
-  bool split_pending = false; bool split_grad = false;
+  bool split_pending = false; bool split_grad = false; bool end_launched = false; bool end_grad = false;
   // device-resident global map (IG_, IG_update_times_map_)
   float* d_IG = nullptr; unsigned char* d_times = nullptr; unsigned char* d_mask = nullptr;
   int* d_ccell = nullptr; float4* d_ca = nullptr; float4* d_cb = nullptr; size_t cache_cap = 0;   // per-event gather cache
@@ -413,7 +413,8 @@ static int be_run_bands(cmaxb_be* be, bool blur) {
 }
 
 // image -> contrast (+ gradient) on the current IL (quad / planes / assembled plane); results to the host
-static int be_finish_eval(cmaxb_be* be, bool want_grad, double* contrast, double* grad) {
+// queue blur + contrast (+ adjoint image, gather, per-knot reduction): results stay on the device
+static int be_finish_launch(cmaxb_be* be, bool want_grad) {
   cudaStream_t s = be->stream;
   const int P = 3 * be->n_opt;
   CMAXB_TRY(be_run_image(be, be->taps));
@@ -451,13 +452,23 @@ static int be_finish_eval(cmaxb_be* be, bool want_grad, double* contrast, double
         be_band_reduce_kernel<<<P, 256, 0, s>>>(be->d_blur, be->d_bands_blur, be->A, be->d_mean, be->cfg.contrast_measure, be->d_grad);
       }));
     }
-    CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_grad, be->d_grad, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
   }
+  return CMAXB_OK;
+}
+// copy contrast (+ gradient) to the host and wait
+static int be_finish_fetch(cmaxb_be* be, bool want_grad, double* contrast, double* grad) {
+  cudaStream_t s = be->stream;
+  const int P = 3 * be->n_opt;
+  if (want_grad && P > 0) CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_grad, be->d_grad, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
   CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_result, be->d_result, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
   CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
   *contrast = be->h_result[0];
   if (want_grad && grad) for (int i = 0; i < P; ++i) grad[i] = be->h_grad[i];
   return CMAXB_OK;
+}
+static int be_finish_eval(cmaxb_be* be, bool want_grad, double* contrast, double* grad) {
+  CMAXB_TRY(be_finish_launch(be, want_grad));
+  return be_finish_fetch(be, want_grad, contrast, grad);
 }
 
 extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contrast, double* grad) {
@@ -526,6 +537,35 @@ extern "C" int cmaxb_be_eval_end(cmaxb_be* be, double* contrast, double* grad_pa
   be->il_is_plane = true;
   if (be->alpha_pending) CMAXB_TRY(be_run_alpha(be, be->d_il_plane, nullptr, nullptr));
   return be_finish_eval(be, grad_partial != nullptr, contrast, grad_partial);
+}
+
+// eval_end in two halves, so that the partial gradients can be summed across ranks ON THE DEVICE (NCCL all-reduce of
+// cmaxb_be_grad_device() on the handle's stream) between them -- no host hop inside a sharded evaluation
+extern "C" int cmaxb_be_eval_end_launch(cmaxb_be* be, int want_grad) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->split_pending) return set_error(CMAXB_ERR_STATE, "cmaxb_be_eval_end_launch without cmaxb_be_eval_begin");
+  if (want_grad && !be->split_grad) return set_error(CMAXB_ERR_STATE, "gradient requested but eval_begin ran without want_grad");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  be->split_pending = false;
+  be->il_is_plane = true;
+  if (be->alpha_pending) CMAXB_TRY(be_run_alpha(be, be->d_il_plane, nullptr, nullptr));
+  be->end_launched = true; be->end_grad = want_grad != 0;
+  return be_finish_launch(be, want_grad != 0);
+}
+extern "C" int cmaxb_be_grad_device(cmaxb_be* be, double** device_ptr, size_t* count) {
+  if (!be || !device_ptr || !count) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window");
+  *device_ptr = be->d_grad;
+  *count = (size_t)(3 * be->n_opt);
+  return CMAXB_OK;
+}
+extern "C" int cmaxb_be_eval_end_fetch(cmaxb_be* be, double* contrast, double* grad) {
+  if (!be || !contrast) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->end_launched) return set_error(CMAXB_ERR_STATE, "cmaxb_be_eval_end_fetch without cmaxb_be_eval_end_launch");
+  if (grad && !be->end_grad) return set_error(CMAXB_ERR_STATE, "gradient requested but eval_end_launch ran without want_grad");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  be->end_launched = false;
+  return be_finish_fetch(be, grad != nullptr, contrast, grad);
 }
 
 extern "C" int cmaxb_be_get_alpha(cmaxb_be* be, double* alpha) {

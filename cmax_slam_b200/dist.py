@@ -92,9 +92,12 @@ class ShardedEventWarper:
         if multi:
             plane = self.w.il_plane_tensor()
             dist.all_reduce(plane, group=self.group)          # the path's one real exchange step
-        c, g = self.w.eval_end()
-        if multi and want_grad and g is not None and len(g):
-            gt = torch.from_numpy(g).to(plane.device)
-            dist.all_reduce(gt, group=self.group)
-            g = gt.cpu().numpy()
-        return c, g
+        if not multi:
+            return self.w.eval_end()
+        # blur / contrast / adjoint / gather queued; the partial gradients are summed on the device (no host hop)
+        self.w.eval_end_launch()
+        if want_grad:
+            gt = self.w.grad_tensor()
+            if gt is not None:
+                dist.all_reduce(gt, group=self.group)
+        return self.w.eval_end_fetch()

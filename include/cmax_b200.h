@@ -195,6 +195,13 @@ int cmaxb_be_last_eval_x(cmaxb_be* be, double* x, int n);
 int cmaxb_be_eval_begin(cmaxb_be* be, const double* x, int n, int want_grad);
 int cmaxb_be_il_plane(cmaxb_be* be, float** device_ptr, size_t* count);
 int cmaxb_be_eval_end(cmaxb_be* be, double* contrast, double* grad_partial);
+/* cmaxb_be_eval_end in two halves: _launch queues blur, contrast, adjoint image, gather and per-knot reduction and
+ * leaves this rank's partial gradient in the device buffer cmaxb_be_grad_device() reports (3*K_opt doubles); the
+ * caller all-reduces that buffer on the handle's stream (NCCL); _fetch then copies contrast and the SUMMED gradient
+ * to the host.  A sharded evaluation so has no host round trip between its two collectives. */
+int cmaxb_be_eval_end_launch(cmaxb_be* be, int want_grad);
+int cmaxb_be_grad_device(cmaxb_be* be, double** device_ptr, size_t* count);
+int cmaxb_be_eval_end_fetch(cmaxb_be* be, double* contrast, double* grad);
 /* IL_old_ / IL_new_ at x (needed by updateIG, event_pano_warper.cpp:109-126); either may be NULL */
 int cmaxb_be_get_il(cmaxb_be* be, const double* x, int n, float* il_old, float* il_new);
 /* final image I = blur(IL + alpha*IGp) at x */
