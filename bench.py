@@ -294,6 +294,7 @@ def run_ours(args, rank, world, local_rank):
         fe.eval_launch(oms[nb][None, :], True)
         rows_b = fe.eval_fetch_all()[:, 0, :]
         assert np.allclose(rows[nb], rows_b[rank], rtol=1e-6, atol=1e-9 * abs(rows[nb, 0])), "exchanged row != local re-evaluation"
+        c_chk = float(rows[rank, 0])
         barrier()
     else:
         c_chk, g_chk = step_resident()
@@ -328,12 +329,40 @@ def run_ours(args, rank, world, local_rank):
     elif world > 1:
         fe2.set_result_mirror(mine2.data_ptr())
     lanes = [(fe, stream, mine), (fe2, stream2, mine2)]
+    # N > 1: the packet is the SAME on every rank (hypothesis sharding), so it crosses PCIe once in total: rank r
+    # uploads shard r (1/N of the events) from pinned host memory over its own PCIe link and the shards are
+    # all-gathered over NVLink (NCCL) into every rank's HBM; cmaxb_fe_set_packet_async then takes the device buffer.
+    shard_upload = world > 1 and args.upload == "sharded"
+    if shard_upload:
+        per = (n_ev + world - 1) // world
+        full_dev = [torch.zeros(world * per * 16, dtype=torch.uint8, device=dev) for _ in lanes]
+        lo, hi = rank * per * 16, min((rank + 1) * per, n_ev) * 16
+        host_shard = ev_pinned[lo:hi]
+
+    def upload(lane_idx):
+        lane = lanes[lane_idx]
+        if not shard_upload:
+            lane[0].set_packet(ev_host, pkt.t_ref_sec, wait=False)
+            return
+        with torch.cuda.stream(lane[1]):
+            buf = full_dev[lane_idx]
+            buf[lo:hi].copy_(host_shard, non_blocking=True)
+            dist.all_gather_into_tensor(buf, buf[rank * per * 16:(rank + 1) * per * 16])
+            lane[0].set_packet((buf.data_ptr(), n_ev), pkt.t_ref_sec, wait=False)
+
+    if shard_upload:   # the all-gathered packet must evaluate to the same contrast as the directly uploaded one
+        upload(0)
+        with torch.cuda.stream(lanes[0][1]):
+            lanes[0][0].eval_launch(omega[None, :], True)
+            c_sh = float(lanes[0][0].eval_fetch_all()[rank, 0, 0]) if use_p2p else float(lanes[0][0].eval_fetch()[0][0])
+        assert abs(c_sh - c_chk) <= 1e-6 * abs(c_chk), ("sharded upload changed the result", c_sh, c_chk)
+        barrier()
 
     def e2e_run(steps, warmup):
         total = steps + warmup
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
-        lanes[0][0].set_packet(ev_host, pkt.t_ref_sec, wait=False)
+        upload(0)
         for i in range(total):
             cur, nxt = lanes[i % 2], lanes[(i + 1) % 2]
             if i == warmup:
@@ -341,7 +370,7 @@ def run_ours(args, rank, world, local_rank):
                 sampler.active = True
                 t0.record(cur[1])
             if i + 1 < total:
-                nxt[0].set_packet(ev_host, pkt.t_ref_sec, wait=False)      # upload of the NEXT step's packet
+                upload((i + 1) % 2)                                          # upload of the NEXT step's packet
             with torch.cuda.stream(cur[1]):
                 flush.fill_(float(i))                                        # L2 flush, inside the timed span
                 cur[0].eval_launch(omega[None, :], True)
@@ -415,10 +444,15 @@ def run_ours(args, rank, world, local_rank):
             "latency": {"us_per_eval": lat_ms / K * 1e3, "value": world * n_ev / (lat_ms / K * 1e-3),
                         "note": "one synchronous contrast+gradient evaluation (the GSL callback): launch, wait for the result on the host, "
                                 "then the next launch; L2 warm"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n_ev + 24, "d2h_bytes_per_step": 32 + 4,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": (16 * n_ev + 24 * world) if shard_upload else world * (16 * n_ev + 24),
+                    "d2h_bytes_per_step": world * (32 * max(world, 1) + 4),
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "path": "cmaxb_fe_set_packet_async(pinned host events) + cmaxb_fe_eval through the C ABI; uploads double-buffered "
-                            "(two handles / streams), L2 flush inside the timed span"},
+                    "path": ("cmaxb_fe_set_packet_async + cmaxb_fe_eval through the C ABI; uploads double-buffered (two handles / streams), "
+                             "L2 flush inside the timed span; " +
+                             ("the replicated packet crosses PCIe once per step in total: every rank uploads 1/N of it from pinned host memory "
+                              "and the shards are all-gathered over NVLink (bytes = whole job)" if shard_upload else
+                              "every rank uploads the whole packet from pinned host memory (bytes = whole job)"))},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -450,6 +484,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grad-mode", default="adjoint", choices=["dense", "adjoint"])
     ap.add_argument("--depth", type=int, default=2, help="evaluations queued on the stream before the oldest result is read (1 = synchronous)")
+    ap.add_argument("--upload", default="sharded", choices=["sharded", "replicated"], help="N>1 e2e: upload 1/N of the (replicated) packet per rank + NVLink all-gather, or the whole packet on every rank")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N>1: fused in-kernel exchange over peer memory, or a separate NCCL all-gather")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

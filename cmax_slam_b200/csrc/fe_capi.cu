@@ -245,7 +245,7 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
   fe->n = (long long)n; fe->nb = nb;
   if (n > 0) {
     cudaStream_t s = fe->stream;
-    CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->d_ev, events, sizeof(cmaxb_event) * n, cudaMemcpyHostToDevice, s));
+    CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->d_ev, events, sizeof(cmaxb_event) * n, cudaMemcpyDefault, s));   // host (pinned: DMA) or device memory (UVA)
     CMAXB_CUDA_TRY(cudaMemsetAsync(fe->d_flags, 0, sizeof(int), s));
     const uint4* ev = fe->d_ev; const long long nn = fe->n; int* flags = fe->d_flags;
     const int W = fe->cfg.width, H = fe->cfg.height; double* dt = fe->d_dt; const int ibs = (int)bs;

@@ -82,7 +82,9 @@ void cmaxb_fe_destroy(cmaxb_fe* fe);
 
 /* Upload one event packet (replaces the copy into event_subset_, ang_vel_estimator.cpp:137-147)
  * and its reference time time_packet_.toSec().  `events` is host memory (pinned memory makes
- * the copy asynchronous).  Validates pixel range and batch time order. */
+ * the copy asynchronous) or device memory of the handle's GPU (e.g. the output of an NVLink all-gather of packet
+ * shards uploaded by several ranks: the copy is then device to device).  Validates pixel range and batch time
+ * order. */
 int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec);
 /* Same, but returns as soon as the copy and the preparation kernels are queued on the handle's stream (events
  * must stay valid -- pinned -- until the next call that waits).  The validation verdict is delivered by the next
