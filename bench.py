@@ -359,29 +359,49 @@ def run_ours(args, rank, world, local_rank):
         barrier()
 
     def e2e_run(steps, warmup):
+        """Every step: upload of the packet (pinned host -> device), L2 flush, evaluation, read-back of the result.  Two
+        lanes (handles / streams) alternate: while lane A evaluates step i the host reads the result of step i-1 and
+        queues the upload of step i+1 on lane B.  The evaluation kernels of the two lanes are chained with events so
+        that every rank runs them in the same order (they wait for their peers inside the kernel)."""
         total = steps + warmup
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
+        done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def fetch(lane):
+            if use_p2p:
+                lane[0].eval_fetch_all()
+            else:
+                lane[0].eval_fetch()
+
         upload(0)
+        pending = None
         for i in range(total):
-            cur, nxt = lanes[i % 2], lanes[(i + 1) % 2]
+            ci = i % 2
+            cur = lanes[ci]
             if i == warmup:
+                if pending is not None:
+                    fetch(lanes[pending])
+                    pending = None
                 barrier()
                 sampler.active = True
                 t0.record(cur[1])
-            if i + 1 < total:
-                upload((i + 1) % 2)                                          # upload of the NEXT step's packet
             with torch.cuda.stream(cur[1]):
+                if i > 0:
+                    cur[1].wait_event(done_ev[1 - ci])
                 flush.fill_(float(i))                                        # L2 flush, inside the timed span
                 cur[0].eval_launch(omega[None, :], True)
-                if use_p2p:
-                    cur[0].eval_fetch_all()
-                else:
-                    if world > 1:
-                        dist.all_gather_into_tensor(gathered.view(-1), cur[2])
-                    cur[0].eval_fetch()
+                if world > 1 and not use_p2p:
+                    dist.all_gather_into_tensor(gathered.view(-1), cur[2])
+                done_ev[ci].record(cur[1])
             if i == total - 1:
                 t1.record(cur[1])
+            if pending is not None:
+                fetch(lanes[pending])                                        # result of the PREVIOUS step (host read)
+            if i + 1 < total:
+                upload((i + 1) % 2)                                          # upload of the NEXT step's packet
+            pending = ci
+        fetch(lanes[pending])
         barrier()
         sampler.active = False
         ms = t0.elapsed_time(t1)
