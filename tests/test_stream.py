@@ -107,3 +107,37 @@ def test_gap_marks_packet_and_uncovered_window_is_an_error():
     with pytest.raises(CmaxbError):
         EventStream(0.0, 2000, 1)
     s.close()
+
+
+def test_randomised_configurations_match_restatement():
+    """Random dt / packet size / subsampling / message size / event rate, short streams with windows now and then."""
+    from oracle.pgo_py import dur, t_add
+    rng = np.random.default_rng(2024)
+    for trial in range(12):
+        dt = float(rng.choice([0.002, 0.005, 0.01, 0.02]))
+        per_packet = int(rng.integers(40, 3000))
+        rate = int(rng.integers(1, 4))
+        msg = int(rng.integers(50, 5000))
+        ev = _events(int(rng.integers(3000, 25000)), 100 + trial, rate_hz=float(rng.choice([2e4, 1e5, 5e5])))
+        s = EventStream(dt, per_packet, rate)
+        o = StreamOracle(dt, per_packet, rate)
+        got = []
+        for i in range(0, len(ev), msg):
+            s.eventsCallback(ev[i:i + msg])
+            o.callback(ev[i:i + msg])
+            while True:
+                p = s.next_packet()
+                if p is None:
+                    break
+                got.append((p[0].copy(), p[1], p[2]))
+        assert len(got) == len(o.packets), trial
+        for (e, t, f), (eo, to, fo) in zip(got, o.packets):
+            assert t == to and f == fo and _same(e, np.array(eo, dtype=synth.EVENT_DTYPE)), trial
+        if len(o.ts_keys) >= 4:                                 # one window over the middle of what the table covers
+            tb, te = o.ts_keys[0], o.ts_keys[len(o.ts_keys) // 2]
+            a = s.window_events(tb, te)
+            b = o.window_events(tb, te)
+            assert _same(a, np.array(b, dtype=synth.EVENT_DTYPE)), trial
+        st = s.state()
+        assert st["n_stored"] == o.total and st["n_ts_map"] == len(o.ts_keys) and st["n_subsets_pending"] == len(o.subsets), trial
+        s.close()
