@@ -44,6 +44,26 @@ def sharded_eval(evaluate, omegas, want_grad=True, group=None, device=None):
     return rows[:, 0].copy(), (rows[:, 1:].copy() if want_grad else None)
 
 
+def sharded_eval_fused(fe, omegas, want_grad=True, group=None):
+    """Hypothesis sharding with the result exchange fused into the evaluation kernel (BASELINE config C3): `fe` is an
+    AngVelEstimatorCMax on which exchange_connect(group) has been called on every rank.  Rank r evaluates hypotheses
+    r, r + N, ... in ONE launch whose publishing CTA also stores the rows into every peer's buffer over NVLink and
+    collects the peers' rows -- no collective call here.  K must be a multiple of the world size with K / N <= 32.
+    Returns (contrasts[K], grads[K,3] or None), identical on every rank."""
+    import torch.distributed as dist
+    om = np.ascontiguousarray(omegas, dtype=np.float64).reshape(-1, 3)
+    K = om.shape[0]
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if K % world or K // world > 32 or K // world > fe.max_hypotheses:
+        raise ValueError("K must be a multiple of the world size with K / world <= min(32, max_hypotheses)")
+    fe.eval_launch(om[shard_indices(K, rank, world)], want_grad)
+    rows = fe.eval_fetch_all()                       # [world, K / world, 4]
+    out = np.zeros((K, 4))
+    for r in range(world):
+        out[shard_indices(K, r, world)] = rows[r]
+    return out[:, 0].copy(), (out[:, 1:].copy() if want_grad else None)
+
+
 # ------------------------------------------------------------------------------------------------
 # One big back-end window sharded by TIME across ranks (SURVEY.md section 8e, BASELINE config C5)
 # ------------------------------------------------------------------------------------------------

@@ -369,7 +369,9 @@ void cmaxb_pgo_destroy(cmaxb_pgo* pgo);
 int cmaxb_pgo_push_ang_vel(cmaxb_pgo* pgo, cmaxb_stamp ts, const double ang_vel[3]);
 /* current window cursors; *ang_vel_ready = the latest angular velocity lies beyond t_win_end (isReadyFrontendPoses) */
 int cmaxb_pgo_window(cmaxb_pgo* pgo, cmaxb_stamp* t_win_beg, cmaxb_stamp* t_win_end, int* ang_vel_ready);
-/* getAngVelSubset + processTimeWindow + slideWindow on the given event subset (host memory) */
+/* getAngVelSubset + processTimeWindow + slideWindow on the given event subset (host memory).  On an error (e.g. fewer
+ * front-end poses than control poses to fit -- the reference aborts on that CHECK_GE, trajectory.cpp:116) the window
+ * is NOT slid but the angular velocities it consumed are gone: treat the handle as dead, as the reference's abort does. */
 int cmaxb_pgo_process_window(cmaxb_pgo* pgo, const cmaxb_event* events, size_t n_events, cmaxb_pgo_report* report);
 /* all control poses so far (x,y,z,w) and the spline's time origin / knot spacing; xyzw may be NULL to query *n */
 int cmaxb_pgo_get_ctrl_poses(cmaxb_pgo* pgo, double* xyzw, int capacity, int* n, int64_t* t0_ns, int64_t* dt_ns);

@@ -176,3 +176,58 @@ def test_fused_result_exchange_between_processes(oracle, tmp_path, world):
     assert np.abs(rows[1][..., 1:]).max() == 0.0                            # value-only step: zero gradient columns
     for st in (0, 2):
         assert np.abs(rows[st][..., 1:] - go[st]).max() <= RTOL * np.abs(go).max()
+
+
+_C3_WORKER = r'''
+import sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from cmax_slam_b200 import synth
+from cmax_slam_b200.dist import sharded_eval_fused
+from cmax_slam_b200.frontend import AngVelEstimatorCMax
+rank, world = int(sys.argv[3]), 2
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=rank, world_size=world)
+torch.cuda.set_device(0)
+pk = synth.fe_config("C1", scale=0.1)
+fe = AngVelEstimatorCMax(pk.width, pk.height, pk.K, pk.lut, max_hypotheses=8)
+fe.set_packet(pk.events, pk.t_ref_sec)
+fe.exchange_connect()
+oms = synth.fe_hypotheses(pk, 16, sigma=0.3)
+c, g = sharded_eval_fused(fe, oms, True)
+cv, gv = sharded_eval_fused(fe, oms[:6], False)
+assert gv is None
+np.save(sys.argv[4] + f"/c3_{rank}.npy", np.concatenate([c, g.ravel(), cv]))
+dist.barrier()
+fe.exchange_close()
+fe.close()
+dist.destroy_process_group()
+print("ok")
+'''
+
+
+def test_c3_style_hypothesis_sweep_with_fused_exchange(oracle, tmp_path):
+    """16 hypotheses over 2 ranks (8 per launch), rows re-interleaved: equal on both ranks and to the oracle."""
+    import socket
+    script = tmp_path / "c3.py"
+    script.write_text(_C3_WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), str(tmp_path)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=240)[0])
+        except subprocess.TimeoutExpired:
+            p.kill()
+            outs.append("timeout: " + p.communicate()[0])
+    assert all(p.returncode == 0 for p in procs), outs
+    a, b = np.load(tmp_path / "c3_0.npy"), np.load(tmp_path / "c3_1.npy")
+    assert np.array_equal(a, b)
+    pk = synth.fe_config("C1", scale=0.1)
+    oms = synth.fe_hypotheses(pk, 16, sigma=0.3)
+    args = oracle.fe_args(pk.events, pk.t_ref_sec, pk.lut, pk.width, pk.height, pk.K)
+    co, go = oracle.fe_eval_batch(args, oms, True, n_threads=4)
+    c, g, cv = a[:16], a[16:64].reshape(16, 3), a[64:]
+    assert np.abs(c - co).max() <= RTOL * np.abs(co).max()
+    assert np.abs(g - go).max() <= RTOL * np.abs(go).max()
+    assert np.abs(cv - co[:6]).max() <= RTOL * np.abs(co).max()
