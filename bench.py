@@ -52,6 +52,33 @@ def ncu_traffic_bytes(kernel):
     return None, None
 
 
+def ncu_secondary(kernel):
+    """Secondary resources of `kernel` from the committed ncu summary (the single-hypothesis working set is
+    L2 resident, so L2 / atomic / issue utilisation is reported beside the HBM fraction).  None when there is no capture."""
+    import glob
+    import re
+    want = {"l2_throughput_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l2_atomic_input_cycles_pct": "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "l1tex_throughput_pct": "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+            "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "fp64_pipe_pct": "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+            "stall_long_scoreboard_per_issue": "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "stall_barrier_per_issue": "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*.txt")), reverse=True):
+        for blk in open(path).read().split("---"):
+            if kernel not in blk:
+                continue
+            out = {}
+            for k, m in want.items():
+                mm = re.search(re.escape(m) + r" = ([0-9.]+)", blk)
+                if mm:
+                    out[k] = float(mm.group(1))
+            if out:
+                out["source"] = os.path.basename(path)
+                return out
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -479,6 +506,7 @@ def run_ours(args, rank, world, local_rank):
                          "note": "the packet (35 MB) is L2 resident across evaluations: DRAM traffic is ~0 in steady state; "
                                  "ncu's figure is a cold-cache replay.  The binding resources are L2 request rate / latency and "
                                  "f64 issue (DESIGN.md section 4), so the HBM fraction is reported, not padded.",
+                         "secondary": ncu_secondary(ncu_name),
                          "algorithmic_bytes_per_launch": alg, "avg_launch_us": kern[dom]["avg_us"],
                          "kernel_share_of_step": kern[dom]["avg_us"] * kern[dom]["launches"] / max(1, min(K, 200)) / step_us_kernels,
                          "per_kernel": per_kernel},
