@@ -1,0 +1,50 @@
+"""bench.py contract pieces that run without a GPU: the reference arm (the reference's CPU algorithm = the oracle port,
+all host threads) prints ONE JSON line with the agreed keys; the ours-arm refuses to run without a device (no CPU
+fallback); the roofline helpers read the committed ncu summaries."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "events/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["warmup"] >= 3 and d["vs_baseline"] is None and "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_our_arm_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_roofline_helpers_read_the_committed_profiles():
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic, src = bench.ncu_traffic_bytes("fe_eval_megakernel")
+    assert traffic and 1e7 < traffic < 1e8 and src.endswith(".txt")
+    sec = bench.ncu_secondary("fe_eval_megakernel")
+    assert sec and 0 < sec["l2_throughput_pct"] < 100 and "l2_atomic_input_cycles_pct" in sec
+    peak, how = bench.load_peaks()
+    assert 3000 < peak < 9000
