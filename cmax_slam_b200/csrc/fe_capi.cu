@@ -168,6 +168,13 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
     if (coop && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && occ > 0) {
       int grid = occ * nsm;
       if (grid > kMegaMaxCtas) grid = kMegaMaxCtas;
+      {
+        // tuning aid: CMAXB_FE_GRID_FRACTION=0.5 launches the fused kernel on half of the co-resident CTAs, so that two
+        // handles on two streams can run their (latency-bound) evaluations side by side; default 1 = whole GPU
+        const char* gf = getenv("CMAXB_FE_GRID_FRACTION");
+        const double f = gf ? atof(gf) : 1.0;
+        if (f > 0.0 && f < 1.0) { grid = (int)(grid * f); if (grid < nsm / 4) grid = nsm / 4; if (grid < 1) grid = 1; }
+      }
       fe->mega_grid = grid;
       fe->mega_th = mega_tile_height(cfg->width, cfg->height, grid);
       const size_t kk = (size_t)fe->kmax;
