@@ -410,6 +410,68 @@ double computeContrast(const float* img, int64_t n, const std::vector<PlaneView>
 // ================================================================================================
 // Front-end
 // ================================================================================================
+// ---- first-party geometry of the reference, restated; pinned against the reference's OWN sources compiled with
+// container stubs (oracle/ref_geom_shim.cpp -> oracle/_ref/libref_geom.so, tests/test_oracle_geom.py) -----------------
+// canonicalProjection, src/utils/image_geom_util.cpp:24-41
+inline void canonicalProjectionO(const V3& p, double* u, double* v, double Jp[2][3]) {
+  const double inv = 1.0 / p.z;
+  *u = p.x * inv;
+  *v = p.y * inv;
+  Jp[0][0] = inv; Jp[0][1] = 0.0; Jp[0][2] = -*u * inv;
+  Jp[1][0] = 0.0; Jp[1][1] = inv; Jp[1][2] = -*v * inv;
+}
+// applyIntrinsics, src/utils/image_geom_util.cpp:7-22
+inline void applyIntrinsicsO(double u, double v, double fx, double fy, double cx, double cy, double* px, double* py) {
+  *px = fx * u + cx;
+  *py = fy * v + cy;
+}
+// cross2Matrix, include/utils/image_geom_util.h:5-8
+inline void cross2MatrixO(const V3& m, double M[3][3]) {
+  M[0][0] = 0;    M[0][1] = -m.z; M[0][2] = m.y;
+  M[1][0] = m.z;  M[1][1] = 0;    M[1][2] = -m.x;
+  M[2][0] = -m.y; M[2][1] = m.x;  M[2][2] = 0;
+}
+// dvs::EquirectangularCamera::projectToImage, include/backend/equirectangular_camera.h:18-45
+inline void equirectProjectO(double wx, double wy, double wz, double fx, double fy, double cxp, double cyp, double* px, double* py,
+                             float dpm_drb[2][3]) {
+  const double phi = std::atan2(wx, wz);
+  const double theta = std::asin(wy / std::sqrt(wx * wx + wy * wy + wz * wz));
+  const double rho = std::sqrt(wx * wx + wy * wy + wz * wz);
+  const double Ydivrho = wy / rho;
+  const double XdivZ = wx / wz;
+  const double tmp1 = fx / ((1 + XdivZ * XdivZ) * wz);
+  const double tmp2 = -fy / std::sqrt(1 - Ydivrho * Ydivrho);
+  const double tmp3 = Ydivrho / (rho * rho);
+  dpm_drb[0][0] = (float)tmp1;
+  dpm_drb[0][1] = 0.f;
+  dpm_drb[0][2] = (float)(-tmp1 * XdivZ);
+  dpm_drb[1][0] = (float)(tmp2 * tmp3 * wx);
+  dpm_drb[1][1] = (float)(tmp2 * (tmp3 * wy - 1 / rho));
+  dpm_drb[1][2] = (float)(tmp2 * tmp3 * wz);
+  *px = cxp + phi * fx;
+  *py = cyp + theta * fy;
+}
+// hooks for the pinning tests
+extern "C" void orc_geom_pinhole(const double p[3], const double K4[4], double uv[2], double px[2], double Jproj[6]) {
+  double Jp[2][3];
+  canonicalProjectionO(V3{p[0], p[1], p[2]}, &uv[0], &uv[1], Jp);
+  applyIntrinsicsO(uv[0], uv[1], K4[0], K4[1], K4[2], K4[3], &px[0], &px[1]);
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) Jproj[i * 3 + j] = Jp[i][j];
+}
+extern "C" void orc_geom_cross2matrix(const double v[3], double M[9]) {
+  double m[3][3];
+  cross2MatrixO(V3{v[0], v[1], v[2]}, m);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[i * 3 + j] = m[i][j];
+}
+extern "C" void orc_geom_equirect(const double w[3], int PW, int PH, double px[2], float J[6]) {
+  // EquirectangularCamera(pano_size, 360, 180): centre and focal lengths, equirectangular_camera.h:11-16,64-67
+  const double cxp = (double)PW / 2.0, cyp = (double)PH / 2.0;
+  const double fx = double((PW / 360.0) * 180.0 / M_PI), fy = double((PH / 180.0) * 180.0 / M_PI);
+  float d[2][3];
+  equirectProjectO(w[0], w[1], w[2], fx, fy, cxp, cyp, &px[0], &px[1], d);
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) J[i * 3 + j] = d[i][j];
+}
+
 extern "C" int orc_fe_eval(const orc_fe_args* a, const double omega[3], int want_grad, orc_fe_out* out) {
   const int W = a->width, H = a->height;
   const int64_t A = (int64_t)W * H;
@@ -440,19 +502,17 @@ extern "C" int orc_fe_eval(const orc_fe_args* a, const double omega[3], int want
       const V3 cr{delta.y * b.z - delta.z * b.y, delta.z * b.x - delta.x * b.z, delta.x * b.y - delta.y * b.x};
       const V3 pr{b.x + cr.x, b.y + cr.y, b.z + cr.z};
 
-      // canonicalProjection, image_geom_util.cpp:24-41
-      const double inv = 1.0 / pr.z;
-      const double u = pr.x * inv, v = pr.y * inv;
-      // applyIntrinsics, image_geom_util.cpp:7-22
-      const double px = a->fx * u + a->cx;
-      const double py = a->fy * v + a->cy;
+      // canonicalProjection + applyIntrinsics (pinned against the reference's own source: tests/test_oracle_geom.py)
+      double u, v, px, py, Jp[2][3];
+      canonicalProjectionO(pr, &u, &v, Jp);
+      applyIntrinsicsO(u, v, a->fx, a->fy, a->cx, a->cy, &px, &py);
 
       double J[2][3] = {{0, 0, 0}, {0, 0, 0}};
       if (want_grad) {
         // cross2Matrix((-dt)*point_3D), image_geom_util.h:5-8, local_image_warped_events.cpp:110
         const V3 mv{(-dt) * b.x, (-dt) * b.y, (-dt) * b.z};
-        const double Mx[3][3] = {{0, -mv.z, mv.y}, {mv.z, 0, -mv.x}, {-mv.y, mv.x, 0}};
-        const double Jp[2][3] = {{inv, 0.0, -u * inv}, {0.0, inv, -v * inv}};
+        double Mx[3][3];
+        cross2MatrixO(mv, Mx);
         double Jc[2][3];
         for (int r = 0; r < 2; ++r)
           for (int c = 0; c < 3; ++c) {  // cv::Matx product: s = 0; s += a(i,k)*b(k,j)
@@ -637,25 +697,9 @@ extern "C" int orc_be_eval(const orc_be_args* a, const double* x, int want_grad,
       const double wy = R(1, 0) * b.x + R(1, 1) * b.y + R(1, 2) * b.z;
       const double wz = R(2, 0) * b.x + R(2, 1) * b.y + R(2, 2) * b.z;
       // projectToImage, equirectangular_camera.h:18-45
-      const double phi = std::atan2(wx, wz);
-      const double theta = std::asin(wy / std::sqrt(wx * wx + wy * wy + wz * wz));
-      const double rho = std::sqrt(wx * wx + wy * wy + wz * wz);
-      const double Ydivrho = wy / rho;
       float dpm_drb[2][3];
-      {
-        const double XdivZ = wx / wz;
-        const double tmp1 = fx / ((1 + XdivZ * XdivZ) * wz);
-        const double tmp2 = -fy / std::sqrt(1 - Ydivrho * Ydivrho);
-        const double tmp3 = Ydivrho / (rho * rho);
-        dpm_drb[0][0] = (float)tmp1;
-        dpm_drb[0][1] = 0.f;
-        dpm_drb[0][2] = (float)(-tmp1 * XdivZ);
-        dpm_drb[1][0] = (float)(tmp2 * tmp3 * wx);
-        dpm_drb[1][1] = (float)(tmp2 * (tmp3 * wy - 1 / rho));
-        dpm_drb[1][2] = (float)(tmp2 * tmp3 * wz);
-      }
-      const double px = cxp + phi * fx;
-      const double py = cyp + theta * fy;
+      double px, py;
+      equirectProjectO(wx, wy, wz, fx, fy, cxp, cyp, &px, &py, dpm_drb);
 
       float jac[2][12];
       if (want_grad) {

@@ -12,8 +12,15 @@
  *     tests/golden/spline_*.npz).
  *   - Gaussian blur / meanStdDev / mean (OpenCV, un-vendored, unpinned by the reference):
  *     pinned by us against cv2 4.13 (tests/golden/blur_*.npz).
- *   - warp / scatter / contrast arithmetic: the reference ships no test or golden vector for
- *     it => "parity unpinned" beyond the line-by-line restatement cited below.
+ *   - first-party geometry (canonicalProjection, applyIntrinsics, cross2Matrix, EquirectangularCamera::
+ *     projectToImage): PINNED bit-exact against the reference's own sources compiled with container stubs
+ *     (oracle/ref_geom_shim.cpp -> oracle/_ref/libref_geom.so, tests/test_oracle_geom.py, tests/golden/geom_ref.npz).
+ *   - spline wrapper (time origin, f32 Jacobian repacking): PINNED against the reference's own
+ *     src/backend/trajectory.cpp compiled with ROS / OpenCV / glog stand-ins (oracle/ref_traj_shim.cpp ->
+ *     oracle/_ref/libref_traj.so, tests/test_traj_firstparty.py, tests/golden/traj_firstparty.npz).
+ *   - the remaining warp / scatter / contrast control flow (batching, bounds, votes, old/new split, band indices,
+ *     focus formulas): the reference ships no test or golden vector for it and those translation units need
+ *     OpenCV image operations + ROS to compile => "parity unpinned" beyond the line-by-line restatement cited below.
  */
 #pragma once
 #include <stdint.h>

@@ -316,3 +316,133 @@ def ref_integrate_ang_vel(latest_stamp, latest_xyzw, prev_stamp, prev_w, first, 
     n = L.ref_integrate_ang_vel(ls.ctypes.data_as(up), _d(lq), ps.ctypes.data_as(up), _d(pw), int(first), st.ctypes.data_as(up), _d(ww), len(st),
                                 os_.ctypes.data_as(up), _d(oq))
     return os_[:n], oq[:n], ps, pw
+
+
+# ---- first-party geometry against the reference's own sources (oracle/_ref/libref_geom.so) ----------------------
+_REF_GEOM = os.path.join(_HERE, "_ref", "libref_geom.so")
+_ref_geom = None
+
+
+def have_ref_geom():
+    return os.path.exists(_REF_GEOM)
+
+
+def ref_geom():
+    global _ref_geom
+    if _ref_geom is None and have_ref_geom():
+        _ref_geom = C.CDLL(_REF_GEOM)
+    return _ref_geom
+
+
+def _geom_pinhole(L, fn, p, K4, with_intr):
+    p = np.ascontiguousarray(p, dtype=np.float64); K4 = np.ascontiguousarray(K4, dtype=np.float64)
+    uv, px, Jp, Ji = np.zeros(2), np.zeros(2), np.zeros(6), np.zeros(4)
+    if with_intr:
+        getattr(L, fn)(_d(p), _d(K4), _d(uv), _d(px), _d(Jp), _d(Ji))
+    else:
+        getattr(L, fn)(_d(p), _d(K4), _d(uv), _d(px), _d(Jp))
+    return uv, px, Jp.reshape(2, 3), Ji.reshape(2, 2)
+
+
+def geom_pinhole(p, K4):
+    """oracle restatement: (uv, pixel, Jproj 2x3)"""
+    return _geom_pinhole(lib(), "orc_geom_pinhole", p, K4, False)[:3]
+
+
+def ref_geom_pinhole(p, K4):
+    """the reference's canonicalProjection + applyIntrinsics: (uv, pixel, Jproj 2x3, Jintr 2x2)"""
+    return _geom_pinhole(ref_geom(), "ref_pinhole", p, K4, True)
+
+
+def _geom_cross(L, fn, v):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    M = np.zeros(9)
+    getattr(L, fn)(_d(v), _d(M))
+    return M.reshape(3, 3)
+
+
+def geom_cross2matrix(v):
+    return _geom_cross(lib(), "orc_geom_cross2matrix", v)
+
+
+def ref_geom_cross2matrix(v):
+    return _geom_cross(ref_geom(), "ref_cross2matrix", v)
+
+
+def _geom_equirect(L, fn, w, PW, PH):
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    px = np.zeros(2)
+    J = np.zeros(6, np.float32)
+    getattr(L, fn)(_d(w), int(PW), int(PH), _d(px), J.ctypes.data_as(_fp))
+    return px, J.reshape(2, 3)
+
+
+def geom_equirect(w, PW, PH):
+    return _geom_equirect(lib(), "orc_geom_equirect", w, PW, PH)
+
+
+def ref_geom_equirect(w, PW, PH):
+    return _geom_equirect(ref_geom(), "ref_equirect", w, PW, PH)
+
+
+# ---- first-party trajectory code of the reference (src/backend/trajectory.cpp compiled with stubs) -----------------
+_REF_TRAJ = os.path.join(_HERE, "_ref", "libref_traj.so")
+_ref_traj = None
+_up = C.POINTER(C.c_uint32)
+
+
+def have_ref_traj():
+    return os.path.exists(_REF_TRAJ)
+
+
+def ref_traj():
+    global _ref_traj
+    if _ref_traj is None and have_ref_traj():
+        _ref_traj = C.CDLL(_REF_TRAJ)
+    return _ref_traj
+
+
+def _u2(t):
+    return np.array([int(t[0]), int(t[1])], dtype=np.uint32)
+
+
+def ref1p_generate_ctrl_poses(order, dt_knots, t_traj_beg, t_beg, t_end, stamps, poses_xyzw):
+    L = ref_traj()
+    st = np.ascontiguousarray(stamps, dtype=np.uint32).reshape(-1, 2)
+    q = np.ascontiguousarray(poses_xyzw, dtype=np.float64).reshape(-1, 4)
+    out = np.zeros((256, 4))
+    a, b, c = _u2(t_traj_beg), _u2(t_beg), _u2(t_end)
+    L.ref1p_generate_ctrl_poses.restype = C.c_int
+    n = L.ref1p_generate_ctrl_poses(int(order), C.c_double(dt_knots), a.ctypes.data_as(_up), b.ctypes.data_as(_up), c.ctypes.data_as(_up),
+                                    st.ctypes.data_as(_up), _d(q), len(q), _d(out), 256)
+    if n < 0:
+        raise ValueError("ref1p_generate_ctrl_poses failed")
+    return out[:n].copy()
+
+
+def ref1p_evaluate(order, t_beg, dt_knots, knots_xyzw, t, want_J=True):
+    """(q, idx_beg, J float32 [3, 3*order]) from the real Linear/CubicTrajectory::evaluate"""
+    L = ref_traj()
+    k = np.ascontiguousarray(knots_xyzw, dtype=np.float64).reshape(-1, 4)
+    q = np.zeros(4)
+    idx = C.c_int32(0)
+    J = np.zeros((3, 3 * order), np.float32)
+    tt = _u2(t)
+    L.ref1p_evaluate(int(order), C.c_double(t_beg), C.c_double(dt_knots), _d(k), len(k), tt.ctypes.data_as(_up), _d(q), C.byref(idx),
+                     J.ctypes.data_as(_fp) if want_J else None)
+    return q, idx.value, J
+
+
+def ref1p_window_evaluate(order, t_traj_beg, dt_knots, knots_xyzw, idx_traj_beg, idx_opt_beg, drotv, t):
+    """CopyAndIncrementalUpdate + evaluate on the temporary trajectory: (q, idx_beg, J f32, knots after incrementalUpdate)"""
+    L = ref_traj()
+    k = np.ascontiguousarray(knots_xyzw, dtype=np.float64).reshape(-1, 4)
+    d = np.ascontiguousarray(drotv, dtype=np.float64).reshape(-1)
+    q = np.zeros(4)
+    idx = C.c_int32(0)
+    J = np.zeros((3, 3 * order), np.float32)
+    after = np.zeros_like(k)
+    a, tt = _u2(t_traj_beg), _u2(t)
+    L.ref1p_window_evaluate(int(order), a.ctypes.data_as(_up), C.c_double(dt_knots), _d(k), len(k), int(idx_traj_beg), int(idx_opt_beg), _d(d),
+                            tt.ctypes.data_as(_up), _d(q), C.byref(idx), J.ctypes.data_as(_fp), _d(after))
+    return q, idx.value, J, after

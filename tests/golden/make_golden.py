@@ -216,14 +216,83 @@ def golden_lut():
     np.savez_compressed(os.path.join(OUT, "lut_cv2.npz"), **d)
 
 
+def golden_geom():
+    """Outputs of the reference's OWN geometry sources (src/utils/image_geom_util.cpp, include/utils/image_geom_util.h,
+    include/backend/equirectangular_camera.h) compiled with container stubs into oracle/_ref/libref_geom.so."""
+    assert O.have_ref_geom(), "oracle/_ref/libref_geom.so missing: run `make -C oracle` with /root/reference present"
+    rng = np.random.default_rng(23)
+    n = 400
+    P = np.concatenate([rng.normal(0, 0.4, (n, 2)), rng.uniform(0.3, 2.0, (n, 1))], 1)      # camera-frame points, z > 0
+    K4 = np.array([588.0999, 593.9887, 339.8259, 242.4252])
+    pin = [O.ref_geom_pinhole(p, K4) for p in P]
+    V = rng.normal(0, 1, (50, 3))
+    Wd = rng.normal(0, 1, (n, 3)); Wd /= np.linalg.norm(Wd, axis=1, keepdims=True)
+    Wd = np.concatenate([Wd, Wd[:50] * rng.uniform(0.5, 3.0, (50, 1))])                      # non-unit rays too
+    eq = [O.ref_geom_equirect(w, 1280, 720) for w in Wd] + [O.ref_geom_equirect(w, 4096, 2048) for w in Wd[:100]]
+    np.savez_compressed(os.path.join(OUT, "geom_ref.npz"), P=P, K4=K4, uv=np.array([a[0] for a in pin]), px=np.array([a[1] for a in pin]),
+                        Jproj=np.array([a[2] for a in pin]), Jintr=np.array([a[3] for a in pin]), V=V,
+                        cross=np.array([O.ref_geom_cross2matrix(v) for v in V]), W=Wd, eq_px=np.array([a[0] for a in eq]),
+                        eq_J=np.array([a[1] for a in eq]))
+
+
+def golden_traj_firstparty():
+    """Outputs of the reference's OWN src/backend/trajectory.cpp (Linear/CubicTrajectory) compiled with ROS / OpenCV / glog
+    stand-ins into oracle/_ref/libref_traj.so: generateCtrlPoses, evaluate (+ f32 knot Jacobians), CopyAndIncrementalUpdate."""
+    assert O.have_ref_traj(), "oracle/_ref/libref_traj.so missing: run `make -C oracle` with /root/reference present"
+    rng = np.random.default_rng(41)
+    d = {}
+    n_gen = 0
+    for order in (2, 4):
+        for dtk, span, n in ((0.1, 0.5, 40), (0.05, 0.2, 12), (0.02, 0.1, 30)):
+            t0 = 1.6e9 + 12.25 + n_gen * 0.37
+            tb = (int(np.floor(t0)), int(round((t0 - np.floor(t0)) * 1e9)))
+            te_s = t0 + span
+            te = (int(np.floor(te_s)), int(round((te_s - np.floor(te_s)) * 1e9)) % 1000000000)
+            stamps, q = _rand_walk_poses(rng, n, t0 + 1e-4, span - 2e-4, 0.03)
+            ctrl = O.ref1p_generate_ctrl_poses(order, dtk, tb, tb, te, stamps, q)
+            d[f"gen{n_gen}_in"] = np.array([order, dtk]); d[f"gen{n_gen}_tb"] = np.array(tb, np.uint32); d[f"gen{n_gen}_te"] = np.array(te, np.uint32)
+            d[f"gen{n_gen}_stamps"] = stamps; d[f"gen{n_gen}_poses"] = q; d[f"gen{n_gen}_ctrl"] = ctrl
+            n_gen += 1
+    d["n_gen"] = np.array(n_gen)
+    # evaluate / window evaluation
+    n_ev = 0
+    for order in (2, 4):
+        K = 12
+        _, knots = _rand_walk_poses(rng, K, 0.0, 1.0, 0.08)
+        dtk = 0.05
+        t_traj = (1600000123, 456789012)
+        t_beg_d = t_traj[0] + 1e-9 * t_traj[1]
+        for idx_traj, idx_opt in ((0, 1 if order == 2 else 3), (2, 3), (4, 6)):
+            drotv = rng.normal(0, 0.02, 3 * (K - idx_opt))
+            n_seg = (K - idx_traj) - order + 1
+            for u in rng.uniform(0.01, n_seg - 0.01, 6):
+                t_s = (t_beg_d + idx_traj * dtk) + u * dtk
+                t = (int(np.floor(t_s)), int((t_s - np.floor(t_s)) * 1e9))
+                q, idx, J, after = O.ref1p_window_evaluate(order, t_traj, dtk, knots, idx_traj, idx_opt, drotv, t)
+                d[f"win{n_ev}_in"] = np.array([order, dtk, idx_traj, idx_opt]); d[f"win{n_ev}_ttraj"] = np.array(t_traj, np.uint32)
+                d[f"win{n_ev}_knots"] = knots; d[f"win{n_ev}_drotv"] = drotv; d[f"win{n_ev}_t"] = np.array(t, np.uint32)
+                d[f"win{n_ev}_q"] = q; d[f"win{n_ev}_idx"] = np.array(idx); d[f"win{n_ev}_J"] = J; d[f"win{n_ev}_after"] = after
+                n_ev += 1
+    d["n_win"] = np.array(n_ev)
+    np.savez_compressed(os.path.join(OUT, "traj_firstparty.npz"), **d)
+
+
 if __name__ == "__main__":
     if "--only-traj" in sys.argv:
         golden_traj()
+        sys.exit(0)
+    if "--only-traj1p" in sys.argv:
+        golden_traj_firstparty()
+        sys.exit(0)
+    if "--only-geom" in sys.argv:
+        golden_geom()
         sys.exit(0)
     if "--only-lut" in sys.argv:
         golden_lut()
         sys.exit(0)
     golden_lut()
+    golden_geom()
+    golden_traj_firstparty()
     golden_traj()
     golden_blur()
     golden_spline()
