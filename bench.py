@@ -145,8 +145,27 @@ def cpu_baseline(pkt, omega, budget_s=8.0):
         O.fe_eval(a, omega, True)
         ts.append(time.perf_counter() - t0)
     med = float(np.median(ts))
-    return {"value": len(pkt.events) / med, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{len(ts)} full contrast+gradient evaluations of the same {len(pkt.events)}-event packet, median {med*1e3:.1f} ms"}
+    out = {"value": len(pkt.events) / med, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"{len(ts)} full contrast+gradient evaluations of the same {len(pkt.events)}-event packet, median {med*1e3:.1f} ms"}
+    # Beside it, when oracle/_ref holds them: the reference's OWN translation units (local_image_warped_events.cpp,
+    # local_focus_funcs.cpp, image_geom_util.cpp) compiled unmodified with stand-in ROS / OpenCV headers -- its warp loop and
+    # focus formulae are the reference's code, the Gaussian blur and reductions underneath are the oracle's (not OpenCV's SIMD ones).
+    try:
+        if O.have_ref_firstparty():
+            sec = int(np.floor(pkt.t_ref_sec)); nsec = int(round((pkt.t_ref_sec - sec) * 1e9))
+            tt = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                iwe, der = O.ref1p_fe_images(pkt.events, (sec, nsec), pkt.lut, pkt.width, pkt.height, pkt.K, omega, True, pkt.blur_sigma, pkt.batch_size)
+                O.ref1p_fe_contrast(iwe, der, 0)
+                tt.append(time.perf_counter() - t0)
+            m2 = float(np.median(tt))
+            out["reference_translation_units"] = {"value": len(pkt.events) / m2, "unit": UNIT, "cores": 1, "ms_per_eval": m2 * 1e3,
+                                                  "note": "the reference's own .cpp files of the path compiled with stand-in ROS/OpenCV headers (oracle/_ref); "
+                                                          "results bit-identical to the port (tests/test_oracle_firstparty.py)"}
+    except Exception as e:  # informational only
+        out["reference_translation_units"] = {"value": None, "note": f"unavailable: {e}"}
+    return out
 
 
 def run_reference(args, rank, world):

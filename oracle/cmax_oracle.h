@@ -18,9 +18,11 @@
  *   - spline wrapper (time origin, f32 Jacobian repacking): PINNED against the reference's own
  *     src/backend/trajectory.cpp compiled with ROS / OpenCV / glog stand-ins (oracle/ref_traj_shim.cpp ->
  *     oracle/_ref/libref_traj.so, tests/test_traj_firstparty.py, tests/golden/traj_firstparty.npz).
- *   - the remaining warp / scatter / contrast control flow (batching, bounds, votes, old/new split, band indices,
- *     focus formulas): the reference ships no test or golden vector for it and those translation units need
- *     OpenCV image operations + ROS to compile => "parity unpinned" beyond the line-by-line restatement cited below.
+ *   - the hot path as a whole (FE / BE image builders, map upkeep, both computeContrast families): PINNED BIT-EXACT
+ *     against the reference's own translation units compiled unmodified with stand-in ROS / OpenCV / glog headers
+ *     (oracle/ref_{fe,focus,warper}_shim.cpp -> oracle/_ref, tests/test_oracle_firstparty.py,
+ *     tests/golden/hotpath_firstparty.npz).  Underneath those translation units the OpenCV image primitives are this
+ *     file's restatements (pinned against cv2 4.13) and ros::Time is restated.
  */
 #pragma once
 #include <stdint.h>

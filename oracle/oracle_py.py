@@ -446,3 +446,126 @@ def ref1p_window_evaluate(order, t_traj_beg, dt_knots, knots_xyzw, idx_traj_beg,
     L.ref1p_window_evaluate(int(order), a.ctypes.data_as(_up), C.c_double(dt_knots), _d(k), len(k), int(idx_traj_beg), int(idx_opt_beg), _d(d),
                             tt.ctypes.data_as(_up), _d(q), C.byref(idx), J.ctypes.data_as(_fp), _d(after))
     return q, idx.value, J, after
+
+
+# ---- the reference's own back-end warp code (src/backend/event_pano_warper.cpp compiled with stubs) --------------------
+_REF_WARPER = os.path.join(_HERE, "_ref", "libref_warper.so")
+_ref_warper = None
+
+
+def have_ref_warper():
+    return os.path.exists(_REF_WARPER)
+
+
+class RefEventWarper:
+    """EventWarper of the reference (real translation unit) behind oracle/ref_warper_shim.cpp."""
+
+    def __init__(self, lut, SW, SH, PW, PH, order=2, blur_sigma=1.0, batch_size=100, sample_rate=1, max_update_times=10):
+        global _ref_warper
+        if _ref_warper is None:
+            _ref_warper = C.CDLL(_REF_WARPER)
+            _ref_warper.ref1p_warper_create.restype = C.c_void_p
+        self.L = _ref_warper
+        self.lut = np.ascontiguousarray(lut, dtype=np.float64)
+        self.PW, self.PH, self.order = PW, PH, order
+        self.h = C.c_void_p(self.L.ref1p_warper_create(_d(self.lut), SW, SH, PW, PH, C.c_double(blur_sigma), batch_size, sample_rate,
+                                                       max_update_times, order))
+
+    def close(self):
+        if self.h:
+            self.L.ref1p_warper_destroy(self.h)
+            self.h = None
+
+    def set_ig(self, IG):
+        a = np.ascontiguousarray(IG, dtype=np.float32)
+        self.L.ref1p_warper_set_ig(self.h, a.ctypes.data_as(_fp))
+
+    def get_map(self):
+        IG = np.zeros((self.PH, self.PW), np.float32)
+        t = np.zeros((self.PH, self.PW), np.uint8)
+        self.L.ref1p_warper_get_map(self.h, IG.ctypes.data_as(_fp), t.ctypes.data_as(C.c_void_p))
+        return IG, t
+
+    def eval(self, events, t_beg, dt_knots, knots_xyzw, n_fixed, tnext, first_iter, want_grad):
+        ev = np.ascontiguousarray(events)
+        k = np.ascontiguousarray(knots_xyzw, dtype=np.float64).reshape(-1, 4)
+        A = self.PW * self.PH
+        P = 3 * (len(k) - n_fixed)
+        iwe = np.zeros((self.PH, self.PW), np.float32)
+        bands = np.zeros((max(P, 1), self.PH, self.PW), np.float32)
+        ilo, iln = np.zeros_like(iwe), np.zeros_like(iwe)
+        alpha = C.c_double(0)
+        tn = np.array([int(tnext[0]), int(tnext[1])], dtype=np.uint32)
+        self.L.ref1p_warper_eval.restype = C.c_int
+        nb = self.L.ref1p_warper_eval(self.h, C.c_void_p(ev.ctypes.data), C.c_longlong(len(ev)), C.c_double(t_beg), C.c_double(dt_knots), _d(k), len(k),
+                                      int(n_fixed), tn.ctypes.data_as(C.POINTER(C.c_uint32)), int(first_iter), int(want_grad), iwe.ctypes.data_as(_fp),
+                                      bands.ctypes.data_as(_fp), ilo.ctypes.data_as(_fp), iln.ctypes.data_as(_fp), C.byref(alpha))
+        return {"iwe": iwe, "bands": bands[:P] if want_grad else None, "il_old": ilo, "il_new": iln, "alpha": alpha.value, "n_bands": nb}
+
+    def update_ig(self):
+        self.L.ref1p_warper_update_ig(self.h)
+
+    def mark_fov(self, q_xyzw, radius):
+        q = np.ascontiguousarray(q_xyzw, dtype=np.float64)
+        self.L.ref1p_warper_mark_fov(self.h, _d(q), int(radius))
+
+
+# ---- the reference's own front-end image builder and focus functions (compiled with stubs) ----------------------------
+_REF_FE = os.path.join(_HERE, "_ref", "libref_fe.so")
+_REF_FOCUS = os.path.join(_HERE, "_ref", "libref_focus.so")
+_ref_fe = _ref_focus = None
+
+
+def have_ref_firstparty():
+    return all(os.path.exists(p) for p in (_REF_FE, _REF_FOCUS, _REF_WARPER))
+
+
+def ref1p_fe_images(events, t_ref, lut, W, H, K4, omega, want_grad=True, blur_sigma=1.0, batch_size=100):
+    """AngVelEstimator::computeImageOfWarpedEvents of the reference (real translation unit): (iwe [H,W], deriv [H,W,3] or None).
+    t_ref = (sec, nsec) of time_packet_."""
+    global _ref_fe
+    if _ref_fe is None:
+        _ref_fe = C.CDLL(_REF_FE)
+    ev = np.ascontiguousarray(events)
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    K = np.ascontiguousarray(K4, dtype=np.float64)
+    om = np.ascontiguousarray(omega, dtype=np.float64)
+    tr = np.array([int(t_ref[0]), int(t_ref[1])], dtype=np.uint32)
+    iwe = np.zeros((H, W), np.float32)
+    der = np.zeros((H, W, 3), np.float32)
+    _ref_fe.ref1p_fe_images(C.c_void_p(ev.ctypes.data), C.c_longlong(len(ev)), tr.ctypes.data_as(C.POINTER(C.c_uint32)), _d(lut), int(W), int(H), _d(K),
+                            C.c_double(blur_sigma), int(batch_size), _d(om), iwe.ctypes.data_as(_fp), der.ctypes.data_as(_fp) if want_grad else None)
+    return iwe, (der if want_grad else None)
+
+
+def _focus():
+    global _ref_focus
+    if _ref_focus is None:
+        _ref_focus = C.CDLL(_REF_FOCUS)
+        _ref_focus.ref1p_fe_contrast.restype = C.c_double
+        _ref_focus.ref1p_be_contrast.restype = C.c_double
+    return _ref_focus
+
+
+def ref1p_fe_contrast(iwe, deriv, measure=0):
+    """computeContrast of src/frontend/local_focus_funcs.cpp: (contrast, grad[3] or None)"""
+    iwe = np.ascontiguousarray(iwe, dtype=np.float32)
+    H, W = iwe.shape
+    if deriv is None:
+        return _focus().ref1p_fe_contrast(iwe.ctypes.data_as(_fp), None, W, H, int(measure), None), None
+    d = np.ascontiguousarray(deriv, dtype=np.float32)
+    g = np.zeros(3)
+    c = _focus().ref1p_fe_contrast(iwe.ctypes.data_as(_fp), d.ctypes.data_as(_fp), W, H, int(measure), _d(g))
+    return c, g
+
+
+def ref1p_be_contrast(iwe, bands, measure=0):
+    """computeContrast of src/backend/global_focus_funcs.cpp: (contrast, grad[P] or None)"""
+    iwe = np.ascontiguousarray(iwe, dtype=np.float32)
+    H, W = iwe.shape
+    if bands is None:
+        return _focus().ref1p_be_contrast(iwe.ctypes.data_as(_fp), None, 0, W, H, int(measure), None), None
+    b = np.ascontiguousarray(bands, dtype=np.float32)
+    g = np.zeros(b.shape[0])
+    c = _focus().ref1p_be_contrast(iwe.ctypes.data_as(_fp), b.ctypes.data_as(_fp), b.shape[0], W, H, int(measure), _d(g))
+    return c, g

@@ -2,14 +2,19 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <ostream>
 
 namespace glogstub {
-struct Null { template <class T> Null& operator<<(const T&) { return *this; } };
+struct Null {
+  template <class T> Null& operator<<(const T&) { return *this; }
+  Null& operator<<(std::ostream& (*)(std::ostream&)) { return *this; }   // std::endl
+};
 struct Fatal {
   const char* what;
   explicit Fatal(const char* w) : what(w) {}
   ~Fatal() { std::fprintf(stderr, "glog stub: CHECK failed: %s\n", what); std::abort(); }
   template <class T> Fatal& operator<<(const T&) { return *this; }
+  Fatal& operator<<(std::ostream& (*)(std::ostream&)) { return *this; }
 };
 }  // namespace glogstub
 #define GLOGSTUB_CHECK_OP(a, b, op) if ((a) op (b)) ; else ::glogstub::Fatal(#a " " #op " " #b)
@@ -20,6 +25,7 @@ struct Fatal {
 #define CHECK_GT(a, b) GLOGSTUB_CHECK_OP(a, b, >)
 #define CHECK_LE(a, b) GLOGSTUB_CHECK_OP(a, b, <=)
 #define CHECK_LT(a, b) GLOGSTUB_CHECK_OP(a, b, <)
+#define CHECK_NOTNULL(p) (p)
 #define VLOG(n) if (true) ; else ::glogstub::Null()
 #define VLOG_IF(n, c) if (true) ; else ::glogstub::Null()
 #define LOG(x) if (true) ; else ::glogstub::Null()

@@ -277,9 +277,50 @@ def golden_traj_firstparty():
     np.savez_compressed(os.path.join(OUT, "traj_firstparty.npz"), **d)
 
 
+def golden_hotpath_firstparty():
+    """Outputs of the reference's OWN hot-path translation units -- src/frontend/local_image_warped_events.cpp,
+    src/frontend/local_focus_funcs.cpp, src/backend/event_pano_warper.cpp, src/backend/global_focus_funcs.cpp (+ trajectory.cpp,
+    image_geom_util.cpp, equirectangular_camera.h, real basalt/Sophus/Eigen) -- compiled unmodified with the stand-in headers of
+    oracle/stubs/ into oracle/_ref/libref_{fe,focus,warper}.so, on small seeded inputs (the inputs are regenerated from the seeds by
+    the test; only the outputs are stored)."""
+    assert O.have_ref_firstparty(), "oracle/_ref/libref_{fe,focus,warper}.so missing: run `make -C oracle` with /root/reference present"
+    d = {}
+    # front-end: 4000 events on a 48x36 sensor
+    pk = synth.make_fe_packet(4000, 48, 36, (40.0, 41.0, 23.5, 17.5), 71, 120)
+    sec = int(np.floor(pk.t_ref_sec)); nsec = int(round((pk.t_ref_sec - sec) * 1e9))
+    for k, om in enumerate((pk.omega_true, np.zeros(3), pk.omega_true + np.array([0.3, -0.2, 0.4]))):
+        iwe, der = O.ref1p_fe_images(pk.events, (sec, nsec), pk.lut, 48, 36, pk.K, om, True)
+        d[f"fe{k}_omega"] = np.asarray(om, float); d[f"fe{k}_iwe"] = iwe; d[f"fe{k}_deriv"] = der
+        for m in (0, 1):
+            c, g = O.ref1p_fe_contrast(iwe, der, m)
+            d[f"fe{k}_contrast{m}"] = np.array(c); d[f"fe{k}_grad{m}"] = g
+    d["fe_tref"] = np.array([sec, nsec], np.uint32)
+    # back-end: 5000 events, 6 knots, 64x32 panorama, 32x24 sensor; linear and cubic; first iteration with a non-empty map
+    for order in (2, 4):
+        w = synth.make_be_window(5000, 6, 64, 32, 72 + order, order=order, sensor=(32, 24), K4=(30.0, 30.5, 15.5, 11.5), n_landmarks=150,
+                                 n_fixed=1 if order == 2 else 3)
+        dtk = w.dt_ns / 1e9
+        t_beg = w.t0_ns / 1e9
+        rng = np.random.default_rng(5)
+        IG = np.abs(rng.normal(0, 0.3, (32, 64))).astype(np.float32)
+        rw = O.RefEventWarper(w.lut, 32, 24, 64, 32, order=order)
+        rw.set_ig(IG)
+        r = rw.eval(w.events, t_beg, dtk, w.knots_xyzw, w.n_fixed, w.tnext, True, True)
+        rw.close()
+        c, g = O.ref1p_be_contrast(r["iwe"], r["bands"], 0)
+        d[f"be{order}_tbeg"] = np.array([t_beg, dtk]); d[f"be{order}_IG"] = IG; d[f"be{order}_alpha"] = np.array(r["alpha"])
+        for k in ("iwe", "bands", "il_old", "il_new"):
+            d[f"be{order}_{k}"] = r[k]
+        d[f"be{order}_contrast"] = np.array(c); d[f"be{order}_grad"] = g
+    np.savez_compressed(os.path.join(OUT, "hotpath_firstparty.npz"), **d)
+
+
 if __name__ == "__main__":
     if "--only-traj" in sys.argv:
         golden_traj()
+        sys.exit(0)
+    if "--only-hotpath1p" in sys.argv:
+        golden_hotpath_firstparty()
         sys.exit(0)
     if "--only-traj1p" in sys.argv:
         golden_traj_firstparty()
@@ -293,6 +334,7 @@ if __name__ == "__main__":
     golden_lut()
     golden_geom()
     golden_traj_firstparty()
+    golden_hotpath_firstparty()
     golden_traj()
     golden_blur()
     golden_spline()
