@@ -569,3 +569,66 @@ def ref1p_be_contrast(iwe, bands, measure=0):
     g = np.zeros(b.shape[0])
     c = _focus().ref1p_be_contrast(iwe.ctypes.data_as(_fp), b.ctypes.data_as(_fp), b.shape[0], W, H, int(measure), _d(g))
     return c, g
+
+
+# ---- the reference's own node classes driven without ROS (oracle/ref_node_shim.cpp) --------------------------------------
+_REF_NODE = os.path.join(_HERE, "_ref", "libref_node.so")
+
+
+def have_ref_node():
+    return os.path.exists(_REF_NODE)
+
+
+class RefNode:
+    """AngVelEstimator + PoseGraphOptimizer of the reference (real translation units); the two GSL solves are stand-ins: the
+    front-end returns the next row of `omegas`, the back-end leaves the control poses unchanged."""
+
+    def __init__(self, W, H, K4, omegas, dt_ang_vel=0.01, num_events_per_packet=2000, fe_sample_rate=1, win_size=0.2, win_stride=0.1,
+                 dt_knots=0.05, spline_degree=1, pano_height=64, y_angle=0.0, min_ev_rate=10, max_update_times=10):
+        self.L = C.CDLL(_REF_NODE)
+        self.L.ref1p_node_create.restype = C.c_void_p
+        K = np.ascontiguousarray(K4, dtype=np.float64)
+        om = np.ascontiguousarray(omegas, dtype=np.float64).reshape(-1, 3)
+        self.h = C.c_void_p(self.L.ref1p_node_create(int(W), int(H), _d(K), C.c_double(dt_ang_vel), int(num_events_per_packet), int(fe_sample_rate),
+                                                     C.c_double(win_size), C.c_double(win_stride), C.c_double(dt_knots), int(spline_degree),
+                                                     int(pano_height), C.c_double(y_angle), int(min_ev_rate), int(max_update_times), _d(om), len(om)))
+
+    def close(self):
+        if self.h:
+            self.L.ref1p_node_destroy(self.h)
+            self.h = None
+
+    def events(self, ev):
+        ev = np.ascontiguousarray(ev)
+        self.L.ref1p_node_events(self.h, C.c_void_p(ev.ctypes.data), C.c_longlong(len(ev)))
+
+    def counts(self):
+        a, b, c = C.c_int(0), C.c_int(0), C.c_longlong(0)
+        self.L.ref1p_node_counts(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def packet(self, i):
+        v = (C.c_longlong * 7)()
+        h = C.c_ulonglong(0)
+        self.L.ref1p_node_packet(self.h, int(i), v, C.byref(h))
+        return list(v), h.value
+
+    def window(self, i):
+        v = (C.c_longlong * 15)()
+        h = C.c_ulonglong(0)
+        q = np.zeros(4)
+        knots = np.zeros((512, 4))
+        self.L.ref1p_node_window(self.h, int(i), v, C.byref(h), _d(q), _d(knots), 2048)
+        v = list(v)
+        return v, h.value, q, knots[: v[9]].copy()
+
+
+def hash_events(ev):
+    """FNV-style hash of (x, y, sec, nsec) per event, as oracle/ref_node_shim.cpp computes it"""
+    h = 1469598103934665603
+    M = (1 << 64) - 1
+    for e in ev:
+        for x in (int(e["x"]), int(e["y"]), int(e["sec"]), int(e["nsec"])):
+            h ^= x
+            h = (h * 1099511628211) & M
+    return h

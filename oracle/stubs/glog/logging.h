@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <iomanip>
 #include <ostream>
 
 namespace glogstub {

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <initializer_list>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -32,6 +33,7 @@ template <class T> struct Point3_ {
   T x, y, z;
   Point3_() : x(0), y(0), z(0) {}
   Point3_(T a, T b, T c) : x(a), y(b), z(c) {}
+  explicit Point3_(T v0) : x(v0), y(0), z(0) {}   // OpenCV reaches this through Vec<T,3>(v0): first element set, rest zero
   Point3_ cross(const Point3_& p) const { return Point3_(y * p.z - z * p.y, z * p.x - x * p.z, x * p.y - y * p.x); }
 };
 typedef Point3_<double> Point3d;
@@ -136,6 +138,7 @@ struct Mat {
   }
   void copyTo(Mat& dst) const { dst.create(rows, cols, type_); std::memcpy(dst.buf->data(), buf->data(), buf->size()); }
   Mat clone() const { Mat m; copyTo(m); return m; }
+  void convertTo(Mat&, int) const { std::abort(); }   // display only, never executed
   Mat mul(const Mat& o) const { Mat r(rows, cols, CV_32FC1); for (size_t i = 0; i < total(); ++i) r.ptr<float>()[i] = ptr<float>()[i] * o.ptr<float>()[i]; return r; }
   inline Mat mul(const struct MatExpr& e) const;
 };

@@ -102,6 +102,14 @@ inline void split(const Mat& src, std::vector<Mat>& channels) {
   }
 }
 inline Mat operator+(const Mat& a, const Mat& b) { Mat r; add(a, b, r); return r; }
+// display-only helpers of publishEventImage (never executed: the stand-in publishers have no subscribers): compile only
+enum { NORM_MINMAX = 32, COLOR_GRAY2BGR = 8 };
+#define CV_GRAY2BGR 8
+inline void cv_stub_unreachable(const char* what) { std::fprintf(stderr, "cv::%s is not part of the stand-in\n", what); std::abort(); }
+inline void hconcat(const Mat&, const Mat&, Mat&) { cv_stub_unreachable("hconcat"); }
+inline void normalize(const Mat&, Mat&, double, double, int, int) { cv_stub_unreachable("normalize"); }
+inline void pow(const Mat&, double, Mat&) { cv_stub_unreachable("pow"); }
+inline void cvtColor(const Mat&, Mat&, int) { cv_stub_unreachable("cvtColor"); }
 // IMAGE_GRADIENT_MAGNITUDE_CONTRAST is unreachable from the reference's launch files and is not restated: compile only
 inline void Sobel(const Mat&, Mat&, int, int, int) { std::fprintf(stderr, "cv::Sobel is not part of the stand-in\n"); std::abort(); }
 

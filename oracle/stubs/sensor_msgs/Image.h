@@ -1,2 +1,5 @@
-// TEST INFRASTRUCTURE stub (type not used by the code that is compiled)
+// TEST INFRASTRUCTURE stub
 #pragma once
+#include <memory>
+#include <ros/ros.h>
+namespace sensor_msgs { struct Image { std_msgs::Header header; }; typedef std::shared_ptr<Image> ImagePtr; }
