@@ -315,9 +315,40 @@ def golden_hotpath_firstparty():
     np.savez_compressed(os.path.join(OUT, "hotpath_firstparty.npz"), **d)
 
 
+def golden_node_firstparty():
+    """Packets, windows and control poses produced by the reference's OWN node classes (ang_vel_estimator.cpp,
+    pose_graph_optimizer.cpp, ... compiled with stand-in headers, oracle/_ref/libref_node.so) for two seeded event streams."""
+    assert O.have_ref_node()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_node_firstparty import _stream
+    d = {}
+    for tag, degree in (("lin", 1), ("cub", 3)):
+        ev = _stream(130000, 21 + degree)
+        omegas = np.random.default_rng(4).normal(0, 1.5, (37, 3))
+        ref = O.RefNode(64, 48, (60.0, 61.0, 31.5, 23.5), omegas, dt_ang_vel=0.01, num_events_per_packet=2000, fe_sample_rate=1, dt_knots=0.05,
+                        spline_degree=degree, y_angle=15.0)
+        ref.events(ev)
+        n_pk, n_win, n_stored = ref.counts()
+        pk = [ref.packet(i) for i in range(n_pk)]
+        d[f"{tag}_packets"] = np.array([v for v, _ in pk], dtype=np.int64)
+        d[f"{tag}_packet_hash"] = np.array([h for _, h in pk], dtype=np.uint64)
+        wins = [ref.window(i) for i in range(n_win)]
+        d[f"{tag}_windows"] = np.array([v for v, _, _, _ in wins], dtype=np.int64)
+        d[f"{tag}_window_hash"] = np.array([h for _, h, _, _ in wins], dtype=np.uint64)
+        d[f"{tag}_latest_q"] = np.array([q for _, _, q, _ in wins])
+        for i, (_, _, _, k) in enumerate(wins):
+            d[f"{tag}_knots{i}"] = k
+        d[f"{tag}_n_stored"] = np.array(n_stored)
+        ref.close()
+    np.savez_compressed(os.path.join(OUT, "node_firstparty.npz"), **d)
+
+
 if __name__ == "__main__":
     if "--only-traj" in sys.argv:
         golden_traj()
+        sys.exit(0)
+    if "--only-node1p" in sys.argv:
+        golden_node_firstparty()
         sys.exit(0)
     if "--only-hotpath1p" in sys.argv:
         golden_hotpath_firstparty()
@@ -335,6 +366,7 @@ if __name__ == "__main__":
     golden_geom()
     golden_traj_firstparty()
     golden_hotpath_firstparty()
+    golden_node_firstparty()
     golden_traj()
     golden_blur()
     golden_spline()

@@ -102,3 +102,55 @@ def test_library_host_logic_matches_reference_node_classes(oracle, degree, fe_ra
     ref.close()
     pgo.close()
     s.close()
+
+
+@pytest.mark.parametrize("tag,degree", [("lin", 1), ("cub", 3)])
+def test_library_host_logic_matches_golden_of_reference_node_classes(oracle, golden, tag, degree):
+    """The same comparison against the committed outputs of the reference's node classes (tests/golden/node_firstparty.npz,
+    generated by tests/golden/make_golden.py through oracle/_ref/libref_node.so): runs without the reference tree."""
+    from cmax_slam_b200._capi import CmaxbError
+    from cmax_slam_b200.backend import PoseGraphOptimizerCMax
+    from cmax_slam_b200.stream import EventStream
+    g = golden("node_firstparty.npz")
+    ev = _stream(130000, 21 + degree)
+    omegas = np.random.default_rng(4).normal(0, 1.5, (37, 3))
+    s = EventStream(0.01, 2000, 1)
+    pgo = PoseGraphOptimizerCMax(None, 4 if degree == 3 else 2, 0.05, 0.2, 0.1, y_angle_deg=15.0)
+    pk_rows, pk_hash, win_rows, win_hash, latest, knots = [], [], [], [], [], []
+    k = 0
+    for i in range(0, len(ev), 3333):
+        s.eventsCallback(ev[i:i + 3333])
+        while True:
+            p = s.next_packet()
+            if p is None:
+                break
+            e, tp, too_long = p
+            assert not too_long
+            pk_rows.append([tp[0], tp[1], len(e), int(e["sec"][0]), int(e["nsec"][0]), int(e["sec"][-1]), int(e["nsec"][-1])])
+            pk_hash.append(oracle.hash_events(e))
+            pgo.pushAngVel(tp, omegas[k % len(omegas)])
+            k += 1
+            while True:
+                tb, te, ready = pgo.window()
+                if not ready:
+                    break
+                try:
+                    wev = s.window_events(tb, te)
+                except CmaxbError:
+                    break
+                rep = pgo.processTimeWindow(wev)
+                win_rows.append([*tb, *te, len(wev), int(wev["sec"][0]), int(wev["nsec"][0]), int(wev["sec"][-1]), int(wev["nsec"][-1]),
+                                 rep["n_ctrl_poses"], rep["idx_cp_traj_beg"], rep["idx_cp_opt_beg"], rep["num_cp_opt"], *rep["pose_latest"][0]])
+                win_hash.append(oracle.hash_events(wev))
+                latest.append(rep["pose_latest"][1])
+                knots.append(pgo.ctrl_poses()[0])
+    assert np.array_equal(np.array(pk_rows, dtype=np.int64), g[f"{tag}_packets"])
+    assert np.array_equal(np.array(pk_hash, dtype=np.uint64), g[f"{tag}_packet_hash"])
+    assert np.array_equal(np.array(win_rows, dtype=np.int64), g[f"{tag}_windows"])
+    assert np.array_equal(np.array(win_hash, dtype=np.uint64), g[f"{tag}_window_hash"])
+    assert _qdist(np.array(latest), g[f"{tag}_latest_q"]) <= 1e-9
+    for i, q in enumerate(knots):
+        assert q.shape == g[f"{tag}_knots{i}"].shape and _qdist(q, g[f"{tag}_knots{i}"]) <= 1e-8, i
+    assert s.state()["n_stored"] == int(g[f"{tag}_n_stored"])
+    pgo.close()
+    s.close()
