@@ -50,6 +50,35 @@ class OptResult(C.Structure):
                 ("f_evals", C.c_int32), ("g_evals", C.c_int32), ("stop_reason", C.c_int32)]
 
 
+COST_F = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p, C.POINTER(C.c_double))
+COST_FDF = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+def optimize_callback(f, fdf, x0, params):
+    """cmaxb_optimize_callback with Python callables: f(x)->cost, fdf(x)->(cost, grad); params = (step, line_tol, max_iter,
+    epsabs_grad, tolfun).  Returns (x, stats dict)."""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n = len(x0)
+
+    def _f(xp, nn, user, out):
+        out[0] = float(f(np.array([xp[i] for i in range(nn)])))
+        return 0
+
+    def _fdf(xp, nn, user, out, g):
+        v, gr = fdf(np.array([xp[i] for i in range(nn)]))
+        out[0] = float(v)
+        for i in range(nn):
+            g[i] = float(gr[i])
+        return 0
+
+    cf, cfdf = COST_F(_f), COST_FDF(_fdf)
+    xo = np.zeros(n)
+    res = OptResult()
+    prm = OptParams(*params)
+    check(lib().cmaxb_optimize_callback(n, dptr(x0), cf, cfdf, None, C.byref(prm), dptr(xo), C.byref(res)))
+    return xo, {k: getattr(res, k) for k, _ in OptResult._fields_}
+
+
 class Stamp(C.Structure):
     _fields_ = [("sec", C.c_uint32), ("nsec", C.c_uint32)]
 
@@ -91,7 +120,7 @@ EXPORTS = [
     "cmaxb_be_get_il", "cmaxb_be_get_iwe", "cmaxb_be_get_bands", "cmaxb_be_get_cells", "cmaxb_be_get_poses",
     "cmaxb_be_map_reset", "cmaxb_be_map_set", "cmaxb_be_map_get", "cmaxb_be_map_use_as_igp", "cmaxb_be_map_update",
     "cmaxb_be_map_mark_fov",
-    "cmaxb_fe_optimize", "cmaxb_be_optimize",
+    "cmaxb_fe_optimize", "cmaxb_be_optimize", "cmaxb_optimize_callback",
     "cmaxb_traj_integrate_ang_vel", "cmaxb_traj_num_ctrl_poses", "cmaxb_traj_fit_ctrl_poses", "cmaxb_traj_evaluate",
     "cmaxb_traj_incremental_update",
     "cmaxb_precompute_bearing_vectors",
@@ -139,6 +168,7 @@ def lib():
     L.cmaxb_be_map_mark_fov.argtypes = [vp, dp, C.c_int, C.c_int]
     L.cmaxb_fe_optimize.argtypes = [vp, dp, C.POINTER(OptParams), dp, C.POINTER(OptResult)]
     L.cmaxb_be_optimize.argtypes = [vp, dp, C.c_int, C.POINTER(OptParams), dp, C.POINTER(OptResult)]
+    L.cmaxb_optimize_callback.argtypes = [C.c_int, dp, COST_F, COST_FDF, vp, C.POINTER(OptParams), dp, C.POINTER(OptResult)]
     sp = C.POINTER(Stamp)
     L.cmaxb_traj_integrate_ang_vel.argtypes = [Stamp, dp, sp, dp, C.c_int, sp, dp, C.c_int, sp, dp, C.POINTER(C.c_int)]
     L.cmaxb_traj_num_ctrl_poses.argtypes = [C.c_int, Stamp, Stamp, C.c_double]

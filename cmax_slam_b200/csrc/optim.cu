@@ -246,6 +246,22 @@ int run_reference_loop(Cost& c, const std::vector<double>& x0, const cmaxb_opt_p
 
 }  // namespace
 
+// The same loop over a caller-supplied cost (to be MINIMISED): the solver without the CUDA cost, for costs that live elsewhere
+// and for pinning this loop on the CPU (tests/test_optim.py drives it with the oracle cost and compares with the reference's own
+// *_optim_contrast_gsl.cpp compiled over a GSL stand-in).
+extern "C" int cmaxb_optimize_callback(int n, const double* x0, cmaxb_cost_f f, cmaxb_cost_fdf fdf, void* user,
+                                       const cmaxb_opt_params* params, double* x_out, cmaxb_opt_result* result) {
+  if (n <= 0 || !x0 || !f || !fdf || !params || !x_out) return set_error(CMAXB_ERR_INVALID, "null argument / no parameters");
+  Cost c;
+  c.n = n;
+  c.f = [=](const double* x, double* v) { return f(x, n, user, v); };
+  c.fdf = [=](const double* x, double* v, double* g) { return fdf(x, n, user, v, g); };
+  std::vector<double> xs(x0, x0 + n), xo;
+  CMAXB_TRY(run_reference_loop(c, xs, *params, xo, result));
+  for (int i = 0; i < n; ++i) x_out[i] = xo[i];
+  return CMAXB_OK;
+}
+
 extern "C" int cmaxb_fe_optimize(cmaxb_fe* fe, const double omega0[3], const cmaxb_opt_params* params, double omega_out[3],
                                  cmaxb_opt_result* result) {
   if (!fe || !omega0 || !omega_out) return set_error(CMAXB_ERR_INVALID, "null argument");

@@ -254,6 +254,12 @@ typedef struct cmaxb_opt_result {
 } cmaxb_opt_result;
 int cmaxb_fe_optimize(cmaxb_fe* fe, const double omega0[3], const cmaxb_opt_params* params, double omega_out[3],
                       cmaxb_opt_result* result);
+/* The same Fletcher-Reeves loop over a caller-supplied cost to be MINIMISED (callbacks return 0 on success); `params` is
+ * required (reference constants: FE {0.1, 0.05, 50, 1e-3, 1e-4}, BE {0.1, 0.1, 50, 1e-4, 1e-4}).  Host code only. */
+typedef int (*cmaxb_cost_f)(const double* x, int n, void* user, double* f);
+typedef int (*cmaxb_cost_fdf)(const double* x, int n, void* user, double* f, double* grad);
+int cmaxb_optimize_callback(int n, const double* x0, cmaxb_cost_f f, cmaxb_cost_fdf fdf, void* user,
+                            const cmaxb_opt_params* params, double* x_out, cmaxb_opt_result* result);
 /* x0 == NULL: start from zero increments (global_optim_contrast_gsl.cpp:36-37) */
 int cmaxb_be_optimize(cmaxb_be* be, const double* x0, int n, const cmaxb_opt_params* params, double* x_out,
                       cmaxb_opt_result* result);

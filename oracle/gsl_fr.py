@@ -29,6 +29,19 @@ class Counter:
         return float(v), np.array(g, dtype=np.float64)
 
 
+def _dot(a, b):
+    """Sequential sum of products, left to right -- the operation order of the reference CBLAS ddot and of the C / C++
+    restatements (oracle/stubs/gsl/gsl_multimin.h, csrc/optim.cu); numpy's BLAS dot may fuse or re-associate."""
+    s = 0.0
+    for u, v in zip(a.tolist(), b.tolist()):
+        s += u * v
+    return s
+
+
+def _nrm2(a):
+    return math.sqrt(_dot(a, a))
+
+
 def _take_step(x, p, step, lam):
     dx = 0.0 + (-step * lam) * p
     return x + 1.0 * dx, dx
@@ -53,7 +66,7 @@ def _minimize(c, x, p, lam, stepa, stepb, stepc, fa, fb, fc, tol, x1, dx1, gradi
     fu, fv, fw = fb, fa, fc
     old2, old1 = abs(w - v), abs(v - u)
     x2, dx2 = x1.copy(), dx1.copy()
-    f, step, gnorm = fb, stepb, float(np.sqrt(np.dot(gradient, gradient)))
+    f, step, gnorm = fb, stepb, _nrm2(gradient)
     it = 0
     while True:
         it += 1
@@ -89,8 +102,8 @@ def _minimize(c, x, p, lam, stepa, stepb, stepc, fa, fb, fc, tol, x1, dx1, gradi
         fw, fv, fu = fv, fu, fm
         x2, dx2 = x1.copy(), dx1.copy()
         gradient = c.df(x1)
-        pg = float(np.dot(p, gradient))
-        gnorm1 = float(np.sqrt(np.dot(gradient, gradient)))
+        pg = _dot(p, gradient)
+        gnorm1 = _nrm2(gradient)
         f, step, gnorm = fm, stepm, gnorm1
         if abs(pg * lam / gnorm1) < tol:
             return x2, dx2, gradient, step, f, gnorm
@@ -108,7 +121,7 @@ def minimize_fr(f, fdf, x0, initial_step=0.1, line_tol=0.05, max_iterations=50, 
     it_state, step, tol = 0, initial_step, line_tol
     fval, gradient = c.fdf(x)
     p, g0 = gradient.copy(), gradient.copy()
-    pnorm = g0norm = float(np.sqrt(np.dot(gradient, gradient)))
+    pnorm = g0norm = _nrm2(gradient)
     cost_initial = fval
     cost_new = cost_old = 1e9
     it, stop = 0, 0
@@ -121,7 +134,7 @@ def minimize_fr(f, fdf, x0, initial_step=0.1, line_tol=0.05, max_iterations=50, 
         if pnorm == 0.0 or g0norm == 0.0:
             status = GSL_ENOPROG
         else:
-            pg = float(np.dot(p, gradient))
+            pg = _dot(p, gradient)
             direction = 1.0 if pg >= 0.0 else -1.0
             x1, dx = _take_step(x, p, stepc, direction / pnorm)
             fc = c.f(x1)
@@ -144,7 +157,7 @@ def minimize_fr(f, fdf, x0, initial_step=0.1, line_tol=0.05, max_iterations=50, 
                         beta = -math.pow(g1norm / g0norm, 2.0)
                         p = (-beta) * p
                         p = p + 1.0 * gradient
-                        pnorm = float(np.sqrt(np.dot(p, p)))
+                        pnorm = _nrm2(p)
                     g0norm, g0 = g1norm, gradient.copy()
                     status = GSL_SUCCESS
         trace.append(x.copy())
@@ -155,7 +168,7 @@ def minimize_fr(f, fdf, x0, initial_step=0.1, line_tol=0.05, max_iterations=50, 
                 stop = 1
                 break
             status = GSL_CONTINUE
-        if float(np.sqrt(np.dot(gradient, gradient))) < epsabs_grad:
+        if _nrm2(gradient) < epsabs_grad:
             stop = 2
             break
         if status != GSL_CONTINUE:

@@ -573,6 +573,11 @@ def ref1p_be_contrast(iwe, bands, measure=0):
 
 # ---- the reference's own node classes driven without ROS (oracle/ref_node_shim.cpp) --------------------------------------
 _REF_NODE = os.path.join(_HERE, "_ref", "libref_node.so")
+_REF_FULL = os.path.join(_HERE, "_ref", "libref_full.so")
+
+
+def have_ref_full():
+    return os.path.exists(_REF_FULL)
 
 
 def have_ref_node():
@@ -584,8 +589,10 @@ class RefNode:
     front-end returns the next row of `omegas`, the back-end leaves the control poses unchanged."""
 
     def __init__(self, W, H, K4, omegas, dt_ang_vel=0.01, num_events_per_packet=2000, fe_sample_rate=1, win_size=0.2, win_stride=0.1,
-                 dt_knots=0.05, spline_degree=1, pano_height=64, y_angle=0.0, min_ev_rate=10, max_update_times=10):
-        self.L = C.CDLL(_REF_NODE)
+                 dt_knots=0.05, spline_degree=1, pano_height=64, y_angle=0.0, min_ev_rate=10, max_update_times=10, full=False):
+        """full=True: oracle/_ref/libref_full.so -- the reference's own *_optim_contrast_gsl*.cpp run the solves (over the GSL
+        stand-in of oracle/stubs/gsl); `omegas` is then unused."""
+        self.L = C.CDLL(_REF_FULL if full else _REF_NODE)
         self.L.ref1p_node_create.restype = C.c_void_p
         K = np.ascontiguousarray(K4, dtype=np.float64)
         om = np.ascontiguousarray(omegas, dtype=np.float64).reshape(-1, 3)
@@ -612,6 +619,17 @@ class RefNode:
         h = C.c_ulonglong(0)
         self.L.ref1p_node_packet(self.h, int(i), v, C.byref(h))
         return list(v), h.value
+
+    def packet_omega(self, i):
+        w = np.zeros(3)
+        self.L.ref1p_node_packet_omega(self.h, int(i), _d(w))
+        return w
+
+    def get_map(self, PW, PH):
+        IG = np.zeros((PH, PW), np.float32)
+        t = np.zeros((PH, PW), np.uint8)
+        self.L.ref1p_node_get_map(self.h, IG.ctypes.data_as(_fp), t.ctypes.data_as(C.c_void_p))
+        return IG, t
 
     def window(self, i):
         v = (C.c_longlong * 15)()

@@ -42,7 +42,7 @@
 
 using namespace cmax_slam;
 
-struct PacketRec { uint32_t sec, nsec; long long n; uint32_t f_sec, f_nsec, l_sec, l_nsec; unsigned long long hash; };
+struct PacketRec { uint32_t sec, nsec; long long n; uint32_t f_sec, f_nsec, l_sec, l_nsec; unsigned long long hash; double w[3]; };
 struct WindowRec {
   uint32_t beg[2], end[2]; long long n_events; uint32_t f[2], l[2]; unsigned long long hash;
   int n_ctrl, idx_traj, idx_opt, num_opt; uint32_t latest[2]; double latest_q[4];
@@ -70,6 +70,7 @@ struct RefNode {
 };
 static RefNode* g_node = nullptr;     /* the stand-in solves find their node here */
 
+#ifndef REF_FULL
 namespace cmax_slam {
 /* stands in for src/frontend/local_optim_contrast_gsl.cpp:74-233 (needs GSL): records the packet, returns the next table entry */
 double AngVelEstimator::setupProblemAndOptimize_gsl(cv::Point3d& ang_vel) {
@@ -87,6 +88,7 @@ double AngVelEstimator::setupProblemAndOptimize_gsl(cv::Point3d& ang_vel) {
 /* stands in for src/backend/global_optim_contrast_gsl.cpp:15-145 (needs GSL): no solve, control poses unchanged */
 void PoseGraphOptimizer::setupProblemAndOptimize_gsl() {}
 }  // namespace cmax_slam
+#endif  /* !REF_FULL: with REF_FULL the reference's own *_optim_contrast_gsl*.cpp are linked (over the GSL stand-in of oracle/stubs/gsl) */
 
 extern "C" RefNode* ref1p_node_create(int W, int H, const double K4[4], double dt_ang_vel, int num_events_per_packet, int fe_sample_rate,
                                       double win_size, double win_stride, double dt_knots, int spline_degree, int pano_height,
@@ -134,10 +136,20 @@ extern "C" void ref1p_node_events(RefNode* n, const dvs_msgs::Event* ev, long lo
     const size_t solved_before = n->packets.size();
     n->fe->pushEvent(ev[i]);
     if (was_init && n->fe->time_packet_ != tp_before && n->packets.size() == solved_before) {
-      /* a packet was consumed without a solve: its time span exceeded 10 dt_ang_vel (ang_vel_estimator.cpp:109-114) */
+      /* a packet was consumed that the stand-in solve did not see: REF_FULL (the real solve ran: n = -2), or its time span
+         exceeded 10 dt_ang_vel and the reference set the angular velocity to zero (ang_vel_estimator.cpp:109-114: n = -1) */
       PacketRec r{};
-      r.sec = tp_before.sec; r.nsec = tp_before.nsec; r.n = -1;
+      r.sec = tp_before.sec; r.nsec = tp_before.nsec;
+#ifdef REF_FULL
+      r.n = -2;
+#else
+      r.n = -1;
+#endif
       n->packets.push_back(r);
+    }
+    if (n->packets.size() > solved_before) {
+      PacketRec& r = n->packets.back();
+      r.w[0] = n->fe->ang_vel_.x; r.w[1] = n->fe->ang_vel_.y; r.w[2] = n->fe->ang_vel_.z;
     }
     PoseGraphOptimizer& b = *n->be;
     while (b.isReadyFrontendPoses()) {
@@ -166,6 +178,34 @@ extern "C" void ref1p_node_events(RefNode* n, const dvs_msgs::Event* ev, long lo
   }
 }
 
+#ifdef REF_FULL
+/* the reference's own front-end solve (src/frontend/local_optim_contrast_gsl.cpp:74-233) on one packet */
+extern "C" double ref1p_fe_solve(const dvs_msgs::Event* events, long long n, const unsigned t_ref[2], int W, int H, const double K4[4],
+                                 double blur_sigma, int batch_size, int measure, const double omega_in[3], double omega_out[3]) {
+  static ros::NodeHandle nh;
+  AngVelEstimator est(&nh);
+  est.params.warp_opt.blur_sigma = blur_sigma; est.params.warp_opt.event_batch_size = batch_size; est.params.warp_opt.event_sample_rate = 1;
+  est.params.process_opt.contrast_measure = measure;
+  est.cam_width_ = W; est.cam_height_ = H;
+  est.camera_matrix_ = cv::Matx33d(K4[0], 0., K4[2], 0., K4[1], K4[3], 0., 0., 1.);
+  est.precomputed_bearing_vectors_.resize((size_t)W * H);
+  for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) est.precomputed_bearing_vectors_[(size_t)y * W + x] = cv::Point3d((x - K4[2]) / K4[0], (y - K4[3]) / K4[1], 1.0);
+  est.event_subset_.assign(events, events + n);
+  est.time_packet_ = ros::Time(t_ref[0], t_ref[1]);
+  cv::Point3d w(omega_in[0], omega_in[1], omega_in[2]);
+  const double cost = est.setupProblemAndOptimize_gsl(w);
+  omega_out[0] = w.x; omega_out[1] = w.y; omega_out[2] = w.z;
+  return cost;
+}
+#endif
+
+extern "C" void ref1p_node_packet_omega(RefNode* n, int i, double w[3]) { std::memcpy(w, n->packets[(size_t)i].w, sizeof(double) * 3); }
+extern "C" void ref1p_node_get_map(RefNode* n, float* IG, unsigned char* times) {
+  EventWarper* w = n->be->event_warper_;
+  const size_t A = (size_t)w->IG_.rows * w->IG_.cols;
+  if (IG) std::memcpy(IG, w->IG_.ptr<float>(), sizeof(float) * A);
+  if (times) std::memcpy(times, w->IG_update_times_map_.ptr<unsigned char>(), A);
+}
 extern "C" int ref1p_node_counts(RefNode* n, int* n_packets, int* n_windows, long long* n_stored) {
   *n_packets = (int)n->packets.size(); *n_windows = (int)n->windows.size(); *n_stored = (long long)n->fe->events_.size();
   return 0;

@@ -343,9 +343,36 @@ def golden_node_firstparty():
     np.savez_compressed(os.path.join(OUT, "node_firstparty.npz"), **d)
 
 
+def golden_pipeline_firstparty():
+    """The reference run AS A WHOLE on the CPU (node classes + warp + focus + its own optimiser glue over the GSL stand-in,
+    oracle/_ref/libref_full.so) on a seeded synthetic sequence: angular velocity per packet, control poses per window, final map."""
+    assert O.have_ref_full()
+    K_T = (120.0, 122.0, 63.0, 47.0)
+    d = {}
+    for tag, degree, seed in (("lin", 1, 31), ("cub", 3, 32)):
+        w = synth.make_be_window(120000, 9, 256, 128, seed, order=2, sensor=(128, 96), K4=K_T, n_landmarks=800, knot_sigma=0.1)
+        ref = O.RefNode(128, 96, K_T, np.zeros((1, 3)), dt_ang_vel=0.01, num_events_per_packet=6000, dt_knots=0.05, spline_degree=degree,
+                        pano_height=128, min_ev_rate=10, max_update_times=30, full=True)
+        ref.events(w.events)
+        n_pk, n_win, _ = ref.counts()
+        d[f"{tag}_stamps"] = np.array([ref.packet(i)[0][:2] for i in range(n_pk)], dtype=np.int64)
+        d[f"{tag}_omegas"] = np.array([ref.packet_omega(i) for i in range(n_pk)])
+        for i in range(n_win):
+            v, _, lq, kn = ref.window(i)
+            d[f"{tag}_win{i}"] = np.array(v, dtype=np.int64); d[f"{tag}_knots{i}"] = kn; d[f"{tag}_latest{i}"] = lq
+        d[f"{tag}_n_win"] = np.array(n_win)
+        IG, times = ref.get_map(256, 128)
+        d[f"{tag}_IG"] = IG; d[f"{tag}_times"] = times
+        ref.close()
+    np.savez_compressed(os.path.join(OUT, "pipeline_firstparty.npz"), **d)
+
+
 if __name__ == "__main__":
     if "--only-traj" in sys.argv:
         golden_traj()
+        sys.exit(0)
+    if "--only-pipeline1p" in sys.argv:
+        golden_pipeline_firstparty()
         sys.exit(0)
     if "--only-node1p" in sys.argv:
         golden_node_firstparty()
@@ -367,6 +394,7 @@ if __name__ == "__main__":
     golden_traj_firstparty()
     golden_hotpath_firstparty()
     golden_node_firstparty()
+    golden_pipeline_firstparty()
     golden_traj()
     golden_blur()
     golden_spline()
