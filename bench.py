@@ -168,9 +168,26 @@ def cpu_baseline(pkt, omega, budget_s=8.0):
     return out
 
 
+def _ref_tu_worker(job):
+    """One hypothesis through the reference's own translation units (oracle/_ref/libref_fe.so + libref_focus.so); its functions
+    keep state in function-local statics, so the all-core run uses one PROCESS per hypothesis."""
+    n, om, reps = job
+    from cmax_slam_b200 import synth
+    from oracle import oracle_py as O
+    pkt = _ref_tu_worker.pkt
+    sec = int(np.floor(pkt.t_ref_sec)); nsec = int(round((pkt.t_ref_sec - sec) * 1e9))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        iwe, der = O.ref1p_fe_images(pkt.events[:n], (sec, nsec), pkt.lut, pkt.width, pkt.height, pkt.K, om, True, pkt.blur_sigma, pkt.batch_size)
+        O.ref1p_fe_contrast(iwe, der, 0)
+    return time.perf_counter() - t0
+
+
 def run_reference(args, rank, world):
-    """Reference arm: the reference's own CPU algorithm (oracle port; the first-party sources need
-    ROS/OpenCV/GSL and do not compile here -- DESIGN.md), all host threads, one hypothesis per thread."""
+    """Reference arm: the reference's CPU algorithm on all host cores, one hypothesis per thread.  `value` times the oracle port
+    (bit-identical to the reference's own translation units, tests/test_oracle_firstparty.py, and faster than them); the same
+    workload through those translation units themselves (compiled with stand-in ROS / OpenCV headers, oracle/_ref; one process per
+    hypothesis because they are not re-entrant) is reported beside it."""
     if rank != 0:
         return
     from cmax_slam_b200 import synth
@@ -202,6 +219,21 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = ncores * n / dt
     sample = f"each step = {ncores} hypotheses x first {n} events of the C2 packet, one thread per hypothesis"
+    ref_tu = None
+    try:
+        if O.have_ref_firstparty():
+            import multiprocessing as mp
+            _ref_tu_worker.pkt = pkt
+            with mp.get_context("fork").Pool(ncores) as pool:
+                pool.map(_ref_tu_worker, [(min(n, 50_000), oms[i], 1) for i in range(ncores)])      # warm-up: load the libraries
+                t0 = time.perf_counter()
+                pool.map(_ref_tu_worker, [(n, oms[i], 1) for i in range(ncores)])
+                dt_tu = time.perf_counter() - t0
+            ref_tu = {"value": ncores * n / dt_tu, "unit": UNIT, "cores": ncores, "ms_per_step": dt_tu * 1e3,
+                      "note": "the same step through the reference's own .cpp files of the path (oracle/_ref: compiled unmodified with stand-in "
+                              "ROS / OpenCV headers), one process per hypothesis"}
+    except Exception as e:  # informational only
+        ref_tu = {"value": None, "note": f"unavailable: {e}"}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 geometry / f32 images", "data": "synthetic",
@@ -209,6 +241,8 @@ def run_reference(args, rank, world):
                        "threads": ncores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if ref_tu is not None:
+        line["reference_translation_units"] = ref_tu
     print(json.dumps(line), flush=True)
 
 
