@@ -58,7 +58,7 @@ def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference is present)."""
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(
             os.path.join(_HERE, "cmax_oracle.cpp")):
-        subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CXX": "g++"})
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-j8"], env={**os.environ, "CXX": "g++"})
     return _LIB
 
 
