@@ -312,6 +312,29 @@ def golden_hotpath_firstparty():
         for k in ("iwe", "bands", "il_old", "il_new"):
             d[f"be{order}_{k}"] = r[k]
         d[f"be{order}_contrast"] = np.array(c); d[f"be{order}_grad"] = g
+    # the same at the sizes the GPU parity tests use (tests/test_gpu_firstparty.py): no band images stored
+    pk = synth.make_fe_packet(6000, 64, 48, (60.0, 61.0, 31.5, 23.5), 81, 200)
+    sec = int(np.floor(pk.t_ref_sec)); nsec = int(round((pk.t_ref_sec - sec) * 1e9))
+    for k, om in enumerate((pk.omega_true, pk.omega_true + np.array([0.3, -0.2, 0.4]))):
+        iwe, der = O.ref1p_fe_images(pk.events, (sec, nsec), pk.lut, 64, 48, pk.K, om, True)
+        d[f"gfe{k}_omega"] = np.asarray(om, float); d[f"gfe{k}_iwe"] = iwe; d[f"gfe{k}_deriv"] = der
+        for m in (0, 1):
+            c, g = O.ref1p_fe_contrast(iwe, der, m)
+            d[f"gfe{k}_contrast{m}"] = np.array(c); d[f"gfe{k}_grad{m}"] = g
+    for order in (2, 4):
+        w = synth.make_be_window(20000, 8, 128, 64, 90 + order, order=order, sensor=(64, 48), K4=(60.0, 61.0, 31.5, 23.5), n_landmarks=300,
+                                 n_fixed=1 if order == 2 else 3)
+        dtk, t_beg = w.dt_ns / 1e9, w.t0_ns / 1e9
+        IG = np.abs(np.random.default_rng(6).normal(0, 0.3, (64, 128))).astype(np.float32)
+        rw = O.RefEventWarper(w.lut, 64, 48, 128, 64, order=order)
+        rw.set_ig(IG)
+        r = rw.eval(w.events, t_beg, dtk, w.knots_xyzw, w.n_fixed, w.tnext, True, True)
+        rw.close()
+        c, g = O.ref1p_be_contrast(r["iwe"], r["bands"], 0)
+        d[f"gbe{order}_tbeg"] = np.array([t_beg, dtk]); d[f"gbe{order}_IG"] = IG; d[f"gbe{order}_alpha"] = np.array(r["alpha"])
+        for k in ("iwe", "il_old", "il_new"):
+            d[f"gbe{order}_{k}"] = r[k]
+        d[f"gbe{order}_contrast"] = np.array(c); d[f"gbe{order}_grad"] = g
     np.savez_compressed(os.path.join(OUT, "hotpath_firstparty.npz"), **d)
 
 
