@@ -46,10 +46,16 @@ struct Cost {
   }
 };
 
-double nrm2(const std::vector<double>& v) {   // gsl_blas_dnrm2 (scaled accumulation is irrelevant at these magnitudes)
-  double s = 0;
-  for (double a : v) s += a * a;
-  return std::sqrt(s);
+double nrm2(const std::vector<double>& v) {   // gsl_blas_dnrm2 -> gslcblas cblas_dnrm2 (source_nrm2_r.h): scaled sum of squares
+  double scale = 0.0, ssq = 1.0;
+  for (double x : v) {
+    if (x != 0.0) {
+      const double ax = std::fabs(x);
+      if (scale < ax) { ssq = 1.0 + ssq * (scale / ax) * (scale / ax); scale = ax; }
+      else { ssq += (ax / scale) * (ax / scale); }
+    }
+  }
+  return scale * std::sqrt(ssq);
 }
 double dot(const std::vector<double>& a, const std::vector<double>& b) {
   double s = 0;

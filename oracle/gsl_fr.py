@@ -39,7 +39,17 @@ def _dot(a, b):
 
 
 def _nrm2(a):
-    return math.sqrt(_dot(a, a))
+    """gsl_blas_dnrm2 -> gslcblas cblas_dnrm2 (source_nrm2_r.h): scaled sum of squares."""
+    scale, ssq = 0.0, 1.0
+    for x in a.tolist():
+        if x != 0.0:
+            ax = abs(x)
+            if scale < ax:
+                ssq = 1.0 + ssq * (scale / ax) * (scale / ax)
+                scale = ax
+            else:
+                ssq += (ax / scale) * (ax / scale)
+    return scale * math.sqrt(ssq)
 
 
 def _take_step(x, p, step, lam):

@@ -48,7 +48,19 @@ static const gsl_multimin_fdfminimizer_type* const gsl_multimin_fdfminimizer_con
 static const gsl_multimin_fdfminimizer_type* const gsl_multimin_fdfminimizer_vector_bfgs = &gslstub_other_type;
 static const gsl_multimin_fdfminimizer_type* const gsl_multimin_fdfminimizer_vector_bfgs2 = &gslstub_other_type;
 
-static inline double gslstub_nrm2(const gsl_vector* v) { double s = 0; for (size_t i = 0; i < v->size; ++i) s += v->data[i] * v->data[i]; return sqrt(s); }
+/* gsl_blas_dnrm2 -> gslcblas cblas_dnrm2 (source_nrm2_r.h): scaled sum of squares */
+static inline double gslstub_nrm2(const gsl_vector* v) {
+  double scale = 0.0, ssq = 1.0;
+  for (size_t i = 0; i < v->size; ++i) {
+    const double x = v->data[i];
+    if (x != 0.0) {
+      const double ax = fabs(x);
+      if (scale < ax) { ssq = 1.0 + ssq * (scale / ax) * (scale / ax); scale = ax; }
+      else { ssq += (ax / scale) * (ax / scale); }
+    }
+  }
+  return scale * sqrt(ssq);
+}
 static inline double gslstub_dot(const gsl_vector* a, const gsl_vector* b) { double s = 0; for (size_t i = 0; i < a->size; ++i) s += a->data[i] * b->data[i]; return s; }
 static inline void gslstub_copy(gsl_vector* d, const gsl_vector* s) { memcpy(d->data, s->data, sizeof(double) * s->size); }
 static inline int gslstub_equal(const gsl_vector* a, const gsl_vector* b) { for (size_t i = 0; i < a->size; ++i) if (a->data[i] != b->data[i]) return 0; return 1; }   /* gsl_vector_equal */
