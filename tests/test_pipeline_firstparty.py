@@ -87,3 +87,39 @@ def test_live_reference_run_equals_python_restatement_pipeline(oracle, degree, s
     IG, times = ref.get_map(256, 128)
     assert np.array_equal(r["IG"], IG) and np.array_equal(r["times"], times)
     ref.close()
+
+
+def test_live_reference_run_with_a_silent_gap_and_skipped_windows(oracle):
+    """A 0.3 s hole in the event stream: the front-end meets a packet spanning more than 10 dt (angular velocity forced to zero,
+    no solve) and the back-end meets windows with fewer events than min_num_ev_per_win_ (no solve, no map update) -- the reference
+    run and the Python restatement pipeline still agree bit for bit."""
+    if not oracle.have_ref_full():
+        pytest.skip("oracle/_ref/libref_full.so not built (reference tree absent)")
+    from oracle import pipeline_py
+    w = synth.make_be_window(100000, 16, 256, 128, 51, order=2, sensor=(128, 96), K4=K_T, n_landmarks=600, knot_sigma=0.08)
+    ev = w.events
+    t = ev["sec"].astype(np.int64) * 1_000_000_000 + ev["nsec"].astype(np.int64)
+    t0 = int(t[0])
+    keep = (t < t0 + 250_000_000) | (t > t0 + 550_000_000)          # drop 0.3 s of events
+    ev = ev[keep]
+    rate = 4000                                                        # events / s needed for a window to be solved (0.2 s -> 800 events)
+    ref = oracle.RefNode(128, 96, K_T, np.zeros((1, 3)), dt_ang_vel=0.01, num_events_per_packet=6000, dt_knots=0.05, spline_degree=1,
+                         pano_height=128, min_ev_rate=rate, max_update_times=30, full=True)
+    ref.events(ev)
+    n_pk, n_win, _ = ref.counts()
+    r = pipeline_py.run(ev, w.lut, 128, 96, K_T, 256, 128, 2, min_ev_rate=rate)
+    assert len(r["packets"]) == n_pk and len(r["windows"]) == n_win >= 3
+    zero = 0
+    for i, (tp, om) in enumerate(r["packets"]):
+        assert np.array_equal(om, ref.packet_omega(i)), i
+        zero += int(not om.any())
+    assert zero >= 1                                                   # the packet across the hole was not solved
+    skipped = 0
+    for i, (rep, kn) in enumerate(r["windows"]):
+        v, _, lq, knots = ref.window(i)
+        assert _qdist(kn, knots) <= 1e-14, i
+        skipped += int(rep["optimized"] == 0)
+    assert 1 <= skipped < n_win                                        # some windows skipped, some solved
+    IG, times = ref.get_map(256, 128)
+    assert np.array_equal(r["IG"], IG) and np.array_equal(r["times"], times)
+    ref.close()
