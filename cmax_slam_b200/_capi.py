@@ -29,7 +29,7 @@ class FeCfg(C.Structure):
                 ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
                 ("lut_xyz", C.c_void_p), ("blur_sigma", C.c_double), ("batch_size", C.c_int32),
                 ("contrast_measure", C.c_int32), ("grad_mode", C.c_int32), ("device", C.c_int32),
-                ("stream", C.c_void_p), ("max_hypotheses", C.c_int32)]
+                ("stream", C.c_void_p), ("max_hypotheses", C.c_int32), ("lanes", C.c_int32), ("packet_slots", C.c_int32)]
 
 
 class BeCfg(C.Structure):
@@ -113,7 +113,8 @@ class BeWindow(C.Structure):
 
 # every symbol include/cmax_b200.h declares
 EXPORTS = [
-    "cmaxb_fe_create", "cmaxb_fe_destroy", "cmaxb_fe_set_packet", "cmaxb_fe_set_packet_async", "cmaxb_fe_eval", "cmaxb_fe_eval_batch",
+    "cmaxb_fe_create", "cmaxb_fe_destroy", "cmaxb_fe_set_packet", "cmaxb_fe_set_packet_async", "cmaxb_fe_set_packet_view",
+    "cmaxb_fe_select_packet", "cmaxb_fe_lanes_fork", "cmaxb_fe_lanes_join", "cmaxb_fe_launch_info", "cmaxb_fe_eval", "cmaxb_fe_eval_batch",
     "cmaxb_fe_eval_launch", "cmaxb_fe_eval_fetch", "cmaxb_fe_exchange_init", "cmaxb_fe_exchange_connect", "cmaxb_fe_exchange_close",
     "cmaxb_fe_eval_fetch_all", "cmaxb_fe_set_result_mirror", "cmaxb_fe_get_iwe", "cmaxb_fe_get_deriv", "cmaxb_fe_get_cells",
     "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_eval_begin", "cmaxb_be_il_plane", "cmaxb_be_eval_end", "cmaxb_be_eval_end_launch", "cmaxb_be_grad_device", "cmaxb_be_eval_end_fetch", "cmaxb_be_get_alpha",
@@ -148,6 +149,11 @@ def lib():
     L.cmaxb_fe_destroy.restype = None
     L.cmaxb_fe_set_packet.argtypes = [vp, vp, C.c_size_t, C.c_double]
     L.cmaxb_fe_set_packet_async.argtypes = [vp, vp, C.c_size_t, C.c_double]
+    L.cmaxb_fe_set_packet_view.argtypes = [vp, vp, C.c_size_t, C.c_double]
+    L.cmaxb_fe_select_packet.argtypes = [vp, C.c_int]
+    L.cmaxb_fe_lanes_fork.argtypes = [vp]
+    L.cmaxb_fe_lanes_join.argtypes = [vp]
+    L.cmaxb_fe_launch_info.argtypes = [vp, ip]
     L.cmaxb_fe_eval.argtypes = [vp, dp, dp, dp]
     L.cmaxb_fe_eval_batch.argtypes = [vp, dp, C.c_int, dp, dp]
     L.cmaxb_fe_eval_launch.argtypes = [vp, dp, C.c_int, C.c_int]

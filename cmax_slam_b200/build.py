@@ -14,8 +14,9 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(_HERE, "build")
 
 
 def sources():
@@ -33,18 +34,35 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
+def _compile_and_link(out, obj_dir, extra, verbose, force):
+    """One nvcc -c per translation unit (in parallel, only the stale ones) + one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    hdr_t = max(os.path.getmtime(p) for p in glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h")))
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", "-o", obj, src])
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for rc in ex.map(lambda c: subprocess.run(c, env=env).returncode, jobs):
+            if rc != 0:
+                raise subprocess.CalledProcessError(rc, "nvcc -c")
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs, env=env)
+    return out
+
+
 def build_variant(name, defines, verbose=False):
     """A/B build with extra -D flags into scratch/variants/libcmax_b200_<name>.so (select it at run time with
     CMAXB_LIB_PATH=<path>); tuning aid, never the shipped library."""
     out_dir = os.path.join(os.path.dirname(_HERE), "scratch", "variants")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, f"libcmax_b200_{name}.so")
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", out] + sources()
-    env = dict(os.environ)
-    env.pop("CXX", None)
-    subprocess.check_call(cmd, env=env)
-    return out
+    return _compile_and_link(out, os.path.join(out_dir, "obj_" + name), [f"-D{d}" for d in defines], verbose, True)
 
 
 def build(force=False, verbose=False):
@@ -62,11 +80,7 @@ def build(force=False, verbose=False):
         if os.path.exists(LIB_PATH):
             return LIB_PATH  # prebuilt library travelled with the snapshot
         raise RuntimeError("nvcc not found and no prebuilt libcmax_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", LIB_PATH] + sources()
-    env = dict(os.environ)
-    env.pop("CXX", None)
-    subprocess.check_call(cmd, env=env)
-    return LIB_PATH
+    return _compile_and_link(LIB_PATH, OBJ_DIR, [], verbose, force)
 
 
 if __name__ == "__main__":

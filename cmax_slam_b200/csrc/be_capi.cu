@@ -154,6 +154,7 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
   cudaStream_t s = be->stream;
   CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
   be->have_window = false;
+  be->il_is_plane = false; be->split_pending = false; be->end_launched = false;
   be->last_x.clear();
   const long long n = (long long)w->n_events, bs = be->cfg.batch_size;
   // the reference loop `for (beg = begin; beg < end-1; beg += bs)` never visits a trailing batch
@@ -313,6 +314,7 @@ static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false
   }
   const BeCache cache{be->d_ccell, be->d_ca, be->d_cb};
   be->il_is_quad = quad;
+  be->il_is_plane = false;   // a fresh scatter supersedes the assembled plane of an earlier sharded evaluation (eval_begin re-sets it)
   CMAXB_TRY(be->prof.run(CMAXB_K_ZERO, s, false, [&] {
     if (quad) cudaMemsetAsync(be->d_ilq, 0, sizeof(float4) * be->A, s);
     else {

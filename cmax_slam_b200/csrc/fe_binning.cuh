@@ -16,7 +16,7 @@ namespace cmaxb {
 constexpr int kBinTile = 32;          // source tile edge in pixels
 constexpr int kBinThreads = 256;
 constexpr int kBinChunk = 8192;       // events per CTA
-constexpr int kBinMaxTiles = 8192;    // shared-memory histogram capacity
+constexpr int kBinMaxTiles = 6144;    // shared-memory histogram capacity: the scatter pass needs 2 x 4 B per tile within the 48 KB default limit
 
 __device__ __forceinline__ int bin_tile_of(uint4 e, int W, int H, int ntx) {
   int x = e.x & 0xffff, y = e.x >> 16;

@@ -1,20 +1,29 @@
 // fe_capi.cu -- C ABI of the front-end path (see include/cmax_b200.h).
+//
+// Handle layout: `packets` = resident event packets (slots; the current one is selected with
+// cmaxb_fe_select_packet), `lanes` = independent evaluation pipelines (stream + accumulators + gather records +
+// reduction state).  Lane 0 is the handle's main stream: packet uploads / preparation, the synchronous
+// cmaxb_fe_eval / _eval_batch (the GSL-callback pattern, whole co-resident grid) and the getters run there.
+// With cfg.lanes >= 2, cmaxb_fe_eval_launch round-robins over lanes 1..cfg.lanes (own streams) with a partial grid,
+// so that the latency-bound phases of several evaluations overlap on the device and with the next packet's upload
+// (profiles/r01f_two_stream_probe.txt).
 #include "capi_common.cuh"
 #include "fe_kernels.cuh"
 #include "image_kernels.cuh"
-#include "fe_mega.cuh"
+#include "fe_fused.cuh"
 #include "fe_binning.cuh"
 
 #include <deque>
 
 using namespace cmaxb;
 
-// evaluations that may be queued on the stream before the oldest is fetched (results live in a ring of
-// mapped host slots, so the host never has to drain the stream between launches)
-constexpr int kFeRing = 4;
+constexpr int kFeRing = CMAXB_FE_MAX_OUTSTANDING;   // launches that may be outstanding (mapped result slots)
+constexpr int kFeMaxLanes = 1 + 4;         // lane 0 (main stream) + up to 4 throughput lanes
+constexpr int kFeMaxPackets = 16;
+static_assert(kXSlots >= 2 * kFeRing, "exchange slots must cover twice the launch ring");
 
 struct FeInflight {
-  int k; bool grad; bool mega; int slot; unsigned long long seq; bool xchg;
+  int k; bool grad; bool fused; int slot; int lane; unsigned long long seq; bool xchg; int pkt;
 };
 
 namespace cmaxb {
@@ -22,50 +31,70 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launch_count{0};
 }  // namespace cmaxb
 
+struct FePacket {
+  uint4* d_ev = nullptr; size_t ev_cap = 0;      // owned copy of the raw events
+  const uint4* ev = nullptr;                     // raw events in use: d_ev, or a caller-owned device buffer (view)
+  double* d_dt = nullptr; size_t dt_cap = 0;
+  uint2* d_bev = nullptr; size_t bev_cap = 0; bool have_bins = false;
+  long long n = 0, nb = 0;
+  bool have = false; bool flags_pending = false;
+  int* d_flags = nullptr; int* h_flags = nullptr;
+  cudaEvent_t ready = nullptr;                   // recorded on lane 0's stream after the preparation kernels
+  unsigned long long gen = 0;                    // bumped by every set_packet
+  int users = 0;                                 // evaluations launched on this packet and not yet fetched
+};
+
+struct FeLane {
+  cudaStream_t stream = nullptr; bool own_stream = false; bool ready = false;
+  // value accumulators: two corner-split ("quad") images used alternately; the image phase of one evaluation clears
+  // the image the next evaluation scatters into (no memset in steady state)
+  float4* d_quad[2] = {nullptr, nullptr}; int quad_cur = 0; int quad_dirty[2] = {0, 0};
+  float4* d_GQ = nullptr;
+  float4* d_reca = nullptr; float4* d_recb = nullptr; float* d_recc = nullptr; size_t rec_cap = 0;
+  double* d_part_img = nullptr; double* d_part_ev = nullptr; unsigned int* d_ticket = nullptr;
+  unsigned long long* d_bar = nullptr; unsigned long long bar_count = 0;
+  unsigned long long* h_done = nullptr; unsigned long long* d_done = nullptr; unsigned long long seq = 0;
+  unsigned long long* h_phase = nullptr; unsigned long long* d_phase = nullptr;
+  CUtensorMap tmap[2][2];                        // [grid mode][quad buffer]
+  unsigned long long seen_gen[kFeMaxPackets] = {};   // packet generation this lane's stream is ordered after
+  int inflight = 0;
+};
+
 struct cmaxb_fe {
   cmaxb_fe_cfg cfg{};
   int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
   long long A = 0;          // pixels
   int kmax = 1;
   Taps taps{};
+  float cxl[kMaxRadius + 1], cxr[kMaxRadius + 1], cyl[kMaxRadius + 1], cyr[kMaxRadius + 1];
   double4* d_lut = nullptr;
-  uint4* d_ev = nullptr; size_t ev_cap = 0;
-  double* d_dt = nullptr; size_t dt_cap = 0;
-  uint2* d_bev = nullptr; size_t bev_cap = 0; bool have_bins = false; bool use_bins = true;   // spatially binned copy of the packet
   unsigned int* d_tile_count = nullptr; unsigned int* d_tile_cursor = nullptr; int ntiles = 0, ntx = 0;
-  long long n = 0, nb = 0;
-  bool have_packet = false; bool flags_pending = false;
-  int* d_flags = nullptr; int* h_flags = nullptr;
-  // value accumulators: two corner-split ("quad") images used alternately; the blur kernel of one
-  // evaluation clears the image the next evaluation scatters into (no memset in steady state)
-  float4* d_quad[2] = {nullptr, nullptr}; int quad_cur = 0; int quad_dirty[2] = {0, 0};
-  float* d_blur1 = nullptr;        // blurred IWE (adjoint mode, get_iwe)
-  float4* d_GQ = nullptr;          // adjoint image, one float4 per cell
-  float4* d_img4 = nullptr; float4* d_blur4 = nullptr;   // DENSE mode: (I, dI/dw) accumulators
+  bool use_bins = true;
+  FePacket packets[kFeMaxPackets]; int npackets = 1; int cur = 0;
+  FeLane lanes[kFeMaxLanes]; int nlanes = 1; int lane_next = 0;   // nlanes = throughput lanes (lanes[1..nlanes]); <= 1: everything on lane 0
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  cudaStream_t stream = nullptr;    // == lanes[0].stream
+  // stand-alone kernels (DENSE gradients, getters, A/B): lane 0 only
+  float* d_blur1 = nullptr; float4* d_img4 = nullptr; float4* d_blur4 = nullptr;
   int* d_cells = nullptr; size_t cells_cap = 0;
   double* d_omegas = nullptr; double* h_omegas = nullptr;
   double* d_acc = nullptr; unsigned int* d_ticket = nullptr; unsigned int* d_ticket2 = nullptr;
   double* d_gacc = nullptr; double* d_result = nullptr; double* d_mean = nullptr; double* h_result = nullptr;
-  // fused (single cooperative kernel) evaluation
-  int mega_grid = 0; int mega_th = 16; bool mega_ok = false;
-  double* d_part_img = nullptr; double* d_part_ev = nullptr;
-  double* h_mega_result = nullptr; double* d_mega_result = nullptr;   // mapped pinned memory
-  bool last_mega = false;
-  unsigned long long* h_phase = nullptr; unsigned long long* d_phase = nullptr;   // mapped: phase boundary timestamps
-  unsigned long long* h_done = nullptr; unsigned long long* d_done = nullptr;     // mapped: completion sequence number
-  unsigned long long seq = 0;
-  double* d_mirror = nullptr;   // caller-owned device buffer [kmax][4] (cmaxb_fe_set_result_mirror)
-  bool force_multi_kernel = false;   // CMAXB_FE_MULTI_KERNEL=1: stand-alone kernels (profiling / A-B comparison)
-  int last_k = 0; bool last_grad = false; bool pending = false;
-  std::deque<FeInflight> inflight;   // launched, not yet fetched (FIFO)
+  // fused evaluation
+  int grid[2] = {0, 0}; int th[2] = {16, 16};   // [0] whole co-resident grid (latency), [1] partial grid (throughput lanes)
+  bool use_tma = false; bool tma_ok = false;
+  int cache_mode = 0;               // gather records: 0 never (default: measured slower, profiles/r02a_*), 1 always, -1 when they fit the budget
+  size_t cache_budget = (size_t)96 << 20;
+  double* h_ring = nullptr; double* d_ring = nullptr;   // mapped pinned memory: [kFeRing][kmax][4]
+  bool force_multi_kernel = false;  // CMAXB_FE_MULTI_KERNEL=1: stand-alone kernels (profiling / A-B comparison)
+  bool pending = false;             // work of ours may still be running on some lane
+  std::deque<FeInflight> inflight;  // launched, not yet fetched (FIFO)
   int ring_next = 0;
-  bool gather_f32 = false;           // CMAXB_FE_GATHER_F32=1: Jacobian chain of the gather in f32 (measured 1.5 % faster; default = the reference's f64 chain)
+  double* d_mirror = nullptr;       // caller-owned device buffer [kmax][4] (cmaxb_fe_set_result_mirror)
   // fused result exchange over peer memory (cmaxb_fe_exchange_*)
   int x_world = 0, x_rank = 0; bool x_on = false;
-  ulonglong2* x_local = nullptr; size_t x_bytes = 0;
-  ulonglong2* x_peer[kXMaxWorld] = {};
+  unsigned long long* x_local = nullptr; size_t x_bytes = 0;
+  unsigned long long* x_peer[kXMaxWorld] = {};
   double* x_all_dev = nullptr;
   double* h_xall = nullptr; double* d_xall = nullptr;        // mapped: [kFeRing][world][kmax][4]
   unsigned int* h_xerr = nullptr; unsigned int* d_xerr = nullptr;
@@ -73,21 +102,111 @@ struct cmaxb_fe {
   KernelProfiler prof;
 };
 
-static FeGeom fe_geom(const cmaxb_fe* fe) {
+static FeGeom fe_geom(const cmaxb_fe* fe, const FePacket& pk) {
   FeGeom g;
-  g.ev = fe->d_ev; g.bev = nullptr; g.n = fe->n; g.batch_size = fe->cfg.batch_size; g.dt_tab = fe->d_dt; g.lut = fe->d_lut;
+  g.ev = pk.ev; g.bev = nullptr; g.n = pk.n; g.batch_size = fe->cfg.batch_size; g.dt_tab = pk.d_dt; g.lut = fe->d_lut;
   g.W = fe->cfg.width; g.H = fe->cfg.height;
   g.fx = fe->cfg.fx; g.fy = fe->cfg.fy; g.cx = fe->cfg.cx; g.cy = fe->cfg.cy;
   return g;
 }
 
+// C = B^T 1 along one axis of length n (see fe_fused.cuh): the adjoint's own formula applied to an all-ones signal
+static void border_table(const Taps& t, int n, float* lo, float* hi) {
+  const int r = t.r;
+  auto conv1 = [&](int j) {
+    float s = 0.f;
+    for (int d = -r; d <= r; ++d) if (j + d >= 0 && j + d < n) s = fmaf(t.w[r + d], 1.0f, s);
+    return s;
+  };
+  auto full = [&](int q) {
+    if (q < 0 || q >= n) return 1.0f;
+    float s = conv1(q);
+    if (q >= 1 && q <= r) for (int d = q; d <= r; ++d) if (-q + d >= 0 && -q + d < n) s = fmaf(t.w[r + d], 1.0f, s);
+    if (q <= n - 2 && q >= n - 1 - r) for (int d = -r; d <= q - (n - 1); ++d) { const int j = 2 * (n - 1) - q + d; if (j >= 0 && j < n) s = fmaf(t.w[r + d], 1.0f, s); }
+    return s;
+  };
+  for (int i = 0; i <= kMaxRadius; ++i) { lo[i] = (i <= r) ? full(i) : 1.0f; hi[i] = (i <= r) ? full(n - 1 - r + i) : 1.0f; }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+// quad accumulator [planes][H][W] float4 seen as a 3-D f32 tensor {4W, H, planes}; box = the staged cell region of a tile
+static bool make_quad_tmap(CUtensorMap* out, float4* base, int W, int H, int planes, int r, int th) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)4 * W, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t gstr[2] = {(cuuint64_t)16 * W, (cuuint64_t)16 * W * H};
+  const cuuint32_t box[3] = {(cuuint32_t)(4 * fused_qw(r)), (cuuint32_t)fused_qh(r, th), 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  if (box[0] > 256u || box[1] > 256u) return false;
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static void* fused_kernel(const cmaxb_fe* fe) {
+  if (fe->use_tma) return fe->taps.r == 4 ? (void*)fe_eval_fused_kernel<4, true> : (void*)fe_eval_fused_kernel<-1, true>;
+  return fe->taps.r == 4 ? (void*)fe_eval_fused_kernel<4, false> : (void*)fe_eval_fused_kernel<-1, false>;
+}
+
+// allocate the buffers of lane `li` on first use
+static int fe_lane_prepare(cmaxb_fe* fe, int li) {
+  FeLane& L = fe->lanes[li];
+  if (L.ready) return CMAXB_OK;
+  const size_t k = (size_t)fe->kmax, A = (size_t)fe->A;
+  if (!L.stream) {
+    CMAXB_CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    L.own_stream = true;
+  }
+  CMAXB_TRY(dev_alloc(&L.d_quad[0], k * A));
+  CMAXB_TRY(dev_alloc(&L.d_quad[1], k * A));
+  CMAXB_TRY(dev_alloc(&L.d_GQ, k * A));
+  CMAXB_TRY(dev_alloc(&L.d_part_img, k * kFusedMaxTiles * 2));
+  CMAXB_TRY(dev_alloc(&L.d_part_ev, k * kFusedMaxCtas * 6));
+  CMAXB_TRY(dev_alloc(&L.d_ticket, 1));
+  CMAXB_TRY(dev_alloc(&L.d_bar, 1));
+  CMAXB_CUDA_TRY(cudaMemset(L.d_quad[0], 0, sizeof(float4) * k * A));
+  CMAXB_CUDA_TRY(cudaMemset(L.d_quad[1], 0, sizeof(float4) * k * A));
+  CMAXB_CUDA_TRY(cudaMemset(L.d_ticket, 0, sizeof(unsigned int)));
+  CMAXB_CUDA_TRY(cudaMemset(L.d_bar, 0, sizeof(unsigned long long)));
+  CMAXB_CUDA_TRY(cudaHostAlloc((void**)&L.h_done, sizeof(unsigned long long) * 8, cudaHostAllocMapped));
+  CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&L.d_done, L.h_done, 0));
+  L.h_done[0] = 0; L.h_done[1] = 0;
+  CMAXB_CUDA_TRY(cudaHostAlloc((void**)&L.h_phase, sizeof(unsigned long long) * 16, cudaHostAllocMapped));
+  CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&L.d_phase, L.h_phase, 0));
+  if (fe->use_tma) {
+    for (int m = 0; m < 2; ++m)
+      for (int b = 0; b < 2; ++b)
+        if (!make_quad_tmap(&L.tmap[m][b], L.d_quad[b], fe->cfg.width, fe->cfg.height, fe->kmax, fe->taps.r, fe->th[m]))
+          return set_error(CMAXB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the accumulator image");
+  }
+  CMAXB_CUDA_TRY(cudaDeviceSynchronize());
+  L.ready = true;
+  return CMAXB_OK;
+}
+
 extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   if (!cfg || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (cfg->width < 4 || cfg->height < 4 || !cfg->lut_xyz || cfg->batch_size <= 0)
+  if (cfg->width < 4 || cfg->height < 4 || cfg->width > 65535 || cfg->height > 65535 || !cfg->lut_xyz || cfg->batch_size <= 0)
     return set_error(CMAXB_ERR_INVALID, "bad front-end configuration");
   if (cfg->grad_mode != CMAXB_GRAD_DENSE && cfg->grad_mode != CMAXB_GRAD_ADJOINT)
     return set_error(CMAXB_ERR_INVALID, "bad grad_mode");
+  if (cfg->lanes < 0 || cfg->lanes > kFeMaxLanes - 1 || cfg->packet_slots < 0 || cfg->packet_slots > kFeMaxPackets)
+    return set_error(CMAXB_ERR_INVALID, "lanes must be 0..4 and packet_slots 0..16");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return set_error(CMAXB_ERR_CUDA, "no CUDA device: libcmax_b200 has no CPU fallback");
@@ -99,24 +218,39 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   fe->device = cfg->device;
   fe->A = (long long)cfg->width * cfg->height;
   fe->kmax = cfg->max_hypotheses > 0 ? cfg->max_hypotheses : 1;
+  fe->nlanes = cfg->lanes > 0 ? cfg->lanes : 3;
+  fe->npackets = cfg->packet_slots > 0 ? cfg->packet_slots : 1;
+  double grid_fraction = 0.5;
+  bool want_tma = true;
   {
     const char* mk = getenv("CMAXB_FE_MULTI_KERNEL");
     fe->force_multi_kernel = mk && mk[0] == '1';
     const char* nb = getenv("CMAXB_FE_NO_BINNING");   // A/B switch: evaluate the packet in arrival (time) order
     fe->use_bins = !(nb && nb[0] == '1');
-    const char* g32 = getenv("CMAXB_FE_GATHER_F32");  // A/B switch: Jacobian chain of the gather pass in f32
-    fe->gather_f32 = g32 && g32[0] == '1';
+    const char* cm = getenv("CMAXB_FE_CACHE");        // A/B switch: 0 = the gather recomputes the geometry, 1 = always from records
+    if (cm && (cm[0] == '0' || cm[0] == '1')) fe->cache_mode = cm[0] - '0';
+    const char* tm = getenv("CMAXB_FE_TMA");          // A/B switch: 0 = tiles staged with per-thread loads
+    if (tm && tm[0] == '0') want_tma = false;
+    const char* ln = getenv("CMAXB_FE_LANES");
+    if (ln && atoi(ln) >= 1 && atoi(ln) <= kFeMaxLanes - 1) fe->nlanes = atoi(ln);
+    const char* gf = getenv("CMAXB_FE_GRID_FRACTION");   // share of the co-resident CTAs one throughput-lane launch uses
+    if (gf && atof(gf) > 0.0 && atof(gf) <= 1.0) grid_fraction = atof(gf);
   }
   int rc = make_taps(cfg->blur_sigma, &fe->taps);
   if (rc != CMAXB_OK) { delete fe; return rc; }
   if (fe->taps.r + 2 > cfg->width || fe->taps.r + 2 > cfg->height) { delete fe; return set_error(CMAXB_ERR_INVALID, "image smaller than the blur kernel"); }
+  border_table(fe->taps, cfg->width, fe->cxl, fe->cxr);
+  border_table(fe->taps, cfg->height, fe->cyl, fe->cyr);
   auto fail = [&](int code) { cmaxb_fe_destroy(fe); return code; };
-  if (cfg->stream) fe->stream = (cudaStream_t)cfg->stream;
+  if (cfg->stream) fe->lanes[0].stream = (cudaStream_t)cfg->stream;
   else {
-    if (cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "cudaStreamCreate failed"));
-    fe->own_stream = true;
+    if (cudaStreamCreateWithFlags(&fe->lanes[0].stream, cudaStreamNonBlocking) != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "cudaStreamCreate failed"));
+    fe->lanes[0].own_stream = true;
   }
+  fe->stream = fe->lanes[0].stream;
   if (fe->prof.init() != CMAXB_OK) return fail(CMAXB_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&fe->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&fe->join_ev, cudaEventDisableTiming) != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "cudaEventCreate failed"));
   // LUT padded to 32-byte records
   {
     std::vector<double4> lut((size_t)fe->A);
@@ -124,11 +258,13 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
     if (dev_alloc(&fe->d_lut, (size_t)fe->A) != CMAXB_OK) return fail(CMAXB_ERR_CUDA);
     if (cudaMemcpy(fe->d_lut, lut.data(), sizeof(double4) * fe->A, cudaMemcpyHostToDevice) != cudaSuccess) return fail(set_error(CMAXB_ERR_CUDA, "LUT upload failed"));
   }
-  const size_t k = (size_t)fe->kmax, A = (size_t)fe->A;
+  const size_t k = (size_t)fe->kmax;
   bool ok = true;
-  ok = ok && dev_alloc(&fe->d_flags, 1) == CMAXB_OK;
-  ok = ok && dev_alloc(&fe->d_quad[0], k * A) == CMAXB_OK;
-  ok = ok && dev_alloc(&fe->d_quad[1], k * A) == CMAXB_OK;
+  for (int s = 0; s < fe->npackets; ++s) {
+    ok = ok && dev_alloc(&fe->packets[s].d_flags, 1) == CMAXB_OK;
+    ok = ok && cudaMallocHost((void**)&fe->packets[s].h_flags, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&fe->packets[s].ready, cudaEventDisableTiming) == cudaSuccess;
+  }
   ok = ok && dev_alloc(&fe->d_omegas, k * 3) == CMAXB_OK;
   ok = ok && dev_alloc(&fe->d_acc, k * kNAcc * kMaxImgCtas) == CMAXB_OK;
   ok = ok && dev_alloc(&fe->d_ticket, k) == CMAXB_OK;
@@ -136,63 +272,51 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   ok = ok && dev_alloc(&fe->d_gacc, k * 3 * kMaxEventCtas) == CMAXB_OK;
   ok = ok && dev_alloc(&fe->d_result, k * 4) == CMAXB_OK;
   ok = ok && dev_alloc(&fe->d_mean, k) == CMAXB_OK;
-  if (cfg->grad_mode == CMAXB_GRAD_ADJOINT) {
-    ok = ok && dev_alloc(&fe->d_blur1, k * A) == CMAXB_OK;
-    ok = ok && dev_alloc(&fe->d_GQ, k * A) == CMAXB_OK;
-  } else {
-    ok = ok && dev_alloc(&fe->d_img4, k * A) == CMAXB_OK;
-  }
-  if (!ok) return fail(CMAXB_ERR_CUDA);
-  ok = ok && cudaMallocHost((void**)&fe->h_flags, sizeof(int)) == cudaSuccess;
+  if (!ok) return fail(set_error(CMAXB_ERR_CUDA, "front-end buffer allocation failed"));
   ok = ok && cudaMallocHost((void**)&fe->h_omegas, sizeof(double) * 3 * k) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&fe->h_result, sizeof(double) * 4 * k) == cudaSuccess;
   ok = ok && cudaMemset(fe->d_ticket, 0, sizeof(unsigned) * k) == cudaSuccess;
   ok = ok && cudaMemset(fe->d_ticket2, 0, sizeof(unsigned) * k) == cudaSuccess;
   ok = ok && cudaMemset(fe->d_result, 0, sizeof(double) * k * 4) == cudaSuccess;
-  ok = ok && cudaMemset(fe->d_quad[0], 0, sizeof(float4) * k * A) == cudaSuccess;
-  ok = ok && cudaMemset(fe->d_quad[1], 0, sizeof(float4) * k * A) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&fe->h_ring, sizeof(double) * 4 * k * kFeRing, cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostGetDevicePointer((void**)&fe->d_ring, fe->h_ring, 0) == cudaSuccess;
   if (!ok) return fail(set_error(CMAXB_ERR_CUDA, "front-end buffer allocation failed"));
-  // fused evaluation kernel: co-resident grid size from the occupancy API
+  // fused evaluation kernel: co-resident grid size from the occupancy API; TMA staging when the tile box fits a tensor map
   {
-    int coop = 0;
+    int coop = 0, nsm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, fe->device);
-    int nsm = 0;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, fe->device);
-    const size_t smem = mega_smem_bytes(fe->taps.r);   // sized for the tallest tile
+    fe->use_tma = want_tma && tmap_encoder() != nullptr && 4 * fused_qw(fe->taps.r) <= 256 && fused_qh(fe->taps.r, kFusedMaxTH) <= 256;
+    const size_t smem_max = fused_smem_bytes(fe->taps.r, kFusedMaxTH);
     int occ = 0;
-    cudaError_t e1 = cudaFuncSetAttribute(fe_eval_megakernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e2 = cudaFuncSetAttribute(fe_eval_megakernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e3 = (fe->taps.r == 4)
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fe_eval_megakernel<4>, kMegaThreads, smem)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fe_eval_megakernel<-1>, kMegaThreads, smem);
-    if (coop && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && occ > 0) {
-      int grid = occ * nsm;
-      if (grid > kMegaMaxCtas) grid = kMegaMaxCtas;
-      {
-        // tuning aid: CMAXB_FE_GRID_FRACTION=0.5 launches the fused kernel on half of the co-resident CTAs, so that two
-        // handles on two streams can run their (latency-bound) evaluations side by side; default 1 = whole GPU
-        const char* gf = getenv("CMAXB_FE_GRID_FRACTION");
-        const double f = gf ? atof(gf) : 1.0;
-        if (f > 0.0 && f < 1.0) { grid = (int)(grid * f); if (grid < nsm / 4) grid = nsm / 4; if (grid < 1) grid = 1; }
-      }
-      fe->mega_grid = grid;
-      fe->mega_th = mega_tile_height(cfg->width, cfg->height, grid);
-      const size_t kk = (size_t)fe->kmax;
-      bool okm = dev_alloc(&fe->d_part_img, kk * kMegaMaxCtas * 2) == CMAXB_OK && dev_alloc(&fe->d_part_ev, kk * kMegaMaxCtas * 3) == CMAXB_OK;
-      okm = okm && cudaHostAlloc((void**)&fe->h_mega_result, sizeof(double) * 4 * kk * kFeRing, cudaHostAllocMapped) == cudaSuccess;
-      okm = okm && cudaHostGetDevicePointer((void**)&fe->d_mega_result, fe->h_mega_result, 0) == cudaSuccess;
-      okm = okm && cudaHostAlloc((void**)&fe->h_done, sizeof(unsigned long long) * 8, cudaHostAllocMapped) == cudaSuccess;
-      okm = okm && cudaHostGetDevicePointer((void**)&fe->d_done, fe->h_done, 0) == cudaSuccess;
-      if (okm) fe->h_done[0] = 0;
-      okm = okm && cudaHostAlloc((void**)&fe->h_phase, sizeof(unsigned long long) * 16, cudaHostAllocMapped) == cudaSuccess;
-      okm = okm && cudaHostGetDevicePointer((void**)&fe->d_phase, fe->h_phase, 0) == cudaSuccess;
-      if (okm && !fe->d_blur1) okm = dev_alloc(&fe->d_blur1, kk * A) == CMAXB_OK;
-      if (okm && !fe->d_GQ) okm = dev_alloc(&fe->d_GQ, kk * A) == CMAXB_OK;
-      fe->mega_ok = okm;
+    void* kern = fused_kernel(fe);
+    cudaError_t e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    cudaError_t e3 = cudaErrorUnknown;
+    if (e1 == cudaSuccess) {
+      if (fe->use_tma) e3 = (fe->taps.r == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fe_eval_fused_kernel<4, true>, kFusedThreads, smem_max)
+                                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fe_eval_fused_kernel<-1, true>, kFusedThreads, smem_max);
+      else e3 = (fe->taps.r == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fe_eval_fused_kernel<4, false>, kFusedThreads, smem_max)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fe_eval_fused_kernel<-1, false>, kFusedThreads, smem_max);
     }
     (void)cudaGetLastError();
-    if (!fe->mega_ok) return fail(set_error(CMAXB_ERR_CUDA, "cooperative launch unavailable: the fused evaluation kernel cannot run on this device"));
+    if (!(coop && e1 == cudaSuccess && e3 == cudaSuccess && occ > 0))
+      return fail(set_error(CMAXB_ERR_CUDA, "cooperative launch unavailable: the fused evaluation kernel cannot run on this device"));
+    int grid = occ * nsm;
+    if (grid > kFusedMaxCtas) grid = kFusedMaxCtas;
+    fe->grid[0] = grid;
+    int part = (int)(grid * grid_fraction);
+    if (part < nsm / 4) part = nsm / 4;
+    if (part < 1) part = 1;
+    if (part > grid) part = grid;
+    fe->grid[1] = part;
+    for (int m = 0; m < 2; ++m) {
+      fe->th[m] = fused_tile_height(cfg->width, cfg->height, fe->grid[m]);
+      const long long tiles = (long long)((cfg->width + kTW - 1) / kTW) * ((cfg->height + fe->th[m] - 1) / fe->th[m]);
+      if (tiles > kFusedMaxTiles) return fail(set_error(CMAXB_ERR_INVALID, "image too large for the fused front-end kernel (more than 8192 tiles)"));
+    }
   }
+  rc = fe_lane_prepare(fe, 0);
+  if (rc != CMAXB_OK) return fail(rc);
   *out = fe;
   return CMAXB_OK;
 }
@@ -200,62 +324,108 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
 extern "C" void cmaxb_fe_destroy(cmaxb_fe* fe) {
   if (!fe) return;
   cudaSetDevice(fe->device);
-  if (fe->stream) cudaStreamSynchronize(fe->stream);
-  cudaFree(fe->d_lut); cudaFree(fe->d_ev); cudaFree(fe->d_dt); cudaFree(fe->d_flags);
-  cudaFree(fe->d_bev); cudaFree(fe->d_tile_count); cudaFree(fe->d_tile_cursor);
-  cudaFree(fe->d_quad[0]); cudaFree(fe->d_quad[1]); cudaFree(fe->d_blur1); cudaFree(fe->d_GQ); cudaFree(fe->d_img4); cudaFree(fe->d_blur4);
+  for (int l = 0; l < kFeMaxLanes; ++l) if (fe->lanes[l].stream) cudaStreamSynchronize(fe->lanes[l].stream);
+  cudaFree(fe->d_lut); cudaFree(fe->d_tile_count); cudaFree(fe->d_tile_cursor);
+  for (int s = 0; s < kFeMaxPackets; ++s) {
+    FePacket& pk = fe->packets[s];
+    cudaFree(pk.d_ev); cudaFree(pk.d_dt); cudaFree(pk.d_bev); cudaFree(pk.d_flags);
+    if (pk.h_flags) cudaFreeHost(pk.h_flags);
+    if (pk.ready) cudaEventDestroy(pk.ready);
+  }
+  for (int l = 0; l < kFeMaxLanes; ++l) {
+    FeLane& L = fe->lanes[l];
+    cudaFree(L.d_quad[0]); cudaFree(L.d_quad[1]); cudaFree(L.d_GQ); cudaFree(L.d_reca); cudaFree(L.d_recb); cudaFree(L.d_recc);
+    cudaFree(L.d_part_img); cudaFree(L.d_part_ev); cudaFree(L.d_ticket); cudaFree(L.d_bar);
+    if (L.h_done) cudaFreeHost(L.h_done);
+    if (L.h_phase) cudaFreeHost(L.h_phase);
+    if (L.own_stream && L.stream) cudaStreamDestroy(L.stream);
+  }
+  cudaFree(fe->d_blur1); cudaFree(fe->d_img4); cudaFree(fe->d_blur4);
   cudaFree(fe->d_cells); cudaFree(fe->d_omegas); cudaFree(fe->d_acc); cudaFree(fe->d_ticket); cudaFree(fe->d_ticket2);
   cudaFree(fe->d_gacc); cudaFree(fe->d_result); cudaFree(fe->d_mean);
-  if (fe->h_flags) cudaFreeHost(fe->h_flags);
   if (fe->h_omegas) cudaFreeHost(fe->h_omegas);
   if (fe->h_result) cudaFreeHost(fe->h_result);
-  if (fe->h_mega_result) cudaFreeHost(fe->h_mega_result);
-  if (fe->h_phase) cudaFreeHost(fe->h_phase);
-  if (fe->h_done) cudaFreeHost(fe->h_done);
-  cudaFree(fe->d_part_img); cudaFree(fe->d_part_ev);
+  if (fe->h_ring) cudaFreeHost(fe->h_ring);
   for (int r = 0; r < fe->x_world; ++r)
     if (r != fe->x_rank && fe->x_peer[r]) cudaIpcCloseMemHandle(fe->x_peer[r]);
   cudaFree(fe->x_local);
   if (fe->h_xall) cudaFreeHost(fe->h_xall);
   if (fe->h_xerr) cudaFreeHost(fe->h_xerr);
   fe->prof.destroy();
-  if (fe->own_stream && fe->stream) cudaStreamDestroy(fe->stream);
+  if (fe->fork_ev) cudaEventDestroy(fe->fork_ev);
+  if (fe->join_ev) cudaEventDestroy(fe->join_ev);
   delete fe;
 }
 
-static int fe_check_packet_flags(cmaxb_fe* fe) {
-  // validation result of an asynchronous set_packet (its D2H copy precedes every later operation on the stream)
-  if (!fe->flags_pending) return CMAXB_OK;
-  fe->flags_pending = false;
-  if (*fe->h_flags & 2) { fe->have_packet = false; return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor"); }
-  if (*fe->h_flags & 1) { fe->have_packet = false; return set_error(CMAXB_ERR_TIME_ORDER, "Events must span a non-negative time interval"); }
+// Wait until every lane is idle.  Evaluations already launched stay fetchable (their rows sit in the mapped ring).
+static int fe_drain(cmaxb_fe* fe) {
+  if (fe->pending) {
+    for (int l = 0; l < kFeMaxLanes; ++l)
+      if (fe->lanes[l].stream && (l == 0 || fe->lanes[l].ready)) CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->lanes[l].stream));
+    fe->pending = false;
+  }
   return CMAXB_OK;
 }
 
-static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec, bool wait) {
+static int fe_check_packet_flags(cmaxb_fe* fe, FePacket& pk) {
+  // validation result of an asynchronous set_packet (its D2H copy precedes every later operation on the stream)
+  if (!pk.flags_pending) return CMAXB_OK;
+  pk.flags_pending = false;
+  if (*pk.h_flags & 2) { pk.have = false; return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor"); }
+  if (*pk.h_flags & 1) { pk.have = false; return set_error(CMAXB_ERR_TIME_ORDER, "Events must span a non-negative time interval"); }
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_select_packet(cmaxb_fe* fe, int slot) {
+  if (!fe) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (slot < 0 || slot >= fe->npackets) return set_error(CMAXB_ERR_INVALID, "packet slot out of range (cfg.packet_slots)");
+  fe->cur = slot;
+  return CMAXB_OK;
+}
+
+// view: use the caller's DEVICE buffer in place (no copy; it must stay valid and unchanged until the slot's next set_packet)
+static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec, bool wait, bool view) {
   if (!fe || (!events && n > 0)) return set_error(CMAXB_ERR_INVALID, "null argument");
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
-  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream)); fe->pending = false; }
-  fe->have_packet = false;
+  FePacket& pk = fe->packets[fe->cur];
+  // evaluations of THIS slot's previous packet must have finished before its buffers are rewritten: lane 0 is ordered
+  // by its stream; a fetched evaluation has finished; the ones still outstanding on a throughput lane are waited for
+  if (pk.users > 0)
+    for (const FeInflight& f : fe->inflight)
+      if (f.pkt == fe->cur && f.lane > 0) CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->lanes[f.lane].stream));
+  pk.have = false;
   const long long bs = fe->cfg.batch_size;
   const long long nb = ((long long)n + bs - 1) / bs;
-  if (n > fe->ev_cap) {
-    cudaFree(fe->d_ev); fe->d_ev = nullptr; fe->ev_cap = 0;
-    CMAXB_TRY(dev_alloc(&fe->d_ev, n));
-    fe->ev_cap = n;
+  if (view) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, events) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != fe->device) {
+      (void)cudaGetLastError();
+      return set_error(CMAXB_ERR_INVALID, "cmaxb_fe_set_packet_view needs device memory of the handle's GPU");
+    }
+  } else if (n > pk.ev_cap) {
+    cudaStreamSynchronize(fe->stream);
+    cudaFree(pk.d_ev); pk.d_ev = nullptr; pk.ev_cap = 0;
+    CMAXB_TRY(dev_alloc(&pk.d_ev, n));
+    pk.ev_cap = n;
   }
-  if ((size_t)nb > fe->dt_cap) {
-    cudaFree(fe->d_dt); fe->d_dt = nullptr; fe->dt_cap = 0;
-    CMAXB_TRY(dev_alloc(&fe->d_dt, (size_t)nb));
-    fe->dt_cap = (size_t)nb;
+  if ((size_t)nb > pk.dt_cap) {
+    cudaStreamSynchronize(fe->stream);
+    cudaFree(pk.d_dt); pk.d_dt = nullptr; pk.dt_cap = 0;
+    CMAXB_TRY(dev_alloc(&pk.d_dt, (size_t)nb));
+    pk.dt_cap = (size_t)nb;
   }
-  fe->n = (long long)n; fe->nb = nb;
+  pk.n = (long long)n; pk.nb = nb;
+  pk.gen += 1;
   if (n > 0) {
     cudaStream_t s = fe->stream;
-    CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->d_ev, events, sizeof(cmaxb_event) * n, cudaMemcpyDefault, s));   // host (pinned: DMA) or device memory (UVA)
-    CMAXB_CUDA_TRY(cudaMemsetAsync(fe->d_flags, 0, sizeof(int), s));
-    const uint4* ev = fe->d_ev; const long long nn = fe->n; int* flags = fe->d_flags;
-    const int W = fe->cfg.width, H = fe->cfg.height; double* dt = fe->d_dt; const int ibs = (int)bs;
+    if (view) pk.ev = reinterpret_cast<const uint4*>(events);
+    else {
+      CMAXB_CUDA_TRY(cudaMemcpyAsync(pk.d_ev, events, sizeof(cmaxb_event) * n, cudaMemcpyDefault, s));   // host (pinned: DMA) or device memory (UVA)
+      pk.ev = pk.d_ev;
+    }
+    CMAXB_CUDA_TRY(cudaMemsetAsync(pk.d_flags, 0, sizeof(int), s));
+    const uint4* ev = pk.ev; const long long nn = pk.n; int* flags = pk.d_flags;
+    const int W = fe->cfg.width, H = fe->cfg.height; double* dt = pk.d_dt; const int ibs = (int)bs;
     CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
       validate_events_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(ev, nn, W, H, flags);
     }));
@@ -263,14 +433,15 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
       fe_batch_dt_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ev, nn, ibs, t_ref_sec, dt, nb, flags);
     }));
     // one-time spatial binning of the packet (reused by every evaluation until the next set_packet)
-    fe->have_bins = false;
+    pk.have_bins = false;
     fe->ntx = (W + kBinTile - 1) / kBinTile;
     fe->ntiles = fe->ntx * ((H + kBinTile - 1) / kBinTile);
     if (fe->use_bins && fe->ntiles <= kBinMaxTiles && nn < (1LL << 32)) {
-      if (n > fe->bev_cap) {
-        cudaFree(fe->d_bev); fe->d_bev = nullptr; fe->bev_cap = 0;
-        CMAXB_TRY(dev_alloc(&fe->d_bev, n));
-        fe->bev_cap = n;
+      if (n > pk.bev_cap) {
+        cudaStreamSynchronize(s);
+        cudaFree(pk.d_bev); pk.d_bev = nullptr; pk.bev_cap = 0;
+        CMAXB_TRY(dev_alloc(&pk.d_bev, n));
+        pk.bev_cap = n;
       }
       if (!fe->d_tile_count) {
         CMAXB_TRY(dev_alloc(&fe->d_tile_count, (size_t)kBinMaxTiles));
@@ -278,6 +449,7 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
       }
       const int ntiles = fe->ntiles, ntx = fe->ntx;
       const unsigned nchunks = (unsigned)((nn + kBinChunk - 1) / kBinChunk);
+      uint2* bev = pk.d_bev;
       CMAXB_CUDA_TRY(cudaMemsetAsync(fe->d_tile_count, 0, sizeof(unsigned int) * ntiles, s));
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
         fe_bin_count_kernel<<<nchunks, kBinThreads, sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, fe->d_tile_count);
@@ -286,73 +458,84 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
         fe_bin_scan_kernel<<<1, 1024, 0, s>>>(fe->d_tile_count, ntiles, fe->d_tile_cursor);
       }));
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-        fe_bin_scatter_kernel<<<nchunks, kBinThreads, 2 * sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, ibs, fe->d_tile_cursor, fe->d_bev);
+        fe_bin_scatter_kernel<<<nchunks, kBinThreads, 2 * sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, ibs, fe->d_tile_cursor, bev);
       }));
-      fe->have_bins = true;
+      pk.have_bins = true;
     }
-    CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->h_flags, fe->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
-    fe->flags_pending = true;
-    fe->have_packet = true;
+    CMAXB_CUDA_TRY(cudaMemcpyAsync(pk.h_flags, pk.d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CMAXB_CUDA_TRY(cudaEventRecord(pk.ready, s));
+    pk.flags_pending = true;
+    pk.have = true;
+    fe->pending = true;
     if (wait) {
       CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
-      return fe_check_packet_flags(fe);
+      return fe_check_packet_flags(fe, pk);
     }
     return CMAXB_OK;
   }
-  fe->have_packet = true;
+  pk.ev = pk.d_ev;
+  CMAXB_CUDA_TRY(cudaEventRecord(pk.ready, fe->stream));
+  pk.have = true;
   return CMAXB_OK;
 }
 
 extern "C" int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec) {
-  return fe_set_packet_impl(fe, events, n, t_ref_sec, true);
+  return fe_set_packet_impl(fe, events, n, t_ref_sec, true, false);
 }
 extern "C" int cmaxb_fe_set_packet_async(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec) {
-  return fe_set_packet_impl(fe, events, n, t_ref_sec, false);
+  return fe_set_packet_impl(fe, events, n, t_ref_sec, false, false);
+}
+extern "C" int cmaxb_fe_set_packet_view(cmaxb_fe* fe, const cmaxb_event* device_events, size_t n, double t_ref_sec) {
+  return fe_set_packet_impl(fe, device_events, n, t_ref_sec, false, true);
 }
 
 static int fe_upload_omegas(cmaxb_fe* fe, const double* omegas, int k) {
-  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream)); fe->pending = false; }
+  CMAXB_TRY(fe_drain(fe));
   std::memcpy(fe->h_omegas, omegas, sizeof(double) * 3 * k);
   CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->d_omegas, fe->h_omegas, sizeof(double) * 3 * k, cudaMemcpyHostToDevice, fe->stream));
   return CMAXB_OK;
 }
 
-static dim3 fe_event_grid(const cmaxb_fe* fe, int k) {
-  long long blocks = (fe->n + kFeThreads - 1) / kFeThreads;
+static dim3 fe_event_grid(long long n, int k) {
+  long long blocks = (n + kFeThreads - 1) / kFeThreads;
   const long long cap = kMaxEventCtas;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return dim3((unsigned)blocks, (unsigned)k, 1);
 }
 
-// scatter the value votes of k hypotheses into the current quad accumulator
+// ---- stand-alone kernels on lane 0 (DENSE gradients, getters, A/B) ------------------------------------------
+// scatter the value votes of k hypotheses into lane 0's current quad accumulator
 static int fe_run_scatter_value(cmaxb_fe* fe, int k) {
+  FeLane& L = fe->lanes[0];
+  const FePacket& pk = fe->packets[fe->cur];
   cudaStream_t s = fe->stream;
-  const int cur = fe->quad_cur;
-  if (fe->quad_dirty[cur] > 0) {   // only after start-up / a change of k / a debug call: steady state skips this
-    const int planes = fe->quad_dirty[cur];
-    CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(fe->d_quad[cur], 0, sizeof(float4) * fe->A * planes, s); }));
-    fe->quad_dirty[cur] = 0;
+  const int cur = L.quad_cur;
+  if (L.quad_dirty[cur] > 0) {   // only after start-up / a change of k / a debug call: steady state skips this
+    const int planes = L.quad_dirty[cur];
+    CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(L.d_quad[cur], 0, sizeof(float4) * fe->A * planes, s); }));
+    L.quad_dirty[cur] = 0;
   }
-  if (fe->n > 0) {
-    const FeGeom g = fe_geom(fe);
+  if (pk.n > 0) {
+    const FeGeom g = fe_geom(fe, pk);
     CMAXB_TRY(fe->prof.run(CMAXB_K_FE_SCATTER, s, true, [&] {
-      fe_scatter_kernel<2><<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, nullptr, fe->d_quad[cur], fe->A);
+      fe_scatter_kernel<2><<<fe_event_grid(pk.n, k), kFeThreads, 0, s>>>(g, fe->d_omegas, nullptr, L.d_quad[cur], fe->A);
     }));
-    fe->quad_dirty[cur] = k;
+    L.quad_dirty[cur] = k;
   }
   return CMAXB_OK;
 }
-// blur + reduce the current quad accumulator (k planes); optionally keep the blurred image; clears the
+// blur + reduce lane 0's current quad accumulator (k planes); optionally keep the blurred image; clears the
 // OTHER quad accumulator and makes it current.
 static int fe_run_value_image(cmaxb_fe* fe, int k, const Taps& taps, bool write_out) {
+  FeLane& L = fe->lanes[0];
   cudaStream_t s = fe->stream;
-  const int cur = fe->quad_cur, oth = cur ^ 1;
-  const SrcQuad src{fe->d_quad[cur], fe->A};
+  const int cur = L.quad_cur, oth = cur ^ 1;
+  const SrcQuad src{L.d_quad[cur], fe->A};
   const ReduceOut ro{fe->d_acc, fe->d_ticket, fe->d_result, fe->d_mean};
   const int W = fe->cfg.width, H = fe->cfg.height, measure = fe->cfg.contrast_measure;
   // the other image can be cleared by this kernel if its dirty planes are covered by our k planes
-  float4* zero_ptr = (fe->quad_dirty[oth] > 0 && fe->quad_dirty[oth] <= k) ? fe->d_quad[oth] : nullptr;
+  float4* zero_ptr = (L.quad_dirty[oth] > 0 && L.quad_dirty[oth] <= k) ? L.d_quad[oth] : nullptr;
   if (write_out && !fe->d_blur1) CMAXB_TRY(dev_alloc(&fe->d_blur1, (size_t)fe->kmax * fe->A));
   cudaError_t le = cudaSuccess;
   CMAXB_TRY(fe->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
@@ -360,69 +543,98 @@ static int fe_run_value_image(cmaxb_fe* fe, int k, const Taps& taps, bool write_
                    : launch_blur_reduce<1, SrcQuad, false>(s, k, src, W, H, taps, nullptr, 0, ro, measure, zero_ptr, fe->A);
   }));
   if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("blur_reduce launch: ") + cudaGetErrorString(le));
-  if (zero_ptr) fe->quad_dirty[oth] = 0;
-  fe->quad_cur = oth;
+  if (zero_ptr) L.quad_dirty[oth] = 0;
+  L.quad_cur = oth;
   return CMAXB_OK;
 }
 static int fe_run_scatter_dense(cmaxb_fe* fe, int k) {
+  const FePacket& pk = fe->packets[fe->cur];
   cudaStream_t s = fe->stream;
   if (!fe->d_img4) CMAXB_TRY(dev_alloc(&fe->d_img4, (size_t)fe->kmax * fe->A));
   CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(fe->d_img4, 0, sizeof(float4) * fe->A * k, s); }));
-  if (fe->n > 0) {
-    const FeGeom g = fe_geom(fe);
+  if (pk.n > 0) {
+    const FeGeom g = fe_geom(fe, pk);
     CMAXB_TRY(fe->prof.run(CMAXB_K_FE_SCATTER, s, true, [&] {
-      fe_scatter_kernel<1><<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, nullptr, fe->d_img4, fe->A);
+      fe_scatter_kernel<1><<<fe_event_grid(pk.n, k), kFeThreads, 0, s>>>(g, fe->d_omegas, nullptr, fe->d_img4, fe->A);
     }));
   }
   return CMAXB_OK;
 }
 
-// Wait until the stream is idle.  Evaluations already launched stay fetchable (their rows sit in the mapped ring).
-static int fe_drain_stream(cmaxb_fe* fe) {
-  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream)); fe->pending = false; }
-  return CMAXB_OK;
-}
-
-// One cooperative launch per <= kMegaMaxHyp hypotheses; omegas travel as kernel parameters and the
-// results land in a ring slot of mapped pinned memory (up to kFeRing launches may be outstanding).
-static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int want_grad) {
-  cudaStream_t s = fe->stream;
+// One cooperative launch per <= kFusedMaxHyp hypotheses; omegas travel as kernel parameters and the results land
+// in a ring slot of mapped pinned memory (up to kFeRing launches may be outstanding).  mode 0: lane 0, whole grid;
+// mode 1: next throughput lane, partial grid.
+static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int want_grad, int mode) {
   if ((int)fe->inflight.size() >= kFeRing)
     return set_error(CMAXB_ERR_STATE, "too many outstanding evaluations: call cmaxb_fe_eval_fetch first");
-  if (!fe->inflight.empty() && !fe->inflight.back().mega) CMAXB_TRY(fe_drain_stream(fe));
-  if (fe->x_on && k > kMegaMaxHyp)
+  if (!fe->inflight.empty() && !fe->inflight.back().fused) CMAXB_TRY(fe_drain(fe));
+  if (fe->x_on && k > kFusedMaxHyp)
     return set_error(CMAXB_ERR_INVALID, "result exchange supports at most 32 hypotheses per launch");
+  int li = 0;
+  if (mode == 1 && fe->nlanes > 1) { li = 1 + fe->lane_next; fe->lane_next = (fe->lane_next + 1) % fe->nlanes; }
+  CMAXB_TRY(fe_lane_prepare(fe, li));
+  FeLane& L = fe->lanes[li];
+  FePacket& pk = fe->packets[fe->cur];
+  cudaStream_t s = L.stream;
+  if (li > 0 && L.seen_gen[fe->cur] != pk.gen) {      // order this lane's stream after the packet's preparation kernels
+    CMAXB_CUDA_TRY(cudaStreamWaitEvent(s, pk.ready, 0));
+    L.seen_gen[fe->cur] = pk.gen;
+  }
+  const int gm = li > 0 ? 1 : 0;
+  const int grid = fe->grid[gm], th = fe->th[gm];
+  const bool use_cache = want_grad && pk.n > 0 &&
+      (fe->cache_mode == 1 || (fe->cache_mode < 0 && (size_t)k * (size_t)pk.n * 36u <= fe->cache_budget));
+  if (use_cache && (size_t)k * (size_t)pk.n > L.rec_cap) {
+    CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFree(L.d_reca); cudaFree(L.d_recb); cudaFree(L.d_recc);
+    L.d_reca = L.d_recb = nullptr; L.d_recc = nullptr; L.rec_cap = 0;
+    const size_t cap = (size_t)k * (size_t)pk.n;
+    CMAXB_TRY(dev_alloc(&L.d_reca, cap));
+    CMAXB_TRY(dev_alloc(&L.d_recb, cap));
+    CMAXB_TRY(dev_alloc(&L.d_recc, cap));
+    L.rec_cap = cap;
+  }
   const int slot = fe->ring_next;
   fe->ring_next = (fe->ring_next + 1) % kFeRing;
-  const int cur = fe->quad_cur, oth = cur ^ 1;
-  if (fe->quad_dirty[cur] > 0) {
-    const int planes = fe->quad_dirty[cur];
-    CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(fe->d_quad[cur], 0, sizeof(float4) * fe->A * planes, s); }));
-    fe->quad_dirty[cur] = 0;
+  const int cur = L.quad_cur, oth = cur ^ 1;
+  if (L.quad_dirty[cur] > 0) {
+    const int planes = L.quad_dirty[cur];
+    CMAXB_TRY(fe->prof.run(CMAXB_K_ZERO, s, false, [&] { cudaMemsetAsync(L.d_quad[cur], 0, sizeof(float4) * fe->A * planes, s); }));
+    L.quad_dirty[cur] = 0;
   }
-  const bool clear_next = fe->quad_dirty[oth] > 0 && fe->quad_dirty[oth] <= k;
-  for (int c0 = 0; c0 < k; c0 += kMegaMaxHyp) {
-    const int kc = (k - c0 < kMegaMaxHyp) ? k - c0 : kMegaMaxHyp;
-    FeMegaParams p;
-    p.g = fe_geom(fe);
-    p.g.bev = fe->have_bins ? fe->d_bev : nullptr;   // the fused kernel walks the tile-binned copy of the packet
-    p.k = kc; p.th = fe->mega_th; p.want_grad = want_grad; p.measure = fe->cfg.contrast_measure; p.taps = fe->taps;
+  const bool clear_next = L.quad_dirty[oth] > 0 && L.quad_dirty[oth] <= k;
+  const int W = fe->cfg.width, H = fe->cfg.height;
+  for (int c0 = 0; c0 < k; c0 += kFusedMaxHyp) {
+    const int kc = (k - c0 < kFusedMaxHyp) ? k - c0 : kFusedMaxHyp;
+    FeFusedParams p;
+    p.g = fe_geom(fe, pk);
+    p.g.bev = pk.have_bins ? pk.d_bev : nullptr;   // the fused kernel walks the tile-binned copy of the packet
+    p.k = kc; p.th = th; p.ntx = (W + kTW - 1) / kTW; p.nty = (H + th - 1) / th;
+    p.want_grad = want_grad; p.measure = fe->cfg.contrast_measure; p.use_cache = use_cache ? 1 : 0;
+    p.quad_plane0 = c0;
+    p.taps = fe->taps;
+    std::memcpy(p.cxl, fe->cxl, sizeof(p.cxl)); std::memcpy(p.cxr, fe->cxr, sizeof(p.cxr));
+    std::memcpy(p.cyl, fe->cyl, sizeof(p.cyl)); std::memcpy(p.cyr, fe->cyr, sizeof(p.cyr));
     for (int i = 0; i < 3 * kc; ++i) p.omegas[i] = omegas[3 * c0 + i];
-    p.quad = fe->d_quad[cur] + (long long)c0 * fe->A;
-    p.quad_next = clear_next ? fe->d_quad[oth] + (long long)c0 * fe->A : nullptr;
-    p.blurred = fe->d_blur1 + (long long)c0 * fe->A;
-    p.GQ = fe->d_GQ + (long long)c0 * fe->A;
+    p.quad = L.d_quad[cur] + (long long)c0 * fe->A;
+    p.quad_next = clear_next ? L.d_quad[oth] + (long long)c0 * fe->A : nullptr;
+    p.GQ = L.d_GQ + (long long)c0 * fe->A;
     p.A = fe->A;
-    p.part_img = fe->d_part_img + (long long)c0 * kMegaMaxCtas * 2;
-    p.part_ev = fe->d_part_ev + (long long)c0 * kMegaMaxCtas * 3;
-    p.ticket = fe->d_ticket;
-    p.contrast_dev = fe->d_mean + c0;
-    p.result = fe->d_mega_result + ((long long)slot * fe->kmax + c0) * 4;
+    p.rec.a = L.d_reca ? L.d_reca + (long long)c0 * pk.n : nullptr;
+    p.rec.b = L.d_recb ? L.d_recb + (long long)c0 * pk.n : nullptr;
+    p.rec.c = L.d_recc ? L.d_recc + (long long)c0 * pk.n : nullptr;
+    p.rec_stride = pk.n;
+    p.part_img = L.d_part_img + (long long)c0 * kFusedMaxTiles * 2;
+    p.part_ev = L.d_part_ev + (long long)c0 * kFusedMaxCtas * 6;
+    p.ticket = L.d_ticket;
+    p.bar = L.d_bar; p.bar_base = L.bar_count;
+    L.bar_count += (unsigned long long)grid * (want_grad ? 2ull : 1ull);
+    p.result = fe->d_ring + ((long long)slot * fe->kmax + c0) * 4;
     p.mirror = fe->d_mirror ? fe->d_mirror + 4 * c0 : nullptr;
-    p.done_flag = fe->d_done;
-    p.seq = ++fe->seq;
-    p.phase_ns = fe->prof.enabled ? fe->d_phase : nullptr;
-    p.gather_f32 = fe->gather_f32 ? 1 : 0;
+    p.done_flag = L.d_done;
+    p.fault_flag = L.d_done + 1;
+    p.seq = ++L.seq;
+    p.phase_ns = fe->prof.enabled ? L.d_phase : nullptr;
     std::memset(&p.x, 0, sizeof(p.x));
     if (fe->x_on) {
       p.x.world = fe->x_world; p.x.rank = fe->x_rank; p.x.kmax = fe->kmax;
@@ -432,37 +644,37 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
       p.x.all_dev = fe->x_all_dev;
       p.x.err = fe->d_xerr;
     }
-    if (fe->prof.enabled) for (int i = 0; i < 16; ++i) fe->h_phase[i] = 0;
-    void* args[] = {&p};
-    const size_t smem = mega_smem_bytes(fe->taps.r);
+    if (fe->prof.enabled) for (int i = 0; i < 16; ++i) L.h_phase[i] = 0;
+    void* args[] = {&p, &L.tmap[gm][cur]};
+    const size_t smem = fused_smem_bytes(fe->taps.r, th);
     cudaError_t le = cudaSuccess;
     CMAXB_TRY(fe->prof.run(CMAXB_K_FE_EVAL_FUSED, s, true, [&] {
-      le = (fe->taps.r == 4)
-          ? cudaLaunchCooperativeKernel((void*)fe_eval_megakernel<4>, dim3(fe->mega_grid), dim3(kMegaThreads), args, smem, s)
-          : cudaLaunchCooperativeKernel((void*)fe_eval_megakernel<-1>, dim3(fe->mega_grid), dim3(kMegaThreads), args, smem, s);
+      le = cudaLaunchCooperativeKernel(fused_kernel(fe), dim3(grid), dim3(kFusedThreads), args, smem, s);
     }));
     if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("fused evaluation launch: ") + cudaGetErrorString(le));
   }
-  if (clear_next) fe->quad_dirty[oth] = 0;
-  if (fe->n > 0) fe->quad_dirty[cur] = k;
-  fe->quad_cur = oth;
-  fe->inflight.push_back(FeInflight{k, want_grad != 0, true, slot, fe->seq, fe->x_on});
-  fe->last_k = k; fe->last_grad = want_grad != 0; fe->pending = true; fe->last_mega = true;
+  if (clear_next) L.quad_dirty[oth] = 0;
+  if (pk.n > 0) L.quad_dirty[cur] = k;
+  L.quad_cur = oth;
+  L.inflight += 1;
+  pk.users += 1;
+  fe->inflight.push_back(FeInflight{k, want_grad != 0, true, slot, li, L.seq, fe->x_on, fe->cur});
+  fe->pending = true;
   return CMAXB_OK;
 }
 
-extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, int want_grad) {
+static int fe_eval_launch_mode(cmaxb_fe* fe, const double* omegas, int k, int want_grad, int mode) {
   if (!fe || !omegas) return set_error(CMAXB_ERR_INVALID, "null argument");
-  if (!fe->have_packet) return set_error(CMAXB_ERR_STATE, "no event packet: call cmaxb_fe_set_packet first");
+  FePacket& pk = fe->packets[fe->cur];
+  if (!pk.have) return set_error(CMAXB_ERR_STATE, "no event packet: call cmaxb_fe_set_packet first");
   if (k < 1 || k > fe->kmax) return set_error(CMAXB_ERR_INVALID, "k exceeds cfg.max_hypotheses");
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
   if (!(want_grad && fe->cfg.grad_mode == CMAXB_GRAD_DENSE) && !fe->force_multi_kernel)
-    return fe_eval_launch_fused(fe, omegas, k, want_grad);
+    return fe_eval_launch_fused(fe, omegas, k, want_grad, mode);
   // multi-kernel pipeline (DENSE gradients, A/B runs): one evaluation outstanding at a time
   if (!fe->inflight.empty())
     return set_error(CMAXB_ERR_STATE, "multi-kernel evaluation: fetch the outstanding evaluation first");
   CMAXB_TRY(fe_upload_omegas(fe, omegas, k));
-  fe->last_mega = false;
   cudaStream_t s = fe->stream;
   const int W = fe->cfg.width, H = fe->cfg.height, measure = fe->cfg.contrast_measure;
   if (want_grad && fe->cfg.grad_mode == CMAXB_GRAD_DENSE) {
@@ -478,50 +690,60 @@ extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, i
     CMAXB_TRY(fe_run_scatter_value(fe, k));
     CMAXB_TRY(fe_run_value_image(fe, k, fe->taps, want_grad != 0));
     if (want_grad) {
-      if (!fe->d_GQ) CMAXB_TRY(dev_alloc(&fe->d_GQ, (size_t)fe->kmax * fe->A));
       cudaError_t le = cudaSuccess;
       CMAXB_TRY(fe->prof.run(CMAXB_K_ADJOINT_BLUR, s, true, [&] {
-        le = launch_adjoint_blur<true>(s, k, fe->d_blur1, fe->A, W, H, fe->taps, fe->d_mean, measure, nullptr, fe->d_GQ);
+        le = launch_adjoint_blur<true>(s, k, fe->d_blur1, fe->A, W, H, fe->taps, fe->d_mean, measure, nullptr, fe->lanes[0].d_GQ);
       }));
       if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("adjoint_blur launch: ") + cudaGetErrorString(le));
-      const FeGeom g = fe_geom(fe);
+      const FeGeom g = fe_geom(fe, pk);
       CMAXB_TRY(fe->prof.run(CMAXB_K_FE_GATHER, s, true, [&] {
-        fe_gather_kernel<true><<<fe_event_grid(fe, k), kFeThreads, 0, s>>>(g, fe->d_omegas, nullptr, fe->d_GQ, fe->A, fe->d_gacc, fe->d_ticket2, fe->d_result);
+        fe_gather_kernel<true><<<fe_event_grid(pk.n, k), kFeThreads, 0, s>>>(g, fe->d_omegas, nullptr, fe->lanes[0].d_GQ, fe->A, fe->d_gacc, fe->d_ticket2, fe->d_result);
       }));
     }
   }
   CMAXB_CUDA_TRY(cudaMemcpyAsync(fe->h_result, fe->d_result, sizeof(double) * 4 * k, cudaMemcpyDeviceToHost, s));
-  fe->inflight.push_back(FeInflight{k, want_grad != 0, false, 0, 0ull, false});
-  fe->last_k = k; fe->last_grad = want_grad != 0; fe->pending = true;
+  pk.users += 1;
+  fe->inflight.push_back(FeInflight{k, want_grad != 0, false, 0, 0, 0ull, false, fe->cur});
+  fe->pending = true;
   return CMAXB_OK;
+}
+
+extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, int want_grad) {
+  return fe_eval_launch_mode(fe, omegas, k, want_grad, 1);
 }
 
 // waits for the OLDEST outstanding launch and pops it; *out = its record
 static int fe_wait_oldest(cmaxb_fe* fe, FeInflight* out) {
   if (fe->inflight.empty()) return set_error(CMAXB_ERR_STATE, "no evaluation launched");
   const FeInflight f = fe->inflight.front();
-  if (f.mega) {
+  if (f.fused) {
     // The fused kernel publishes its results in mapped pinned memory and then stores its sequence
-    // number (monotonic): spin on that word (~1 us) instead of paying the driver's stream-synchronise
+    // number (monotonic per lane): spin on that word (~1 us) instead of paying the driver's stream-synchronise
     // latency; check the stream now and then so that a faulted kernel cannot hang the caller.
-    volatile unsigned long long* done = fe->h_done;
+    FeLane& L = fe->lanes[f.lane];
+    volatile unsigned long long* done = L.h_done;
     unsigned long long spins = 0;
     while (*done < f.seq) {
       if ((++spins & 0x3fff) == 0) {
-        cudaError_t q = cudaStreamQuery(fe->stream);
+        cudaError_t q = cudaStreamQuery(L.stream);
         if (q == cudaSuccess) break;                       // finished (flag write raced the query) or faulted
-        if (q != cudaErrorNotReady) { fe->inflight.clear(); return set_error(CMAXB_ERR_CUDA, std::string("fused evaluation kernel: ") + cudaGetErrorString(q)); }
+        if (q != cudaErrorNotReady) { fe->inflight.clear(); for (auto& pp : fe->packets) pp.users = 0; return set_error(CMAXB_ERR_CUDA, std::string("fused evaluation kernel: ") + cudaGetErrorString(q)); }
       }
     }
-    if (*done < f.seq) CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
-    if (*done < f.seq) { fe->inflight.clear(); return set_error(CMAXB_ERR_CUDA, "fused evaluation kernel finished without publishing its result"); }
+    if (*done < f.seq) CMAXB_CUDA_TRY(cudaStreamSynchronize(L.stream));
+    if (*done < f.seq) { fe->inflight.clear(); for (auto& pp : fe->packets) pp.users = 0; return set_error(CMAXB_ERR_CUDA, "fused evaluation kernel finished without publishing its result"); }
+    L.inflight -= 1;
+    if (L.h_done[1]) {
+      fe->inflight.clear(); for (auto& pp : fe->packets) pp.users = 0;
+      return set_error(CMAXB_ERR_CUDA, L.h_done[1] == 2 ? "fused evaluation kernel: tile copy (TMA) timed out" : "fused evaluation kernel: grid barrier timed out");
+    }
   } else {
     CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
   }
   fe->inflight.pop_front();
-  if (fe->inflight.empty() && (!f.mega || *fe->h_done >= fe->seq)) fe->pending = false;   // nothing of ours is left on the stream
+  fe->packets[f.pkt].users -= 1;
   *out = f;
-  return fe_check_packet_flags(fe);
+  return fe_check_packet_flags(fe, fe->packets[f.pkt]);
 }
 
 extern "C" int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grads3k) {
@@ -529,7 +751,7 @@ extern "C" int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grad
   FeInflight f;
   CMAXB_TRY(fe_wait_oldest(fe, &f));
   if (f.xchg && *fe->h_xerr) return set_error(CMAXB_ERR_CUDA, "result exchange: a peer's rows did not arrive (timeout)");
-  const double* res = f.mega ? fe->h_mega_result + (long long)f.slot * fe->kmax * 4 : fe->h_result;
+  const double* res = f.fused ? fe->h_ring + (long long)f.slot * fe->kmax * 4 : fe->h_result;
   for (int h = 0; h < f.k; ++h) {
     contrasts[h] = res[4 * h];
     if (grads3k && f.grad)
@@ -544,9 +766,9 @@ extern "C" int cmaxb_fe_exchange_init(cmaxb_fe* fe, int world, int rank, void* h
   if (world < 1 || world > kXMaxWorld || rank < 0 || rank >= world) return set_error(CMAXB_ERR_INVALID, "bad world / rank (at most 8 ranks)");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
-  CMAXB_TRY(fe_drain_stream(fe));
+  CMAXB_TRY(fe_drain(fe));
   if (fe->x_local) return set_error(CMAXB_ERR_STATE, "exchange already initialised");
-  const size_t need = sizeof(ulonglong2) * 2 * (size_t)world * fe->kmax * 4;
+  const size_t need = sizeof(unsigned long long) * 8 * (size_t)kXSlots * world * fe->kmax;
   size_t bytes = (size_t)2 << 20;            // a whole 2 MiB block: the IPC handle exports nothing else
   while (bytes < need) bytes <<= 1;
   CMAXB_CUDA_TRY(cudaMalloc((void**)&fe->x_local, bytes));
@@ -564,14 +786,14 @@ extern "C" int cmaxb_fe_exchange_connect(cmaxb_fe* fe, const void* handles, doub
   if (!fe || !handles) return set_error(CMAXB_ERR_INVALID, "null argument");
   if (!fe->x_local) return set_error(CMAXB_ERR_STATE, "call cmaxb_fe_exchange_init first");
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
-  CMAXB_TRY(fe_drain_stream(fe));
+  CMAXB_TRY(fe_drain(fe));
   for (int r = 0; r < fe->x_world; ++r) {
     if (r == fe->x_rank) { fe->x_peer[r] = fe->x_local; continue; }
     cudaIpcMemHandle_t h;
     std::memcpy(&h, (const char*)handles + 64 * r, 64);
     void* ptr = nullptr;
     CMAXB_CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    fe->x_peer[r] = (ulonglong2*)ptr;
+    fe->x_peer[r] = (unsigned long long*)ptr;
   }
   if (!fe->h_xall) {
     CMAXB_CUDA_TRY(cudaHostAlloc((void**)&fe->h_xall, sizeof(double) * 4 * (size_t)fe->kmax * fe->x_world * kFeRing, cudaHostAllocMapped));
@@ -588,8 +810,8 @@ extern "C" int cmaxb_fe_exchange_connect(cmaxb_fe* fe, const void* handles, doub
 extern "C" int cmaxb_fe_exchange_close(cmaxb_fe* fe) {
   if (!fe) return set_error(CMAXB_ERR_INVALID, "null argument");
   cudaSetDevice(fe->device);
-  if (fe->stream) cudaStreamSynchronize(fe->stream);
-  fe->pending = false;
+  fe->pending = true;
+  fe_drain(fe);
   fe->x_on = false;
   for (int r = 0; r < fe->x_world; ++r) {
     if (r != fe->x_rank && fe->x_peer[r]) cudaIpcCloseMemHandle(fe->x_peer[r]);
@@ -613,7 +835,7 @@ extern "C" int cmaxb_fe_eval_fetch_all(cmaxb_fe* fe, double* rows) {
 
 extern "C" int cmaxb_fe_eval_batch(cmaxb_fe* fe, const double* omegas, int k, double* contrasts, double* grads3k) {
   if (fe && !fe->inflight.empty()) return set_error(CMAXB_ERR_STATE, "outstanding cmaxb_fe_eval_launch calls: fetch them first");
-  CMAXB_TRY(cmaxb_fe_eval_launch(fe, omegas, k, grads3k != nullptr));
+  CMAXB_TRY(fe_eval_launch_mode(fe, omegas, k, grads3k != nullptr, 0));
   return cmaxb_fe_eval_fetch(fe, contrasts, grads3k);
 }
 
@@ -623,7 +845,8 @@ extern "C" int cmaxb_fe_eval(cmaxb_fe* fe, const double omega[3], double* contra
 
 extern "C" int cmaxb_fe_get_iwe(cmaxb_fe* fe, const double omega[3], int blurred, float* out) {
   if (!fe || !omega || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
-  if (!fe->have_packet) return set_error(CMAXB_ERR_STATE, "no event packet");
+  if (!fe->packets[fe->cur].have) return set_error(CMAXB_ERR_STATE, "no event packet");
+  if (!fe->inflight.empty()) return set_error(CMAXB_ERR_STATE, "outstanding cmaxb_fe_eval_launch calls: fetch them first");
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
   CMAXB_TRY(fe_upload_omegas(fe, omega, 1));
   CMAXB_TRY(fe_run_scatter_value(fe, 1));
@@ -637,7 +860,8 @@ extern "C" int cmaxb_fe_get_iwe(cmaxb_fe* fe, const double omega[3], int blurred
 
 extern "C" int cmaxb_fe_get_deriv(cmaxb_fe* fe, const double omega[3], int blurred, float* out) {
   if (!fe || !omega || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
-  if (!fe->have_packet) return set_error(CMAXB_ERR_STATE, "no event packet");
+  if (!fe->packets[fe->cur].have) return set_error(CMAXB_ERR_STATE, "no event packet");
+  if (!fe->inflight.empty()) return set_error(CMAXB_ERR_STATE, "outstanding cmaxb_fe_eval_launch calls: fetch them first");
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
   CMAXB_TRY(fe_upload_omegas(fe, omega, 1));
   CMAXB_TRY(fe_run_scatter_dense(fe, 1));
@@ -664,22 +888,48 @@ extern "C" int cmaxb_fe_get_deriv(cmaxb_fe* fe, const double omega[3], int blurr
 
 extern "C" int cmaxb_fe_get_cells(cmaxb_fe* fe, const double omega[3], int32_t* out) {
   if (!fe || !omega || !out) return set_error(CMAXB_ERR_INVALID, "null argument");
-  if (!fe->have_packet) return set_error(CMAXB_ERR_STATE, "no event packet");
+  const FePacket& pk = fe->packets[fe->cur];
+  if (!pk.have) return set_error(CMAXB_ERR_STATE, "no event packet");
   CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
-  if (fe->n == 0) return CMAXB_OK;
+  if (pk.n == 0) return CMAXB_OK;
   CMAXB_TRY(fe_upload_omegas(fe, omega, 1));
-  if ((size_t)fe->n > fe->cells_cap) {
+  if ((size_t)pk.n > fe->cells_cap) {
     cudaFree(fe->d_cells); fe->d_cells = nullptr; fe->cells_cap = 0;
-    CMAXB_TRY(dev_alloc(&fe->d_cells, (size_t)fe->n));
-    fe->cells_cap = (size_t)fe->n;
+    CMAXB_TRY(dev_alloc(&fe->d_cells, (size_t)pk.n));
+    fe->cells_cap = (size_t)pk.n;
   }
   cudaStream_t s = fe->stream;
-  const FeGeom g = fe_geom(fe);
+  const FeGeom g = fe_geom(fe, pk);
   CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-    fe_cells_kernel<<<(unsigned)((fe->n + 255) / 256), 256, 0, s>>>(g, fe->d_omegas, fe->d_cells);
+    fe_cells_kernel<<<(unsigned)((pk.n + 255) / 256), 256, 0, s>>>(g, fe->d_omegas, fe->d_cells);
   }));
-  CMAXB_CUDA_TRY(cudaMemcpyAsync(out, fe->d_cells, sizeof(int) * fe->n, cudaMemcpyDeviceToHost, s));
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(out, fe->d_cells, sizeof(int) * pk.n, cudaMemcpyDeviceToHost, s));
   CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  return CMAXB_OK;
+}
+
+// lanes_fork: every throughput lane's stream waits for the work queued so far on the main stream (e.g. a timing event);
+// lanes_join: the main stream waits for everything queued so far on the throughput lanes.
+extern "C" int cmaxb_fe_lanes_fork(cmaxb_fe* fe) {
+  if (!fe) return set_error(CMAXB_ERR_INVALID, "null argument");
+  CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  if (fe->nlanes <= 1) return CMAXB_OK;
+  CMAXB_CUDA_TRY(cudaEventRecord(fe->fork_ev, fe->stream));
+  for (int l = 1; l <= fe->nlanes; ++l) {
+    CMAXB_TRY(fe_lane_prepare(fe, l));
+    CMAXB_CUDA_TRY(cudaStreamWaitEvent(fe->lanes[l].stream, fe->fork_ev, 0));
+  }
+  return CMAXB_OK;
+}
+extern "C" int cmaxb_fe_lanes_join(cmaxb_fe* fe) {
+  if (!fe) return set_error(CMAXB_ERR_INVALID, "null argument");
+  CMAXB_CUDA_TRY(cudaSetDevice(fe->device));
+  if (fe->nlanes <= 1) return CMAXB_OK;
+  for (int l = 1; l <= fe->nlanes; ++l) {
+    if (!fe->lanes[l].ready) continue;
+    CMAXB_CUDA_TRY(cudaEventRecord(fe->join_ev, fe->lanes[l].stream));
+    CMAXB_CUDA_TRY(cudaStreamWaitEvent(fe->stream, fe->join_ev, 0));
+  }
   return CMAXB_OK;
 }
 
@@ -691,20 +941,30 @@ extern "C" int cmaxb_fe_profile(cmaxb_fe* fe, int enable) {
 }
 extern "C" int cmaxb_fe_set_result_mirror(cmaxb_fe* fe, double* device_ptr) {
   if (!fe) return set_error(CMAXB_ERR_INVALID, "null argument");
-  if (fe->pending) { CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream)); fe->pending = false; }
+  CMAXB_TRY(fe_drain(fe));
   fe->d_mirror = device_ptr;
   return CMAXB_OK;
 }
 extern "C" int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10) {
   if (!fe || !us10) return set_error(CMAXB_ERR_INVALID, "null argument");
-  CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
+  fe->pending = true;
+  CMAXB_TRY(fe_drain(fe));
+  const FeLane& L = fe->lanes[0];
   for (int i = 0; i < 10; ++i)
-    us10[i] = (fe->h_phase && fe->h_phase[i] && fe->h_phase[0]) ? (double)(fe->h_phase[i] - fe->h_phase[0]) * 1e-3 : -1.0;
+    us10[i] = (i < 8 && L.h_phase && L.h_phase[i] && L.h_phase[0]) ? (double)(L.h_phase[i] - L.h_phase[0]) * 1e-3 : -1.0;
   return CMAXB_OK;
 }
 extern "C" int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms, uint64_t* launches) {
   if (!fe || !ms || !launches) return set_error(CMAXB_ERR_INVALID, "null argument");
   for (int i = 0; i < CMAXB_K_COUNT; ++i) { ms[i] = fe->prof.ms[i]; launches[i] = fe->prof.launches[i]; }
+  return CMAXB_OK;
+}
+/* geometry of the fused launches: [0] whole-grid CTAs, [1] throughput-lane CTAs, [2] lanes, [3] TMA staging on/off,
+ * [4] tile height (whole grid), [5] tile height (lane), [6] gather records in use by the last policy (-1 auto, 0, 1) */
+extern "C" int cmaxb_fe_launch_info(cmaxb_fe* fe, int32_t* info7) {
+  if (!fe || !info7) return set_error(CMAXB_ERR_INVALID, "null argument");
+  info7[0] = fe->grid[0]; info7[1] = fe->grid[1]; info7[2] = fe->nlanes; info7[3] = fe->use_tma ? 1 : 0;
+  info7[4] = fe->th[0]; info7[5] = fe->th[1]; info7[6] = fe->cache_mode;
   return CMAXB_OK;
 }
 

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kImgThreads)
 blur_reduce_kernel(Src src, int W, int H, Taps taps, typename PixT<C>::type* out, long long out_stride_h,
                    ReduceOut ro, int measure, float4* zero_ptr = nullptr, long long zero_stride_h = 0) {
   using Pix = typename PixT<C>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int r = (R >= 0) ? R : taps.r;
   const int IW = kTW + 2 * r, IH = kTH + 2 * r;
   // quad sources: the cells of the tile (+halo+1) are staged once as float4 (one 16-byte request per
@@ -381,7 +381,7 @@ template <bool QUAD_OUT, int R = -1>
 __global__ void __launch_bounds__(kImgThreads)
 adjoint_blur_kernel(const float* __restrict__ blurred, long long stride_h, int W, int H, Taps taps,
                     const double* __restrict__ mean, int measure, float* __restrict__ G, float4* __restrict__ GQ) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int r = (R >= 0) ? R : taps.r;
   const int IW = kTW + 1 + 2 * r, IH = kTH + 1 + 2 * r;   // one extra row/column for the quad packing
   constexpr int OW = kTW + 1, OH = kTH + 1;

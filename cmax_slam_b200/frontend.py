@@ -18,14 +18,15 @@ class AngVelEstimatorCMax:
     """Device-resident front-end contrast functor (one handle = one CUDA stream)."""
 
     def __init__(self, width, height, K4, lut_xyz, blur_sigma=1.0, event_batch_size=100, contrast_measure=0,
-                 grad_mode=GRAD_ADJOINT, device=0, stream=None, max_hypotheses=1):
+                 grad_mode=GRAD_ADJOINT, device=0, stream=None, max_hypotheses=1, lanes=0, packet_slots=1):
         self._L = _capi.lib()
         lut = np.ascontiguousarray(lut_xyz, dtype=np.float64).reshape(-1, 3)
         if lut.shape[0] != width * height:
             raise ValueError("lut_xyz must hold width*height bearing vectors")
         cfg = _capi.FeCfg(width, height, K4[0], K4[1], K4[2], K4[3], lut.ctypes.data, float(blur_sigma),
                           int(event_batch_size), int(contrast_measure), int(grad_mode), int(device),
-                          None if stream is None else C.c_void_p(int(stream)), int(max_hypotheses))
+                          None if stream is None else C.c_void_p(int(stream)), int(max_hypotheses), int(lanes),
+                          int(packet_slots))
         h = C.c_void_p()
         _capi.check(self._L.cmaxb_fe_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -46,10 +47,11 @@ class AngVelEstimatorCMax:
     __del__ = close
 
     # -- packet ---------------------------------------------------------------------------------
-    def set_packet(self, events, t_ref_sec, wait=True):
+    def set_packet(self, events, t_ref_sec, wait=True, view=False):
         """events: numpy structured array with the 16-byte dvs_msgs::Event layout (synth.EVENT_DTYPE)
-        or a (ptr, n) tuple of pinned host memory; t_ref_sec = time_packet_.toSec().  wait=False queues the
-        upload and returns (the validation verdict comes with the next evaluation)."""
+        or a (ptr, n) tuple of pinned host / device memory; t_ref_sec = time_packet_.toSec().  wait=False queues the
+        upload and returns (the validation verdict comes with the next evaluation).  view=True: (ptr, n) is DEVICE
+        memory that is used in place (cmaxb_fe_set_packet_view)."""
         if isinstance(events, tuple):
             ptr, n = events
         else:
@@ -58,9 +60,25 @@ class AngVelEstimatorCMax:
                 raise ValueError("events must be 16-byte dvs_msgs::Event records")
             self._ev_keep = ev
             ptr, n = ev.ctypes.data, len(ev)
-        fn = self._L.cmaxb_fe_set_packet if wait else self._L.cmaxb_fe_set_packet_async
+        fn = self._L.cmaxb_fe_set_packet_view if view else (self._L.cmaxb_fe_set_packet if wait else self._L.cmaxb_fe_set_packet_async)
         _capi.check(fn(self._h, C.c_void_p(ptr), n, float(t_ref_sec)))
         self.n_events = n
+
+    def select_packet(self, slot):
+        """Resident packet slot (0 .. packet_slots-1) the following set_packet / eval / getter calls act on."""
+        _capi.check(self._L.cmaxb_fe_select_packet(self._h, int(slot)))
+
+    def lanes_fork(self):
+        _capi.check(self._L.cmaxb_fe_lanes_fork(self._h))
+
+    def lanes_join(self):
+        _capi.check(self._L.cmaxb_fe_lanes_join(self._h))
+
+    def launch_info(self):
+        info = np.zeros(7, np.int32)
+        _capi.check(self._L.cmaxb_fe_launch_info(self._h, info.ctypes.data_as(C.POINTER(C.c_int32))))
+        return {"grid_full": int(info[0]), "grid_lane": int(info[1]), "lanes": int(info[2]), "tma": bool(info[3]),
+                "tile_h_full": int(info[4]), "tile_h_lane": int(info[5]), "gather_records": int(info[6])}
 
     # -- cost ------------------------------------------------------------------------------------
     def eval(self, ang_vel, want_grad=True):
@@ -80,7 +98,7 @@ class AngVelEstimatorCMax:
         return c, (g if want_grad else None)
 
     def eval_launch(self, ang_vels, want_grad=True):
-        """Queue one evaluation (up to 4 may be outstanding); results come back in launch order from eval_fetch."""
+        """Queue one evaluation (up to 8 may be outstanding); results come back in launch order from eval_fetch."""
         om = np.ascontiguousarray(ang_vels, dtype=np.float64).reshape(-1, 3)
         k = om.shape[0]
         self._om[:k] = om

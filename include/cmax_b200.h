@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CMAXB_VERSION 100
+#define CMAXB_VERSION 200
 
 typedef enum cmaxb_status {
   CMAXB_OK = 0,
@@ -75,6 +75,10 @@ typedef struct cmaxb_fe_cfg {
   int32_t device;            /* CUDA device ordinal */
   void* stream;              /* optional cudaStream_t to run on; NULL = library-owned stream */
   int32_t max_hypotheses;    /* capacity of eval_batch (<=0: 1) */
+  int32_t lanes;             /* throughput lanes of cmaxb_fe_eval_launch: 0 = default (3); 1 = none, every evaluation runs on
+                                the handle's stream with the whole GPU; 2..4 = that many library-owned streams, each launch on
+                                a partial grid so that consecutive evaluations overlap on the device */
+  int32_t packet_slots;      /* resident packets (cmaxb_fe_select_packet); 0 = 1 */
 } cmaxb_fe_cfg;
 
 int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out);
@@ -92,6 +96,15 @@ int cmaxb_fe_set_packet(cmaxb_fe* fe, const cmaxb_event* events, size_t n, doubl
  * evaluations of packet i. */
 int cmaxb_fe_set_packet_async(cmaxb_fe* fe, const cmaxb_event* events, size_t n, double t_ref_sec);
 
+/* Same as _async for events that ALREADY live in device memory of the handle's GPU (e.g. a device-resident event store,
+ * cmaxb_stream_*_device): nothing is copied, the library reads the caller's buffer in place, which must stay valid and
+ * unchanged until the slot's next set_packet.  Overlapping packets of one store so cross PCIe once. */
+int cmaxb_fe_set_packet_view(cmaxb_fe* fe, const cmaxb_event* device_events, size_t n, double t_ref_sec);
+/* A handle holds cfg.packet_slots resident packets; set_packet*, the evaluations and the getters act on the selected
+ * slot (default 0).  An evaluation keeps the slot it was launched on, so packet i+1 can be uploaded into another slot
+ * while packet i is still being evaluated. */
+int cmaxb_fe_select_packet(cmaxb_fe* fe, int slot);
+
 /* One cost evaluation = computeImageOfWarpedEvents + computeContrast.  grad3 == NULL => value
  * only (the local_contrast_f path, local_optim_contrast_gsl.cpp:58-63). */
 int cmaxb_fe_eval(cmaxb_fe* fe, const double omega[3], double* contrast, double* grad3);
@@ -104,9 +117,14 @@ int cmaxb_fe_eval_batch(cmaxb_fe* fe, const double* omegas, int k, double* contr
  * results (FIFO).  Up to CMAXB_FE_MAX_OUTSTANDING launches may be queued before the first fetch (each has its
  * own result slot in mapped host memory), so consecutive evaluations run back to back on the device with no
  * host round trip between them; one more launch returns CMAXB_ERR_STATE. */
-#define CMAXB_FE_MAX_OUTSTANDING 4
+#define CMAXB_FE_MAX_OUTSTANDING 8
 int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, int want_grad);
 int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grads3k);
+/* With cfg.lanes >= 2 the launches above run on library-owned streams.  _fork makes those streams wait for the work
+ * queued so far on the handle's stream (cfg.stream), _join makes the handle's stream wait for the launches queued so
+ * far -- e.g. to bracket a batch of launches with events recorded on the handle's stream. */
+int cmaxb_fe_lanes_fork(cmaxb_fe* fe);
+int cmaxb_fe_lanes_join(cmaxb_fe* fe);
 
 /* Fused result exchange for hypothesis sharding across GPUs (BASELINE config C3): one process
  * per GPU, every rank holds the packet and evaluates its own hypotheses.  After connect, the evaluation kernel
@@ -399,9 +417,13 @@ enum {
 };
 int cmaxb_fe_profile(cmaxb_fe* fe, int enable);
 int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms /*CMAXB_K_COUNT*/, uint64_t* launches /*CMAXB_K_COUNT*/);
-/* Fused evaluation kernel, profiling enabled: microseconds from kernel entry (CTA 0) to each of its 10
- * phase boundaries (scatter end, barrier, blur end, barrier, ...; -1 = not reached) of the LAST launch. */
+/* Fused evaluation kernel, profiling enabled: microseconds from kernel entry (CTA 0) to the phase boundaries of the LAST
+ * synchronous evaluation: [1] scatter end, [2] grid barrier, [3] image phase end, [4] grid barrier, [5] gather end,
+ * [6] last CTA starts the final sums, [7] result published; [8], [9] unused; -1 = not reached. */
 int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10);
+/* fused launches: [0] CTAs of a whole-GPU launch, [1] CTAs of a throughput-lane launch, [2] throughput lanes,
+ * [3] TMA tile staging on, [4] / [5] image tile height of the two launch shapes, [6] gather-record policy (-1 auto, 0, 1) */
+int cmaxb_fe_launch_info(cmaxb_fe* fe, int32_t* info7);
 int cmaxb_be_profile(cmaxb_be* be, int enable);
 int cmaxb_be_kernel_times(cmaxb_be* be, double* ms, uint64_t* launches);
 const char* cmaxb_kernel_name(int kind);

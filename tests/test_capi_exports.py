@@ -45,7 +45,7 @@ def test_event_record_layout():
 
 def test_version_and_error_string():
     L = _capi.lib()
-    assert L.cmaxb_version() == 100
+    assert L.cmaxb_version() == 200
     assert isinstance(L.cmaxb_last_error(), bytes)
     assert L.cmaxb_kernel_name(1) == b"fe_scatter"
 

@@ -1,4 +1,4 @@
-"""Front-end launch ring (up to 4 evaluations queued before the first fetch), the f32 / f64 gather variants,
+"""Front-end launch ring (up to 8 evaluations queued before the first fetch), the two gather variants (per-event records / recomputed geometry),
 and the fused result exchange over peer memory (two processes sharing cuda:0, CUDA IPC) -- through the C ABI,
 against the CPU oracle."""
 import os
@@ -29,8 +29,9 @@ def test_launch_ring_fifo_matches_oracle(oracle):
     oms = synth.fe_hypotheses(pk, 12, sigma=0.3)
     a = oracle.fe_args(pk.events, pk.t_ref_sec, pk.lut, pk.width, pk.height, pk.K)
     co, go = oracle.fe_eval_batch(a, oms, True, n_threads=4)
-    # 4 launches of different shapes queued back to back: k=1 f+g, k=3 value, k=2 f+g, k=1 value
-    plan = [(slice(0, 1), True), (slice(1, 4), False), (slice(4, 6), True), (slice(6, 7), False)]
+    # 8 launches of different shapes queued back to back (they spread over the throughput lanes): k=1 f+g, k=3 value, k=2 f+g, k=1 value, ...
+    plan = [(slice(0, 1), True), (slice(1, 4), False), (slice(4, 6), True), (slice(6, 7), False),
+            (slice(7, 10), True), (slice(10, 11), False), (slice(11, 12), True), (slice(2, 4), True)]
     for sl, wg in plan:
         fe.eval_launch(oms[sl], wg)
     with pytest.raises(CmaxbError) as e:                      # ring full
@@ -84,9 +85,10 @@ np.save(sys.argv[2], np.concatenate([c, g.ravel(), [c1], g1]))
 '''
 
 
-def test_gather_f32_and_f64_both_meet_the_bar(oracle, tmp_path):
-    """The gather's Jacobian chain in f64 (default) and in f32 (CMAXB_FE_GATHER_F32=1) against the oracle; the
-    true angular velocity (gradient near its zero crossing) is among the hypotheses."""
+def test_gather_from_records_and_recomputed_both_meet_the_bar(oracle, tmp_path):
+    """The gradient gather streaming the scatter's per-event records (CMAXB_FE_CACHE=1) and recomputing the event
+    geometry (CMAXB_FE_CACHE=0), TMA tile staging on and off, against the oracle; the true angular velocity (gradient
+    near its zero crossing) is among the hypotheses."""
     pk = synth.fe_config("C1", scale=0.5)
     oms = np.concatenate([synth.fe_hypotheses(pk, 5, sigma=0.4), pk.omega_true[None, :]])
     a = oracle.fe_args(pk.events, pk.t_ref_sec, pk.lut, pk.width, pk.height, pk.K)
@@ -94,7 +96,8 @@ def test_gather_f32_and_f64_both_meet_the_bar(oracle, tmp_path):
     script = tmp_path / "g.py"
     script.write_text(_GATHER_WORKER)
     out = {}
-    for tag, env in (("f64", {}), ("f32", {"CMAXB_FE_GATHER_F32": "1"})):
+    for tag, env in (("records", {"CMAXB_FE_CACHE": "1"}), ("recomputed", {"CMAXB_FE_CACHE": "0"}),
+                     ("records_no_tma", {"CMAXB_FE_CACHE": "1", "CMAXB_FE_TMA": "0"}), ("one_lane", {"CMAXB_FE_LANES": "1"})):
         path = tmp_path / f"{tag}.npy"
         r = subprocess.run([sys.executable, str(script), ROOT, str(path)], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
@@ -105,8 +108,9 @@ def test_gather_f32_and_f64_both_meet_the_bar(oracle, tmp_path):
         assert (np.abs(g - go) <= RTOL * gmax + 1e-7 * np.abs(go).max()).all(), (tag, np.abs(g - go).max(), gmax.ravel())
         assert abs(c1 - co[5]) <= RTOL * co[5] and np.abs(g1 - go[5]).max() <= RTOL * gmax[5] + 1e-7 * np.abs(go).max()
         out[tag] = g
-    # the two variants agree far below the bar
-    assert np.abs(out["f32"] - out["f64"]).max() <= 2e-6 * np.abs(go).max()
+    # the variants agree far below the bar
+    assert np.abs(out["records"] - out["recomputed"]).max() <= 2e-6 * np.abs(go).max()
+    assert np.abs(out["records"] - out["records_no_tma"]).max() <= 2e-6 * np.abs(go).max()
 
 
 _XCHG_WORKER = r'''

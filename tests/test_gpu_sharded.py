@@ -107,3 +107,39 @@ def test_two_ranks_time_sharded_equals_unsharded(oracle, tmp_path):
     assert abs(r0[0] - ro["contrast"]) <= 1e-5 * ro["contrast"]
     assert np.abs(r0[5:] - ro["grad"]).max() <= 1e-5 * np.abs(ro["grad"]).max()
     be.close()
+
+
+def test_plain_eval_after_a_sharded_evaluation(oracle):
+    """A handle that ran begin/end (its IL assembled into the exchange plane) must return to the scatter's own
+    accumulators for plain evaluations -- at other parameters and after a new window (round-1 advisor finding:
+    il_is_plane was never reset, so the contrast came from the stale plane)."""
+    from cmax_slam_b200.backend import EventWarperCMax
+    w = _window()
+    rng = np.random.default_rng(3)
+    IGp = np.abs(rng.normal(0, 0.3, (64, 128))).astype(np.float32)
+    x = rng.normal(0, 0.02, 21)
+    x2 = rng.normal(0, 0.05, 21)
+    be = EventWarperCMax(64, 48, w.lut, 128, 64, spline_order=2)
+    ref = EventWarperCMax(64, 48, w.lut, 128, 64, spline_order=2)
+    for h in (be, ref):
+        h.set_window(w.events, w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.4)
+    be.eval_begin(x, True)
+    c_s, g_s = be.eval_end()
+    c_r, g_r = ref.eval(x, True)
+    assert abs(c_s - c_r) <= 1e-6 * abs(c_r) and np.abs(g_s - g_r).max() <= 1e-6 * np.abs(g_r).max()
+    # plain evaluation at OTHER parameters on the handle that was sharded
+    c2, g2 = be.eval(x2, True)
+    c2r, g2r = ref.eval(x2, True)
+    assert abs(c2 - c2r) <= 1e-9 * abs(c2r), (c2, c2r, c_s)
+    assert np.abs(g2 - g2r).max() <= 1e-7 * np.abs(g2r).max()
+    assert np.allclose(be.computeImageOfWarpedEvents(x2), ref.computeImageOfWarpedEvents(x2), rtol=0, atol=1e-4)
+    # ... and after a new window (half of the events)
+    n2 = 10000
+    for h in (be, ref):
+        h.set_window(w.events[:n2], w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.4)
+    c3, _ = be.eval(x2, True)
+    c3r, _ = ref.eval(x2, True)
+    assert abs(c3 - c3r) <= 1e-9 * abs(c3r)
+    a = oracle.be_args(w.events[:n2], w.lut, 64, 48, 128, 64, w.knots_xyzw, w.t0_ns, w.dt_ns, 2, w.n_fixed, w.tnext, IGp, 0.4)
+    assert abs(c3 - oracle.be_eval(a, x2, False)["contrast"]) <= 1e-5 * abs(c3)
+    be.close(); ref.close()
