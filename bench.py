@@ -246,6 +246,31 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ---- algorithmic bytes of the reference's DENSE algorithm per evaluation --------------------------------
+def b_alg_fe(n_ev, A, n_hyp=1, want_grad=True):
+    """16 N (events, once per device) + 8 A (1 + P) per hypothesis (every accumulator plane written once and read once;
+    P = 3 derivative planes) + 12 A_sensor (bearing LUT, the figure SURVEY uses)."""
+    P = 3 if want_grad else 0
+    return 16 * n_ev + 8 * A * (1 + P) * n_hyp + 12 * A
+
+
+def b_alg_be(n_ev, A, A_sensor, P):
+    """16 N + 8 A (1 + P) + 4 A (IGp read) + 12 A_sensor; P = 3 K_opt derivative bands."""
+    return 16 * n_ev + 8 * A * (1 + P) + 4 * A + 12 * A_sensor
+
+
+def roofline_block(alg_bytes, min_bytes, seconds, peak, peak_src, **extra):
+    """`frac` follows SURVEY 8(d): bytes of the reference's dense algorithm / time / measured HBM peak.  The adjoint
+    formulation this library runs needs fewer bytes (`adjoint_min_bytes` = 32 N + 24 A); that figure is beside it under
+    its own keys, never folded into `frac`."""
+    ach = alg_bytes / seconds / 1e9
+    out = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+           "algorithmic_bytes": alg_bytes, "seconds": seconds,
+           "adjoint_min_bytes": min_bytes, "adjoint_min_frac": (min_bytes / seconds / 1e9) / peak}
+    out.update(extra)
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -259,57 +284,53 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    pkt = synth.fe_config("C2")
-    n_ev = len(pkt.events)
-    oms = synth.fe_hypotheses(pkt, max(world, 1), seed=3, sigma=0.05)
-    omega = oms[rank]
+    peak, peak_src = load_peaks()
+    K, Wm = args.steps, args.warmup
+    R = max(1, args.rotation)
+    depth = max(1, min(args.depth, 8))
     grad_mode = GRAD_ADJOINT if args.grad_mode == "adjoint" else GRAD_DENSE
-    # A dedicated (non-default) torch stream: the library is handed THIS stream, so the L2 flush, the
-    # evaluation kernels, the NCCL all-reduce and the timing events are all ordered on one stream.
-    # (torch's default stream has handle 0, which the C ABI reads as "create your own stream".)
+
+    # ---- workload: C2 -- R distinct resident packets of 1M events on a 640x480 sensor -----------------------------------------
+    pkt = synth.fe_config("C2")
+    pkts = [pkt] + [synth.make_fe_packet(len(pkt.events), pkt.width, pkt.height, pkt.K, 2 + 10 * i, 20000, name="C2") for i in range(1, R)]
+    n_ev = len(pkt.events)
+    W, H, A = pkt.width, pkt.height, pkt.width * pkt.height
+    oms = synth.fe_hypotheses(pkt, max(world, 1) * 4, seed=3, sigma=0.05)
+    omega = oms[rank]
+    # A dedicated (non-default) torch stream: the library is handed THIS stream as its main stream (uploads, packet
+    # preparation, synchronous evaluations); cmaxb_fe_eval_launch runs on library-owned lane streams that are forked
+    # from / joined to it around the timed region, so the timing events on it bracket everything.
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    fe = AngVelEstimatorCMax(pkt.width, pkt.height, pkt.K, pkt.lut, blur_sigma=pkt.blur_sigma,
-                             event_batch_size=pkt.batch_size, grad_mode=grad_mode, device=local_rank,
-                             stream=stream.cuda_stream)
-    # pinned host copy of the packet (source of the e2e H2D copy)
-    ev_pinned = torch.empty(n_ev * 16, dtype=torch.uint8).pin_memory()
-    ev_pinned.numpy()[:] = pkt.events.view(np.uint8).reshape(-1)
-    ev_host = (ev_pinned.data_ptr(), n_ev)
-    fe.set_packet(ev_host, pkt.t_ref_sec)
-
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
-    # multi-GPU: the evaluation kernel also writes its (contrast, g) row into `mine` on the device; ONE NCCL
-    # collective per step combines the rows of all ranks (an all-gather == the all-reduce of a zero-padded
-    # [N,4] buffer the north star words) on the same stream, with no host hop.
-    gathered = torch.zeros(max(world, 1), 4, dtype=torch.float64, device=dev)
-    mine = torch.zeros(4, dtype=torch.float64, device=dev)
-    if world > 1:
-        fe.set_result_mirror(mine.data_ptr())
+    fe = AngVelEstimatorCMax(W, H, pkt.K, pkt.lut, blur_sigma=pkt.blur_sigma, event_batch_size=pkt.batch_size, grad_mode=grad_mode,
+                             device=local_rank, stream=stream.cuda_stream, lanes=args.lanes, packet_slots=R, max_hypotheses=32)
+    info = fe.launch_info()
+    pinned = []
+    for s_, p_ in enumerate(pkts):
+        buf = torch.empty(n_ev * 16, dtype=torch.uint8).pin_memory()
+        buf.numpy()[:] = p_.events.view(np.uint8).reshape(-1)
+        pinned.append(buf)
+        fe.select_packet(s_)
+        fe.set_packet((buf.data_ptr(), n_ev), p_.t_ref_sec)
+    fe.select_packet(0)
 
     use_p2p = world > 1 and args.collective == "p2p"
+    gathered = torch.zeros(max(world, 1), 4, dtype=torch.float64, device=dev)
+    mine = torch.zeros(4, dtype=torch.float64, device=dev)
     if use_p2p:
         # fused compute + all-gather: the evaluation kernel stores its row into every peer's exchange buffer over
         # NVLink (CUDA IPC mappings) and returns the rows of all ranks -- no separate collective launch
         fe.exchange_connect(gathered_dev_ptr=gathered.data_ptr())
-        fe.set_result_mirror(None)
+    elif world > 1:
+        fe.set_result_mirror(mine.data_ptr())
 
-    def launch_step():
-        fe.eval_launch(omega[None, :], True)
-        if world > 1 and not use_p2p:
-            dist.all_gather_into_tensor(gathered.view(-1), mine)
-
-    def fetch_step():
+    def fetch_one():
         if use_p2p:
             rows = fe.eval_fetch_all()
             return rows[rank, 0, 0], rows[rank, 0, 1:]
         c, g = fe.eval_fetch()
         return c[0], g[0]
-
-    def step_resident():
-        launch_step()
-        return fetch_step()
 
     def barrier():
         if world > 1:
@@ -319,262 +340,387 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    def timed(steps, warmup, do_flush, depth):
-        """K steps, each bracketed by CUDA events on the launching stream.  depth = evaluations queued on the
-        stream before the oldest result is read back (1: the host waits for every result before the next launch
-        -- the latency of one GSL callback; >= 2: consecutive evaluations run back to back on the device, the
-        host reads result i while evaluation i+1 runs -- throughput).  Every result is fetched inside the region."""
-        for _ in range(warmup):
-            step_resident()
-        barrier()
-        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        launches0 = _capi.launch_count()
-        sampler.active = True
-        wall0 = time.perf_counter()
-        outstanding = 0
-        for i in range(steps):
-            if do_flush:
-                flush.fill_(float(i))     # evict L2 between timed iterations (outside the event pair)
-            ev0[i].record(stream)
-            launch_step()
-            ev1[i].record(stream)
-            outstanding += 1
-            if outstanding >= depth:
-                fetch_step()
-                outstanding -= 1
-        while outstanding:
-            fetch_step()
-            outstanding -= 1
-        barrier()
-        wall = time.perf_counter() - wall0
-        sampler.active = False
-        launches = _capi.launch_count() - launches0
-        ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
-        total_ms = float(ms.sum())
-        if world > 1:
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-            lc = torch.tensor([launches], dtype=torch.int64, device=dev)
-            dist.all_reduce(lc)
-            launches = int(lc.item())
-        return total_ms, launches, wall, ms
+    def timed(steps, warmup, depth_, rot, want_grad=True, flush=None, k=1):
+        """`steps` evaluations between two CUDA events on the main stream (lane streams forked after the first, joined
+        before the second), a barrier + device synchronise on both sides.  depth_ = launches outstanding before the oldest
+        result is read back (1 = the synchronous GSL-callback pattern); rot = resident packets the steps rotate over (the
+        working set of 6 packets x (16 MB binned events + images) exceeds the 126 MB L2: no evaluation finds its packet in
+        cache); flush = a buffer written before every step instead (round-1 method, serialises the lanes)."""
+        om = oms[rank:rank + 1] if k == 1 else synth.fe_hypotheses(pkt, k, seed=5, sigma=0.05)
 
-    # sanity: the collective really delivers every rank's row
-    if use_p2p:
-        launch_step()
-        rows = fe.eval_fetch_all()[:, 0, :]
-        barrier()
-        assert np.array_equal(rows, gathered.cpu().numpy()), "device copy of the gathered rows != host copy"
-        assert np.all(rows[:, 0] > 0), "a rank's row is missing from the gathered buffer"
-        # every rank re-evaluates its right neighbour's hypothesis (again a symmetric, exchanged launch) and
-        # compares with the row the neighbour delivered
-        nb = (rank + 1) % world
-        fe.eval_launch(oms[nb][None, :], True)
-        rows_b = fe.eval_fetch_all()[:, 0, :]
-        assert np.allclose(rows[nb], rows_b[rank], rtol=1e-6, atol=1e-9 * abs(rows[nb, 0])), "exchanged row != local re-evaluation"
-        c_chk = float(rows[rank, 0])
-        barrier()
-    else:
-        c_chk, g_chk = step_resident()
-        barrier()
-        if world > 1:
-            rows = gathered.cpu().numpy()
-            assert abs(rows[rank, 0] - c_chk) <= 1e-12 * abs(c_chk) and np.allclose(rows[rank, 1:], g_chk, rtol=1e-12), "mirror row != fetched result"
-            assert np.all(rows[:, 0] > 0), "a rank's row is missing from the gathered buffer"
-
-    K, Wm = args.steps, args.warmup
-    depth = max(1, min(args.depth, 4))
-    total_ms, launches, wall, ms = timed(K, Wm, True, depth)
-    ms_per_step = total_ms / K
-    value = world * n_ev / (ms_per_step * 1e-3)
-    # same loop without the L2 flush (the optimiser's real regime: ~100-300 evals per packet, L2 warm)
-    warm_ms, _, _, _ = timed(K, 3, False, depth)
-    # latency of ONE synchronous evaluation (launch -> result on the host before the next launch), L2 warm
-    lat_ms, _, _, _ = timed(K, 3, False, 1)
-    # End to end through the C ABI with HOST buffers: every step uploads its 16 MB packet from pinned host memory
-    # (cmaxb_fe_set_packet_async: H2D copy + validation + batch table + binning), evaluates contrast + gradient and
-    # reads the result back.  Two handles on two streams are used alternately so that the upload of step i+1 overlaps
-    # the evaluation of step i (what a front-end thread does with the next packet); everything -- copies, L2 flush,
-    # kernels, collective -- is inside the timed span [start event, end event].
-    stream2 = torch.cuda.Stream(device=dev)
-    fe2 = AngVelEstimatorCMax(pkt.width, pkt.height, pkt.K, pkt.lut, blur_sigma=pkt.blur_sigma,
-                              event_batch_size=pkt.batch_size, grad_mode=grad_mode, device=local_rank,
-                              stream=stream2.cuda_stream)
-    mine2 = torch.zeros(4, dtype=torch.float64, device=dev)
-    gathered2 = torch.zeros(max(world, 1), 4, dtype=torch.float64, device=dev)
-    if use_p2p:
-        fe2.exchange_connect(gathered_dev_ptr=gathered2.data_ptr())
-    elif world > 1:
-        fe2.set_result_mirror(mine2.data_ptr())
-    lanes = [(fe, stream, mine), (fe2, stream2, mine2)]
-    # N > 1: the packet is the SAME on every rank (hypothesis sharding), so it crosses PCIe once in total: rank r
-    # uploads shard r (1/N of the events) from pinned host memory over its own PCIe link and the shards are
-    # all-gathered over NVLink (NCCL) into every rank's HBM; cmaxb_fe_set_packet_async then takes the device buffer.
-    shard_upload = world > 1 and args.upload == "sharded"
-    if shard_upload:
-        per = (n_ev + world - 1) // world
-        full_dev = [torch.zeros(world * per * 16, dtype=torch.uint8, device=dev) for _ in lanes]
-        lo, hi = rank * per * 16, min((rank + 1) * per, n_ev) * 16
-        host_shard = ev_pinned[lo:hi]
-
-    def upload(lane_idx):
-        lane = lanes[lane_idx]
-        if not shard_upload:
-            lane[0].set_packet(ev_host, pkt.t_ref_sec, wait=False)
-            return
-        with torch.cuda.stream(lane[1]):
-            buf = full_dev[lane_idx]
-            buf[lo:hi].copy_(host_shard, non_blocking=True)
-            dist.all_gather_into_tensor(buf, buf[rank * per * 16:(rank + 1) * per * 16])
-            lane[0].set_packet((buf.data_ptr(), n_ev), pkt.t_ref_sec, wait=False)
-
-    if shard_upload:   # the all-gathered packet must evaluate to the same contrast as the directly uploaded one
-        upload(0)
-        with torch.cuda.stream(lanes[0][1]):
-            lanes[0][0].eval_launch(omega[None, :], True)
-            c_sh = float(lanes[0][0].eval_fetch_all()[rank, 0, 0]) if use_p2p else float(lanes[0][0].eval_fetch()[0][0])
-        assert abs(c_sh - c_chk) <= 1e-6 * abs(c_chk), ("sharded upload changed the result", c_sh, c_chk)
-        barrier()
-
-    def e2e_run(steps, warmup):
-        """Every step: upload of the packet (pinned host -> device), L2 flush, evaluation, read-back of the result.  Two
-        lanes (handles / streams) alternate: while lane A evaluates step i the host reads the result of step i-1 and
-        queues the upload of step i+1 on lane B.  The evaluation kernels of the two lanes are chained with events so
-        that every rank runs them in the same order (they wait for their peers inside the kernel)."""
-        total = steps + warmup
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        done_ev = [torch.cuda.Event(), torch.cuda.Event()]
-
-        def fetch(lane):
-            if use_p2p:
-                lane[0].eval_fetch_all()
-            else:
-                lane[0].eval_fetch()
-
-        upload(0)
-        pending = None
-        for i in range(total):
-            ci = i % 2
-            cur = lanes[ci]
-            if i == warmup:
-                if pending is not None:
-                    fetch(lanes[pending])
-                    pending = None
-                barrier()
-                sampler.active = True
-                t0.record(cur[1])
-            with torch.cuda.stream(cur[1]):
-                if i > 0:
-                    cur[1].wait_event(done_ev[1 - ci])
-                flush.fill_(float(i))                                        # L2 flush, inside the timed span
-                cur[0].eval_launch(omega[None, :], True)
+        def loop(n):
+            out = 0
+            for i in range(n):
+                if rot > 1:
+                    fe.select_packet(i % rot)
+                if flush is not None:
+                    fe.lanes_join()
+                    flush.fill_(float(i))
+                    fe.lanes_fork()
+                fe.eval_launch(om, want_grad)
                 if world > 1 and not use_p2p:
-                    dist.all_gather_into_tensor(gathered.view(-1), cur[2])
-                done_ev[ci].record(cur[1])
-            if i == total - 1:
-                t1.record(cur[1])
-            if pending is not None:
-                fetch(lanes[pending])                                        # result of the PREVIOUS step (host read)
-            if i + 1 < total:
-                upload((i + 1) % 2)                                          # upload of the NEXT step's packet
-            pending = ci
-        fetch(lanes[pending])
+                    dist.all_gather_into_tensor(gathered.view(-1), mine)
+                out += 1
+                if out >= depth_:
+                    fetch_one() if k == 1 else fe.eval_fetch()
+                    out -= 1
+            while out:
+                fetch_one() if k == 1 else fe.eval_fetch()
+                out -= 1
+
+        loop(warmup)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = _capi.launch_count()
+        sampler.active = True
+        e0.record(stream)
+        fe.lanes_fork()
+        loop(steps)
+        fe.lanes_join()
+        e1.record(stream)
         barrier()
         sampler.active = False
-        ms = t0.elapsed_time(t1)
+        ms = e0.elapsed_time(e1)
+        launches = _capi.launch_count() - l0
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms
+            lc = torch.tensor([launches], dtype=torch.int64, device=dev)
+            dist.all_reduce(lc)
+            launches = int(lc.item())
+        fe.select_packet(0)
+        return ms, launches
 
-    e2e_steps = max(10, min(K, 200))
-    e2e_ms = e2e_run(e2e_steps, 3)
-    e2e_value = world * n_ev / (e2e_ms / e2e_steps * 1e-3)
-    torch.cuda.set_stream(stream)
-    fe.set_packet(ev_host, pkt.t_ref_sec)      # back to the resident packet for the profiled pass
+    # sanity: the collective really delivers every rank's row
+    fe.eval_launch(oms[rank:rank + 1], True)
+    if use_p2p:
+        rows = fe.eval_fetch_all()[:, 0, :]
+        barrier()
+        assert np.array_equal(rows, gathered.cpu().numpy()), "device copy of the gathered rows != host copy"
+        assert np.all(rows[:, 0] > 0), "a rank's row is missing from the gathered buffer"
+        c_chk = float(rows[rank, 0])
+    else:
+        c_chk, g_chk = fetch_one()
+        barrier()
 
-    # per-kernel device times (CUDA events on the launching stream, library profiler), rank 0
+    total_ms, launches = timed(K, Wm, depth, R)
+    ms_per_step = total_ms / K
+    value = world * n_ev / (ms_per_step * 1e-3)
+    extra = {}
+    if world == 1:
+        warm_ms, _ = timed(K, 3, depth, 1)                      # one resident packet: the optimiser's regime, L2 warm
+        lat_ms, _ = timed(K, 3, 1, 1)                           # synchronous evaluations (whole-GPU launches through cmaxb_fe_eval_launch/fetch)
+        val_ms, _ = timed(K, 3, depth, R, want_grad=False)      # value-only evaluations (local_contrast_f)
+        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+        ser_ms, _ = timed(min(K, 100), 3, 1, 1, flush=flush)    # round-1 method: 256 MiB L2 flush before every step
+        del flush
+        extra = {"l2_warm": {"ms_per_step": warm_ms / K, "value": n_ev / (warm_ms / K * 1e-3),
+                             "note": "the same loop on ONE resident packet (optimiser regime: 100-300 evaluations per packet)"},
+                 "latency_pipelined_1": {"us_per_eval": lat_ms / K * 1e3, "note": "depth 1: launch, wait for the rows on the host, next launch (lane launches)"},
+                 "value_only": {"ms_per_step": val_ms / K, "value": n_ev / (val_ms / K * 1e-3), "note": "contrast without gradient (local_contrast_f)"},
+                 "flushed_serial": {"ms_per_step": ser_ms / min(K, 100), "note": "round-1 method: L2 flushed (256 MiB fill, inside the timed span) before EVERY "
+                                    "evaluation, which serialises the lanes; includes the ~45 us fill"}}
+        # latency of the synchronous C-ABI call the GSL callback makes (cmaxb_fe_eval: whole-GPU grid on the main stream)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            fe.eval(omega, True)
+        extra["latency"] = {"us_per_eval": (time.perf_counter() - t0) / K * 1e6, "value": n_ev / ((time.perf_counter() - t0) / K),
+                            "note": "cmaxb_fe_eval: one synchronous contrast+gradient evaluation (the GSL callback), wall clock, L2 warm"}
+        t0 = time.perf_counter()
+        for _ in range(K):
+            fe.eval(omega, False)
+        extra["latency_value_only_us"] = (time.perf_counter() - t0) / K * 1e6
+
+    # ---- end to end ---------------------------------------------------------------------------------------------------
+    e2e = bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt, omega)
+
+    # ---- dominant kernel: CUDA-event time of the fused launch (library profiler: serialised whole-GPU launches, L2 cold) -----
+    fe.select_packet(0)
     fe.profile(True)
-    for i in range(min(K, 200)):
-        flush.fill_(float(i))
-        step_resident()
+    nprof = min(K, 100)
+    for i in range(nprof):
+        fe.select_packet(i % R)
+        fe.eval(omega, True)
     ktimes = fe.kernel_times()
+    phase = [float(x) for x in fe.phase_times()]
     fe.profile(False)
+    fe.select_packet(0)
+
+    configs = None
+    if not args.skip_configs:
+        configs = bench_configs(args, rank, world, local_rank, dev, stream, peak, peak_src, barrier)
     sampler.stop()
 
     if rank == 0:
-        peak, peak_src = load_peaks()
-        W, H, A = pkt.width, pkt.height, pkt.width * pkt.height
         per_kernel = {k: {"avg_us": v[0] / v[1] * 1e3, "launches": v[1]} for k, v in ktimes.items()}
-        kern = {k: v for k, v in per_kernel.items() if k != "zero"}
-        dom = max(kern, key=lambda k: kern[k]["avg_us"] * kern[k]["launches"])
-        # algorithmic bytes of the dominant kernel per launch (DESIGN.md section "Kernels")
-        alg = {
-            # fused evaluation (ADJOINT f+g): events + f64 LUT read by the scatter AND the gather pass;
-            # quad accumulator cleared + read (16 B/cell each), blurred image written + read (4 B),
-            # adjoint image GQ written + read (16 B)  -- DESIGN.md section 4
-            "fe_eval_fused": 2 * (16 * n_ev + 24 * A) + (16 + 16 + 4 + 4 + 16 + 16) * A,
-            "fe_scatter": 16 * n_ev + 24 * A + 16 * A,           # DENSE: events + LUT + (I,dI) accumulator
-            "blur_reduce": 16 * A,
-        }.get(dom, 0)
-        ncu_name = {"fe_eval_fused": "fe_eval_megakernel", "fe_scatter": "fe_scatter_kernel", "blur_reduce": "blur_reduce_kernel"}.get(dom, dom)
-        traffic, traffic_src = ncu_traffic_bytes(ncu_name)
-        dur_s = kern[dom]["avg_us"] * 1e-6
-        achieved = alg / dur_s / 1e9 if dur_s > 0 else 0.0
-        step_us_kernels = sum(v["avg_us"] * v["launches"] for v in per_kernel.values()) / max(1, min(K, 200))
+        dom = "fe_eval_fused"
+        dur_s = per_kernel[dom]["avg_us"] * 1e-6
+        traffic, traffic_src = ncu_traffic_bytes("fe_eval_fused_kernel")
+        alg = b_alg_fe(n_ev, A, 1, True)
+        roof = roofline_block(alg, 32 * n_ev + 24 * A, dur_s, peak, peak_src, kernel=dom, traffic=traffic, traffic_source=traffic_src,
+                              avg_launch_us=per_kernel[dom]["avg_us"], per_kernel=per_kernel,
+                              throughput_frac=(alg / (ms_per_step * 1e-3) / 1e9) / peak,
+                              phase_us={"scatter_end": phase[1], "barrier1": phase[2], "image_end": phase[3], "barrier2": phase[4],
+                                        "gather_end": phase[5], "final_start": phase[6], "published": phase[7],
+                                        "slowest_cta_scatter_end": phase[8], "slowest_cta_image_end": phase[9]},
+                              secondary=ncu_secondary("fe_eval_fused_kernel"),
+                              note="frac = SURVEY 8(d) bytes of the dense reference algorithm (16 N + 8 A (1+3) + 12 A = 29.5 MB) / the fused "
+                                   "kernel's CUDA-event time (one whole-GPU launch at a time, packet not in L2) / measured HBM peak; "
+                                   "throughput_frac = the same bytes / ms_per_step (three launches in flight).  The path is bound by f64 issue, "
+                                   "L2 latency and grid barriers, not by HBM (DESIGN.md section 4): the fraction is reported, not padded.")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 geometry / f32 images / f64 reductions", "data": "synthetic",
             "config": {"workload": "C2 front-end: 1M events, 640x480 IWE, single omega hypothesis per GPU, contrast+gradient",
                        "events": n_ev, "image": [W, H], "batch_size": pkt.batch_size, "blur_sigma": pkt.blur_sigma,
-                       "grad_mode": args.grad_mode, "l2": "flushed between timed iterations (256 MiB fill)",
+                       "grad_mode": args.grad_mode,
+                       "l2": f"no flush: the steps rotate over {R} distinct resident packets (16 MB of binned events each + three lanes' images, "
+                             f"> 126 MB L2), so no evaluation finds its packet in cache",
                        "parallelism": f"hypothesis-sharded x{world}" if world > 1 else "single GPU",
-                       "pipeline_depth": depth,
+                       "pipeline_depth": depth, "lanes": info["lanes"], "grid_ctas": [info["grid_full"], info["grid_lane"]], "tma": info["tma"],
                        "collective": ("none" if world == 1 else
-                                      "fused in the evaluation kernel: peer-to-peer stores of the [k,4] f64 rows into every rank's exchange buffer "
-                                      "over NVLink (CUDA IPC) + flag wait, one launch per step" if use_p2p else
+                                      "fused in the evaluation kernel: peer-to-peer stores of the [k,4] f64 rows (tagged 8-byte words) into every rank's "
+                                      "exchange buffer over NVLink (CUDA IPC) + tag wait, one launch per step" if use_p2p else
                                       "1 NCCL all-gather of the [N,4] f64 result rows per step, device-resident")},
-            "l2_warm": {"ms_per_step": warm_ms / K, "value": world * n_ev / (warm_ms / K * 1e-3),
-                        "note": "no L2 flush between iterations (optimiser regime)"},
-            "latency": {"us_per_eval": lat_ms / K * 1e3, "value": world * n_ev / (lat_ms / K * 1e-3),
-                        "note": "one synchronous contrast+gradient evaluation (the GSL callback): launch, wait for the result on the host, "
-                                "then the next launch; L2 warm"},
-            "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": (16 * n_ev + 24 * world) if shard_upload else world * (16 * n_ev + 24),
-                    "d2h_bytes_per_step": world * (32 * max(world, 1) + 4),
-                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "path": ("cmaxb_fe_set_packet_async + cmaxb_fe_eval through the C ABI; uploads double-buffered (two handles / streams), "
-                             "L2 flush inside the timed span; " +
-                             ("the replicated packet crosses PCIe once per step in total: every rank uploads 1/N of it from pinned host memory "
-                              "and the shards are all-gathered over NVLink (bytes = whole job)" if shard_upload else
-                              "every rank uploads the whole packet from pinned host memory (bytes = whole job)"))},
+            "e2e": e2e,
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "note": "the packet (35 MB) is L2 resident across evaluations: DRAM traffic is ~0 in steady state; "
-                                 "ncu's figure is a cold-cache replay.  The binding resources are L2 request rate / latency and "
-                                 "f64 issue (DESIGN.md section 4), so the HBM fraction is reported, not padded.",
-                         "secondary": ncu_secondary(ncu_name),
-                         "algorithmic_bytes_per_launch": alg, "avg_launch_us": kern[dom]["avg_us"],
-                         "kernel_share_of_step": kern[dom]["avg_us"] * kern[dom]["launches"] / max(1, min(K, 200)) / step_us_kernels,
-                         "per_kernel": per_kernel},
+            "roofline": roof,
             "clocks": sampler.summary(),
         }
+        line.update(extra)
+        if configs is not None:
+            line["configs"] = configs
         try:
-            line["cpu_baseline"] = cpu_baseline(pkt, omega) if world == 1 or True else None
+            line["cpu_baseline"] = cpu_baseline(pkt, omega)
         except Exception as e:  # the oracle is test infrastructure; its absence must not kill the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
         print(json.dumps(line), flush=True)
     fe.close()
-    fe2.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt, omega):
+    """End to end through the C ABI with HOST buffers, as the reference's front-end thread works: the DVS driver's messages
+    (200k events per 10 ms tick, page-locked host memory) are pushed into the event store, which copies every event to the
+    device ONCE (cmaxb_stream_push_ex, device ring); every tick the packet cutter hands out the overlapping 1M-event packet
+    as a view of that ring (cmaxb_stream_next_packet_device), the packet is prepared (validated, batch times, binned) and
+    evaluated (contrast + gradient), the result rows come back to the host.  Everything -- copies, preparation kernels,
+    evaluations, exchange -- lies between the two timing events.  value = events of the evaluated packets / time."""
+    import torch
+    import torch.distributed as dist
+    from cmax_slam_b200 import synth
+    from cmax_slam_b200.stream import EventStream
+    steps = max(10, min(args.steps, 40))
+    warm = 4
+    per_packet = len(pkt.events)
+    tick = 0.01
+    n_total = int((steps + warm + 8) * 2.0e5 + 1.6 * per_packet)
+    ev, _ = synth.make_fe_stream(n_total, pkt.width, pkt.height, pkt.K, 11 + rank)
+    pinned = torch.empty(len(ev) * 16, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = ev.view(np.uint8).reshape(-1)
+    base = pinned.data_ptr()
+    t_ns = ev["sec"].astype(np.int64) * 1_000_000_000 + ev["nsec"]
+    # message boundaries: one message per 10 ms tick (as the driver would deliver them)
+    edges = np.searchsorted(t_ns, t_ns[0] + (np.arange(1, steps + warm + 40) * int(tick * 1e9)))
+    edges = np.concatenate([[0], edges[edges < len(ev)], [len(ev)]])
+    st = EventStream(tick, per_packet, 1)
+    st.attach_device(dev.index, stream.cuda_stream, ring_events=8 * per_packet)
+    slots = fe._slots if hasattr(fe, "_slots") else None
+    nslots = 4
+    FL = EventStream.PUSH_BORROW | EventStream.PUSH_SORTED
+    state = {"msg": 0, "slot": 0, "out": 0, "packets": 0, "h2d": 0}
+    depth = 3
+
+    def fetch():
+        if use_p2p:
+            fe.eval_fetch_all()
+        else:
+            fe.eval_fetch()
+
+    def step():
+        """push the next message; evaluate every packet that became complete"""
+        m = state["msg"]
+        lo, hi = int(edges[m]), int(edges[m + 1])
+        st.eventsCallback((base + 16 * lo, hi - lo), FL)
+        state["h2d"] += 16 * (hi - lo)
+        state["msg"] = m + 1
+        got = 0
+        while True:
+            q = st.next_packet_device()
+            if q is None:
+                break
+            (ptr, n), tp, too_long = q
+            fe.select_packet(state["slot"] % nslots)
+            state["slot"] += 1
+            fe.set_packet((ptr, n), float(tp[0]) + 1e-9 * float(tp[1]), view=True)
+            fe.eval_launch(omega[None, :], True)
+            state["out"] += 1
+            got += 1
+            if state["out"] >= depth:
+                fetch()
+                state["out"] -= 1
+        return got
+
+    # fill the pipeline until packets come out steadily
+    while state["packets"] < warm:
+        state["packets"] += step()
+    while state["out"]:
+        fetch(); state["out"] -= 1
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    sampler.active = True
+    h0 = state["h2d"]
+    e0.record(stream)
+    fe.lanes_fork()
+    done = 0
+    n_steps = 0
+    while done < steps and state["msg"] + 1 < len(edges):
+        done += step()
+        n_steps += 1
+    while state["out"]:
+        fetch(); state["out"] -= 1
+    fe.lanes_join()
+    e1.record(stream)
+    barrier()
+    sampler.active = False
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    h2d = (state["h2d"] - h0) / max(done, 1)
+    st.close()
+    fe.select_packet(0)
+    return {"value": world * done * per_packet / (ms * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * (64 * max(world, 1) + 8),
+            "ms_per_step": ms / max(done, 1), "steps": done,
+            "path": "cmaxb_stream_push_ex (page-locked driver messages, 10 ms = ~190k events each, copied to the device ring once) -> "
+                    "cmaxb_stream_next_packet_device (overlapping 1M-event packet = ring view) -> cmaxb_fe_set_packet_view (validate, "
+                    "batch times, binning) -> cmaxb_fe_eval_launch / _fetch; one packet per step; the reference re-copies each packet "
+                    "out of its host vector (ang_vel_estimator.cpp:137-147) -- here every event crosses PCIe once",
+            "events_per_packet": per_packet, "new_events_per_step": h2d / 16}
+
+
+def bench_configs(args, rank, world, local_rank, dev, stream, peak, peak_src, barrier):
+    """The other BASELINE.json configs on this run's GPUs, each with the SURVEY 8(d) roofline of its own formula.
+    N = 1: C1, C3 (one GPU's share: 32 hypotheses per launch), C4, C5 (the whole window on one GPU).
+    N > 1: C3 as specified (256 hypotheses sharded over the ranks), C5 sharded by time."""
+    import torch
+    import torch.distributed as dist
+    from cmax_slam_b200 import synth
+    from cmax_slam_b200.backend import EventWarperCMax
+    from cmax_slam_b200.frontend import AngVelEstimatorCMax
+    out = {}
+
+    def wall(fn, n, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / n
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- C1: 1e5 events, 240x180 (the reference's CPU-runnable case) ------------------------------------------------------
+    if world == 1:
+        p1 = synth.fe_config("C1")
+        f1 = AngVelEstimatorCMax(p1.width, p1.height, p1.K, p1.lut, device=local_rank)
+        f1.set_packet(p1.events, p1.t_ref_sec)
+        w1 = p1.omega_true + np.array([0.2, -0.1, 0.15])
+        tg = wall(lambda: f1.eval(w1, True), 200, 10)
+        tv = wall(lambda: f1.eval(w1, False), 200, 10)
+
+        def thr(n):
+            outn = 0
+            for i in range(n):
+                f1.eval_launch(w1[None, :], True); outn += 1
+                if outn >= 6:
+                    f1.eval_fetch(); outn -= 1
+            while outn:
+                f1.eval_fetch(); outn -= 1
+        thr(30)
+        t0 = time.perf_counter(); thr(300); tt = (time.perf_counter() - t0) / 300
+        n1, A1 = len(p1.events), p1.width * p1.height
+        out["C1"] = {"workload": "front-end: 1e5 events, 240x180 IWE, 1 hypothesis", "latency_fg_us": tg * 1e6, "latency_value_us": tv * 1e6,
+                     "throughput_fg_us_per_eval": tt * 1e6, "events_per_s": n1 / tt,
+                     "roofline": roofline_block(b_alg_fe(n1, A1), 32 * n1 + 24 * A1, tg, peak, peak_src,
+                                                note="latency of one synchronous evaluation; 3.5 MB of algorithmic bytes: launch-latency bound")}
+        f1.close()
+
+    # ---- C3: 1e6 events x 256 hypotheses over 8 GPUs = 32 hypotheses per launch per GPU ---------------------------------------
+    p3 = synth.fe_config("C3")
+    n3, A3 = len(p3.events), p3.width * p3.height
+    k_total = 256 if world > 1 else 32
+    k_rank = k_total // world
+    f3 = AngVelEstimatorCMax(p3.width, p3.height, p3.K, p3.lut, device=local_rank, max_hypotheses=32, lanes=1)
+    f3.set_packet(p3.events, p3.t_ref_sec)
+    om3 = synth.fe_hypotheses(p3, k_total, seed=3, sigma=0.5)[rank::world]
+
+    def c3(grad):
+        for c0 in range(0, k_rank, 32):
+            f3.eval_batch(om3[c0:c0 + 32], grad)
+    barrier()
+    tg = maxr(wall(lambda: c3(True), 10, 2))
+    barrier()
+    tv = maxr(wall(lambda: c3(False), 10, 2))
+    out["C3"] = {"workload": f"front-end sweep: 1e6 events x {k_total} hypotheses over {world} GPU(s), {k_rank} per GPU in launches of 32",
+                 "fg_ms": tg * 1e3, "value_ms": tv * 1e3, "warped_events_per_s": k_total * n3 / tg, "warped_events_per_s_value_only": k_total * n3 / tv,
+                 "roofline": roofline_block(b_alg_fe(n3, A3, k_rank), 32 * n3 * k_rank + 24 * A3 * k_rank, tg, peak, peak_src,
+                                            note="per GPU: 16 N once + 8 A (1+3) per hypothesis + LUT")}
+    f3.close()
+
+    # ---- C4: back-end window, 1e7 events, 64 knots, 1280x720 panorama ----------------------------------------------------
+    def be_case(name, label, seed):
+        w = synth.be_config(name, device=str(dev))
+        rng = np.random.default_rng(seed)
+        IGp = np.abs(rng.normal(0, 0.3, (w.pano_height, w.pano_width))).astype(np.float32)
+        x = rng.normal(0, 0.01, 3 * (len(w.knots_xyzw) - w.n_fixed))
+        P = len(x)
+        N, A, As = len(w.events), w.pano_width * w.pano_height, w.sensor_width * w.sensor_height
+        if world == 1:
+            be = EventWarperCMax(w.sensor_width, w.sensor_height, w.lut, w.pano_width, w.pano_height, spline_order=2, device=local_rank)
+            be.set_window(w.events, w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.5)
+            tg = wall(lambda: be.eval(x, True), 8, 2)
+            tv = wall(lambda: be.eval(x, False), 8, 2)
+            c, g = be.eval(x, True)
+            be.close()
+            how = "one GPU"
+        else:
+            from cmax_slam_b200.dist import ShardedEventWarper
+            torch.cuda.set_stream(stream)
+            sh = ShardedEventWarper(EventWarperCMax(w.sensor_width, w.sensor_height, w.lut, w.pano_width, w.pano_height, spline_order=2,
+                                                    device=local_rank, stream=stream.cuda_stream))
+            sh.set_window(w.events, w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.5)
+            barrier()
+            tg = maxr(wall(lambda: sh.eval(x, True), 8, 2))
+            barrier()
+            tv = maxr(wall(lambda: sh.eval(x, False), 8, 2))
+            c, g = sh.eval(x, True)
+            sh.w.close()
+            how = f"sharded by time over {world} GPUs (IL plane all-reduced over NVLink, gradient all-reduced)"
+        out[name] = {"workload": label + ", " + how, "events": N, "knots": len(w.knots_xyzw), "pano": [w.pano_width, w.pano_height],
+                     "fg_ms": tg * 1e3, "value_ms": tv * 1e3, "events_per_s": N / tg, "events_per_s_value_only": N / tv,
+                     "contrast": c, "grad_finite": bool(np.all(np.isfinite(g))),
+                     "roofline": roofline_block(b_alg_be(N, A, As, P) / world, (32 * N + 24 * A) / world, tg, peak, peak_src,
+                                                note="SURVEY 8(d) dense-band bytes (16 N + 8 A (1+P) + 4 A + 12 A_s, P = 3 K_opt) per GPU; the adjoint "
+                                                     "formulation run here keeps no bands: adjoint_min_bytes = 32 N + 24 A")}
+
+    be_case("C4", "back-end BA: 1e7 events, 64 knots, 1280x720 panorama", 4)
+    if not args.skip_c5:
+        be_case("C5", "back-end BA: 5e7 events, 256 knots, 4096x2048 panorama", 5)
+    return out
 
 
 def main():
@@ -584,8 +730,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grad-mode", default="adjoint", choices=["dense", "adjoint"])
-    ap.add_argument("--depth", type=int, default=2, help="evaluations queued on the stream before the oldest result is read (1 = synchronous)")
-    ap.add_argument("--upload", default="sharded", choices=["sharded", "replicated"], help="N>1 e2e: upload 1/N of the (replicated) packet per rank + NVLink all-gather, or the whole packet on every rank")
+    ap.add_argument("--depth", type=int, default=6, help="evaluations outstanding before the oldest result is read (1 = synchronous)")
+    ap.add_argument("--lanes", type=int, default=0, help="throughput lanes of cmaxb_fe_eval_launch (0 = library default 3, 1 = none)")
+    ap.add_argument("--rotation", type=int, default=6, help="distinct resident packets the timed steps rotate over (working set > L2)")
+    ap.add_argument("--skip-configs", action="store_true", help="only the C2 headline (no C1 / C3 / C4 / C5 block)")
+    ap.add_argument("--skip-c5", action="store_true", help="leave out the 5e7-event window")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N>1: fused in-kernel exchange over peer memory, or a separate NCCL all-gather")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

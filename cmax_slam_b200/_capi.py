@@ -126,7 +126,7 @@ EXPORTS = [
     "cmaxb_traj_incremental_update",
     "cmaxb_precompute_bearing_vectors",
     "cmaxb_stream_create", "cmaxb_stream_destroy", "cmaxb_stream_push", "cmaxb_stream_next_packet", "cmaxb_stream_window_events",
-    "cmaxb_stream_state",
+    "cmaxb_stream_state", "cmaxb_stream_attach_device", "cmaxb_stream_push_ex", "cmaxb_stream_next_packet_device", "cmaxb_stream_released",
     "cmaxb_pgo_create", "cmaxb_pgo_destroy", "cmaxb_pgo_push_ang_vel", "cmaxb_pgo_window", "cmaxb_pgo_process_window",
     "cmaxb_pgo_get_ctrl_poses", "cmaxb_be_last_eval_x",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
@@ -189,6 +189,10 @@ def lib():
     L.cmaxb_stream_next_packet.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), sp, C.POINTER(C.c_int)]
     L.cmaxb_stream_window_events.argtypes = [vp, Stamp, Stamp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.cmaxb_stream_state.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), sp]
+    L.cmaxb_stream_attach_device.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.cmaxb_stream_push_ex.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
+    L.cmaxb_stream_next_packet_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), sp, C.POINTER(C.c_int)]
+    L.cmaxb_stream_released.argtypes = [vp, C.POINTER(C.c_int64)]
     L.cmaxb_pgo_create.argtypes = [C.POINTER(PgoCfg), vp, C.POINTER(vp)]
     L.cmaxb_pgo_destroy.argtypes = [vp]
     L.cmaxb_pgo_destroy.restype = None

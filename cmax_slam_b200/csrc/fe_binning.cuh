@@ -4,10 +4,12 @@
 // packet arrive in time order, so consecutive threads touch unrelated pixels -- every bearing-vector
 // read, every vote and every adjoint-image read is its own L2 request.  A packet is evaluated ~100-300
 // times by the optimiser, so it pays to reorder it ONCE by 32x32 source tile: a warp's events then share
-// a few LUT / accumulator / adjoint-image lines (L1 hits, merged L2 requests).  The binned record is 8
-// bytes {x | y<<16, batch index}: the batch index keeps the reference's "one dt per 100 consecutive
-// events" semantics (local_image_warped_events.cpp:67-76) after the reorder and removes the division.
+// a few LUT / accumulator / adjoint-image lines, and the fused kernel can stage the tile's bearing vectors in
+// shared memory.  The binned record is 16 bytes {x | y<<16, batch index, dt (f64)}: dt is the reference's ONE time
+// offset per 100 consecutive events (local_image_warped_events.cpp:67-76) of the event's batch in ARRIVAL order,
+// carried along so that the evaluation kernels have no dependent table lookup left.
 // Order inside a tile is arbitrary (atomic cursors); sums are reordered anyway by the f32 atomics.
+// After pass 3, tile_cursor[t] = end offset of tile t's run (= start of tile t+1's).
 #pragma once
 #include "common.cuh"
 
@@ -62,7 +64,7 @@ fe_bin_scan_kernel(const unsigned int* __restrict__ tile_count, int ntiles, unsi
 // pass 3: write the 8-byte records tile by tile
 __global__ void __launch_bounds__(kBinThreads)
 fe_bin_scatter_kernel(const uint4* __restrict__ ev, long long n, int W, int H, int ntx, int ntiles, int batch_size,
-                      unsigned int* __restrict__ tile_cursor, uint2* __restrict__ binned) {
+                      const double* __restrict__ dt_tab, unsigned int* __restrict__ tile_cursor, uint4* __restrict__ binned) {
   extern __shared__ unsigned int s_mem[];
   unsigned int* s_hist = s_mem;            // counts, then running local cursor
   unsigned int* s_base = s_mem + ntiles;   // global base of this CTA's run inside each tile
@@ -82,7 +84,9 @@ fe_bin_scatter_kernel(const uint4* __restrict__ ev, long long n, int W, int H, i
     const uint4 e = __ldg(ev + i);
     const int t = bin_tile_of(e, W, H, ntx);
     const unsigned int pos = s_base[t] + atomicAdd(&s_hist[t], 1u);
-    binned[pos] = make_uint2(e.x, (unsigned int)(i / batch_size));
+    const unsigned int b = (unsigned int)(i / batch_size);
+    const double dt = __ldg(dt_tab + b);
+    binned[pos] = make_uint4(e.x, b, (unsigned int)__double2loint(dt), (unsigned int)__double2hiint(dt));
   }
 }
 

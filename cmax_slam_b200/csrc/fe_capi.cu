@@ -23,7 +23,7 @@ constexpr int kFeMaxPackets = 16;
 static_assert(kXSlots >= 2 * kFeRing, "exchange slots must cover twice the launch ring");
 
 struct FeInflight {
-  int k; bool grad; bool fused; int slot; int lane; unsigned long long seq; bool xchg; int pkt;
+  int k; bool grad; bool fused; int slot; int lane; unsigned long long tag; bool xchg; int pkt;
 };
 
 namespace cmaxb {
@@ -35,7 +35,8 @@ struct FePacket {
   uint4* d_ev = nullptr; size_t ev_cap = 0;      // owned copy of the raw events
   const uint4* ev = nullptr;                     // raw events in use: d_ev, or a caller-owned device buffer (view)
   double* d_dt = nullptr; size_t dt_cap = 0;
-  uint2* d_bev = nullptr; size_t bev_cap = 0; bool have_bins = false;
+  uint4* d_bev = nullptr; size_t bev_cap = 0; bool have_bins = false;   // tile-binned records {x|y<<16, batch, dt}
+  unsigned int* d_tile_end = nullptr;            // [ntiles] end offset of every source tile's run (cursor after the binning scatter)
   long long n = 0, nb = 0;
   bool have = false; bool flags_pending = false;
   int* d_flags = nullptr; int* h_flags = nullptr;
@@ -50,11 +51,11 @@ struct FeLane {
   // the image the next evaluation scatters into (no memset in steady state)
   float4* d_quad[2] = {nullptr, nullptr}; int quad_cur = 0; int quad_dirty[2] = {0, 0};
   float4* d_GQ = nullptr;
-  float4* d_reca = nullptr; float4* d_recb = nullptr; float* d_recc = nullptr; size_t rec_cap = 0;
-  double* d_part_img = nullptr; double* d_part_ev = nullptr; unsigned int* d_ticket = nullptr;
+  double* d_sums = nullptr;                      // [kmax][8] accumulators, kSumStride doubles apart
+  unsigned int* d_ticket = nullptr;
   unsigned long long* d_bar = nullptr; unsigned long long bar_count = 0;
-  unsigned long long* h_done = nullptr; unsigned long long* d_done = nullptr; unsigned long long seq = 0;
-  unsigned long long* h_phase = nullptr; unsigned long long* d_phase = nullptr;
+  unsigned long long* h_fault = nullptr; unsigned long long* d_fault = nullptr;   // mapped: barrier / tile-copy timeout
+  unsigned long long* d_phase = nullptr;         // [16] device words: phase stamps of the last profiled launch
   CUtensorMap tmap[2][2];                        // [grid mode][quad buffer]
   unsigned long long seen_gen[kFeMaxPackets] = {};   // packet generation this lane's stream is ordered after
   int inflight = 0;
@@ -67,8 +68,11 @@ struct cmaxb_fe {
   int kmax = 1;
   Taps taps{};
   float cxl[kMaxRadius + 1], cxr[kMaxRadius + 1], cyl[kMaxRadius + 1], cyr[kMaxRadius + 1];
+  float acorr[4 * kMaxRadius + 1];
+  float* d_adj_tab = nullptr;       // [xl | xr | yl | yr][2r][4r+1]
   double4* d_lut = nullptr;
-  unsigned int* d_tile_count = nullptr; unsigned int* d_tile_cursor = nullptr; int ntiles = 0, ntx = 0;
+  unsigned int* d_tile_count = nullptr; int ntiles = 0, ntx = 0;
+  CUtensorMap tmap_lut;             // bearing-vector LUT as a 2-D tensor, box = one 32 x 32 source tile
   bool use_bins = true;
   FePacket packets[kFeMaxPackets]; int npackets = 1; int cur = 0;
   FeLane lanes[kFeMaxLanes]; int nlanes = 1; int lane_next = 0;   // nlanes = throughput lanes (lanes[1..nlanes]); <= 1: everything on lane 0
@@ -83,9 +87,8 @@ struct cmaxb_fe {
   // fused evaluation
   int grid[2] = {0, 0}; int th[2] = {16, 16};   // [0] whole co-resident grid (latency), [1] partial grid (throughput lanes)
   bool use_tma = false; bool tma_ok = false;
-  int cache_mode = 0;               // gather records: 0 never (default: measured slower, profiles/r02a_*), 1 always, -1 when they fit the budget
-  size_t cache_budget = (size_t)96 << 20;
-  double* h_ring = nullptr; double* d_ring = nullptr;   // mapped pinned memory: [kFeRing][kmax][4]
+  unsigned long long* h_ring = nullptr; unsigned long long* d_ring = nullptr;   // mapped pinned memory, tagged words: [kFeRing][kmax][4][2]
+  unsigned long long launch_no = 0; // tags the result words of a launch
   bool force_multi_kernel = false;  // CMAXB_FE_MULTI_KERNEL=1: stand-alone kernels (profiling / A-B comparison)
   bool pending = false;             // work of ours may still be running on some lane
   std::deque<FeInflight> inflight;  // launched, not yet fetched (FIFO)
@@ -96,7 +99,7 @@ struct cmaxb_fe {
   unsigned long long* x_local = nullptr; size_t x_bytes = 0;
   unsigned long long* x_peer[kXMaxWorld] = {};
   double* x_all_dev = nullptr;
-  double* h_xall = nullptr; double* d_xall = nullptr;        // mapped: [kFeRing][world][kmax][4]
+  unsigned long long* h_xall = nullptr; unsigned long long* d_xall = nullptr;   // mapped, tagged words: [kFeRing][world][kmax][4][2]
   unsigned int* h_xerr = nullptr; unsigned int* d_xerr = nullptr;
   unsigned long long x_seq = 0;
   KernelProfiler prof;
@@ -104,7 +107,7 @@ struct cmaxb_fe {
 
 static FeGeom fe_geom(const cmaxb_fe* fe, const FePacket& pk) {
   FeGeom g;
-  g.ev = pk.ev; g.bev = nullptr; g.n = pk.n; g.batch_size = fe->cfg.batch_size; g.dt_tab = pk.d_dt; g.lut = fe->d_lut;
+  g.ev = pk.ev; g.n = pk.n; g.batch_size = fe->cfg.batch_size; g.dt_tab = pk.d_dt; g.lut = fe->d_lut;
   g.W = fe->cfg.width; g.H = fe->cfg.height;
   g.fx = fe->cfg.fx; g.fy = fe->cfg.fy; g.cx = fe->cfg.cx; g.cy = fe->cfg.cy;
   return g;
@@ -126,6 +129,40 @@ static void border_table(const Taps& t, int n, float* lo, float* hi) {
     return s;
   };
   for (int i = 0; i <= kMaxRadius; ++i) { lo[i] = (i <= r) ? full(i) : 1.0f; hi[i] = (i <= r) ? full(n - 1 - r + i) : 1.0f; }
+}
+
+// B^T B along one axis of length n (B = the Gaussian row filter with BORDER_REFLECT_101): away from the borders it is the
+// autocorrelation of the taps, acorr[s + 2r] = sum_d w[d] w[d + s]; rows q < 2r (lo) and q >= n - 2r (hi) differ and are
+// tabulated: lo[q][s + 2r] = (B^T B)[q][q + s], hi[m][s + 2r] = (B^T B)[n - 2r + m][n - 2r + m + s] (0 outside [0, n)).
+static void adjoint_tables(const Taps& t, int n, float* acorr, float* lo, float* hi) {
+  const int r = t.r, r2 = 2 * r, nt = 4 * r + 1;
+  for (int s = -r2; s <= r2; ++s) {
+    double v = 0.0;
+    for (int d = -r; d <= r; ++d) if (d + s >= -r && d + s <= r) v += (double)t.w[r + d] * (double)t.w[r + d + s];
+    acorr[s + r2] = (float)v;
+  }
+  auto refl = [&](int p) { if (n == 1) return 0; while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p; return p; };
+  auto bval = [&](int i, int col) {        // B[i][col]
+    double v = 0.0;
+    for (int d = -r; d <= r; ++d) if (refl(i + d) == col) v += (double)t.w[r + d];
+    return v;
+  };
+  auto ata = [&](int q, int j) {           // (B^T B)[q][j] = sum_i B[i][q] B[i][j]; B[i][q] != 0 needs |i - q| <= r or a reflection: i <= r - q, i >= 2(n-1) - q - r
+    if (q < 0 || q >= n || j < 0 || j >= n) return 0.0;
+    double v = 0.0;
+    for (int i = 0; i < n; ++i) {
+      if (!(std::abs(i - q) <= r || i <= r - q || i >= 2 * (n - 1) - q - r)) continue;
+      const double a = bval(i, q);
+      if (a != 0.0) v += a * bval(i, j);
+    }
+    return v;
+  };
+  for (int q = 0; q < r2; ++q)
+    for (int s = -r2; s <= r2; ++s) {
+      lo[q * nt + s + r2] = (float)ata(q, q + s);
+      const int qh = n - r2 + q;
+      hi[q * nt + s + r2] = (float)ata(qh, qh + s);
+    }
 }
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -157,6 +194,18 @@ static bool make_quad_tmap(CUtensorMap* out, float4* base, int W, int H, int pla
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// bearing-vector LUT [H][W] double4 seen as a 2-D tensor of 8-byte words {4W, H}; box = one 32 x 32 source tile (32 KB)
+static bool make_lut_tmap(CUtensorMap* out, double4* base, int W, int H) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)4 * W, (cuuint64_t)H};
+  const cuuint64_t gstr[1] = {(cuuint64_t)32 * W};
+  const cuuint32_t box[2] = {(cuuint32_t)(4 * kBinTile), (cuuint32_t)kBinTile};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static void* fused_kernel(const cmaxb_fe* fe) {
   if (fe->use_tma) return fe->taps.r == 4 ? (void*)fe_eval_fused_kernel<4, true> : (void*)fe_eval_fused_kernel<-1, true>;
   return fe->taps.r == 4 ? (void*)fe_eval_fused_kernel<4, false> : (void*)fe_eval_fused_kernel<-1, false>;
@@ -174,19 +223,19 @@ static int fe_lane_prepare(cmaxb_fe* fe, int li) {
   CMAXB_TRY(dev_alloc(&L.d_quad[0], k * A));
   CMAXB_TRY(dev_alloc(&L.d_quad[1], k * A));
   CMAXB_TRY(dev_alloc(&L.d_GQ, k * A));
-  CMAXB_TRY(dev_alloc(&L.d_part_img, k * kFusedMaxTiles * 2));
-  CMAXB_TRY(dev_alloc(&L.d_part_ev, k * kFusedMaxCtas * 6));
+  CMAXB_TRY(dev_alloc(&L.d_sums, k * 8 * kSumStride));
+  CMAXB_CUDA_TRY(cudaMemset(L.d_sums, 0, sizeof(double) * k * 8 * kSumStride));
   CMAXB_TRY(dev_alloc(&L.d_ticket, 1));
   CMAXB_TRY(dev_alloc(&L.d_bar, 1));
   CMAXB_CUDA_TRY(cudaMemset(L.d_quad[0], 0, sizeof(float4) * k * A));
   CMAXB_CUDA_TRY(cudaMemset(L.d_quad[1], 0, sizeof(float4) * k * A));
   CMAXB_CUDA_TRY(cudaMemset(L.d_ticket, 0, sizeof(unsigned int)));
   CMAXB_CUDA_TRY(cudaMemset(L.d_bar, 0, sizeof(unsigned long long)));
-  CMAXB_CUDA_TRY(cudaHostAlloc((void**)&L.h_done, sizeof(unsigned long long) * 8, cudaHostAllocMapped));
-  CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&L.d_done, L.h_done, 0));
-  L.h_done[0] = 0; L.h_done[1] = 0;
-  CMAXB_CUDA_TRY(cudaHostAlloc((void**)&L.h_phase, sizeof(unsigned long long) * 16, cudaHostAllocMapped));
-  CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&L.d_phase, L.h_phase, 0));
+  CMAXB_CUDA_TRY(cudaHostAlloc((void**)&L.h_fault, sizeof(unsigned long long) * 8, cudaHostAllocMapped));
+  CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&L.d_fault, L.h_fault, 0));
+  L.h_fault[0] = 0;
+  CMAXB_TRY(dev_alloc(&L.d_phase, 16));
+  CMAXB_CUDA_TRY(cudaMemset(L.d_phase, 0, sizeof(unsigned long long) * 16));
   if (fe->use_tma) {
     for (int m = 0; m < 2; ++m)
       for (int b = 0; b < 2; ++b)
@@ -227,8 +276,6 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
     fe->force_multi_kernel = mk && mk[0] == '1';
     const char* nb = getenv("CMAXB_FE_NO_BINNING");   // A/B switch: evaluate the packet in arrival (time) order
     fe->use_bins = !(nb && nb[0] == '1');
-    const char* cm = getenv("CMAXB_FE_CACHE");        // A/B switch: 0 = the gather recomputes the geometry, 1 = always from records
-    if (cm && (cm[0] == '0' || cm[0] == '1')) fe->cache_mode = cm[0] - '0';
     const char* tm = getenv("CMAXB_FE_TMA");          // A/B switch: 0 = tiles staged with per-thread loads
     if (tm && tm[0] == '0') want_tma = false;
     const char* ln = getenv("CMAXB_FE_LANES");
@@ -241,6 +288,17 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   if (fe->taps.r + 2 > cfg->width || fe->taps.r + 2 > cfg->height) { delete fe; return set_error(CMAXB_ERR_INVALID, "image smaller than the blur kernel"); }
   border_table(fe->taps, cfg->width, fe->cxl, fe->cxr);
   border_table(fe->taps, cfg->height, fe->cyl, fe->cyr);
+  {
+    const int r2 = 2 * fe->taps.r, nt = 4 * fe->taps.r + 1;
+    std::vector<float> tab((size_t)4 * (r2 > 0 ? r2 : 1) * nt, 0.f);
+    std::memset(fe->acorr, 0, sizeof(fe->acorr));
+    adjoint_tables(fe->taps, cfg->width, fe->acorr, tab.data(), tab.data() + (size_t)r2 * nt);
+    adjoint_tables(fe->taps, cfg->height, fe->acorr, tab.data() + (size_t)2 * r2 * nt, tab.data() + (size_t)3 * r2 * nt);
+    if (dev_alloc(&fe->d_adj_tab, tab.size()) != CMAXB_OK) { delete fe; return CMAXB_ERR_CUDA; }
+    if (cudaMemcpy(fe->d_adj_tab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(fe->d_adj_tab); delete fe; return set_error(CMAXB_ERR_CUDA, "adjoint table upload failed");
+    }
+  }
   auto fail = [&](int code) { cmaxb_fe_destroy(fe); return code; };
   if (cfg->stream) fe->lanes[0].stream = (cudaStream_t)cfg->stream;
   else {
@@ -278,15 +336,17 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   ok = ok && cudaMemset(fe->d_ticket, 0, sizeof(unsigned) * k) == cudaSuccess;
   ok = ok && cudaMemset(fe->d_ticket2, 0, sizeof(unsigned) * k) == cudaSuccess;
   ok = ok && cudaMemset(fe->d_result, 0, sizeof(double) * k * 4) == cudaSuccess;
-  ok = ok && cudaHostAlloc((void**)&fe->h_ring, sizeof(double) * 4 * k * kFeRing, cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&fe->h_ring, sizeof(unsigned long long) * 8 * k * kFeRing, cudaHostAllocMapped) == cudaSuccess;
   ok = ok && cudaHostGetDevicePointer((void**)&fe->d_ring, fe->h_ring, 0) == cudaSuccess;
+  if (ok) std::memset(fe->h_ring, 0, sizeof(unsigned long long) * 8 * k * kFeRing);
   if (!ok) return fail(set_error(CMAXB_ERR_CUDA, "front-end buffer allocation failed"));
   // fused evaluation kernel: co-resident grid size from the occupancy API; TMA staging when the tile box fits a tensor map
   {
     int coop = 0, nsm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, fe->device);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, fe->device);
-    fe->use_tma = want_tma && tmap_encoder() != nullptr && 4 * fused_qw(fe->taps.r) <= 256 && fused_qh(fe->taps.r, kFusedMaxTH) <= 256;
+    fe->use_tma = want_tma && tmap_encoder() != nullptr && 4 * fused_qw(fe->taps.r) <= 256 && fused_qh(fe->taps.r, kFusedMaxTH) <= 256 &&
+                  make_lut_tmap(&fe->tmap_lut, fe->d_lut, cfg->width, cfg->height);
     const size_t smem_max = fused_smem_bytes(fe->taps.r, kFusedMaxTH);
     int occ = 0;
     void* kern = fused_kernel(fe);
@@ -311,8 +371,6 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
     fe->grid[1] = part;
     for (int m = 0; m < 2; ++m) {
       fe->th[m] = fused_tile_height(cfg->width, cfg->height, fe->grid[m]);
-      const long long tiles = (long long)((cfg->width + kTW - 1) / kTW) * ((cfg->height + fe->th[m] - 1) / fe->th[m]);
-      if (tiles > kFusedMaxTiles) return fail(set_error(CMAXB_ERR_INVALID, "image too large for the fused front-end kernel (more than 8192 tiles)"));
     }
   }
   rc = fe_lane_prepare(fe, 0);
@@ -325,19 +383,18 @@ extern "C" void cmaxb_fe_destroy(cmaxb_fe* fe) {
   if (!fe) return;
   cudaSetDevice(fe->device);
   for (int l = 0; l < kFeMaxLanes; ++l) if (fe->lanes[l].stream) cudaStreamSynchronize(fe->lanes[l].stream);
-  cudaFree(fe->d_lut); cudaFree(fe->d_tile_count); cudaFree(fe->d_tile_cursor);
+  cudaFree(fe->d_lut); cudaFree(fe->d_tile_count); cudaFree(fe->d_adj_tab);
   for (int s = 0; s < kFeMaxPackets; ++s) {
     FePacket& pk = fe->packets[s];
-    cudaFree(pk.d_ev); cudaFree(pk.d_dt); cudaFree(pk.d_bev); cudaFree(pk.d_flags);
+    cudaFree(pk.d_ev); cudaFree(pk.d_dt); cudaFree(pk.d_bev); cudaFree(pk.d_flags); cudaFree(pk.d_tile_end);
     if (pk.h_flags) cudaFreeHost(pk.h_flags);
     if (pk.ready) cudaEventDestroy(pk.ready);
   }
   for (int l = 0; l < kFeMaxLanes; ++l) {
     FeLane& L = fe->lanes[l];
-    cudaFree(L.d_quad[0]); cudaFree(L.d_quad[1]); cudaFree(L.d_GQ); cudaFree(L.d_reca); cudaFree(L.d_recb); cudaFree(L.d_recc);
-    cudaFree(L.d_part_img); cudaFree(L.d_part_ev); cudaFree(L.d_ticket); cudaFree(L.d_bar);
-    if (L.h_done) cudaFreeHost(L.h_done);
-    if (L.h_phase) cudaFreeHost(L.h_phase);
+    cudaFree(L.d_quad[0]); cudaFree(L.d_quad[1]); cudaFree(L.d_GQ);
+    cudaFree(L.d_sums); cudaFree(L.d_ticket); cudaFree(L.d_bar); cudaFree(L.d_phase);
+    if (L.h_fault) cudaFreeHost(L.h_fault);
     if (L.own_stream && L.stream) cudaStreamDestroy(L.stream);
   }
   cudaFree(fe->d_blur1); cudaFree(fe->d_img4); cudaFree(fe->d_blur4);
@@ -443,22 +500,21 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
         CMAXB_TRY(dev_alloc(&pk.d_bev, n));
         pk.bev_cap = n;
       }
-      if (!fe->d_tile_count) {
-        CMAXB_TRY(dev_alloc(&fe->d_tile_count, (size_t)kBinMaxTiles));
-        CMAXB_TRY(dev_alloc(&fe->d_tile_cursor, (size_t)kBinMaxTiles));
-      }
+      if (!fe->d_tile_count) CMAXB_TRY(dev_alloc(&fe->d_tile_count, (size_t)kBinMaxTiles));
+      if (!pk.d_tile_end) CMAXB_TRY(dev_alloc(&pk.d_tile_end, (size_t)kBinMaxTiles));
       const int ntiles = fe->ntiles, ntx = fe->ntx;
       const unsigned nchunks = (unsigned)((nn + kBinChunk - 1) / kBinChunk);
-      uint2* bev = pk.d_bev;
+      uint4* bev = pk.d_bev;
+      unsigned int* cursor = pk.d_tile_end;
       CMAXB_CUDA_TRY(cudaMemsetAsync(fe->d_tile_count, 0, sizeof(unsigned int) * ntiles, s));
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
         fe_bin_count_kernel<<<nchunks, kBinThreads, sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, fe->d_tile_count);
       }));
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-        fe_bin_scan_kernel<<<1, 1024, 0, s>>>(fe->d_tile_count, ntiles, fe->d_tile_cursor);
+        fe_bin_scan_kernel<<<1, 1024, 0, s>>>(fe->d_tile_count, ntiles, cursor);
       }));
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-        fe_bin_scatter_kernel<<<nchunks, kBinThreads, 2 * sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, ibs, fe->d_tile_cursor, bev);
+        fe_bin_scatter_kernel<<<nchunks, kBinThreads, 2 * sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, ibs, dt, cursor, bev);
       }));
       pk.have_bins = true;
     }
@@ -582,20 +638,11 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
   }
   const int gm = li > 0 ? 1 : 0;
   const int grid = fe->grid[gm], th = fe->th[gm];
-  const bool use_cache = want_grad && pk.n > 0 &&
-      (fe->cache_mode == 1 || (fe->cache_mode < 0 && (size_t)k * (size_t)pk.n * 36u <= fe->cache_budget));
-  if (use_cache && (size_t)k * (size_t)pk.n > L.rec_cap) {
-    CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
-    cudaFree(L.d_reca); cudaFree(L.d_recb); cudaFree(L.d_recc);
-    L.d_reca = L.d_recb = nullptr; L.d_recc = nullptr; L.rec_cap = 0;
-    const size_t cap = (size_t)k * (size_t)pk.n;
-    CMAXB_TRY(dev_alloc(&L.d_reca, cap));
-    CMAXB_TRY(dev_alloc(&L.d_recb, cap));
-    CMAXB_TRY(dev_alloc(&L.d_recc, cap));
-    L.rec_cap = cap;
-  }
   const int slot = fe->ring_next;
   fe->ring_next = (fe->ring_next + 1) % kFeRing;
+  fe->launch_no += 1;
+  if ((fe->launch_no & 0xffffffffull) == 0) fe->launch_no += 1;       // tag 0 = "never written"
+  const unsigned long long tag = (fe->launch_no & 0xffffffffull) << 32;
   const int cur = L.quad_cur, oth = cur ^ 1;
   if (L.quad_dirty[cur] > 0) {
     const int planes = L.quad_dirty[cur];
@@ -608,44 +655,40 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
     const int kc = (k - c0 < kFusedMaxHyp) ? k - c0 : kFusedMaxHyp;
     FeFusedParams p;
     p.g = fe_geom(fe, pk);
-    p.g.bev = pk.have_bins ? pk.d_bev : nullptr;   // the fused kernel walks the tile-binned copy of the packet
+    p.bev = pk.have_bins ? pk.d_bev : nullptr;     // the fused kernel walks the tile-binned copy of the packet
+    p.tile_end = pk.d_tile_end; p.bin_ntx = fe->ntx; p.bin_ntiles = fe->ntiles;
     p.k = kc; p.th = th; p.ntx = (W + kTW - 1) / kTW; p.nty = (H + th - 1) / th;
-    p.want_grad = want_grad; p.measure = fe->cfg.contrast_measure; p.use_cache = use_cache ? 1 : 0;
+    p.want_grad = want_grad; p.measure = fe->cfg.contrast_measure; 
     p.quad_plane0 = c0;
     p.taps = fe->taps;
     std::memcpy(p.cxl, fe->cxl, sizeof(p.cxl)); std::memcpy(p.cxr, fe->cxr, sizeof(p.cxr));
     std::memcpy(p.cyl, fe->cyl, sizeof(p.cyl)); std::memcpy(p.cyr, fe->cyr, sizeof(p.cyr));
+    std::memcpy(p.acorr, fe->acorr, sizeof(p.acorr)); p.adj_tab = fe->d_adj_tab;
     for (int i = 0; i < 3 * kc; ++i) p.omegas[i] = omegas[3 * c0 + i];
     p.quad = L.d_quad[cur] + (long long)c0 * fe->A;
     p.quad_next = clear_next ? L.d_quad[oth] + (long long)c0 * fe->A : nullptr;
     p.GQ = L.d_GQ + (long long)c0 * fe->A;
     p.A = fe->A;
-    p.rec.a = L.d_reca ? L.d_reca + (long long)c0 * pk.n : nullptr;
-    p.rec.b = L.d_recb ? L.d_recb + (long long)c0 * pk.n : nullptr;
-    p.rec.c = L.d_recc ? L.d_recc + (long long)c0 * pk.n : nullptr;
-    p.rec_stride = pk.n;
-    p.part_img = L.d_part_img + (long long)c0 * kFusedMaxTiles * 2;
-    p.part_ev = L.d_part_ev + (long long)c0 * kFusedMaxCtas * 6;
+    p.sums = L.d_sums + (long long)c0 * 8 * kSumStride;
     p.ticket = L.d_ticket;
     p.bar = L.d_bar; p.bar_base = L.bar_count;
     L.bar_count += (unsigned long long)grid * (want_grad ? 2ull : 1ull);
-    p.result = fe->d_ring + ((long long)slot * fe->kmax + c0) * 4;
+    p.result = fe->d_ring + ((long long)slot * fe->kmax + c0) * 8;
+    p.tag = tag;
     p.mirror = fe->d_mirror ? fe->d_mirror + 4 * c0 : nullptr;
-    p.done_flag = L.d_done;
-    p.fault_flag = L.d_done + 1;
-    p.seq = ++L.seq;
+    p.fault_flag = L.d_fault;
     p.phase_ns = fe->prof.enabled ? L.d_phase : nullptr;
     std::memset(&p.x, 0, sizeof(p.x));
     if (fe->x_on) {
       p.x.world = fe->x_world; p.x.rank = fe->x_rank; p.x.kmax = fe->kmax;
       p.x.seq = ++fe->x_seq;
       for (int r = 0; r < fe->x_world; ++r) p.x.peer[r] = fe->x_peer[r];
-      p.x.all_host = fe->d_xall + (long long)slot * fe->x_world * fe->kmax * 4;
+      p.x.all_host = fe->d_xall + (long long)slot * fe->x_world * fe->kmax * 8;
       p.x.all_dev = fe->x_all_dev;
       p.x.err = fe->d_xerr;
     }
-    if (fe->prof.enabled) for (int i = 0; i < 16; ++i) L.h_phase[i] = 0;
-    void* args[] = {&p, &L.tmap[gm][cur]};
+    if (fe->prof.enabled) CMAXB_CUDA_TRY(cudaMemsetAsync(L.d_phase, 0, sizeof(unsigned long long) * 16, s));
+    void* args[] = {&p, &L.tmap[gm][cur], &fe->tmap_lut};
     const size_t smem = fused_smem_bytes(fe->taps.r, th);
     cudaError_t le = cudaSuccess;
     CMAXB_TRY(fe->prof.run(CMAXB_K_FE_EVAL_FUSED, s, true, [&] {
@@ -658,7 +701,7 @@ static int fe_eval_launch_fused(cmaxb_fe* fe, const double* omegas, int k, int w
   L.quad_cur = oth;
   L.inflight += 1;
   pk.users += 1;
-  fe->inflight.push_back(FeInflight{k, want_grad != 0, true, slot, li, L.seq, fe->x_on, fe->cur});
+  fe->inflight.push_back(FeInflight{k, want_grad != 0, true, slot, li, tag, fe->x_on, fe->cur});
   fe->pending = true;
   return CMAXB_OK;
 }
@@ -712,30 +755,55 @@ extern "C" int cmaxb_fe_eval_launch(cmaxb_fe* fe, const double* omegas, int k, i
   return fe_eval_launch_mode(fe, omegas, k, want_grad, 1);
 }
 
+// All `count` doubles of a tagged-word block carry `tag`?  (see ll_store in fe_fused.cuh)
+static bool ll_ready(const volatile unsigned long long* words, int count, unsigned long long tag) {
+  for (int i = 2 * count - 1; i >= 0; --i)
+    if ((words[i] & 0xffffffff00000000ull) != tag) return false;
+  return true;
+}
+static double ll_value(const volatile unsigned long long* words, int i) {
+  const unsigned long long bits = (words[2 * i] & 0xffffffffull) | (words[2 * i + 1] << 32);
+  double v;
+  std::memcpy(&v, &bits, sizeof(v));
+  return v;
+}
+
 // waits for the OLDEST outstanding launch and pops it; *out = its record
 static int fe_wait_oldest(cmaxb_fe* fe, FeInflight* out) {
   if (fe->inflight.empty()) return set_error(CMAXB_ERR_STATE, "no evaluation launched");
   const FeInflight f = fe->inflight.front();
+  auto abandon = [&](const std::string& msg) {
+    fe->inflight.clear();
+    for (auto& pp : fe->packets) pp.users = 0;
+    for (auto& ll : fe->lanes) ll.inflight = 0;
+    return set_error(CMAXB_ERR_CUDA, msg);
+  };
   if (f.fused) {
-    // The fused kernel publishes its results in mapped pinned memory and then stores its sequence
-    // number (monotonic per lane): spin on that word (~1 us) instead of paying the driver's stream-synchronise
-    // latency; check the stream now and then so that a faulted kernel cannot hang the caller.
+    // The fused kernel publishes its rows as tagged words in mapped pinned memory: poll the words themselves (no
+    // completion flag, no stream synchronisation); check the stream now and then so that a faulted kernel cannot
+    // hang the caller.
     FeLane& L = fe->lanes[f.lane];
-    volatile unsigned long long* done = L.h_done;
+    const volatile unsigned long long* words = f.xchg ? fe->h_xall + (long long)f.slot * fe->x_world * fe->kmax * 8
+                                                      : fe->h_ring + (long long)f.slot * fe->kmax * 8;
+    const int count = f.xchg ? 4 * f.k * fe->x_world : 4 * f.k;
     unsigned long long spins = 0;
-    while (*done < f.seq) {
+    bool ready = false;
+    while (!(ready = ll_ready(words, count, f.tag))) {
       if ((++spins & 0x3fff) == 0) {
         cudaError_t q = cudaStreamQuery(L.stream);
-        if (q == cudaSuccess) break;                       // finished (flag write raced the query) or faulted
-        if (q != cudaErrorNotReady) { fe->inflight.clear(); for (auto& pp : fe->packets) pp.users = 0; return set_error(CMAXB_ERR_CUDA, std::string("fused evaluation kernel: ") + cudaGetErrorString(q)); }
+        if (q == cudaSuccess) break;                       // finished (the words raced the query) or faulted
+        if (q != cudaErrorNotReady) return abandon(std::string("fused evaluation kernel: ") + cudaGetErrorString(q));
       }
     }
-    if (*done < f.seq) CMAXB_CUDA_TRY(cudaStreamSynchronize(L.stream));
-    if (*done < f.seq) { fe->inflight.clear(); for (auto& pp : fe->packets) pp.users = 0; return set_error(CMAXB_ERR_CUDA, "fused evaluation kernel finished without publishing its result"); }
+    if (!ready) {
+      CMAXB_CUDA_TRY(cudaStreamSynchronize(L.stream));
+      if (!ll_ready(words, count, f.tag)) return abandon("fused evaluation kernel finished without publishing its result");
+    }
     L.inflight -= 1;
-    if (L.h_done[1]) {
-      fe->inflight.clear(); for (auto& pp : fe->packets) pp.users = 0;
-      return set_error(CMAXB_ERR_CUDA, L.h_done[1] == 2 ? "fused evaluation kernel: tile copy (TMA) timed out" : "fused evaluation kernel: grid barrier timed out");
+    if (L.h_fault[0]) {
+      const unsigned long long why = L.h_fault[0];
+      L.h_fault[0] = 0;
+      return abandon(why == 2 ? "fused evaluation kernel: tile copy (TMA) timed out" : "fused evaluation kernel: grid barrier timed out");
     }
   } else {
     CMAXB_CUDA_TRY(cudaStreamSynchronize(fe->stream));
@@ -751,7 +819,19 @@ extern "C" int cmaxb_fe_eval_fetch(cmaxb_fe* fe, double* contrasts, double* grad
   FeInflight f;
   CMAXB_TRY(fe_wait_oldest(fe, &f));
   if (f.xchg && *fe->h_xerr) return set_error(CMAXB_ERR_CUDA, "result exchange: a peer's rows did not arrive (timeout)");
-  const double* res = f.fused ? fe->h_ring + (long long)f.slot * fe->kmax * 4 : fe->h_result;
+  if (f.fused) {
+    // own rows: the result ring (without exchange) or this rank's block of the gathered rows
+    const volatile unsigned long long* words = f.xchg
+        ? fe->h_xall + (long long)f.slot * fe->x_world * fe->kmax * 8 + (long long)fe->x_rank * f.k * 8     // rows are packed [world][k][4]
+        : fe->h_ring + (long long)f.slot * fe->kmax * 8;
+    for (int h = 0; h < f.k; ++h) {
+      contrasts[h] = ll_value(words, 4 * h);
+      if (grads3k && f.grad)
+        for (int c = 0; c < 3; ++c) grads3k[3 * h + c] = ll_value(words, 4 * h + 1 + c);
+    }
+    return CMAXB_OK;
+  }
+  const double* res = fe->h_result;
   for (int h = 0; h < f.k; ++h) {
     contrasts[h] = res[4 * h];
     if (grads3k && f.grad)
@@ -796,7 +876,9 @@ extern "C" int cmaxb_fe_exchange_connect(cmaxb_fe* fe, const void* handles, doub
     fe->x_peer[r] = (unsigned long long*)ptr;
   }
   if (!fe->h_xall) {
-    CMAXB_CUDA_TRY(cudaHostAlloc((void**)&fe->h_xall, sizeof(double) * 4 * (size_t)fe->kmax * fe->x_world * kFeRing, cudaHostAllocMapped));
+    const size_t xbytes = sizeof(unsigned long long) * 8 * (size_t)fe->kmax * fe->x_world * kFeRing;
+    CMAXB_CUDA_TRY(cudaHostAlloc((void**)&fe->h_xall, xbytes, cudaHostAllocMapped));
+    std::memset(fe->h_xall, 0, xbytes);
     CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&fe->d_xall, fe->h_xall, 0));
     CMAXB_CUDA_TRY(cudaHostAlloc((void**)&fe->h_xerr, sizeof(unsigned int) * 4, cudaHostAllocMapped));
     CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&fe->d_xerr, fe->h_xerr, 0));
@@ -828,8 +910,8 @@ extern "C" int cmaxb_fe_eval_fetch_all(cmaxb_fe* fe, double* rows) {
   FeInflight f;
   CMAXB_TRY(fe_wait_oldest(fe, &f));
   if (*fe->h_xerr) return set_error(CMAXB_ERR_CUDA, "result exchange: a peer's rows did not arrive (timeout)");
-  const double* all = fe->h_xall + (long long)f.slot * fe->x_world * fe->kmax * 4;
-  std::memcpy(rows, all, sizeof(double) * 4 * (size_t)f.k * fe->x_world);
+  const volatile unsigned long long* all = fe->h_xall + (long long)f.slot * fe->x_world * fe->kmax * 8;
+  for (int i = 0; i < 4 * f.k * fe->x_world; ++i) rows[i] = ll_value(all, i);
   return CMAXB_OK;
 }
 
@@ -949,9 +1031,9 @@ extern "C" int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10) {
   if (!fe || !us10) return set_error(CMAXB_ERR_INVALID, "null argument");
   fe->pending = true;
   CMAXB_TRY(fe_drain(fe));
-  const FeLane& L = fe->lanes[0];
-  for (int i = 0; i < 10; ++i)
-    us10[i] = (i < 8 && L.h_phase && L.h_phase[i] && L.h_phase[0]) ? (double)(L.h_phase[i] - L.h_phase[0]) * 1e-3 : -1.0;
+  unsigned long long ph[16];
+  CMAXB_CUDA_TRY(cudaMemcpy(ph, fe->lanes[0].d_phase, sizeof(ph), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 10; ++i) us10[i] = (ph[i] && ph[0]) ? (double)(ph[i] - ph[0]) * 1e-3 : -1.0;
   return CMAXB_OK;
 }
 extern "C" int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms, uint64_t* launches) {
@@ -964,7 +1046,7 @@ extern "C" int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms, uint64_t* launche
 extern "C" int cmaxb_fe_launch_info(cmaxb_fe* fe, int32_t* info7) {
   if (!fe || !info7) return set_error(CMAXB_ERR_INVALID, "null argument");
   info7[0] = fe->grid[0]; info7[1] = fe->grid[1]; info7[2] = fe->nlanes; info7[3] = fe->use_tma ? 1 : 0;
-  info7[4] = fe->th[0]; info7[5] = fe->th[1]; info7[6] = fe->cache_mode;
+  info7[4] = fe->th[0]; info7[5] = fe->th[1]; info7[6] = 0;
   return CMAXB_OK;
 }
 

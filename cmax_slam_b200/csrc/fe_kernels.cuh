@@ -12,7 +12,6 @@ namespace cmaxb {
 
 struct FeGeom {
   const uint4* ev;          // raw 16-byte dvs_msgs::Event records
-  const uint2* bev;         // the same events binned by 32x32 source tile: {x | y<<16, batch index} (or null)
   long long n;
   int batch_size;
   const double* dt_tab;     // per batch: t_mid.toSec() - t_ref            (:68-75)

@@ -69,17 +69,13 @@ class CMaxSLAM:
                 self._run_backend()
 
     def _run_backend(self):
-        from ._capi import CmaxbError
         while True:
             tb, te, ready = self.pgo.window()
             if not ready:
                 return
-            try:
-                ev = self.stream.window_events(tb, te)
-            except CmaxbError as e:               # the event store does not reach the end of the window yet
-                if e.code == -6:
-                    return
-                raise
+            ev = self.stream.window_events(tb, te)
+            if ev is None:                        # the event store does not reach the end of the window yet
+                return
             self.windows.append(self.pgo.processTimeWindow(ev))
 
     def trajectory(self):

@@ -30,11 +30,37 @@ class EventStream:
 
     __del__ = close
 
-    def eventsCallback(self, msg_events):
-        """One dvs_msgs::EventArray (16-byte records).  Returns the number of complete packets waiting."""
-        ev = np.ascontiguousarray(msg_events)
+    PUSH_BORROW, PUSH_SORTED = 1, 2
+
+    def eventsCallback(self, msg_events, flags=0):
+        """One dvs_msgs::EventArray (16-byte records, numpy array or a (ptr, n) tuple).  Returns the number of complete
+        packets waiting.  flags: PUSH_BORROW (page-locked message referenced in place), PUSH_SORTED (time-sorted message)."""
+        if isinstance(msg_events, tuple):
+            ptr, n = msg_events
+        else:
+            ev = np.ascontiguousarray(msg_events)
+            ptr, n = ev.ctypes.data, len(ev)
         k = C.c_int(0)
-        _capi.check(self._L.cmaxb_stream_push(self._s, C.c_void_p(ev.ctypes.data), len(ev), C.byref(k)))
+        _capi.check(self._L.cmaxb_stream_push_ex(self._s, C.c_void_p(ptr), n, int(flags), C.byref(k)))
+        return k.value
+
+    def attach_device(self, device=0, cuda_stream=None, ring_events=0):
+        """Device-resident event store: every pushed event crosses PCIe once; next_packet_device hands out ring views."""
+        _capi.check(self._L.cmaxb_stream_attach_device(self._s, int(device), C.c_void_p(int(cuda_stream)) if cuda_stream else None,
+                                                       int(ring_events)))
+
+    def next_packet_device(self):
+        """None, or ((device pointer, n), (sec, nsec) time_packet, span_too_long) -- input of set_packet(..., view=True)."""
+        p, n, t, f = C.c_void_p(), C.c_size_t(0), _capi.Stamp(), C.c_int(0)
+        rc = self._L.cmaxb_stream_next_packet_device(self._s, C.byref(p), C.byref(n), C.byref(t), C.byref(f))
+        if rc == 1:
+            return None
+        _capi.check(rc)
+        return (p.value, n.value), (t.sec, t.nsec), bool(f.value)
+
+    def released(self):
+        k = C.c_int64(0)
+        _capi.check(self._L.cmaxb_stream_released(self._s, C.byref(k)))
         return k.value
 
     def _view(self, ptr, n):
@@ -53,9 +79,13 @@ class EventStream:
         return self._view(p.value, n.value), (t.sec, t.nsec), bool(f.value)
 
     def window_events(self, t_beg, t_end):
+        """Events of the back-end window, or None when the store does not cover the window yet."""
         p, n = C.c_void_p(), C.c_size_t(0)
-        _capi.check(self._L.cmaxb_stream_window_events(self._s, _capi.Stamp(int(t_beg[0]), int(t_beg[1])),
-                                                       _capi.Stamp(int(t_end[0]), int(t_end[1])), C.byref(p), C.byref(n)))
+        rc = self._L.cmaxb_stream_window_events(self._s, _capi.Stamp(int(t_beg[0]), int(t_beg[1])),
+                                                _capi.Stamp(int(t_end[0]), int(t_end[1])), C.byref(p), C.byref(n))
+        if rc == 1:
+            return None
+        _capi.check(rc)
         return self._view(p.value, n.value)
 
     def state(self):

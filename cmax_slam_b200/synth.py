@@ -93,6 +93,51 @@ def make_fe_packet(n_events, W, H, K4, seed, n_landmarks, omega_true=(0.6, -1.1,
     return FePacket(ev, t_ref_sec, bearing_lut(W, H, K4), W, H, tuple(K4), w, name=name)
 
 
+def make_fe_stream(n_events, W, H, K4, seed, rate_hz=2.0e7, n_landmarks=60000, amp_rad=0.08, period_s=0.2,
+                   axis=(0.6, -1.1, 2.3)):
+    """A continuous front-end event stream (what the DVS driver delivers message by message): `n_events` events at a
+    constant rate, time-sorted with nanosecond stamps; the camera oscillates about `axis` with amplitude `amp_rad`
+    (angle = amp sin(2 pi t / period)), landmarks lie on the sensor plane extended by the largest displacement.
+    Returns (events, lut).  rate 2e7 events/s = 200 000 events per 10 ms angular-velocity tick, i.e. the C2 packet
+    (1 000 000 events over 50 ms) as `num_events_per_packet` of the reference's packet cutter."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    fx, fy, cx, cy = K4
+    ax = np.asarray(axis, np.float64); ax = ax / np.linalg.norm(ax)
+    margin = int(np.ceil(amp_rad * max(fx, fy) * 1.6)) + 8
+    lx = rng.uniform(-margin, W - 1 + margin, n_landmarks)
+    ly = rng.uniform(-margin, H - 1 + margin, n_landmarks)
+    L = np.stack([(lx - cx) / fx, (ly - cy) / fy, np.ones(n_landmarks)], 1)
+    xs, ys, ts = [], [], []
+    need = n_events
+    t_cursor = 0.0
+    chunk = 2_000_000
+    while need > 0:
+        m = min(chunk, int(need * 1.8) + 4096)
+        span = m / (rate_hz * 1.6)                    # ~60 % of the candidates survive: keep the event RATE at rate_hz
+        t = np.sort(rng.uniform(t_cursor, t_cursor + span, m))
+        li = rng.integers(0, n_landmarks, m)
+        th = amp_rad * np.sin(2 * np.pi * t / period_s)
+        b = L[li]
+        k = ax[None, :]
+        c, sn = np.cos(th)[:, None], np.sin(th)[:, None]
+        rot = b * c + np.cross(k, b) * sn + k * (b @ ax)[:, None] * (1 - c)     # Rodrigues
+        px = np.rint(fx * rot[:, 0] / rot[:, 2] + cx).astype(np.int64)
+        py = np.rint(fy * rot[:, 1] / rot[:, 2] + cy).astype(np.int64)
+        ok = (px >= 0) & (px < W) & (py >= 0) & (py < H)
+        idx = np.nonzero(ok)[0][:need]
+        xs.append(px[idx]); ys.append(py[idx]); ts.append(t[idx])
+        need -= len(idx)
+        t_cursor = t[idx[-1]] if len(idx) else t_cursor + span
+    x = np.concatenate(xs); y = np.concatenate(ys); t = np.concatenate(ts)
+    t_ns = (t * 1e9).astype(np.int64) + 500_000_000
+    ev = np.zeros(len(x), EVENT_DTYPE)
+    ev["x"] = x; ev["y"] = y
+    ev["sec"] = EPOCH_SEC + t_ns // 1_000_000_000
+    ev["nsec"] = t_ns % 1_000_000_000
+    ev["polarity"] = np.arange(len(x)) & 1
+    return ev, bearing_lut(W, H, K4)
+
+
 def fe_config(name, scale=1.0):
     """BASELINE.json configs: 'C1' (1e5 ev, 240x180), 'C2' (1e6 ev, 640x480). `scale` shrinks the
     event count for tests."""
@@ -229,12 +274,93 @@ def make_be_window(n_events, n_knots, pano_w, pano_h, seed, order=2, sensor=(640
                     n_fixed, tnext, name=name)
 
 
-def be_config(name, scale=1.0, order=2):
+def make_be_window_torch(n_events, n_knots, pano_w, pano_h, seed, order=2, sensor=(640, 480), K4=K_ECROT,
+                         dt_knots_s=0.05, knot_sigma=0.04, n_landmarks=50000, n_fixed=1, name="", device="cuda"):
+    """make_be_window with the per-event sampling on a torch device (the numpy version needs ~5 s per million events;
+    the full-size C4 / C5 windows of the benchmark are drawn on the GPU in about a second).  Same construction -- knots,
+    landmark cap, geodesic interpolation, rounding to the sensor grid -- with torch's generator for the per-event draws, so
+    the events differ from the numpy version's (both are synthetic; tests that need the oracle use the numpy one)."""
+    import torch
+    rng = np.random.Generator(np.random.PCG64(seed))
+    W, H = sensor
+    fx, fy, cx, cy = K4
+    knots = np.zeros((n_knots, 4))
+    knots[0] = [0, 0, 0, 1]
+    for k in range(1, n_knots):
+        knots[k] = _qmul(knots[k - 1], _qexp(rng.normal(0, knot_sigma, 3)))
+        knots[k] /= np.linalg.norm(knots[k])
+    dt_ns = int(round(dt_knots_s * 1e9))
+    t0_rel_us = 250_000
+    t0_ns = EPOCH_SEC * 1_000_000_000 + t0_rel_us * 1000
+    n_seg = n_knots - order + 1
+    seg_us = dt_ns // 1000
+    span_us = n_seg * seg_us
+    axis = _qrot(knots, np.array([0.0, 0.0, 1.0]))
+    half_fov = np.arctan(np.hypot(W / (2 * fx), H / (2 * fy)))
+    ang = min(np.arccos(np.clip(axis[:, 2], -1, 1)).max() + half_fov + 0.05, np.pi)
+    z = rng.uniform(np.cos(ang), 1.0, n_landmarks)
+    ph = rng.uniform(0, 2 * np.pi, n_landmarks)
+    sq = np.sqrt(1 - z * z)
+    dev = torch.device(device)
+    Lw = torch.tensor(np.stack([sq * np.cos(ph), sq * np.sin(ph), z], 1), dtype=torch.float64, device=dev)
+    # per-segment rotation (knot k) and relative rotation vector, as rotation matrices / vectors on the device
+    qa = torch.tensor(knots[:-1], dtype=torch.float64, device=dev)
+    d = torch.tensor(_qlog(_qmul(_qconj(knots[:-1]), knots[1:])), dtype=torch.float64, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+
+    def qmul(a, b):
+        ax, ay, az, aw = a.unbind(-1)
+        bx, by, bz, bw = b.unbind(-1)
+        return torch.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                            aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz], -1)
+
+    def qexp(w):
+        th = w.norm(dim=-1, keepdim=True)
+        small = th < 1e-12
+        sc = torch.where(small, torch.full_like(th, 0.5), torch.sin(0.5 * th) / torch.where(small, torch.ones_like(th), th))
+        return torch.cat([sc * w, torch.cos(0.5 * th)], -1)
+
+    def qrot_conj(q, v):     # rotate v by the conjugate of q
+        u = -q[..., :3]
+        w = q[..., 3:4]
+        t = 2.0 * torch.cross(u, v, dim=-1)
+        return v + w * t + torch.cross(u, t, dim=-1)
+
+    xs, ys, ts = [], [], []
+    need = n_events
+    chunk = 4_000_000
+    while need > 0:
+        m = min(chunk, int(need * 3) + 4096)
+        li = torch.randint(0, n_landmarks, (m,), generator=gen, device=dev)
+        t_us = torch.randint(1, span_us - 1, (m,), generator=gen, device=dev)
+        sidx = torch.div(t_us, seg_us, rounding_mode="floor")
+        u = (t_us % seg_us).to(torch.float64) / float(dt_ns / 1000.0)
+        q = qmul(qa[sidx], qexp(d[sidx] * u[:, None]))
+        pc = qrot_conj(q, Lw[li])
+        zc = pc[:, 2]
+        px = torch.round(fx * pc[:, 0] / zc + cx)
+        py = torch.round(fy * pc[:, 1] / zc + cy)
+        ok = (zc > 1e-3) & (px >= 0) & (px < W) & (py >= 0) & (py < H)
+        sel = torch.nonzero(ok).squeeze(1)[:need]
+        xs.append(px[sel].to(torch.int64).cpu().numpy()); ys.append(py[sel].to(torch.int64).cpu().numpy())
+        ts.append(t_us[sel].cpu().numpy())
+        need -= len(xs[-1])
+    x = np.concatenate(xs); y = np.concatenate(ys); t = np.concatenate(ts) + t0_rel_us
+    ev = _pack_events(x, y, t)
+    t_next_us = t0_rel_us + span_us // 2
+    tnext = (EPOCH_SEC + t_next_us // 1_000_000, (t_next_us % 1_000_000) * 1000)
+    return BeWindow(ev, bearing_lut(W, H, K4), W, H, pano_w, pano_h, knots, t0_ns, dt_ns, order,
+                    n_fixed, tnext, name=name)
+
+
+def be_config(name, scale=1.0, order=2, device=None):
     """'C4': 1e7 ev, 64 knots, 1280x720 pano; 'C5': 5e7 ev, 256 knots, 4096x2048 pano."""
+    make = make_be_window if device is None else (lambda *a, **kw: make_be_window_torch(*a, device=device, **kw))
     if name == "C4":
-        return make_be_window(int(10_000_000 * scale), 64, 1280, 720, 4, order=order,
-                              n_landmarks=50000, n_fixed=1 if order == 2 else 3, name="C4")
+        return make(int(10_000_000 * scale), 64, 1280, 720, 4, order=order,
+                    n_landmarks=50000, n_fixed=1 if order == 2 else 3, name="C4")
     if name == "C5":
-        return make_be_window(int(50_000_000 * scale), 256, 4096, 2048, 5, order=order,
-                              n_landmarks=200000, n_fixed=1 if order == 2 else 3, name="C5")
+        return make(int(50_000_000 * scale), 256, 4096, 2048, 5, order=order,
+                    n_landmarks=200000, n_fixed=1 if order == 2 else 3, name="C5")
     raise ValueError(name)

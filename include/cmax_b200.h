@@ -352,9 +352,32 @@ int cmaxb_stream_next_packet(cmaxb_stream* s, const cmaxb_event** events, size_t
                              int* span_too_long);
 /* events of the back-end window [t_beg, t_end) by the reference's coarse-to-fine search (packet-level look-up table,
  * then 100-event strides back from the end); consumes the look-up entries and deletes the events no end needs any
- * more.  CMAXB_ERR_STATE when the store does not cover the window yet. */
+ * more.  Returns 1 (not an error, nothing consumed) when the store does not cover the window yet; CMAXB_ERR_STATE is
+ * reserved for an inconsistent store. */
 int cmaxb_stream_window_events(cmaxb_stream* s, cmaxb_stamp t_beg, cmaxb_stamp t_end, const cmaxb_event** events, size_t* n);
 int cmaxb_stream_state(cmaxb_stream* s, int64_t* n_stored, int64_t* n_subsets_pending, int64_t* n_ts_map, cmaxb_stamp* time_packet);
+
+/* Device-resident event store.  The reference cuts OVERLAPPING packets out of one host vector (a packet = the half
+ * packet before and after every dt_ang_vel tick, ang_vel_estimator.cpp:84-92,137-147), so handing each packet to the
+ * device separately moves every event over PCIe several times.  With a device store attached, every pushed event is
+ * copied to a ring in device memory ONCE (asynchronously, on `cuda_stream`) and packets are handed out as views of that
+ * ring for cmaxb_fe_set_packet_view (same stream => ordered after the copy).
+ *   cmaxb_stream_attach_device   before the first push; ring_events = ring capacity in events (0: 8 packets)
+ *   cmaxb_stream_push_ex         flags: CMAXB_PUSH_BORROW -- msg_events is page-locked host memory that stays valid and
+ *                                unchanged until cmaxb_stream_released() has passed it: the message is referenced in place
+ *                                (no host copy) and DMA-ed from where it lies (needs event_sample_rate 1);
+ *                                CMAXB_PUSH_SORTED -- the message is sorted by time stamp (as DVS drivers deliver it): the
+ *                                packet ticks inside it are found by bisection instead of an event-by-event scan
+ *   cmaxb_stream_next_packet_device   like cmaxb_stream_next_packet, but *device_events points into the device ring (valid
+ *                                until ring_events - packet more events have been pushed)
+ *   cmaxb_stream_released        number of events, counted from the first push, that the store has dropped */
+#define CMAXB_PUSH_BORROW 1
+#define CMAXB_PUSH_SORTED 2
+int cmaxb_stream_attach_device(cmaxb_stream* s, int device, void* cuda_stream, size_t ring_events);
+int cmaxb_stream_push_ex(cmaxb_stream* s, const cmaxb_event* msg_events, size_t n, int flags, int* packets_ready);
+int cmaxb_stream_next_packet_device(cmaxb_stream* s, const cmaxb_event** device_events, size_t* n, cmaxb_stamp* time_packet,
+                                    int* span_too_long);
+int cmaxb_stream_released(cmaxb_stream* s, int64_t* n_released);
 
 /* ------------------------------------------------------------------ back-end window pipeline ---- */
 /* Everything PoseGraphOptimizer does for one sliding time window (pose_graph_optimizer.cpp:72-354), as host C++
@@ -419,10 +442,11 @@ int cmaxb_fe_profile(cmaxb_fe* fe, int enable);
 int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms /*CMAXB_K_COUNT*/, uint64_t* launches /*CMAXB_K_COUNT*/);
 /* Fused evaluation kernel, profiling enabled: microseconds from kernel entry (CTA 0) to the phase boundaries of the LAST
  * synchronous evaluation: [1] scatter end, [2] grid barrier, [3] image phase end, [4] grid barrier, [5] gather end,
- * [6] last CTA starts the final sums, [7] result published; [8], [9] unused; -1 = not reached. */
+ * [6] last CTA starts the final sums, [7] result rows stored (all CTA 0 except [6], [7]); [8] / [9]: the SLOWEST CTA's
+ * scatter end / image phase end; -1 = not reached. */
 int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10);
 /* fused launches: [0] CTAs of a whole-GPU launch, [1] CTAs of a throughput-lane launch, [2] throughput lanes,
- * [3] TMA tile staging on, [4] / [5] image tile height of the two launch shapes, [6] gather-record policy (-1 auto, 0, 1) */
+ * [3] TMA tile staging on, [4] / [5] image tile height of the two launch shapes, [6] reserved (0) */
 int cmaxb_fe_launch_info(cmaxb_fe* fe, int32_t* info7);
 int cmaxb_be_profile(cmaxb_be* be, int enable);
 int cmaxb_be_kernel_times(cmaxb_be* be, double* ms, uint64_t* launches);

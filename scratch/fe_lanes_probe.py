@@ -30,7 +30,9 @@ def run(lanes, depth, rot, want_grad=True, n=600):
     info = fe.launch_info()
     fe.close()
     return dt * 1e6, res[-1], info
-for lanes, depth, rot in ((1, 1, 1), (1, 2, 1), (2, 2, 1), (2, 4, 1), (3, 3, 1), (3, 6, 1), (4, 8, 1), (3, 6, 6), (1, 2, 6)):
+import sys as _s
+CASES = ((1, 1, 1), (1, 2, 1), (2, 4, 1), (3, 6, 1), (4, 8, 1), (3, 6, 6)) if len(_s.argv) < 2 else ((3, 6, 1), (3, 6, 6))
+for lanes, depth, rot in CASES:
     us, c, info = run(lanes, depth, rot)
     print(f"{tag} lanes {lanes} depth {depth} rot {rot}: {us:.1f} us/eval f+g ({len(pk.events)/us*1e6:.3e} ev/s) contrast {c:.6f} grid {info['grid_full']}/{info['grid_lane']} tma {info['tma']}", flush=True)
 us, c, info = run(3, 6, 1, want_grad=False)

@@ -186,7 +186,9 @@ def test_gsl_callbacks_on_device(oracle):
     ro = oracle.fe_eval(a, [0.1, 0.2, 0.3], True)
     f, df = frontend.local_contrast_fdf([0.1, 0.2, 0.3], fe)
     assert abs(f + ro["contrast"]) <= RTOL * ro["contrast"] and np.abs(df + ro["grad"]).max() <= RTOL * np.abs(ro["grad"]).max()
-    assert abs(frontend.local_contrast_f([0.1, 0.2, 0.3], fe) - f) <= 1e-7 * abs(f)
+    # value-only evaluations sum the squared blurred image; gradient evaluations get S2 = <I, B^T B I> / 2 from the adjoint
+    # image (csrc/fe_fused.cuh): the two agree to the f32 rounding of the filter coefficients
+    assert abs(frontend.local_contrast_f([0.1, 0.2, 0.3], fe) - f) <= 2e-6 * abs(f)
     fe.close()
 
 

@@ -1,4 +1,4 @@
-"""Front-end launch ring (up to 8 evaluations queued before the first fetch), the two gather variants (per-event records / recomputed geometry),
+"""Front-end launch ring (up to 8 evaluations queued before the first fetch), the fused kernel's variants (TMA / binning on and off),
 and the fused result exchange over peer memory (two processes sharing cuda:0, CUDA IPC) -- through the C ABI,
 against the CPU oracle."""
 import os
@@ -85,10 +85,10 @@ np.save(sys.argv[2], np.concatenate([c, g.ravel(), [c1], g1]))
 '''
 
 
-def test_gather_from_records_and_recomputed_both_meet_the_bar(oracle, tmp_path):
-    """The gradient gather streaming the scatter's per-event records (CMAXB_FE_CACHE=1) and recomputing the event
-    geometry (CMAXB_FE_CACHE=0), TMA tile staging on and off, against the oracle; the true angular velocity (gradient
-    near its zero crossing) is among the hypotheses."""
+def test_fused_kernel_variants_meet_the_bar(oracle, tmp_path):
+    """The fused evaluation with TMA-staged tiles + binned event walk (default), without TMA (arrival-order fallback),
+    without binning, and on one lane, against the oracle; the true angular velocity (gradient near its zero crossing)
+    is among the hypotheses."""
     pk = synth.fe_config("C1", scale=0.5)
     oms = np.concatenate([synth.fe_hypotheses(pk, 5, sigma=0.4), pk.omega_true[None, :]])
     a = oracle.fe_args(pk.events, pk.t_ref_sec, pk.lut, pk.width, pk.height, pk.K)
@@ -96,8 +96,8 @@ def test_gather_from_records_and_recomputed_both_meet_the_bar(oracle, tmp_path):
     script = tmp_path / "g.py"
     script.write_text(_GATHER_WORKER)
     out = {}
-    for tag, env in (("records", {"CMAXB_FE_CACHE": "1"}), ("recomputed", {"CMAXB_FE_CACHE": "0"}),
-                     ("records_no_tma", {"CMAXB_FE_CACHE": "1", "CMAXB_FE_TMA": "0"}), ("one_lane", {"CMAXB_FE_LANES": "1"})):
+    for tag, env in (("default", {}), ("no_tma", {"CMAXB_FE_TMA": "0"}), ("no_binning", {"CMAXB_FE_NO_BINNING": "1"}),
+                     ("one_lane", {"CMAXB_FE_LANES": "1"})):
         path = tmp_path / f"{tag}.npy"
         r = subprocess.run([sys.executable, str(script), ROOT, str(path)], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
@@ -109,8 +109,8 @@ def test_gather_from_records_and_recomputed_both_meet_the_bar(oracle, tmp_path):
         assert abs(c1 - co[5]) <= RTOL * co[5] and np.abs(g1 - go[5]).max() <= RTOL * gmax[5] + 1e-7 * np.abs(go).max()
         out[tag] = g
     # the variants agree far below the bar
-    assert np.abs(out["records"] - out["recomputed"]).max() <= 2e-6 * np.abs(go).max()
-    assert np.abs(out["records"] - out["records_no_tma"]).max() <= 2e-6 * np.abs(go).max()
+    assert np.abs(out["default"] - out["no_tma"]).max() <= 2e-6 * np.abs(go).max()
+    assert np.abs(out["default"] - out["no_binning"]).max() <= 2e-6 * np.abs(go).max()
 
 
 _XCHG_WORKER = r'''

@@ -130,8 +130,8 @@ def test_plain_eval_after_a_sharded_evaluation(oracle):
     # plain evaluation at OTHER parameters on the handle that was sharded
     c2, g2 = be.eval(x2, True)
     c2r, g2r = ref.eval(x2, True)
-    assert abs(c2 - c2r) <= 1e-9 * abs(c2r), (c2, c2r, c_s)
-    assert np.abs(g2 - g2r).max() <= 1e-7 * np.abs(g2r).max()
+    assert abs(c2 - c2r) <= 1e-6 * abs(c2r), (c2, c2r, c_s)      # two handles: f32 atomic order
+    assert np.abs(g2 - g2r).max() <= 1e-5 * np.abs(g2r).max()
     assert np.allclose(be.computeImageOfWarpedEvents(x2), ref.computeImageOfWarpedEvents(x2), rtol=0, atol=1e-4)
     # ... and after a new window (half of the events)
     n2 = 10000
@@ -139,7 +139,7 @@ def test_plain_eval_after_a_sharded_evaluation(oracle):
         h.set_window(w.events[:n2], w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.4)
     c3, _ = be.eval(x2, True)
     c3r, _ = ref.eval(x2, True)
-    assert abs(c3 - c3r) <= 1e-9 * abs(c3r)
+    assert abs(c3 - c3r) <= 1e-6 * abs(c3r)
     a = oracle.be_args(w.events[:n2], w.lut, 64, 48, 128, 64, w.knots_xyzw, w.t0_ns, w.dt_ns, 2, w.n_fixed, w.tnext, IGp, 0.4)
     assert abs(c3 - oracle.be_eval(a, x2, False)["contrast"]) <= 1e-5 * abs(c3)
     be.close(); ref.close()

@@ -101,9 +101,9 @@ def test_gap_marks_packet_and_uncovered_window_is_an_error():
         flags.append(p[2])
     assert flags == [f for _, _, f in o.packets] and any(flags) and not all(flags)
     t_last = (int(ev["sec"][-1]) + 10, 0)
-    with pytest.raises(CmaxbError) as e:                    # beyond the store
-        s.window_events((int(ev["sec"][0]), int(ev["nsec"][0])), t_last)
-    assert e.value.code == -6
+    n_before = s.state()
+    assert s.window_events((int(ev["sec"][0]), int(ev["nsec"][0])), t_last) is None      # beyond the store: "not yet", nothing consumed
+    assert s.state() == n_before
     with pytest.raises(CmaxbError):
         EventStream(0.0, 2000, 1)
     s.close()
@@ -141,3 +141,48 @@ def test_randomised_configurations_match_restatement():
         st = s.state()
         assert st["n_stored"] == o.total and st["n_ts_map"] == len(o.ts_keys) and st["n_subsets_pending"] == len(o.subsets), trial
         s.close()
+
+
+@pytest.mark.parametrize("msg,per_packet", [(1500, 2000), (4096, 600), (977, 1500)])
+def test_sorted_bisection_and_borrowed_messages_give_the_same_packets(msg, per_packet):
+    """cmaxb_stream_push_ex: CMAXB_PUSH_SORTED finds the packet ticks inside a time-sorted message by bisection,
+    CMAXB_PUSH_BORROW references the caller's buffer in place -- packets, windows and bookkeeping must equal the
+    event-by-event scan over copied messages (which test_packets_match_per_event_restatement pins to the reference)."""
+    ev = _events(70000, 21)
+    ref = EventStream(0.01, per_packet, 1)
+    streams = {"sorted": (EventStream(0.01, per_packet, 1), EventStream.PUSH_SORTED),
+               "borrow": (EventStream(0.01, per_packet, 1), EventStream.PUSH_BORROW),
+               "both": (EventStream(0.01, per_packet, 1), EventStream.PUSH_SORTED | EventStream.PUSH_BORROW)}
+    dur = lambda sec: (int(sec), int(round((sec - int(sec)) * 1e9)))
+    def t_add(t, d):
+        ns = t[1] + d[1]
+        return (t[0] + d[0] + ns // 1_000_000_000, ns % 1_000_000_000)
+    wb = (int(ev["sec"][0]), int(ev["nsec"][0])); we = t_add(wb, dur(0.06))
+    n_pk = n_win = 0
+    for i in range(0, len(ev), msg):
+        chunk = ev[i:i + msg]                                  # a view of `ev`: stays valid (borrowed messages)
+        k0 = ref.eventsCallback(chunk)
+        for name, (s, fl) in streams.items():
+            assert s.eventsCallback(chunk, fl) == k0, name
+        while True:
+            p = ref.next_packet()
+            if p is None:
+                break
+            n_pk += 1
+            for name, (s, fl) in streams.items():
+                q = s.next_packet()
+                assert q is not None and q[1] == p[1] and q[2] == p[2] and _same(q[0], p[0]), name
+        last = (int(chunk["sec"][-1]), int(chunk["nsec"][-1]))
+        if last > t_add(we, dur(0.02)):
+            a = ref.window_events(wb, we)
+            for name, (s, fl) in streams.items():
+                b = s.window_events(wb, we)
+                assert b is not None and _same(a, b), name
+                assert s.state() == ref.state(), name
+            assert streams["borrow"][0].released() > 0
+            wb, we = t_add(wb, dur(0.05)), t_add(we, dur(0.05))
+            n_win += 1
+    assert n_pk > 10 and n_win >= 3
+    for s, _ in streams.values():
+        s.close()
+    ref.close()
