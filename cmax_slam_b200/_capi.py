@@ -42,12 +42,12 @@ class BeCfg(C.Structure):
 
 class OptParams(C.Structure):
     _fields_ = [("initial_step", C.c_double), ("line_tol", C.c_double), ("max_iterations", C.c_int32),
-                ("epsabs_grad", C.c_double), ("tolfun", C.c_double)]
+                ("epsabs_grad", C.c_double), ("tolfun", C.c_double), ("fused_trials", C.c_int32)]
 
 
 class OptResult(C.Structure):
     _fields_ = [("cost_initial", C.c_double), ("cost_final", C.c_double), ("iterations", C.c_int32),
-                ("f_evals", C.c_int32), ("g_evals", C.c_int32), ("stop_reason", C.c_int32)]
+                ("f_evals", C.c_int32), ("g_evals", C.c_int32), ("stop_reason", C.c_int32), ("cost_launches", C.c_int32)]
 
 
 COST_F = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p, C.POINTER(C.c_double))
@@ -126,7 +126,7 @@ EXPORTS = [
     "cmaxb_traj_incremental_update",
     "cmaxb_precompute_bearing_vectors",
     "cmaxb_stream_create", "cmaxb_stream_destroy", "cmaxb_stream_push", "cmaxb_stream_next_packet", "cmaxb_stream_window_events",
-    "cmaxb_stream_state", "cmaxb_stream_attach_device", "cmaxb_stream_push_ex", "cmaxb_stream_next_packet_device", "cmaxb_stream_released",
+    "cmaxb_stream_state", "cmaxb_stream_attach_device", "cmaxb_stream_push_ex", "cmaxb_stream_next_packet_device", "cmaxb_stream_released", "cmaxb_stream_wait_copied",
     "cmaxb_pgo_create", "cmaxb_pgo_destroy", "cmaxb_pgo_push_ang_vel", "cmaxb_pgo_window", "cmaxb_pgo_process_window",
     "cmaxb_pgo_get_ctrl_poses", "cmaxb_be_last_eval_x",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
@@ -193,6 +193,7 @@ def lib():
     L.cmaxb_stream_push_ex.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_int)]
     L.cmaxb_stream_next_packet_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), sp, C.POINTER(C.c_int)]
     L.cmaxb_stream_released.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.cmaxb_stream_wait_copied.argtypes = [vp, vp]
     L.cmaxb_pgo_create.argtypes = [C.POINTER(PgoCfg), vp, C.POINTER(vp)]
     L.cmaxb_pgo_destroy.argtypes = [vp]
     L.cmaxb_pgo_destroy.restype = None

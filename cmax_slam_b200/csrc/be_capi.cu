@@ -32,7 +32,7 @@ struct cmaxb_be {
   bool split_pending = false; bool split_grad = false; bool end_launched = false; bool end_grad = false;
   // device-resident global map (IG_, IG_update_times_map_)
   float* d_IG = nullptr; unsigned char* d_times = nullptr; unsigned char* d_mask = nullptr;
-  int* d_ccell = nullptr; float4* d_ca = nullptr; float4* d_cb = nullptr; size_t cache_cap = 0;   // per-event gather cache
+  float4* d_ca = nullptr; float2* d_cb = nullptr; size_t cache_cap = 0;   // per-event gather cache (24 B)
   long long n_visit = 0; int m_visit = 1;
   float* d_bands = nullptr; float* d_bands_blur = nullptr; size_t bands_cap = 0;
   double* d_acc = nullptr; unsigned int* d_ticket = nullptr; double* d_result = nullptr; double* d_mean = nullptr;
@@ -42,6 +42,13 @@ struct cmaxb_be {
   int* d_flags = nullptr; int* h_flags = nullptr;
   int* d_cells = nullptr; size_t cells_cap = 0;
   bool have_window = false;
+  // CUDA-graph replay of a whole evaluation (x upload, poses, zeroing, scatter, blur, adjoint, gather, per-knot reduction,
+  // result download): small windows are launch-bound (ten launches + a synchronisation, ~90 us at 9k events); the first
+  // evaluation of each kind (value / value + gradient) after set_window runs launch by launch (it allocates and fixes
+  // alpha), the second is captured, later ones are one cudaGraphLaunch.  CMAXB_BE_GRAPH=0 turns it off.
+  bool graph_on = true;
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  int evals_in_window[2] = {0, 0};
   std::vector<double> last_x;   // parameter vector of the most recent cmaxb_be_eval (the reference's IL_old_ / IL_new_ members hold THAT evaluation's images)
   KernelProfiler prof;
 };
@@ -81,6 +88,7 @@ extern "C" int cmaxb_be_create(const cmaxb_be_cfg* cfg, cmaxb_be** out) {
   be->device = cfg->device;
   be->N = cfg->spline_order;
   be->A = (long long)cfg->pano_width * cfg->pano_height;
+  { const char* gr = getenv("CMAXB_BE_GRAPH"); be->graph_on = !(gr && gr[0] == '0'); }
   be->SA = (long long)cfg->sensor_width * cfg->sensor_height;
   int rc = make_taps(cfg->blur_sigma, &be->taps);
   if (rc != CMAXB_OK) { delete be; return rc; }
@@ -125,12 +133,13 @@ extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
   if (!be) return;
   cudaSetDevice(be->device);
   if (be->stream) cudaStreamSynchronize(be->stream);
+  for (int k = 0; k < 2; ++k) if (be->gexec[k]) cudaGraphExecDestroy(be->gexec[k]);
   cudaFree(be->d_lut); cudaFree(be->d_ev); cudaFree(be->d_bt); cudaFree(be->d_poses); cudaFree(be->d_wgrad); cudaFree(be->d_idx);
   cudaFree(be->d_knots0); cudaFree(be->d_knots); cudaFree(be->d_x); cudaFree(be->d_grad);
   cudaFree(be->d_seg_lo); cudaFree(be->d_seg_hi);
   cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
   cudaFree(be->d_bands); cudaFree(be->d_bands_blur); cudaFree(be->d_ilq); cudaFree(be->d_GQ);
-  cudaFree(be->d_ccell); cudaFree(be->d_ca); cudaFree(be->d_cb); cudaFree(be->d_il_plane);
+  cudaFree(be->d_ca); cudaFree(be->d_cb); cudaFree(be->d_il_plane);
   cudaFree(be->d_IG); cudaFree(be->d_times); cudaFree(be->d_mask);
 
   cudaFree(be->d_acc); cudaFree(be->d_ticket); cudaFree(be->d_result); cudaFree(be->d_mean);
@@ -155,6 +164,10 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
   CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
   be->have_window = false;
   be->il_is_plane = false; be->split_pending = false; be->end_launched = false;
+  for (int k = 0; k < 2; ++k) {        // buffers may move and the window geometry is baked into the captured launches
+    if (be->gexec[k]) { cudaGraphExecDestroy(be->gexec[k]); be->gexec[k] = nullptr; }
+    be->evals_in_window[k] = 0;
+  }
   be->last_x.clear();
   const long long n = (long long)w->n_events, bs = be->cfg.batch_size;
   // the reference loop `for (beg = begin; beg < end-1; beg += bs)` never visits a trailing batch
@@ -262,10 +275,13 @@ static unsigned be_warp_grid(const cmaxb_be* be) {
 }
 
 // x -> updated knots -> per-batch pose table
-static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
+static int be_fill_x(cmaxb_be* be, const double* x, int n) {
   if (x && n != 3 * be->n_opt) return set_error(CMAXB_ERR_INVALID, "x must have 3*(n_knots-n_fixed) entries");
-  cudaStream_t s = be->stream;
   for (int i = 0; i < 3 * be->n_opt; ++i) be->h_x[i] = x ? x[i] : 0.0;
+  return CMAXB_OK;
+}
+static int be_enqueue_poses(cmaxb_be* be, bool want_grad) {
+  cudaStream_t s = be->stream;
   if (be->n_opt > 0) CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_x, be->h_x, sizeof(double) * 3 * be->n_opt, cudaMemcpyHostToDevice, s));
   if (be->nb > 0) {
     const unsigned grid = (unsigned)((be->nb + 127) / 128);
@@ -275,6 +291,10 @@ static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
     }));
   }
   return CMAXB_OK;
+}
+static int be_run_poses(cmaxb_be* be, const double* x, int n, bool want_grad) {
+  CMAXB_TRY(be_fill_x(be, x, n));
+  return be_enqueue_poses(be, want_grad);
 }
 
 // updateAlpha (event_pano_warper.cpp:134-165) from the current IL; il_old may be an assembled plane (il_new = null)
@@ -305,14 +325,13 @@ static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false
   cudaStream_t s = be->stream;
   const bool quad = allow_quad && be->use_quad;
   if (want_cache && (size_t)be->n_visit > be->cache_cap) {
-    cudaFree(be->d_ccell); cudaFree(be->d_ca); cudaFree(be->d_cb);
-    be->d_ccell = nullptr; be->d_ca = nullptr; be->d_cb = nullptr; be->cache_cap = 0;
-    CMAXB_TRY(dev_alloc(&be->d_ccell, (size_t)be->n_visit));
+    cudaFree(be->d_ca); cudaFree(be->d_cb);
+    be->d_ca = nullptr; be->d_cb = nullptr; be->cache_cap = 0;
     CMAXB_TRY(dev_alloc(&be->d_ca, (size_t)be->n_visit));
     CMAXB_TRY(dev_alloc(&be->d_cb, (size_t)be->n_visit));
     be->cache_cap = (size_t)be->n_visit;
   }
-  const BeCache cache{be->d_ccell, be->d_ca, be->d_cb};
+  const BeCache cache{be->d_ca, be->d_cb};
   be->il_is_quad = quad;
   be->il_is_plane = false;   // a fresh scatter supersedes the assembled plane of an earlier sharded evaluation (eval_begin re-sets it)
   CMAXB_TRY(be->prof.run(CMAXB_K_ZERO, s, false, [&] {
@@ -432,7 +451,7 @@ static int be_finish_launch(cmaxb_be* be, bool want_grad) {
       if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("adjoint_blur launch: ") + cudaGetErrorString(le));
       if (be->nb > 0) {
         const BeGeom g = be_geom(be);
-        const BeCache cache{be->d_ccell, be->d_ca, be->d_cb};
+        const BeCache cache{be->d_ca, be->d_cb};
         CMAXB_TRY(be->prof.run(CMAXB_K_BE_GATHER, s, true, [&] {
           if (be->N == 2) {
             if (quad) be_gather_kernel<2, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, be->d_GQ, cache, be->d_wgrad);
@@ -457,16 +476,24 @@ static int be_finish_launch(cmaxb_be* be, bool want_grad) {
   }
   return CMAXB_OK;
 }
-// copy contrast (+ gradient) to the host and wait
-static int be_finish_fetch(cmaxb_be* be, bool want_grad, double* contrast, double* grad) {
+// copy contrast (+ gradient) to the host (queued) / wait and hand over
+static int be_enqueue_fetch(cmaxb_be* be, bool want_grad) {
   cudaStream_t s = be->stream;
   const int P = 3 * be->n_opt;
   if (want_grad && P > 0) CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_grad, be->d_grad, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
   CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_result, be->d_result, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
-  CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
+  return CMAXB_OK;
+}
+static int be_wait_fetch(cmaxb_be* be, bool want_grad, double* contrast, double* grad) {
+  const int P = 3 * be->n_opt;
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(be->stream));
   *contrast = be->h_result[0];
   if (want_grad && grad) for (int i = 0; i < P; ++i) grad[i] = be->h_grad[i];
   return CMAXB_OK;
+}
+static int be_finish_fetch(cmaxb_be* be, bool want_grad, double* contrast, double* grad) {
+  CMAXB_TRY(be_enqueue_fetch(be, want_grad));
+  return be_wait_fetch(be, want_grad, contrast, grad);
 }
 static int be_finish_eval(cmaxb_be* be, bool want_grad, double* contrast, double* grad) {
   CMAXB_TRY(be_finish_launch(be, want_grad));
@@ -481,9 +508,39 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
   const int P = 3 * be->n_opt;
   const bool adjoint_grad = want_grad && P > 0 && be->cfg.grad_mode == CMAXB_GRAD_ADJOINT;
   be->split_pending = false;
-  CMAXB_TRY(be_run_poses(be, x, n, want_grad));
-  CMAXB_TRY(be_run_scatter(be, true, adjoint_grad));
+  const int kind = want_grad ? 1 : 0;
+  CMAXB_TRY(be_fill_x(be, x, n));
   if (x && n > 0) be->last_x.assign(x, x + n); else be->last_x.assign((size_t)(n > 0 ? n : 0), 0.0);
+  const bool replay = be->graph_on && !be->prof.enabled && !be->alpha_pending && be->evals_in_window[kind] >= 1 &&
+                      !(want_grad && be->cfg.grad_mode == CMAXB_GRAD_DENSE);
+  be->evals_in_window[kind] += 1;
+  if (replay) {
+    cudaStream_t s = be->stream;
+    if (!be->gexec[kind]) {
+      cudaGraph_t graph = nullptr;
+      CMAXB_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int rc = be_enqueue_poses(be, want_grad);
+      if (rc == CMAXB_OK) rc = be_run_scatter(be, true, adjoint_grad);
+      if (rc == CMAXB_OK) rc = be_finish_launch(be, want_grad);
+      if (rc == CMAXB_OK) rc = be_enqueue_fetch(be, want_grad);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc != CMAXB_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+        be->graph_on = false;                 // fall back to launch-by-launch evaluation for good
+        if (rc != CMAXB_OK) return rc;
+        return set_error(CMAXB_ERR_CUDA, std::string("graph capture of the back-end evaluation failed: ") + cudaGetErrorString(ce));
+      }
+      ce = cudaGraphInstantiate(&be->gexec[kind], graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { be->gexec[kind] = nullptr; be->graph_on = false; return set_error(CMAXB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+    }
+    CMAXB_CUDA_TRY(cudaGraphLaunch(be->gexec[kind], s));
+    g_launch_count.fetch_add(want_grad ? 6 : 3, std::memory_order_relaxed);    // kernels replayed by the graph
+    return be_wait_fetch(be, want_grad, contrast, grad);
+  }
+  CMAXB_TRY(be_enqueue_poses(be, want_grad));
+  CMAXB_TRY(be_run_scatter(be, true, adjoint_grad));
   return be_finish_eval(be, want_grad, contrast, grad);
 }
 

@@ -46,11 +46,12 @@ struct BeGeom {
   long long n_visit;       // total visited events
 };
 
-// per visited event, written by the gradient scatter pass and consumed by the gather pass
+// per visited event, written by the gradient scatter pass and consumed by the gather pass: 24 bytes
+// (round 1 stored the 2x3 Jacobian factor as well, 36 bytes: 2.6x the algorithmic traffic at C4; the factor is a
+// closed form of the rotated ray, rebuilt in f32 by the gather)
 struct BeCache {
-  int* cell;               // yy*W+xx or -1
-  float4* a;               // (dx, dy, dd00, dd01)
-  float4* b;               // (dd02, dd10, dd11, dd12)
+  float4* a;               // (cell = yy*W+xx as int bits or -1, dx, dy, ray.x)
+  float2* b;               // (ray.y, ray.z)   ray = R * bearing (world frame), f32
 };
 
 // t_mid of each batch -> (s, u); flags |= 4 when outside the spline (BASALT_ASSERT, so3_spline.h:221-230)
@@ -125,6 +126,7 @@ struct BeWarp {
   int xx, yy;
   float dx, dy;
   bool is_old;
+  float rx, ry, rz;  // R * bearing as f32 (drb_ddrot is built from exactly these casts, :280-281)
   float dd[2][3];   // dpm_ddrot = dpm_drb * drb_ddrot (2x3, f32)            (:273-282)
 };
 
@@ -160,6 +162,7 @@ __device__ __forceinline__ BeWarp be_warp(const BeGeom& g, const double* R, uint
     }
   }
   o.is_old = (e.y < g.tnext_sec) || (e.y == g.tnext_sec && e.z < g.tnext_nsec);   // ev->ts < t_next_win_beg_ (:298)
+  o.rx = (float)wx; o.ry = (float)wy; o.rz = (float)wz;
   if (GRAD) {
     const double Ydivrho = wy / rho;
     const double XdivZ = wx / wz;
@@ -204,13 +207,10 @@ __device__ __forceinline__ void be_scatter_range(const BeGeom& g, const BePose* 
 #pragma unroll
     for (int q = 0; q < 9; ++q) R[q] = __ldcg(&poses[b].R[q]);
     const uint4 e = load_event(g.ev, i);
-    const BeWarp w = be_warp<CACHE>(g, R, e);
+    const BeWarp w = be_warp<false>(g, R, e);
     if (CACHE) {
-      cache.cell[j] = w.in ? w.yy * g.W + w.xx : -1;
-      if (w.in) {
-        cache.a[j] = make_float4(w.dx, w.dy, w.dd[0][0], w.dd[0][1]);
-        cache.b[j] = make_float4(w.dd[0][2], w.dd[1][0], w.dd[1][1], w.dd[1][2]);
-      }
+      __stcg(cache.a + j, make_float4(__int_as_float(w.in ? w.yy * g.W + w.xx : -1), w.dx, w.dy, w.rx));
+      if (w.in) __stcg(cache.b + j, make_float2(w.ry, w.rz));
     }
     if (!w.in) continue;
     const float dx = w.dx, dy = w.dy;
@@ -299,8 +299,11 @@ __global__ void be_cells_kernel(BeGeom g, const BePose* __restrict__ poses, long
 // jac = dd * Jk, the contribution to g_j is  (a*dd[0,:] + b*dd[1,:]) . Jk[:, j]  with
 // a = sum_c s_c G(c), b = sum_c t_c G(c).  The bracket is summed over the batch first (3 numbers),
 // then multiplied by the batch's Jk once: wgrad[b][c] = V_b . Jk[:, c].
-// One WARP per batch; the per-event geometry is NOT recomputed: (cell, dx, dy, dd) come from the
-// cache the gradient scatter pass wrote (36 bytes per event, streamed once).
+// One WARP per batch; the f64 geometry (atan2 / asin) is NOT recomputed: (cell, dx, dy, rotated ray) come from the
+// cache the gradient scatter pass wrote (24 bytes per event, streamed once), and the 2x3 factor
+// dpm_ddrot = dpm_drb * drb_ddrot (event_pano_warper.cpp:273-282, equirectangular_camera.h:30-42) is rebuilt from the
+// ray in f32 through its closed form (s2 = x^2 + z^2, rho2 = s2 + y^2):
+//   dpm_drb = [ fx z / s2, 0, -fx x / s2 ;  -fy x y / (rho2 s),  fy s / rho2,  -fy y z / (rho2 s) ]
 template <int N, bool QUAD>
 __device__ __forceinline__ void be_gather_range(const BeGeom& g, const BePose* __restrict__ poses, const float* __restrict__ G,
                                                 const float4* __restrict__ GQ, const BeCache& cache, double* __restrict__ wgrad,
@@ -312,9 +315,25 @@ __device__ __forceinline__ void be_gather_range(const BeGeom& g, const BePose* _
     if (b == g.nb - 1 || j1 > g.n_visit) j1 = g.n_visit;
     double v0 = 0, v1 = 0, v2 = 0;
     for (long long j = j0 + lane; j < j1; j += 32) {
-      const int cell = __ldcg(cache.cell + j);
+      const float4 ca4 = __ldcg(cache.a + j);
+      const int cell = __float_as_int(ca4.x);
       if (cell < 0) continue;
-      const float4 ca = __ldcg(cache.a + j), cb = __ldcg(cache.b + j);
+      const float2 cb2 = __ldcg(cache.b + j);
+      float dd[2][3];
+      {
+        const float rx = ca4.w, ry = cb2.x, rz = cb2.y;
+        const float s2 = rx * rx + rz * rz, rho2 = s2 + ry * ry;
+        const float sr = sqrtf(s2);
+        const float i_s2 = __fdividef(1.0f, s2), i_r2s = __fdividef(1.0f, rho2 * sr);
+        const float ffx = (float)g.fx, ffy = (float)g.fy;
+        const float j00 = ffx * rz * i_s2, j02 = -ffx * rx * i_s2;
+        const float j10 = -ffy * rx * ry * i_r2s, j11 = ffy * sr * __fdividef(1.0f, rho2), j12 = -ffy * ry * rz * i_r2s;
+        // dpm_ddrot = dpm_drb * (-[ray]x)
+        dd[0][0] = j02 * ry;               dd[0][1] = j00 * rz - j02 * rx;   dd[0][2] = -j00 * ry;
+        dd[1][0] = -j11 * rz + j12 * ry;   dd[1][1] = j10 * rz - j12 * rx;   dd[1][2] = -j10 * ry + j11 * rx;
+      }
+      const float4 ca = make_float4(ca4.y, ca4.z, dd[0][0], dd[0][1]);
+      const float4 cb = make_float4(dd[0][2], dd[1][0], dd[1][1], dd[1][2]);
       double g00, g01, g10, g11;
       if (QUAD) {
         const float4 q = __ldcg(GQ + cell);

@@ -17,7 +17,7 @@ namespace cmaxb {
 
 constexpr int kBinTile = 32;          // source tile edge in pixels
 constexpr int kBinThreads = 256;
-constexpr int kBinChunk = 8192;       // events per CTA
+constexpr int kBinChunk = 2048;       // events per CTA (8 per thread: ~490 CTAs for a 1M-event packet)
 constexpr int kBinMaxTiles = 6144;    // shared-memory histogram capacity: the scatter pass needs 2 x 4 B per tile within the 48 KB default limit
 
 __device__ __forceinline__ int bin_tile_of(uint4 e, int W, int H, int ntx) {
@@ -26,15 +26,23 @@ __device__ __forceinline__ int bin_tile_of(uint4 e, int W, int H, int ntx) {
   return (y / kBinTile) * ntx + (x / kBinTile);
 }
 
-// pass 1: tile histogram (per-CTA shared histogram, one global atomic per non-empty bin)
+// pass 1: tile histogram (per-CTA shared histogram, one global atomic per non-empty bin) + validation of the pixel range
+// (flags[0] |= 2: the reference's precomputed_bearing_vectors_.at(...) would throw, local_image_warped_events.cpp:100)
 __global__ void __launch_bounds__(kBinThreads)
-fe_bin_count_kernel(const uint4* __restrict__ ev, long long n, int W, int H, int ntx, int ntiles, unsigned int* __restrict__ tile_count) {
+fe_bin_count_kernel(const uint4* __restrict__ ev, long long n, int W, int H, int ntx, int ntiles, unsigned int* __restrict__ tile_count,
+                    int* __restrict__ flags) {
   extern __shared__ unsigned int s_hist[];
   for (int i = threadIdx.x; i < ntiles; i += kBinThreads) s_hist[i] = 0u;
   __syncthreads();
   const long long beg = blockIdx.x * (long long)kBinChunk;
   const long long end = min(beg + (long long)kBinChunk, n);
-  for (long long i = beg + threadIdx.x; i < end; i += kBinThreads) atomicAdd(&s_hist[bin_tile_of(__ldg(ev + i), W, H, ntx)], 1u);
+  bool bad = false;
+  for (long long i = beg + threadIdx.x; i < end; i += kBinThreads) {
+    const uint4 e = __ldg(ev + i);
+    bad = bad || (int)(e.x & 0xffff) >= W || (int)(e.x >> 16) >= H;
+    atomicAdd(&s_hist[bin_tile_of(e, W, H, ntx)], 1u);
+  }
+  if (bad) atomicOr(flags, 2);
   __syncthreads();
   for (int i = threadIdx.x; i < ntiles; i += kBinThreads)
     if (s_hist[i]) atomicAdd(&tile_count[i], s_hist[i]);

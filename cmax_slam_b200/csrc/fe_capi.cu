@@ -483,17 +483,21 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
     CMAXB_CUDA_TRY(cudaMemsetAsync(pk.d_flags, 0, sizeof(int), s));
     const uint4* ev = pk.ev; const long long nn = pk.n; int* flags = pk.d_flags;
     const int W = fe->cfg.width, H = fe->cfg.height; double* dt = pk.d_dt; const int ibs = (int)bs;
-    CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-      validate_events_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(ev, nn, W, H, flags);
-    }));
+    // one-time spatial binning of the packet (reused by every evaluation until the next set_packet); its counting pass
+    // also validates the pixel range (without bins a stand-alone validation kernel does)
+    fe->ntx = (W + kBinTile - 1) / kBinTile;
+    fe->ntiles = fe->ntx * ((H + kBinTile - 1) / kBinTile);
+    const bool do_bins = fe->use_bins && fe->ntiles <= kBinMaxTiles && nn < (1LL << 32);
+    if (!do_bins) {
+      CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
+        validate_events_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(ev, nn, W, H, flags);
+      }));
+    }
     CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
       fe_batch_dt_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ev, nn, ibs, t_ref_sec, dt, nb, flags);
     }));
-    // one-time spatial binning of the packet (reused by every evaluation until the next set_packet)
     pk.have_bins = false;
-    fe->ntx = (W + kBinTile - 1) / kBinTile;
-    fe->ntiles = fe->ntx * ((H + kBinTile - 1) / kBinTile);
-    if (fe->use_bins && fe->ntiles <= kBinMaxTiles && nn < (1LL << 32)) {
+    if (do_bins) {
       if (n > pk.bev_cap) {
         cudaStreamSynchronize(s);
         cudaFree(pk.d_bev); pk.d_bev = nullptr; pk.bev_cap = 0;
@@ -508,7 +512,7 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
       unsigned int* cursor = pk.d_tile_end;
       CMAXB_CUDA_TRY(cudaMemsetAsync(fe->d_tile_count, 0, sizeof(unsigned int) * ntiles, s));
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-        fe_bin_count_kernel<<<nchunks, kBinThreads, sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, fe->d_tile_count);
+        fe_bin_count_kernel<<<nchunks, kBinThreads, sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, fe->d_tile_count, flags);
       }));
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
         fe_bin_scan_kernel<<<1, 1024, 0, s>>>(fe->d_tile_count, ntiles, cursor);

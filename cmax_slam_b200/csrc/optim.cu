@@ -27,22 +27,46 @@ struct Cost {
   // f: value only; df: gradient only (the reference's df recomputes the value too); fdf: both.  cost = -contrast.
   std::function<int(const double*, double*)> f;
   std::function<int(const double*, double*, double*)> fdf;
-  int f_evals = 0, g_evals = 0;
+  int f_evals = 0, g_evals = 0;      // value / gradient REQUESTS of the minimiser (what GSL would have called)
+  int launches = 0;                  // cost evaluations actually run
   int rc = CMAXB_OK;
+  // fused trials (cmaxb_opt_params.fused_trials): GSL evaluates every accepted line-search point twice -- f(x) for the
+  // test, then df(x) at the SAME x (conjugate_fr.c / directional_minimize.c; the reference's df recomputes the value as
+  // well, local_optim_contrast_gsl.cpp:65-70).  On the device a value + gradient evaluation costs less than a value-only
+  // one plus a second value + gradient one, so every trial is evaluated with its gradient and remembered: the df request
+  // at an already evaluated point is answered from the memo.  Same requests, same iterates; only the launches change.
+  bool fuse = false;
+  std::vector<double> memo_x, memo_g;
+  double memo_f = 0;
+  bool memo_ok = false;
+  void run_fdf(const std::vector<double>& x, double* v, std::vector<double>& g) {
+    if (rc == CMAXB_OK) rc = fdf(x.data(), v, g.data());
+    ++launches;
+    if (fuse) { memo_x = x; memo_g = g; memo_f = *v; memo_ok = rc == CMAXB_OK; }
+  }
   double eval_f(const std::vector<double>& x) {
     double v = 0;
-    if (rc == CMAXB_OK) rc = f(x.data(), &v);
     ++f_evals;
+    if (fuse) {
+      if (memo_ok && memo_x == x) return memo_f;
+      std::vector<double> g(x.size());
+      run_fdf(x, &v, g);
+      return v;
+    }
+    if (rc == CMAXB_OK) rc = f(x.data(), &v);
+    ++launches;
     return v;
   }
   void eval_df(const std::vector<double>& x, std::vector<double>& g) {
     double v = 0;
-    if (rc == CMAXB_OK) rc = fdf(x.data(), &v, g.data());
     ++g_evals;
+    if (fuse && memo_ok && memo_x == x) { g = memo_g; return; }
+    run_fdf(x, &v, g);
   }
   void eval_fdf(const std::vector<double>& x, double* v, std::vector<double>& g) {
-    if (rc == CMAXB_OK) rc = fdf(x.data(), v, g.data());
     ++f_evals; ++g_evals;
+    if (fuse && memo_ok && memo_x == x) { *v = memo_f; g = memo_g; return; }
+    run_fdf(x, v, g);
   }
 };
 
@@ -220,6 +244,7 @@ struct ConjugateFr {
 int run_reference_loop(Cost& c, const std::vector<double>& x0, const cmaxb_opt_params& prm, std::vector<double>& x_out,
                        cmaxb_opt_result* res) {
   ConjugateFr s;
+  c.fuse = prm.fused_trials != 0;
   s.set(c, x0, prm.initial_step, prm.line_tol);
   if (c.rc != CMAXB_OK) return c.rc;
   const double initial_cost = s.f;
@@ -246,6 +271,7 @@ int run_reference_loop(Cost& c, const std::vector<double>& x0, const cmaxb_opt_p
     res->f_evals = c.f_evals;
     res->g_evals = c.g_evals;
     res->stop_reason = stop;   // 0 iteration limit, 1 cost stagnation, 2 gradient norm, 3 no progress (GSL_ENOPROG)
+    res->cost_launches = c.launches;
   }
   return CMAXB_OK;
 }
@@ -272,7 +298,7 @@ extern "C" int cmaxb_fe_optimize(cmaxb_fe* fe, const double omega0[3], const cma
                                  cmaxb_opt_result* result) {
   if (!fe || !omega0 || !omega_out) return set_error(CMAXB_ERR_INVALID, "null argument");
   // local_optim_contrast_gsl.cpp:106-122: step 0.1, tol 0.05, <= 50 iterations, |g| < 1e-3, rel. change < 1e-4
-  cmaxb_opt_params prm{0.1, 0.05, 50, 1e-3, 1e-4};
+  cmaxb_opt_params prm{0.1, 0.05, 50, 1e-3, 1e-4, 0};
   if (params) prm = *params;
   Cost c;
   c.n = 3;
@@ -294,7 +320,7 @@ extern "C" int cmaxb_be_optimize(cmaxb_be* be, const double* x0, int n, const cm
                                  cmaxb_opt_result* result) {
   if (!be || !x_out || n <= 0) return set_error(CMAXB_ERR_INVALID, "null argument / no parameters");
   // global_optim_contrast_gsl.cpp:41-53: step 0.1, tol 0.1, <= 50 iterations, |g| < 1e-4, rel. change < 1e-4; x0 = 0
-  cmaxb_opt_params prm{0.1, 0.1, 50, 1e-4, 1e-4};
+  cmaxb_opt_params prm{0.1, 0.1, 50, 1e-4, 1e-4, 0};
   if (params) prm = *params;
   Cost c;
   c.n = n;

@@ -142,6 +142,7 @@ struct cmaxb_stream {
   int device = -1; cudaStream_t cu_stream = nullptr;
   cmaxb_event* d_ring = nullptr; size_t cap = 0, mirror = 0;
   StageBuf bounce[2]; int bounce_cur = 0; cudaEvent_t bounce_done[2] = {nullptr, nullptr};   // owned copies travel through pinned memory
+  cudaEvent_t copied = nullptr;                    // recorded on cu_stream after the copies of every push
 };
 
 extern "C" int cmaxb_stream_create(const cmaxb_stream_cfg* cfg, cmaxb_stream** out) {
@@ -164,6 +165,7 @@ extern "C" void cmaxb_stream_destroy(cmaxb_stream* s) {
     if (s->cu_stream) cudaStreamSynchronize(s->cu_stream);
     cudaFree(s->d_ring);
     for (int i = 0; i < 2; ++i) if (s->bounce_done[i]) cudaEventDestroy(s->bounce_done[i]);
+    if (s->copied) cudaEventDestroy(s->copied);
   }
   s->packet[0].release(); s->packet[1].release(); s->window.release();
   s->bounce[0].release(); s->bounce[1].release();
@@ -182,6 +184,7 @@ extern "C" int cmaxb_stream_attach_device(cmaxb_stream* s, int device, void* cud
   if (C < 2 * L) C = 2 * L;
   CMAXB_CUDA_TRY(cudaMalloc((void**)&s->d_ring, sizeof(cmaxb_event) * (C + L)));
   for (int i = 0; i < 2; ++i) CMAXB_CUDA_TRY(cudaEventCreateWithFlags(&s->bounce_done[i], cudaEventDisableTiming));
+  CMAXB_CUDA_TRY(cudaEventCreateWithFlags(&s->copied, cudaEventDisableTiming));
   s->device = device; s->cu_stream = (cudaStream_t)cuda_stream; s->cap = C; s->mirror = L;
   return CMAXB_OK;
 }
@@ -268,6 +271,7 @@ extern "C" int cmaxb_stream_push_ex(cmaxb_stream* s, const cmaxb_event* msg_even
           CMAXB_TRY(stream_to_device(s, abs0, bb.p, m));
           CMAXB_CUDA_TRY(cudaEventRecord(s->bounce_done[s->bounce_cur], s->cu_stream));
         }
+        CMAXB_CUDA_TRY(cudaEventRecord(s->copied, s->cu_stream));
       }
     }
   }
@@ -375,6 +379,17 @@ extern "C" int cmaxb_stream_window_events(cmaxb_stream* s, cmaxb_stamp t_beg, cm
   *events = s->window.p; *n = cnt;
   s->ts_map.erase(s->ts_map.begin(), ib + 1);                         // erase(begin, std::next(ev_beg_iter))
   stream_delete_old(s, beg);
+  return CMAXB_OK;
+}
+
+// makes `consumer_stream` wait for the device copies of everything pushed so far (needed when the packets are consumed
+// on another stream than the one the store copies on, e.g. a dedicated copy stream that overlaps the evaluations)
+extern "C" int cmaxb_stream_wait_copied(cmaxb_stream* s, void* consumer_stream) {
+  if (!s) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!s->d_ring) return set_error(CMAXB_ERR_STATE, "no device store");
+  CMAXB_CUDA_TRY(cudaSetDevice(s->device));
+  if ((cudaStream_t)consumer_stream != s->cu_stream && s->num_event_total + s->abs_front > 0)
+    CMAXB_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)consumer_stream, s->copied, 0));
   return CMAXB_OK;
 }
 

@@ -58,6 +58,10 @@ class EventStream:
         _capi.check(rc)
         return (p.value, n.value), (t.sec, t.nsec), bool(f.value)
 
+    def wait_copied(self, consumer_stream):
+        """consumer_stream (cudaStream_t) waits for the device copies of everything pushed so far."""
+        _capi.check(self._L.cmaxb_stream_wait_copied(self._s, C.c_void_p(int(consumer_stream)) if consumer_stream else None))
+
     def released(self):
         k = C.c_int64(0)
         _capi.check(self._L.cmaxb_stream_released(self._s, C.byref(k)))

@@ -264,11 +264,17 @@ typedef struct cmaxb_opt_params {
   int32_t max_iterations;/* 50 */
   double epsabs_grad;    /* FE 1e-3, BE 1e-4 */
   double tolfun;         /* 1e-4 */
+  int32_t fused_trials;  /* 0: the reference's call pattern (value-only trials, then df at the accepted point);
+                            1: every line-search trial is evaluated WITH its gradient and memoised, so the df request GSL
+                            issues at the accepted trial point costs no second evaluation -- same requests, same iterates
+                            (up to the ~1e-7 by which the value of a value+gradient evaluation differs from a value-only
+                            one), fewer launches */
 } cmaxb_opt_params;
 typedef struct cmaxb_opt_result {
   double cost_initial, cost_final;   /* -contrast */
   int32_t iterations, f_evals, g_evals;
   int32_t stop_reason;               /* 0 iteration limit, 1 cost stagnation, 2 gradient norm, 3 no progress */
+  int32_t cost_launches;             /* cost evaluations actually run (f_evals / g_evals count the minimiser's requests) */
 } cmaxb_opt_result;
 int cmaxb_fe_optimize(cmaxb_fe* fe, const double omega0[3], const cmaxb_opt_params* params, double omega_out[3],
                       cmaxb_opt_result* result);
@@ -378,6 +384,9 @@ int cmaxb_stream_push_ex(cmaxb_stream* s, const cmaxb_event* msg_events, size_t 
 int cmaxb_stream_next_packet_device(cmaxb_stream* s, const cmaxb_event** device_events, size_t* n, cmaxb_stamp* time_packet,
                                     int* span_too_long);
 int cmaxb_stream_released(cmaxb_stream* s, int64_t* n_released);
+/* makes consumer_stream wait for the device copies of everything pushed so far: needed when the store copies on its own
+ * stream (so that uploads overlap the evaluations) and the packets are prepared on another one */
+int cmaxb_stream_wait_copied(cmaxb_stream* s, void* consumer_stream);
 
 /* ------------------------------------------------------------------ back-end window pipeline ---- */
 /* Everything PoseGraphOptimizer does for one sliding time window (pose_graph_optimizer.cpp:72-354), as host C++

@@ -11,7 +11,11 @@ METRICS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", 
            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-           "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+           "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+           "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__shared_mem_per_block_dynamic",
+           "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
 rep = sys.argv[1]
 print("# " + (sys.argv[2] if len(sys.argv) > 2 else rep))
 print(f"# source report: {rep} (not committed; gpurun_out/ is scratch)")

@@ -42,9 +42,9 @@ def test_our_arm_has_no_cpu_fallback():
 def test_roofline_helpers_read_the_committed_profiles():
     sys.path.insert(0, ROOT)
     import bench
-    traffic, src = bench.ncu_traffic_bytes("fe_eval_megakernel")
+    traffic, src = bench.ncu_traffic_bytes("fe_eval_fused_kernel")
     assert traffic and 1e7 < traffic < 1e8 and src.endswith(".txt")
-    sec = bench.ncu_secondary("fe_eval_megakernel")
+    sec = bench.ncu_secondary("fe_eval_fused_kernel")
     assert sec and 0 < sec["l2_throughput_pct"] < 100 and "l2_atomic_input_cycles_pct" in sec
     peak, how = bench.load_peaks()
     assert 3000 < peak < 9000

@@ -47,6 +47,7 @@ def test_device_packets_equal_host_packets(flags):
                 break
             q = dev.next_packet_device()
             assert q is not None and q[1] == p[1] and q[2] == p[2] and q[0][1] == len(p[0])
+            dev.wait_copied(0)            # legacy default stream waits for the store's copy stream
             stream.synchronize()
             got = torch.empty(len(p[0]) * 16, dtype=torch.uint8, device="cuda")
             import ctypes

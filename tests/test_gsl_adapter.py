@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 _SRC = r'''
 #include "cmax_b200_gsl.hpp"
+#include <vector>
 static cmaxb_gsl::Api g_api;
 extern "C" int adapter_load(const char* path) { return g_api.load(path) ? 0 : -1; }
 extern "C" int adapter_fe_roundtrip(const cmaxb_fe_cfg* cfg, const cmaxb_event* ev, size_t n, double t_ref,
@@ -31,6 +32,26 @@ extern "C" int adapter_fe_roundtrip(const cmaxb_fe_cfg* cfg, const cmaxb_event* 
   cmaxb_gsl::local_contrast_df(&x, &p, &g);
   for (int i = 0; i < 3; ++i) if (gv[i] != df3[i] && !(gv[i] - df3[i] < 1e-6 && df3[i] - gv[i] < 1e-6)) { g_api.fe_destroy(fe); return -3; }
   g_api.fe_destroy(fe);
+  return 0;
+}
+extern "C" int adapter_be_roundtrip(const cmaxb_be_cfg* cfg, const cmaxb_be_window* win, const double* x0, int n,
+                                    double* f_only, double* f, double* df) {
+  cmaxb_be* be = nullptr;
+  if (g_api.be_create(cfg, &be) != CMAXB_OK) return -1;
+  if (g_api.be_set_window(be, win) != CMAXB_OK) { g_api.be_destroy(be); return -2; }
+  cmaxb_gsl::BeParams p{&g_api, be, n};
+  std::vector<double> xv(x0, x0 + n), gv(n), gv2(n);
+  gsl_vector x{(size_t)n, 1, xv.data(), nullptr, 0};
+  gsl_vector g{(size_t)n, 1, gv.data(), nullptr, 0};
+  gsl_vector g2{(size_t)n, 1, gv2.data(), nullptr, 0};
+  *f_only = cmaxb_gsl::global_contrast_f(&x, &p);
+  cmaxb_gsl::global_contrast_fdf(&x, &p, f, &g);
+  for (int i = 0; i < n; ++i) df[i] = gv[i];
+  cmaxb_gsl::global_contrast_df(&x, &p, &g2);
+  double gmax = 0;
+  for (int i = 0; i < n; ++i) gmax = gv[i] > gmax ? gv[i] : (-gv[i] > gmax ? -gv[i] : gmax);
+  for (int i = 0; i < n; ++i) { const double d = gv2[i] - gv[i]; if (d > 1e-5 * gmax || -d > 1e-5 * gmax) { g_api.be_destroy(be); return -3; } }
+  g_api.be_destroy(be);
   return 0;
 }
 '''
@@ -73,4 +94,35 @@ def test_adapter_gsl_callbacks_on_device(adapter, oracle):
     ro = oracle.fe_eval(a, om, True)
     assert abs(f.value + ro["contrast"]) <= 1e-5 * ro["contrast"]          # callbacks return MINUS contrast
     assert abs(f0.value + ro["contrast"]) <= 1e-5 * ro["contrast"]
+    assert np.abs(df + ro["grad"]).max() <= 1e-5 * np.abs(ro["grad"]).max()
+
+
+@pytest.mark.gpu
+def test_adapter_backend_gsl_callbacks_on_device(adapter, oracle):
+    """global_contrast_f / _fdf / _df of include/cmax_b200_gsl.hpp executed from C++ on the device (round-1 verdict: the
+    back-end callbacks were compiled but never run), against the oracle: minus contrast, minus gradient."""
+    from cmax_slam_b200 import _capi, build, synth
+    assert adapter.adapter_load(build.build().encode()) == 0
+    w = synth.make_be_window(20000, 8, 256, 128, 7, order=2, n_landmarks=1000)
+    lut = np.ascontiguousarray(w.lut)
+    cfg = _capi.BeCfg(w.sensor_width, w.sensor_height, lut.ctypes.data, 256, 128, 1.0, 100, 1, 2, 0, 1, 0, None)
+    ev = np.ascontiguousarray(w.events)
+    kn = np.ascontiguousarray(w.knots_xyzw, dtype=np.float64)
+    rng = np.random.default_rng(5)
+    IGp = np.abs(rng.normal(0, 0.3, (128, 256))).astype(np.float32)
+    win = _capi.BeWindow(ev.ctypes.data, len(ev), kn.ctypes.data, kn.shape[0], int(w.t0_ns), int(w.dt_ns), int(w.n_fixed),
+                         int(w.tnext[0]), int(w.tnext[1]), IGp.ctypes.data, 0.5)
+    n = 3 * (kn.shape[0] - w.n_fixed)
+    x = rng.normal(0, 0.01, n)
+    f0, f = C.c_double(), C.c_double()
+    df = np.zeros(n)
+    dp = C.POINTER(C.c_double)
+    adapter.adapter_be_roundtrip.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_int, dp, dp, dp]
+    rc = adapter.adapter_be_roundtrip(C.addressof(cfg), C.addressof(win), x.ctypes.data_as(dp), n, C.byref(f0), C.byref(f),
+                                      df.ctypes.data_as(dp))
+    assert rc == 0
+    a = oracle.be_args(w.events, w.lut, w.sensor_width, w.sensor_height, 256, 128, w.knots_xyzw, w.t0_ns, w.dt_ns, 2, w.n_fixed,
+                       w.tnext, IGp, 0.5)
+    ro = oracle.be_eval(a, x, True)
+    assert abs(f.value + ro["contrast"]) <= 1e-5 * ro["contrast"] and abs(f0.value + ro["contrast"]) <= 1e-5 * ro["contrast"]
     assert np.abs(df + ro["grad"]).max() <= 1e-5 * np.abs(ro["grad"]).max()

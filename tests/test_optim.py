@@ -97,3 +97,46 @@ def test_library_be_solve_improves_contrast_and_matches_restatement(oracle):
     assert np.abs(x - x_ref).max() < 5e-3
     assert abs(st["cost_final"] - st_ref["cost_final"]) <= 1e-3 * abs(st_ref["cost_final"])
     be.close()
+
+
+def test_fused_trials_same_iterates_fewer_launches_callback():
+    """cmaxb_opt_params.fused_trials over a caller-supplied cost (CPU): identical requests and iterates, and every df request
+    at an already evaluated trial point is answered from the memo."""
+    from cmax_slam_b200 import _capi
+    calls = {"f": 0, "fdf": 0}
+    A = np.array([[3.0, 0.4, 0.1], [0.4, 2.0, 0.3], [0.1, 0.3, 1.0]])
+    b = np.array([1.0, -2.0, 0.5])
+
+    def f(x):
+        calls["f"] += 1
+        return float(0.5 * x @ A @ x - b @ x + 0.1 * np.sum(x ** 4))
+
+    def fdf(x):
+        calls["fdf"] += 1
+        return float(0.5 * x @ A @ x - b @ x + 0.1 * np.sum(x ** 4)), A @ x - b + 0.4 * x ** 3
+
+    x0 = np.array([2.0, 2.0, -1.0])
+    x_ref, st_ref = _capi.optimize_callback(f, fdf, x0, (0.1, 0.05, 50, 1e-6, 1e-9))
+    ref_calls = dict(calls)
+    calls.update(f=0, fdf=0)
+    x_fu, st_fu = _capi.optimize_callback(f, fdf, x0, (0.1, 0.05, 50, 1e-6, 1e-9, 1))
+    assert np.array_equal(x_ref, x_fu) and st_ref["iterations"] == st_fu["iterations"]
+    assert st_ref["f_evals"] == st_fu["f_evals"] and st_ref["g_evals"] == st_fu["g_evals"]          # same requests
+    assert calls["f"] == 0 and calls["fdf"] == st_fu["cost_launches"]                                   # every trial with its gradient
+    assert st_fu["cost_launches"] < st_ref["cost_launches"] == ref_calls["f"] + ref_calls["fdf"]
+
+
+@pytest.mark.gpu
+def test_fused_trials_on_device_same_outcome():
+    from cmax_slam_b200.frontend import AngVelEstimatorCMax
+    pk = synth.fe_config("C1", scale=0.3)
+    fe = AngVelEstimatorCMax(pk.width, pk.height, pk.K, pk.lut)
+    fe.set_packet(pk.events, pk.t_ref_sec)
+    x0 = np.array([0.3, -0.5, 1.0])
+    x, st = fe.setupProblemAndOptimize(x0)
+    xf, stf = fe.setupProblemAndOptimize(x0, params=(0.1, 0.05, 50, 1e-3, 1e-4, 1))
+    assert np.abs(x - xf).max() < 2e-3 and abs(st["iterations"] - stf["iterations"]) <= 3
+    assert abs(st["cost_final"] - stf["cost_final"]) <= 1e-4 * abs(st["cost_final"])
+    assert stf["cost_launches"] < st["cost_launches"]
+    assert np.abs(xf - pk.omega_true).max() < 0.02
+    fe.close()
