@@ -438,7 +438,13 @@ def run_ours(args, rank, world, local_rank):
         extra["latency_value_only_us"] = (time.perf_counter() - t0) / K * 1e6
 
     # ---- end to end ---------------------------------------------------------------------------------------------------
-    e2e = bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt, omega)
+    # N > 1: every rank tracks its OWN event stream (N independent front-ends: units = packets, no data-path collective),
+    # so the result exchange of the hypothesis-sharded loop above is switched off first
+    if use_p2p:
+        barrier()
+        fe.exchange_close()
+        barrier()
+    e2e = bench_e2e(args, fe, stream, dev, rank, world, False, barrier, sampler, pkt, omega)
 
     # ---- dominant kernel: CUDA-event time of the fused launch (library profiler: serialised whole-GPU launches, L2 cold) -----
     fe.select_packet(0)
@@ -625,8 +631,9 @@ def bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt
     st.close()
     fe.select_packet(0)
     return {"value": world * done * per_packet / (ms * 1e-3), "unit": UNIT,
-            "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * (64 * max(world, 1) + 8),
+            "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * (64 + 4),
             "ms_per_step": ms / max(done, 1), "steps": done,
+            "sharding": "none" if world == 1 else f"{world} independent event streams, one per GPU (weak scaling, no collective)",
             "path": "cmaxb_stream_push_ex (page-locked driver messages, 10 ms = ~190k events each, copied to the device ring once) -> "
                     "cmaxb_stream_next_packet_device (overlapping 1M-event packet = ring view) -> cmaxb_fe_set_packet_view (validate, "
                     "batch times, binning) -> cmaxb_fe_eval_launch / _fetch; one packet per step; the reference re-copies each packet "

@@ -33,6 +33,8 @@ class EventWarperCMax:
         _capi.check(self._L.cmaxb_be_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self.pano_width, self.pano_height = pano_width, pano_height
+        # radius of cv::GaussianBlur(Size(0,0), sigma) on CV_32F, as csrc/capi_common.cuh make_taps computes it
+        self.blur_radius = ((int(round(float(blur_sigma) * 8 + 1)) | 1) // 2) if blur_sigma > 0 else 0
         self.spline_order = spline_order
         self.n_events = 0
         self.n_params = 0
@@ -129,6 +131,43 @@ class EventWarperCMax:
         g = np.zeros(max(self.n_params, 1))
         _capi.check(self._L.cmaxb_be_eval_end_fetch(self._h, C.byref(c), _capi.dptr(g) if self._split_grad else None))
         return c.value, (g[: self.n_params] if self._split_grad else None)
+
+    # -- the same with the image phases sharded by row band (cmaxb_be_shard_*) ------------------------------
+    @staticmethod
+    def _dev_tensor(ptr, count, typestr):
+        import torch
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+        return torch.as_tensor(_View(), device="cuda")
+
+    def shard_begin(self, x, want_grad, world, rank):
+        """Poses + scatter of this rank's events.  Returns (send, recv) float32 tensor views: `send` holds `world` extended
+        bands, `recv` receives this rank's band summed over ranks (reduce_scatter_tensor(recv, send))."""
+        xx, n = self._x(x)
+        send, recv, chunk = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        _capi.check(self._L.cmaxb_be_shard_begin(self._h, None if xx is None else _capi.dptr(xx), n, int(want_grad), int(world),
+                                                 int(rank), C.byref(send), C.byref(recv), C.byref(chunk)))
+        self._split_grad = bool(want_grad)
+        return (self._dev_tensor(send.value, chunk.value * world, "<f4"), self._dev_tensor(recv.value, chunk.value, "<f4"))
+
+    def shard_image(self):
+        """Blur of the band; returns the (S1, S2) float64 tensor view to all-reduce."""
+        p = C.c_void_p()
+        _capi.check(self._L.cmaxb_be_shard_image(self._h, C.byref(p)))
+        return self._dev_tensor(p.value, 2, "<f8")
+
+    def shard_adjoint(self, world):
+        """Contrast + mean; gradient evaluations: adjoint blur of the band.  Returns (g_own, g_full) views or (None, None)."""
+        own, full, cnt = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        _capi.check(self._L.cmaxb_be_shard_adjoint(self._h, C.byref(own), C.byref(full), C.byref(cnt)))
+        if not own.value:
+            return None, None
+        return self._dev_tensor(own.value, cnt.value, "<f4"), self._dev_tensor(full.value, cnt.value * world, "<f4")
+
+    def shard_gather(self):
+        _capi.check(self._L.cmaxb_be_shard_gather(self._h))
 
     # -- device-resident global map (event_pano_warper.cpp:81-132) --------------------------------------------
     def resetIG(self):

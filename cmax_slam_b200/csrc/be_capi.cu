@@ -29,6 +29,11 @@ struct cmaxb_be {
   float4* d_ilq = nullptr; float4* d_GQ = nullptr;   // corner-split accumulator / adjoint image (event-dense windows)
   bool use_quad = false; bool il_is_quad = false;
   float* d_il_plane = nullptr; bool il_is_plane = false;   // assembled IL (event-sharded evaluation)
+  // row-band sharding of the image phases (cmaxb_be_shard_*)
+  int sh_world = 0, sh_rank = 0, sh_hb = 0, sh_hl = 0, sh_ce = 0, sh_y0 = 0, sh_y1 = 0, sh_first = 0, sh_rows = 0;
+  float* d_sh_send = nullptr; float* d_sh_recv = nullptr; float* d_sh_blur = nullptr; float* d_sh_gband = nullptr;
+  float* d_sh_gfull = nullptr; double* d_sh_sums = nullptr; size_t sh_cap = 0;
+  int sh_stage = 0; bool sh_grad = false;
   bool split_pending = false; bool split_grad = false; bool end_launched = false; bool end_grad = false;
   // device-resident global map (IG_, IG_update_times_map_)
   float* d_IG = nullptr; unsigned char* d_times = nullptr; unsigned char* d_mask = nullptr;
@@ -140,6 +145,7 @@ extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
   cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
   cudaFree(be->d_bands); cudaFree(be->d_bands_blur); cudaFree(be->d_ilq); cudaFree(be->d_GQ);
   cudaFree(be->d_ca); cudaFree(be->d_cb); cudaFree(be->d_il_plane);
+  cudaFree(be->d_sh_send); cudaFree(be->d_sh_recv); cudaFree(be->d_sh_blur); cudaFree(be->d_sh_gband); cudaFree(be->d_sh_gfull); cudaFree(be->d_sh_sums);
   cudaFree(be->d_IG); cudaFree(be->d_times); cudaFree(be->d_mask);
 
   cudaFree(be->d_acc); cudaFree(be->d_ticket); cudaFree(be->d_result); cudaFree(be->d_mean);
@@ -163,7 +169,7 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
   cudaStream_t s = be->stream;
   CMAXB_CUDA_TRY(cudaStreamSynchronize(s));
   be->have_window = false;
-  be->il_is_plane = false; be->split_pending = false; be->end_launched = false;
+  be->il_is_plane = false; be->split_pending = false; be->end_launched = false; be->sh_stage = 0;
   for (int k = 0; k < 2; ++k) {        // buffers may move and the window geometry is baked into the captured launches
     if (be->gexec[k]) { cudaGraphExecDestroy(be->gexec[k]); be->gexec[k] = nullptr; }
     be->evals_in_window[k] = 0;
@@ -433,6 +439,32 @@ static int be_run_bands(cmaxb_be* be, bool blur) {
   return CMAXB_OK;
 }
 
+// adjoint gather over this handle's events + per-knot reduction -> d_grad (G: float plane, or GQ: corner-packed cells)
+static int be_gather_launch(cmaxb_be* be, const float* G, const float4* GQ) {
+  cudaStream_t s = be->stream;
+  const int W = be->cfg.pano_width, H = be->cfg.pano_height;
+  const bool quad = GQ != nullptr;
+  if (be->nb > 0) {
+    const BeGeom g = be_geom(be);
+    const BeCache cache{be->d_ca, be->d_cb};
+    CMAXB_TRY(be->prof.run(CMAXB_K_BE_GATHER, s, true, [&] {
+      if (be->N == 2) {
+        if (quad) be_gather_kernel<2, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, GQ, cache, be->d_wgrad);
+        else be_gather_kernel<2, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, G, nullptr, cache, be->d_wgrad);
+      } else {
+        if (quad) be_gather_kernel<4, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, GQ, cache, be->d_wgrad);
+        else be_gather_kernel<4, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, G, nullptr, cache, be->d_wgrad);
+      }
+    }));
+  }
+  const double inv_np = 1.0 / ((double)W * (double)H);
+  CMAXB_TRY(be->prof.run(CMAXB_K_BE_GRAD_REDUCE, s, true, [&] {
+    if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+    else be_grad_reduce_kernel<4><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+  }));
+  return CMAXB_OK;
+}
+
 // image -> contrast (+ gradient) on the current IL (quad / planes / assembled plane); results to the host
 // queue blur + contrast (+ adjoint image, gather, per-knot reduction): results stay on the device
 static int be_finish_launch(cmaxb_be* be, bool want_grad) {
@@ -449,24 +481,7 @@ static int be_finish_launch(cmaxb_be* be, bool want_grad) {
                   : launch_adjoint_blur<false>(s, 1, be->d_blur, 0, W, H, be->taps, be->d_mean, be->cfg.contrast_measure, be->d_G, nullptr);
       }));
       if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("adjoint_blur launch: ") + cudaGetErrorString(le));
-      if (be->nb > 0) {
-        const BeGeom g = be_geom(be);
-        const BeCache cache{be->d_ca, be->d_cb};
-        CMAXB_TRY(be->prof.run(CMAXB_K_BE_GATHER, s, true, [&] {
-          if (be->N == 2) {
-            if (quad) be_gather_kernel<2, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, be->d_GQ, cache, be->d_wgrad);
-            else be_gather_kernel<2, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, nullptr, cache, be->d_wgrad);
-          } else {
-            if (quad) be_gather_kernel<4, true><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, nullptr, be->d_GQ, cache, be->d_wgrad);
-            else be_gather_kernel<4, false><<<be_warp_grid(be), kBeThreads, 0, s>>>(g, be->d_poses, be->d_G, nullptr, cache, be->d_wgrad);
-          }
-        }));
-      }
-      const double inv_np = 1.0 / ((double)W * (double)H);
-      CMAXB_TRY(be->prof.run(CMAXB_K_BE_GRAD_REDUCE, s, true, [&] {
-        if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
-        else be_grad_reduce_kernel<4><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
-      }));
+      CMAXB_TRY(be_gather_launch(be, quad ? nullptr : be->d_G, quad ? be->d_GQ : nullptr));
     } else {
       CMAXB_TRY(be_run_bands(be, true));
       CMAXB_TRY(be->prof.run(CMAXB_K_BE_GRAD_REDUCE, s, true, [&] {
@@ -625,6 +640,125 @@ extern "C" int cmaxb_be_eval_end_fetch(cmaxb_be* be, double* contrast, double* g
   CMAXB_CUDA_TRY(cudaSetDevice(be->device));
   be->end_launched = false;
   return be_finish_fetch(be, grad != nullptr, contrast, grad);
+}
+
+// ---- row-band sharding of the image phases (time-sharded window over several GPUs) ----------------------------------
+// begin:   poses + scatter of THIS rank's events; IL packed as `world` extended bands (send buffer)
+// (caller) reduce_scatter(recv <- send, SUM): every rank now holds the summed rows of its band + halo
+// image:   blur of the band (+ alpha IGp), S1 / S2 over the band's OWN rows -> sums (2 doubles)
+// (caller) all_reduce(sums, SUM)
+// adjoint: contrast + mean from the sums; adjoint blur of the band -> own rows of G
+// (caller) all_gather(g_full <- g_own)
+// gather:  adjoint gather over this rank's events with the full G plane -> partial gradient (cmaxb_be_grad_device)
+// (caller) all_reduce(gradient, SUM); cmaxb_be_eval_end_fetch
+// Compared with the whole-plane exchange (cmaxb_be_eval_begin / _end) the same bytes cross NVLink (reduce-scatter + all-gather
+// = one all-reduce) but blur and adjoint blur run on 1/world of the panorama instead of being replicated on every rank.
+extern "C" int cmaxb_be_shard_begin(cmaxb_be* be, const double* x, int n, int want_grad, int world, int rank, float** send_dev,
+                                    float** recv_dev, size_t* chunk_floats) {
+  if (!be || !send_dev || !recv_dev || !chunk_floats) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window: call cmaxb_be_set_window first");
+  if (be->alpha_pending) return set_error(CMAXB_ERR_STATE, "alpha is not fixed yet: run the window's first evaluation through cmaxb_be_eval_begin / _end");
+  if (want_grad && be->cfg.grad_mode != CMAXB_GRAD_ADJOINT) return set_error(CMAXB_ERR_INVALID, "event-sharded evaluation needs CMAXB_GRAD_ADJOINT");
+  const int W = be->cfg.pano_width, H = be->cfg.pano_height;
+  const int hl = 2 * be->taps.r + 1;
+  const int hb = (H + world - 1) / world;
+  if (world < 1 || rank < 0 || rank >= world || hb < hl || (long long)(world - 1) * hb >= H)
+    return set_error(CMAXB_ERR_INVALID, "bad world / rank, or bands thinner than the halo (use the whole-plane exchange)");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  const int ce = hb + 2 * hl;
+  const size_t need = (size_t)world * ce * W;
+  if (need > be->sh_cap || be->sh_world != world) {
+    cudaFree(be->d_sh_send); cudaFree(be->d_sh_recv); cudaFree(be->d_sh_blur); cudaFree(be->d_sh_gband); cudaFree(be->d_sh_gfull); cudaFree(be->d_sh_sums);
+    be->d_sh_send = be->d_sh_recv = be->d_sh_blur = be->d_sh_gband = be->d_sh_gfull = nullptr; be->d_sh_sums = nullptr; be->sh_cap = 0;
+    CMAXB_TRY(dev_alloc(&be->d_sh_send, need));
+    CMAXB_TRY(dev_alloc(&be->d_sh_recv, (size_t)ce * W));
+    CMAXB_TRY(dev_alloc(&be->d_sh_blur, (size_t)ce * W));
+    CMAXB_TRY(dev_alloc(&be->d_sh_gband, (size_t)ce * W));
+    CMAXB_TRY(dev_alloc(&be->d_sh_gfull, (size_t)world * hb * W + W + 1));
+    CMAXB_TRY(dev_alloc(&be->d_sh_sums, 2));
+    CMAXB_CUDA_TRY(cudaMemset(be->d_sh_gfull, 0, sizeof(float) * ((size_t)world * hb * W + W + 1)));
+    be->sh_cap = need;
+  }
+  be->sh_world = world; be->sh_rank = rank; be->sh_hb = hb; be->sh_hl = hl; be->sh_ce = ce;
+  be->sh_y0 = rank * hb; be->sh_y1 = std::min(H, (rank + 1) * hb);
+  be->sh_first = std::max(0, be->sh_y0 - hl);                  // first REAL panorama row of the extended band
+  be->sh_rows = std::min(H, be->sh_y1 + hl) - be->sh_first;     // real rows in it
+  const int P = 3 * be->n_opt;
+  const bool g = want_grad && P > 0;
+  CMAXB_TRY(be_run_poses(be, x, n, want_grad != 0));
+  CMAXB_TRY(be_run_scatter(be, true, g, /*defer_alpha=*/true));
+  cudaStream_t s = be->stream;
+  CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+    be_pack_bands_kernel<<<148 * 8, 256, 0, s>>>(be->d_il_old, be->d_il_new, be->il_is_quad ? be->d_ilq : nullptr, W, H, world, hb, hl, be->d_sh_send);
+  }));
+  if (x && n > 0) be->last_x.assign(x, x + n); else be->last_x.assign((size_t)(n > 0 ? n : 0), 0.0);
+  be->sh_stage = 1; be->sh_grad = g;
+  *send_dev = be->d_sh_send; *recv_dev = be->d_sh_recv; *chunk_floats = (size_t)ce * W;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_shard_image(cmaxb_be* be, double** sums_dev) {
+  if (!be || !sums_dev) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (be->sh_stage != 1) return set_error(CMAXB_ERR_STATE, "cmaxb_be_shard_image without cmaxb_be_shard_begin");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  cudaStream_t s = be->stream;
+  const int W = be->cfg.pano_width;
+  // the band as a stand-alone image of its REAL rows: a true panorama edge gets BORDER_REFLECT_101 as it should, an
+  // artificial one spoils r rows of the blur and r more of the adjoint -- inside the halo, never used
+  const int skip = be->sh_first - (be->sh_y0 - be->sh_hl);      // zero rows above the panorama (first rank only)
+  const float* il = be->d_sh_recv + (size_t)skip * W;
+  const float* igp = be->have_igp ? be->d_igp + (size_t)be->sh_first * W : nullptr;
+  ReduceOut ro{be->d_acc, be->d_ticket, be->d_result, be->d_mean};
+  ro.raw = be->d_sh_sums;
+  ro.sum_y0 = be->sh_y0 - be->sh_first; ro.sum_y1 = be->sh_y1 - be->sh_first;
+  const SrcBePlane src{il, igp, (float)be->alpha};
+  cudaError_t le = cudaSuccess;
+  CMAXB_TRY(be->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+    le = launch_blur_reduce<1, SrcBePlane, true>(s, 1, src, W, be->sh_rows, be->taps, be->d_sh_blur, 0, ro, be->cfg.contrast_measure);
+  }));
+  if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("blur_reduce launch: ") + cudaGetErrorString(le));
+  be->sh_stage = 2;
+  *sums_dev = be->d_sh_sums;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_shard_adjoint(cmaxb_be* be, float** g_own_dev, float** g_full_dev, size_t* own_floats) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (be->sh_stage != 2) return set_error(CMAXB_ERR_STATE, "cmaxb_be_shard_adjoint without cmaxb_be_shard_image");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  cudaStream_t s = be->stream;
+  const int W = be->cfg.pano_width, H = be->cfg.pano_height;
+  CMAXB_TRY(be->prof.run(CMAXB_K_MISC, s, true, [&] {
+    be_band_finalize_kernel<<<1, 32, 0, s>>>(be->d_sh_sums, (double)W * (double)H, be->cfg.contrast_measure, be->d_result, be->d_mean);
+  }));
+  if (g_own_dev) *g_own_dev = nullptr;
+  if (g_full_dev) *g_full_dev = nullptr;
+  if (own_floats) *own_floats = (size_t)be->sh_hb * W;
+  if (be->sh_grad) {
+    cudaError_t le = cudaSuccess;
+    CMAXB_TRY(be->prof.run(CMAXB_K_ADJOINT_BLUR, s, true, [&] {
+      le = launch_adjoint_blur<false>(s, 1, be->d_sh_blur, 0, W, be->sh_rows, be->taps, be->d_mean, be->cfg.contrast_measure, be->d_sh_gband, nullptr);
+    }));
+    if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("adjoint_blur launch: ") + cudaGetErrorString(le));
+    // the band's own rows of G (hb rows; a short last band is zero padded by the allocation)
+    if (g_own_dev) *g_own_dev = be->d_sh_gband + (size_t)(be->sh_y0 - be->sh_first) * W;
+    if (g_full_dev) *g_full_dev = be->d_sh_gfull;
+    be->sh_stage = 3;
+  } else {
+    be->sh_stage = 0;
+    be->end_launched = true; be->end_grad = false;
+  }
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_shard_gather(cmaxb_be* be) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (be->sh_stage != 3) return set_error(CMAXB_ERR_STATE, "cmaxb_be_shard_gather without cmaxb_be_shard_adjoint (gradient evaluation)");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_TRY(be_gather_launch(be, be->d_sh_gfull, nullptr));
+  be->sh_stage = 0;
+  be->end_launched = true; be->end_grad = true;
+  return CMAXB_OK;
 }
 
 extern "C" int cmaxb_be_get_alpha(cmaxb_be* be, double* alpha) {

@@ -501,6 +501,53 @@ be_assemble_il_kernel(const float* __restrict__ il_old, const float* __restrict_
   }
 }
 
+// Row-band sharding of the image phases (one window sharded by time over several GPUs): the IL of THIS
+// rank's events is packed as `world` chunks of ce = hb + 2 hl rows -- chunk c = rows [c hb - hl, (c+1) hb + hl) of the
+// panorama, zero outside it -- so that ONE reduce-scatter hands every rank the summed rows of its own band INCLUDING the
+// halo the blur and the adjoint blur need (hl = 2 r + 1).
+__global__ void __launch_bounds__(256)
+be_pack_bands_kernel(const float* __restrict__ il_old, const float* __restrict__ il_new, const float4* __restrict__ il_quad,
+                     int W, int H, int world, int hb, int hl, float* __restrict__ send) {
+  const int ce = hb + 2 * hl;
+  const long long total = (long long)world * ce * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const long long row = i / W;
+    const int c = (int)(row / ce), j = (int)(row - (long long)c * ce);
+    const int y = c * hb - hl + j;
+    float l = 0.f;
+    if (y >= 0 && y < H) {
+      const long long p = (long long)y * W + x;
+      if (il_quad) {
+        l = il_quad[p].x;
+        if (x > 0) l += il_quad[p - 1].y;
+        if (y > 0) { l += il_quad[p - W].z; if (x > 0) l += il_quad[p - W - 1].w; }
+      } else {
+        l = il_old[p] + il_new[p];
+      }
+    }
+    send[i] = l;
+  }
+}
+
+// contrast and mean from the (all-reduced) sums of the whole panorama
+__global__ void be_band_finalize_kernel(const double* __restrict__ sums2, double Np, int measure, double* __restrict__ result,
+                                        double* __restrict__ mean) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double S1 = sums2[0], S2 = sums2[1];
+  const double m = S1 / Np;
+  double contrast;
+  if (measure == CMAXB_CONTRAST_MEAN_SQUARE) contrast = S2 / Np;
+  else {
+    double var = S2 / Np - m * m;
+    if (var < 0.0) var = 0.0;
+    const double sd = sqrt(var);
+    contrast = sd * sd;
+  }
+  result[0] = contrast;
+  mean[0] = m;
+}
+
 // updateAlpha sums (event_pano_warper.cpp:134-165): out[0..4] = sum(1-exp(-IGp)), sum(IGp),
 // sum(1-exp(-IL)), sum(IL), countNonZero(IGp); IL = IL_old + IL_new.
 // il_quad != nullptr: IL is re-assembled from the corner-split accumulator.

@@ -119,6 +119,8 @@ struct ReduceOut {
   unsigned int* ticket; // [n_planes]
   double* result;       // [n_planes][4]  contrast, g0, g1, g2
   double* mean;         // [n_planes]     mean of the blurred image (for the adjoint pass)
+  double* raw = nullptr;        // optional [n_planes][2]: the plain sums S1, S2 (row-band evaluation: summed across ranks by the caller)
+  int sum_y0 = 0, sum_y1 = 0x7fffffff;   // rows whose pixels enter the sums (row-band evaluation: the band's own rows)
 };
 
 // Deterministic block-wide sum of NV doubles per thread; result valid in thread 0.
@@ -266,7 +268,9 @@ blur_reduce_kernel(Src src, int W, int H, Taps taps, typename PixT<C>::type* out
 #pragma unroll
         for (int j = 1; j <= r; ++j) s = pfma(taps.w[r + j], padd(c[j * kTW], c[-j * kTW]), s);
         if (WRITE_OUT) out[h * out_stride_h + (long long)gy * W + gx] = s;
-        if constexpr (C == 1) {
+        if (gy < ro.sum_y0 || gy >= ro.sum_y1) {
+          // outside the rows this launch is responsible for (halo rows of a row band)
+        } else if constexpr (C == 1) {
           const double v = (double)s;
           a[0] += v; a[1] += v * v;
         } else {
@@ -319,6 +323,7 @@ blur_reduce_kernel(Src src, int W, int H, Taps taps, typename PixT<C>::type* out
       if constexpr (C == 4) for (int c = 0; c < 3; ++c) res[1 + c] = 2.0 * (t[5 + c] / Np - mean * (t[2 + c] / Np));
     }
     res[0] = contrast;
+    if (ro.raw) { ro.raw[2 * h] = S1; ro.raw[2 * h + 1] = S2; }
     ro.mean[h] = mean;
     ro.ticket[h] = 0u;
     __threadfence();

@@ -86,37 +86,82 @@ def time_slab(n_events, batch_size, rank, world):
 
 
 class ShardedEventWarper:
-    """Event-sharded contrast functor: rank r holds the events of its time slab and all knots.
-    eval(x) = begin (local scatter) -> all-reduce SUM of the un-blurred IL plane (image sized, NCCL over NVLink)
-    -> end (blur, variance -- identical on every rank --, adjoint, gather over own events) -> all-reduce SUM
-    of the partial gradients (3*K_opt doubles).  Results are identical on all ranks."""
+    """Event-sharded contrast functor: rank r holds the events of its time slab and all knots.  Two exchanges:
+      mode "plane": begin (local scatter) -> all-reduce SUM of the un-blurred IL plane -> end (blur, variance, adjoint --
+                    replicated on every rank --, gather over own events) -> all-reduce SUM of the partial gradients;
+      mode "bands": the image phases are sharded too: reduce-scatter of the IL by row band (+ halo) -> blur of the band ->
+                    all-reduce of (S1, S2) -> adjoint blur of the band -> all-gather of G -> gather -> gradient all-reduce.
+                    Same bytes over NVLink, 1/world of the blur / adjoint work per rank (cmaxb_be_shard_*).
+    Results are identical on all ranks.  "auto" = bands when the bands are thick enough (>= 2 r + 1 rows), else plane."""
 
-    def __init__(self, warper, group=None):
+    def __init__(self, warper, group=None, mode="auto"):
         self.w = warper
         self.group = group
+        self.mode = mode
+        self._first = True
 
     def set_window(self, events, knots_xyzw, t0_ns, dt_ns, n_fixed, t_next_win_beg, IGp=None, alpha=float("nan"),
                    batch_size=100):
+        import math
         import torch.distributed as dist
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         beg, end = time_slab(len(events), batch_size, rank, world)
         self.slab = (beg, end)
         self.w.set_window(events[beg:end], knots_xyzw, t0_ns, dt_ns, n_fixed, t_next_win_beg, IGp, alpha)
+        self._alpha_pending = isinstance(alpha, float) and math.isnan(alpha)
+
+    def _use_bands(self, world):
+        if self.mode == "plane" or world < 2 or self._alpha_pending:
+            return False      # the window's first evaluation fixes alpha from the WHOLE summed IL: plane path
+        r = self.w.blur_radius
+        thick = -(-self.w.pano_height // world) >= 2 * r + 1 and (world - 1) * -(-self.w.pano_height // world) < self.w.pano_height
+        if self.mode == "bands" and not thick:
+            raise ValueError("bands thinner than the blur halo: use mode='plane'")
+        return thick
 
     def eval(self, x=None, want_grad=True):
-        import torch
         import torch.distributed as dist
         multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
-        self.w.eval_begin(x, want_grad)
-        if multi:
-            plane = self.w.il_plane_tensor()
-            dist.all_reduce(plane, group=self.group)          # the path's one real exchange step
         if not multi:
+            self.w.eval_begin(x, want_grad)
             return self.w.eval_end()
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self._use_bands(world):
+            return self._eval_bands(x, want_grad, world, rank)
+        self.w.eval_begin(x, want_grad)
+        plane = self.w.il_plane_tensor()
+        dist.all_reduce(plane, group=self.group)          # the path's one real exchange step
+        self._alpha_pending = False
         # blur / contrast / adjoint / gather queued; the partial gradients are summed on the device (no host hop)
         self.w.eval_end_launch()
         if want_grad:
+            gt = self.w.grad_tensor()
+            if gt is not None:
+                dist.all_reduce(gt, group=self.group)
+        return self.w.eval_end_fetch()
+
+    def _eval_bands(self, x, want_grad, world, rank):
+        import torch
+        import torch.distributed as dist
+        send, recv = self.w.shard_begin(x, want_grad, world, rank)
+        if dist.get_backend(self.group) == "gloo":       # CPU-side test backend: no reduce_scatter_tensor / CUDA tensors
+            full = send.clone()
+            dist.all_reduce(full, group=self.group)
+            recv.copy_(full.view(world, -1)[rank])
+        else:
+            dist.reduce_scatter_tensor(recv, send, group=self.group)
+        sums = self.w.shard_image()
+        dist.all_reduce(sums, group=self.group)
+        g_own, g_full = self.w.shard_adjoint(world)
+        if g_own is not None:
+            if dist.get_backend(self.group) == "gloo":
+                g_full.zero_()
+                g_full.view(world, -1)[rank].copy_(g_own)
+                dist.all_reduce(g_full, group=self.group)
+            else:
+                dist.all_gather_into_tensor(g_full, g_own, group=self.group)
+            self.w.shard_gather()
             gt = self.w.grad_tensor()
             if gt is not None:
                 dist.all_reduce(gt, group=self.group)

@@ -222,6 +222,25 @@ int cmaxb_be_eval_end(cmaxb_be* be, double* contrast, double* grad_partial);
 int cmaxb_be_eval_end_launch(cmaxb_be* be, int want_grad);
 int cmaxb_be_grad_device(cmaxb_be* be, double** device_ptr, size_t* count);
 int cmaxb_be_eval_end_fetch(cmaxb_be* be, double* contrast, double* grad);
+/* The same time-sharded evaluation with the IMAGE PHASES sharded by row band (each rank blurs / adjoint-blurs 1/world of the
+ * panorama instead of all of it; the bytes over NVLink are those of the whole-plane exchange: reduce-scatter + all-gather):
+ *   cmaxb_be_shard_begin   poses + scatter of this rank's events; IL packed as `world` bands of chunk_floats floats each
+ *                          (band + halo of 2 r + 1 rows, zero outside the panorama) in *send_dev
+ *   (caller)               reduce_scatter: *recv_dev <- SUM over ranks of chunk `rank` of *send_dev
+ *   cmaxb_be_shard_image   blur of the band, S1 / S2 over the band's own rows -> *sums_dev (2 doubles)
+ *   (caller)               all_reduce SUM of *sums_dev
+ *   cmaxb_be_shard_adjoint contrast and mean; gradient evaluations: adjoint blur of the band, *g_own_dev = the band's own rows
+ *                          of G (own_floats floats), *g_full_dev = the buffer to all-gather them into (world * own_floats)
+ *   (caller)               all_gather: *g_full_dev <- *g_own_dev of every rank
+ *   cmaxb_be_shard_gather  gather over this rank's events -> partial gradient in cmaxb_be_grad_device()
+ *   (caller)               all_reduce SUM of the gradient; cmaxb_be_eval_end_fetch returns contrast (+ gradient)
+ * alpha must be fixed (run the first evaluation of a NaN-alpha window through cmaxb_be_eval_begin / _end); bands must be at
+ * least 2 r + 1 rows high. */
+int cmaxb_be_shard_begin(cmaxb_be* be, const double* x, int n, int want_grad, int world, int rank, float** send_dev,
+                         float** recv_dev, size_t* chunk_floats);
+int cmaxb_be_shard_image(cmaxb_be* be, double** sums_dev);
+int cmaxb_be_shard_adjoint(cmaxb_be* be, float** g_own_dev, float** g_full_dev, size_t* own_floats);
+int cmaxb_be_shard_gather(cmaxb_be* be);
 /* IL_old_ / IL_new_ at x (needed by updateIG, event_pano_warper.cpp:109-126); either may be NULL */
 int cmaxb_be_get_il(cmaxb_be* be, const double* x, int n, float* il_old, float* il_new);
 /* final image I = blur(IL + alpha*IGp) at x */

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from cmax_slam_b200 import synth
+from cmax_slam_b200._capi import CmaxbError
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -68,9 +69,12 @@ torch.cuda.set_stream(stream)
 sh = ShardedEventWarper(EventWarperCMax(64, 48, w.lut, 128, 64, spline_order=2, stream=stream.cuda_stream))
 sh.set_window(w.events, w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, float("nan"))
 c, g = sh.eval(x, True)
-c_f, _ = sh.eval(x, False)
+c_f, _ = sh.eval(x, False)          # alpha fixed by now: row-band path, value only
+c_b, g_b = sh.eval(x, True)         # row-band path with gradient
+assert sh._use_bands(2)
 alpha = sh.w.alpha
 np.save(sys.argv[4] + f"/r{rank}.npy", np.concatenate([[c, c_f, alpha, sh.slab[0], sh.slab[1]], g]))
+np.save(sys.argv[4] + f"/b{rank}.npy", np.concatenate([[c_b], g_b]))
 dist.barrier()
 dist.destroy_process_group()
 print("ok")
@@ -106,7 +110,76 @@ def test_two_ranks_time_sharded_equals_unsharded(oracle, tmp_path):
     ro = oracle.be_eval(a, x, True)
     assert abs(r0[0] - ro["contrast"]) <= 1e-5 * ro["contrast"]
     assert np.abs(r0[5:] - ro["grad"]).max() <= 1e-5 * np.abs(ro["grad"]).max()
+    # the row-band exchange (reduce-scatter / all-gather) gives the same numbers on both ranks
+    b0, b1 = np.load(tmp_path / "b0.npy"), np.load(tmp_path / "b1.npy")
+    assert np.allclose(b0, b1, rtol=1e-12)
+    assert abs(b0[0] - c) <= 1e-6 * abs(c) and np.abs(b0[1:] - g).max() <= 1e-6 * np.abs(g).max()
     be.close()
+
+
+@pytest.mark.parametrize("world,pano", [(2, (128, 64)), (3, (128, 64)), (4, (256, 100))])
+def test_row_band_sharding_emulated_in_one_process(oracle, world, pano):
+    """cmaxb_be_shard_*: `world` handles on one GPU play the ranks; the collectives are emulated with torch ops on the
+    library's own buffers.  Uneven bands (64 rows / 3 ranks, 100 rows / 4), halo rows off the panorama, IGp, value-only
+    and gradient evaluations -- against the un-sharded evaluation and the oracle."""
+    import torch
+    from cmax_slam_b200.backend import EventWarperCMax
+    from cmax_slam_b200.dist import time_slab
+    pw, ph = pano
+    w = synth.make_be_window(24001, 8, pw, ph, 77, order=2, sensor=(64, 48), K4=K_T, n_landmarks=300, n_fixed=1)
+    rng = np.random.default_rng(5)
+    IGp = np.abs(rng.normal(0, 0.3, (ph, pw))).astype(np.float32)
+    x = rng.normal(0, 0.02, 21)
+    st = torch.cuda.Stream()                 # the handles work on torch's stream: library launches and torch ops stay ordered
+    torch.cuda.set_stream(st)
+    ref = EventWarperCMax(64, 48, w.lut, pw, ph, spline_order=2, stream=st.cuda_stream)
+    ref.set_window(w.events, w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.5)
+    c0, g0 = ref.eval(x, True)
+    hs = []
+    for r in range(world):
+        b, e = time_slab(len(w.events), 100, r, world)
+        h = EventWarperCMax(64, 48, w.lut, pw, ph, spline_order=2, stream=st.cuda_stream)
+        h.set_window(w.events[b:e], w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.5)
+        hs.append(h)
+    for want_grad in (True, False, True):
+        bufs = [h.shard_begin(x, want_grad, world, r) for r, h in enumerate(hs)]
+        total = sum(b[0] for b in bufs)                                  # reduce ...
+        for r, (_, recv) in enumerate(bufs):
+            recv.copy_(total.view(world, -1)[r])                         # ... scatter
+        sums = [h.shard_image() for h in hs]
+        tot = sum(sums)
+        for s_ in sums:
+            s_.copy_(tot)
+        outs = [h.shard_adjoint(world) for h in hs]
+        if want_grad:
+            full = torch.cat([o[0] for o in outs])                       # all-gather
+            for h, o in zip(hs, outs):
+                o[1].copy_(full)
+                h.shard_gather()
+            gts = [h.grad_tensor() for h in hs]
+            gsum = sum(gts)
+            for gt in gts:
+                gt.copy_(gsum)
+        res = [h.eval_end_fetch() for h in hs]
+        for c, g in res:
+            assert abs(c - c0) <= 1e-6 * abs(c0)
+            if want_grad:
+                assert np.abs(g - g0).max() <= 1e-6 * np.abs(g0).max()
+            else:
+                assert g is None
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    a = oracle.be_args(w.events, w.lut, 64, 48, pw, ph, w.knots_xyzw, w.t0_ns, w.dt_ns, 2, w.n_fixed, w.tnext, IGp, 0.5)
+    ro = oracle.be_eval(a, x, True)
+    assert abs(res[0][0] - ro["contrast"]) <= 1e-5 * ro["contrast"]
+    assert np.abs(res[0][1] - ro["grad"]).max() <= 1e-5 * np.abs(ro["grad"]).max()
+    # thin bands are refused, and so is a window whose alpha is still to be computed
+    with pytest.raises(CmaxbError):
+        hs[0].shard_begin(x, True, 16, 0)
+    hs[0].set_window(w.events, w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, float("nan"))
+    with pytest.raises(CmaxbError):
+        hs[0].shard_begin(x, True, world, 0)
+    for h in hs + [ref]:
+        h.close()
 
 
 def test_plain_eval_after_a_sharded_evaluation(oracle):
