@@ -739,16 +739,25 @@ def bench_configs(args, rank, world, local_rank, dev, stream, peak, peak_src, ba
             sh = ShardedEventWarper(EventWarperCMax(w.sensor_width, w.sensor_height, w.lut, w.pano_width, w.pano_height, spline_order=2,
                                                     device=local_rank, stream=stream.cuda_stream))
             sh.set_window(w.events, w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.5)
-            barrier()
-            tg = maxr(wall(lambda: sh.eval(x, True), 8, 2))
-            barrier()
-            tv = maxr(wall(lambda: sh.eval(x, False), 8, 2))
+            modes = {}
+            for mode in ("plane", "auto"):
+                sh.mode = mode
+                barrier()
+                tg = maxr(wall(lambda: sh.eval(x, True), 8, 2))
+                barrier()
+                tv = maxr(wall(lambda: sh.eval(x, False), 8, 2))
+                modes["bands" if mode == "auto" and sh._use_bands(world) else "plane"] = (tg, tv)
+            best = min(modes, key=lambda k: modes[k][0])
+            sh.mode = "plane" if best == "plane" else "auto"
+            tg, tv = modes[best]
             c, g = sh.eval(x, True)
             sh.w.close()
-            how = f"sharded by time over {world} GPUs (IL plane all-reduced over NVLink, gradient all-reduced)"
+            how = (f"sharded by time over {world} GPUs; " + ("image phases sharded by row band: IL reduce-scattered, G all-gathered over NVLink"
+                   if best == "bands" else "IL plane all-reduced over NVLink, image phases replicated") + ", gradient all-reduced")
+            extra_modes = {k: {"fg_ms": v[0] * 1e3, "value_ms": v[1] * 1e3} for k, v in modes.items()}
         out[name] = {"workload": label + ", " + how, "events": N, "knots": len(w.knots_xyzw), "pano": [w.pano_width, w.pano_height],
                      "fg_ms": tg * 1e3, "value_ms": tv * 1e3, "events_per_s": N / tg, "events_per_s_value_only": N / tv,
-                     "contrast": c, "grad_finite": bool(np.all(np.isfinite(g))),
+                     "contrast": c, "grad_finite": bool(np.all(np.isfinite(g))), **({"exchange_modes": extra_modes} if world > 1 else {}),
                      "roofline": roofline_block(b_alg_be(N, A, As, P) / world, (32 * N + 24 * A) / world, tg, peak, peak_src, frac_on="adjoint",
                                                 note="SURVEY 8(d) dense-band bytes (16 N + 8 A (1+P) + 4 A + 12 A_s, P = 3 K_opt) per GPU; the adjoint "
                                                      "formulation run here keeps no bands: adjoint_min_bytes = 32 N + 24 A")}
