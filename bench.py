@@ -740,20 +740,26 @@ def bench_configs(args, rank, world, local_rank, dev, stream, peak, peak_src, ba
                                                     device=local_rank, stream=stream.cuda_stream))
             sh.set_window(w.events, w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.5)
             modes = {}
-            for mode in ("plane", "auto"):
+            sh.eval(x, True)
+            sh.connect()
+            for mode in ("plane", "auto", "p2p"):
                 sh.mode = mode
                 barrier()
                 tg = maxr(wall(lambda: sh.eval(x, True), 8, 2))
                 barrier()
                 tv = maxr(wall(lambda: sh.eval(x, False), 8, 2))
-                modes["bands" if mode == "auto" and sh._use_bands(world) else "plane"] = (tg, tv)
+                modes[{"plane": "plane", "p2p": "p2p", "auto": "bands" if sh._use_bands(world) else "plane"}[mode]] = (tg, tv)
             best = min(modes, key=lambda k: modes[k][0])
-            sh.mode = "plane" if best == "plane" else "auto"
+            sh.mode = {"plane": "plane", "bands": "auto", "p2p": "p2p"}[best]
             tg, tv = modes[best]
             c, g = sh.eval(x, True)
+            barrier()
+            sh.w.exchange_close()
             sh.w.close()
-            how = (f"sharded by time over {world} GPUs; " + ("image phases sharded by row band: IL reduce-scattered, G all-gathered over NVLink"
-                   if best == "bands" else "IL plane all-reduced over NVLink, image phases replicated") + ", gradient all-reduced")
+            how = (f"sharded by time over {world} GPUs; " + {
+                "bands": "image phases sharded by row band: IL reduce-scattered, G all-gathered (NCCL over NVLink), gradient all-reduced",
+                "plane": "IL plane all-reduced (NCCL over NVLink), image phases replicated, gradient all-reduced",
+                "p2p": "exchange by the kernels over peer memory (NVLink, CUDA IPC), dirty panorama tiles only; image phases sharded by row band"}[best])
             extra_modes = {k: {"fg_ms": v[0] * 1e3, "value_ms": v[1] * 1e3} for k, v in modes.items()}
         out[name] = {"workload": label + ", " + how, "events": N, "knots": len(w.knots_xyzw), "pano": [w.pano_width, w.pano_height],
                      "fg_ms": tg * 1e3, "value_ms": tv * 1e3, "events_per_s": N / tg, "events_per_s_value_only": N / tv,

@@ -8,7 +8,8 @@ import numpy as np
 from . import build as _build
 
 K_NAMES = ["zero", "fe_scatter", "fe_gather", "blur_reduce", "adjoint_blur", "be_poses", "be_scatter",
-           "be_gather", "be_grad_reduce", "misc", "fe_eval_fused", "be_eval_fused"]
+           "be_gather", "be_grad_reduce", "misc", "fe_eval_fused", "be_eval_fused", "be_x_push", "be_x_sums", "be_x_pull",
+           "be_x_grad"]
 K_COUNT = len(K_NAMES)
 
 GRAD_DENSE, GRAD_ADJOINT = 0, 1
@@ -117,7 +118,7 @@ EXPORTS = [
     "cmaxb_fe_select_packet", "cmaxb_fe_lanes_fork", "cmaxb_fe_lanes_join", "cmaxb_fe_launch_info", "cmaxb_fe_eval", "cmaxb_fe_eval_batch",
     "cmaxb_fe_eval_launch", "cmaxb_fe_eval_fetch", "cmaxb_fe_exchange_init", "cmaxb_fe_exchange_connect", "cmaxb_fe_exchange_close",
     "cmaxb_fe_eval_fetch_all", "cmaxb_fe_set_result_mirror", "cmaxb_fe_get_iwe", "cmaxb_fe_get_deriv", "cmaxb_fe_get_cells",
-    "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_eval_begin", "cmaxb_be_il_plane", "cmaxb_be_eval_end", "cmaxb_be_eval_end_launch", "cmaxb_be_grad_device", "cmaxb_be_eval_end_fetch", "cmaxb_be_shard_begin", "cmaxb_be_shard_image", "cmaxb_be_shard_adjoint", "cmaxb_be_shard_gather", "cmaxb_be_get_alpha",
+    "cmaxb_be_create", "cmaxb_be_destroy", "cmaxb_be_set_window", "cmaxb_be_eval", "cmaxb_be_eval_begin", "cmaxb_be_il_plane", "cmaxb_be_eval_end", "cmaxb_be_eval_end_launch", "cmaxb_be_grad_device", "cmaxb_be_eval_end_fetch", "cmaxb_be_shard_begin", "cmaxb_be_shard_image", "cmaxb_be_shard_adjoint", "cmaxb_be_shard_gather", "cmaxb_be_exchange_init", "cmaxb_be_exchange_connect", "cmaxb_be_exchange_close", "cmaxb_be_xeval", "cmaxb_be_exchange_stats", "cmaxb_be_get_alpha",
     "cmaxb_be_get_il", "cmaxb_be_get_iwe", "cmaxb_be_get_bands", "cmaxb_be_get_cells", "cmaxb_be_get_poses",
     "cmaxb_be_map_reset", "cmaxb_be_map_set", "cmaxb_be_map_get", "cmaxb_be_map_use_as_igp", "cmaxb_be_map_update",
     "cmaxb_be_map_mark_fov",
@@ -226,6 +227,11 @@ def lib():
     L.cmaxb_be_shard_image.argtypes = [vp, C.POINTER(vp)]
     L.cmaxb_be_shard_adjoint.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.cmaxb_be_shard_gather.argtypes = [vp]
+    L.cmaxb_be_exchange_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.cmaxb_be_exchange_connect.argtypes = [vp, C.c_char_p]
+    L.cmaxb_be_exchange_close.argtypes = [vp]
+    L.cmaxb_be_exchange_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.cmaxb_be_xeval.argtypes = [vp, dp, C.c_int, C.POINTER(C.c_double), dp]
     L.cmaxb_be_eval_end_fetch.argtypes = [vp, dp, dp]
     L.cmaxb_be_get_il.argtypes = [vp, dp, C.c_int, vp, vp]
     L.cmaxb_be_get_iwe.argtypes = [vp, dp, C.c_int, C.c_int, vp]

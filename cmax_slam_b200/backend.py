@@ -169,6 +169,38 @@ class EventWarperCMax:
     def shard_gather(self):
         _capi.check(self._L.cmaxb_be_shard_gather(self._h))
 
+    # -- exchange by the kernels over peer memory (cmaxb_be_exchange_* / cmaxb_be_xeval) ----------------------
+    def exchange_connect(self, group=None):
+        """Collective over `group` (torch.distributed, any backend: only the 64-byte IPC handles travel through it)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        h = C.create_string_buffer(64)
+        _capi.check(self._L.cmaxb_be_exchange_init(self._h, world, rank, h))
+        handles = [None] * world
+        dist.all_gather_object(handles, h.raw, group=group)
+        _capi.check(self._L.cmaxb_be_exchange_connect(self._h, b"".join(handles)))
+        dist.barrier(group)
+        self._xworld = world
+
+    def exchange_close(self):
+        _capi.check(self._L.cmaxb_be_exchange_close(self._h))
+        self._xworld = 0
+
+    def exchange_stats(self):
+        """(panorama tiles this rank's events touched in the last xeval, tiles of the panorama)"""
+        t = (C.c_int64 * 2)()
+        _capi.check(self._L.cmaxb_be_exchange_stats(self._h, t))
+        return int(t[0]), int(t[1])
+
+    def xeval(self, x=None, want_grad=True):
+        """Collective evaluation of the time-sharded window: (contrast, gradient) of the WHOLE window on every rank."""
+        xx, n = self._x(x)
+        c = C.c_double()
+        g = np.zeros(max(self.n_params, 1))
+        _capi.check(self._L.cmaxb_be_xeval(self._h, None if xx is None else _capi.dptr(xx), n, C.byref(c),
+                                           _capi.dptr(g) if want_grad else None))
+        return c.value, (g[: self.n_params] if want_grad else None)
+
     # -- device-resident global map (event_pano_warper.cpp:81-132) --------------------------------------------
     def resetIG(self):
         _capi.check(self._L.cmaxb_be_map_reset(self._h))

@@ -1,6 +1,7 @@
 // be_capi.cu -- C ABI of the back-end (panoramic CMax bundle adjustment) path, include/cmax_b200.h.
 #include "capi_common.cuh"
 #include "be_kernels.cuh"
+#include "be_xchg.cuh"
 #include "image_kernels.cuh"
 
 using namespace cmaxb;
@@ -34,6 +35,10 @@ struct cmaxb_be {
   float* d_sh_send = nullptr; float* d_sh_recv = nullptr; float* d_sh_blur = nullptr; float* d_sh_gband = nullptr;
   float* d_sh_gfull = nullptr; double* d_sh_sums = nullptr; size_t sh_cap = 0;
   int sh_stage = 0; bool sh_grad = false;
+  // exchange by the kernels themselves over peer memory (cmaxb_be_exchange_* / cmaxb_be_xeval, be_xchg.cuh)
+  char* x_local = nullptr; BeXLayout x_lay{}; BeXPeers x_peers{}; bool x_on = false; unsigned long long x_seq = 0;
+  unsigned int* d_dirty = nullptr; unsigned int* d_xticket = nullptr; bool x_invariant = false;
+  unsigned long long* h_xfault = nullptr; unsigned long long* d_xfault = nullptr;
   bool split_pending = false; bool split_grad = false; bool end_launched = false; bool end_grad = false;
   // device-resident global map (IG_, IG_update_times_map_)
   float* d_IG = nullptr; unsigned char* d_times = nullptr; unsigned char* d_mask = nullptr;
@@ -145,6 +150,8 @@ extern "C" void cmaxb_be_destroy(cmaxb_be* be) {
   cudaFree(be->d_igp); cudaFree(be->d_il_old); cudaFree(be->d_il_new); cudaFree(be->d_blur); cudaFree(be->d_G);
   cudaFree(be->d_bands); cudaFree(be->d_bands_blur); cudaFree(be->d_ilq); cudaFree(be->d_GQ);
   cudaFree(be->d_ca); cudaFree(be->d_cb); cudaFree(be->d_il_plane);
+  cudaFree(be->x_local); cudaFree(be->d_dirty); cudaFree(be->d_xticket);
+  if (be->h_xfault) cudaFreeHost(be->h_xfault);
   cudaFree(be->d_sh_send); cudaFree(be->d_sh_recv); cudaFree(be->d_sh_blur); cudaFree(be->d_sh_gband); cudaFree(be->d_sh_gfull); cudaFree(be->d_sh_sums);
   cudaFree(be->d_IG); cudaFree(be->d_times); cudaFree(be->d_mask);
 
@@ -327,9 +334,12 @@ static unsigned be_event_grid(const cmaxb_be* be) {
   return (unsigned)blocks;
 }
 
-static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false, bool defer_alpha = false) {
+static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false, bool defer_alpha = false, unsigned int* dirty = nullptr) {
   cudaStream_t s = be->stream;
-  const bool quad = allow_quad && be->use_quad;
+  const bool quad = dirty ? true : (allow_quad && be->use_quad);
+  const int dirty_ntx = (be->cfg.pano_width + kBeXTile - 1) / kBeXTile;
+  const int dirty_ntiles = dirty_ntx * ((be->cfg.pano_height + kBeXTile - 1) / kBeXTile);
+  if (!dirty) be->x_invariant = false;      // the accumulator is about to hold votes the peer exchange's tile flags do not know of
   if (want_cache && (size_t)be->n_visit > be->cache_cap) {
     cudaFree(be->d_ca); cudaFree(be->d_cb);
     be->d_ca = nullptr; be->d_cb = nullptr; be->cache_cap = 0;
@@ -341,6 +351,7 @@ static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false
   be->il_is_quad = quad;
   be->il_is_plane = false;   // a fresh scatter supersedes the assembled plane of an earlier sharded evaluation (eval_begin re-sets it)
   CMAXB_TRY(be->prof.run(CMAXB_K_ZERO, s, false, [&] {
+    if (dirty) return;                       // peer exchange: the caller cleaned the dirty tiles
     if (quad) cudaMemsetAsync(be->d_ilq, 0, sizeof(float4) * be->A, s);
     else {
       cudaMemsetAsync(be->d_il_old, 0, sizeof(float) * be->A, s);
@@ -352,8 +363,8 @@ static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false
     CMAXB_TRY(be->prof.run(CMAXB_K_BE_SCATTER, s, true, [&] {
       const unsigned grid = be_event_grid(be);
       if (quad) {
-        if (want_cache) be_scatter_kernel<2, true><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, nullptr, nullptr, be->d_ilq, cache);
-        else be_scatter_kernel<2, false><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, nullptr, nullptr, be->d_ilq, cache);
+        if (want_cache) be_scatter_kernel<2, true><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, nullptr, nullptr, be->d_ilq, cache, dirty, dirty_ntx, dirty_ntiles);
+        else be_scatter_kernel<2, false><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, nullptr, nullptr, be->d_ilq, cache, dirty, dirty_ntx, dirty_ntiles);
       } else {
         if (want_cache) be_scatter_kernel<0, true><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, be->d_il_old, be->d_il_new, nullptr, cache);
         else be_scatter_kernel<0, false><<<grid, kBeThreads, 0, s>>>(g, be->d_poses, be->d_il_old, be->d_il_new, nullptr, cache);
@@ -459,8 +470,8 @@ static int be_gather_launch(cmaxb_be* be, const float* G, const float4* GQ) {
   }
   const double inv_np = 1.0 / ((double)W * (double)H);
   CMAXB_TRY(be->prof.run(CMAXB_K_BE_GRAD_REDUCE, s, true, [&] {
-    if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
-    else be_grad_reduce_kernel<4><<<be->n_opt, 256, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+    if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, kBeReduceThreads, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+    else be_grad_reduce_kernel<4><<<be->n_opt, kBeReduceThreads, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
   }));
   return CMAXB_OK;
 }
@@ -642,6 +653,23 @@ extern "C" int cmaxb_be_eval_end_fetch(cmaxb_be* be, double* contrast, double* g
   return be_finish_fetch(be, grad != nullptr, contrast, grad);
 }
 
+// row band of `rank` among `world`: own rows [y0, y1), extended by the halo hl = 2 r + 1 the blur and its adjoint need
+static void be_band_geometry(cmaxb_be* be, int world, int rank) {
+  const int H = be->cfg.pano_height;
+  const int hl = 2 * be->taps.r + 1;
+  const int hb = (H + world - 1) / world;
+  be->sh_world = world; be->sh_rank = rank; be->sh_hb = hb; be->sh_hl = hl; be->sh_ce = hb + 2 * hl;
+  be->sh_y0 = rank * hb; be->sh_y1 = std::min(H, (rank + 1) * hb);
+  be->sh_first = std::max(0, be->sh_y0 - hl);                  // first REAL panorama row of the extended band
+  be->sh_rows = std::min(H, be->sh_y1 + hl) - be->sh_first;     // real rows in it
+}
+
+static bool be_bands_ok(const cmaxb_be* be, int world) {
+  const int H = be->cfg.pano_height;
+  const int hb = (H + world - 1) / world;
+  return world >= 1 && hb >= 2 * be->taps.r + 1 && (long long)(world - 1) * hb < H;
+}
+
 // ---- row-band sharding of the image phases (time-sharded window over several GPUs) ----------------------------------
 // begin:   poses + scatter of THIS rank's events; IL packed as `world` extended bands (send buffer)
 // (caller) reduce_scatter(recv <- send, SUM): every rank now holds the summed rows of its band + halo
@@ -679,10 +707,7 @@ extern "C" int cmaxb_be_shard_begin(cmaxb_be* be, const double* x, int n, int wa
     CMAXB_CUDA_TRY(cudaMemset(be->d_sh_gfull, 0, sizeof(float) * ((size_t)world * hb * W + W + 1)));
     be->sh_cap = need;
   }
-  be->sh_world = world; be->sh_rank = rank; be->sh_hb = hb; be->sh_hl = hl; be->sh_ce = ce;
-  be->sh_y0 = rank * hb; be->sh_y1 = std::min(H, (rank + 1) * hb);
-  be->sh_first = std::max(0, be->sh_y0 - hl);                  // first REAL panorama row of the extended band
-  be->sh_rows = std::min(H, be->sh_y1 + hl) - be->sh_first;     // real rows in it
+  be_band_geometry(be, world, rank);
   const int P = 3 * be->n_opt;
   const bool g = want_grad && P > 0;
   CMAXB_TRY(be_run_poses(be, x, n, want_grad != 0));
@@ -758,6 +783,181 @@ extern "C" int cmaxb_be_shard_gather(cmaxb_be* be) {
   CMAXB_TRY(be_gather_launch(be, be->d_sh_gfull, nullptr));
   be->sh_stage = 0;
   be->end_launched = true; be->end_grad = true;
+  return CMAXB_OK;
+}
+
+// ---- the same evaluation with the exchange done by the kernels over peer memory (be_xchg.cuh) ---------------------------
+extern "C" int cmaxb_be_exchange_init(cmaxb_be* be, int world, int rank, void* handle64_out) {
+  if (!be || !handle64_out) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (world < 1 || world > kBeXMaxWorld || rank < 0 || rank >= world) return set_error(CMAXB_ERR_INVALID, "bad world / rank (at most 8 ranks)");
+  if (!be_bands_ok(be, world)) return set_error(CMAXB_ERR_INVALID, "row bands thinner than the blur halo: use the whole-plane exchange");
+  if (be->x_local) return set_error(CMAXB_ERR_STATE, "exchange already initialised");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(be->stream));
+  const int W = be->cfg.pano_width, H = be->cfg.pano_height;
+  be_band_geometry(be, world, rank);
+  be->x_lay = be_x_layout(W, be->sh_ce, world);
+  size_t bytes = (size_t)2 << 20;            // whole 2 MiB blocks: the IPC handle exports nothing else
+  while (bytes < be->x_lay.total) bytes += (size_t)2 << 20;
+  CMAXB_CUDA_TRY(cudaMalloc((void**)&be->x_local, bytes));
+  CMAXB_CUDA_TRY(cudaMemset(be->x_local, 0, bytes));
+  const int ntiles = ((W + kBeXTile - 1) / kBeXTile) * ((H + kBeXTile - 1) / kBeXTile);
+  if (ntiles > 32 * kBeDirtyWords) return set_error(CMAXB_ERR_INVALID, "panorama too large for the dirty-tile bitmap (32768 tiles of 32 x 32)");
+  CMAXB_TRY(dev_alloc(&be->d_dirty, (size_t)kBeDirtyWords));
+  CMAXB_CUDA_TRY(cudaMemset(be->d_dirty, 0, sizeof(unsigned int) * kBeDirtyWords));
+  CMAXB_TRY(dev_alloc(&be->d_xticket, 1));
+  CMAXB_CUDA_TRY(cudaMemset(be->d_xticket, 0, sizeof(unsigned int)));
+  CMAXB_CUDA_TRY(cudaHostAlloc((void**)&be->h_xfault, sizeof(unsigned long long), cudaHostAllocMapped));
+  CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&be->d_xfault, be->h_xfault, 0));
+  be->h_xfault[0] = 0;
+  if (!be->d_sh_blur) {
+    CMAXB_TRY(dev_alloc(&be->d_sh_blur, (size_t)be->sh_ce * W));
+    CMAXB_TRY(dev_alloc(&be->d_sh_sums, 2));
+  }
+  CMAXB_CUDA_TRY(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CMAXB_CUDA_TRY(cudaIpcGetMemHandle(&h, be->x_local));
+  std::memcpy(handle64_out, &h, 64);
+  be->x_peers.world = world; be->x_peers.rank = rank;
+  be->x_invariant = false; be->x_seq = 0;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_exchange_connect(cmaxb_be* be, const void* handles) {
+  if (!be || !handles) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->x_local) return set_error(CMAXB_ERR_STATE, "call cmaxb_be_exchange_init first");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  for (int r = 0; r < be->x_peers.world; ++r) {
+    if (r == be->x_peers.rank) { be->x_peers.base[r] = be->x_local; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* ptr = nullptr;
+    CMAXB_CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    be->x_peers.base[r] = (char*)ptr;
+  }
+  be->x_on = true;
+  return CMAXB_OK;
+}
+
+extern "C" int cmaxb_be_exchange_close(cmaxb_be* be) {
+  if (!be) return set_error(CMAXB_ERR_INVALID, "null argument");
+  cudaSetDevice(be->device);
+  cudaStreamSynchronize(be->stream);
+  be->x_on = false;
+  for (int r = 0; r < be->x_peers.world; ++r) {
+    if (r != be->x_peers.rank && be->x_peers.base[r]) cudaIpcCloseMemHandle(be->x_peers.base[r]);
+    be->x_peers.base[r] = nullptr;
+  }
+  // the local block stays allocated until destroy: a peer may still have it mapped
+  return CMAXB_OK;
+}
+
+// tiles[0] = panorama tiles this rank's events touched in the last cmaxb_be_xeval, tiles[1] = tiles of the panorama
+extern "C" int cmaxb_be_exchange_stats(cmaxb_be* be, int64_t* tiles2) {
+  if (!be || !tiles2) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->d_dirty) return set_error(CMAXB_ERR_STATE, "no peer exchange");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  std::vector<unsigned int> bits(kBeDirtyWords);
+  CMAXB_CUDA_TRY(cudaMemcpyAsync(bits.data(), be->d_dirty, sizeof(unsigned int) * kBeDirtyWords, cudaMemcpyDeviceToHost, be->stream));
+  CMAXB_CUDA_TRY(cudaStreamSynchronize(be->stream));
+  int64_t n = 0;
+  for (unsigned int w : bits) n += __builtin_popcount(w);
+  tiles2[0] = n;
+  tiles2[1] = (int64_t)((be->cfg.pano_width + kBeXTile - 1) / kBeXTile) * ((be->cfg.pano_height + kBeXTile - 1) / kBeXTile);
+  return CMAXB_OK;
+}
+
+// Collective: every rank of the exchange calls it with the same x, in the same order.  contrast and gradient of the WHOLE
+// window come back on every rank (bitwise identical: all sums across ranks are formed in rank order).
+extern "C" int cmaxb_be_xeval(cmaxb_be* be, const double* x, int n, double* contrast, double* grad) {
+  if (!be || !contrast) return set_error(CMAXB_ERR_INVALID, "null argument");
+  if (!be->x_on) return set_error(CMAXB_ERR_STATE, "no peer exchange: call cmaxb_be_exchange_init / _connect first");
+  if (!be->have_window) return set_error(CMAXB_ERR_STATE, "no window: call cmaxb_be_set_window first");
+  if (be->alpha_pending) return set_error(CMAXB_ERR_STATE, "alpha is not fixed yet: run the window's first evaluation through cmaxb_be_eval_begin / _end");
+  if (grad && be->cfg.grad_mode != CMAXB_GRAD_ADJOINT) return set_error(CMAXB_ERR_INVALID, "event-sharded evaluation needs CMAXB_GRAD_ADJOINT");
+  const int P = 3 * be->n_opt;
+  if (P > kBeXGradMax) return set_error(CMAXB_ERR_INVALID, "too many free control poses for the gradient exchange (1024)");
+  CMAXB_CUDA_TRY(cudaSetDevice(be->device));
+  cudaStream_t s = be->stream;
+  const int W = be->cfg.pano_width, H = be->cfg.pano_height;
+  const bool g = grad != nullptr && P > 0;
+  if (!be->d_ilq) {
+    CMAXB_TRY(dev_alloc(&be->d_ilq, (size_t)be->A));
+    CMAXB_TRY(dev_alloc(&be->d_GQ, (size_t)be->A));
+  }
+  BeXGeom xg{W, H, (W + kBeXTile - 1) / kBeXTile, (H + kBeXTile - 1) / kBeXTile, be->sh_hb, be->sh_hl, be->sh_ce};
+  const int ntiles = xg.ntx * xg.nty;
+  const BeXLayout& L = be->x_lay;
+  const BeXPeers& peers = be->x_peers;
+  const unsigned long long seq = ++be->x_seq;
+  const int par = (int)(seq & 1);
+  const unsigned tile_grid = (unsigned)std::min(ntiles, 148 * 8);
+  // 1. accumulator: only the tiles the previous evaluation touched are non-zero
+  CMAXB_TRY(be->prof.run(CMAXB_K_ZERO, s, true, [&] {
+    if (!be->x_invariant) {
+      cudaMemsetAsync(be->d_ilq, 0, sizeof(float4) * be->A, s);
+      cudaMemsetAsync(be->d_dirty, 0, sizeof(unsigned int) * kBeDirtyWords, s);
+    } else {
+      be_x_clean_kernel<<<tile_grid, 256, 0, s>>>(be->d_ilq, be->d_dirty, xg);
+    }
+  }));
+  // 2. poses + scatter of the own slab (tiles flagged)
+  CMAXB_TRY(be_run_poses(be, x, n, g));
+  CMAXB_TRY(be_run_scatter(be, true, g, /*defer_alpha=*/true, be->d_dirty));
+  be->x_invariant = true;
+  // 3. dirty tiles -> the band owners' accumulators; flag at every peer
+  CMAXB_TRY(be->prof.run(CMAXB_K_BE_X_PUSH, s, true, [&] {
+    be_x_push_kernel<<<tile_grid, 256, 0, s>>>(be->d_ilq, be->d_dirty, xg, peers, L.acc[par], L.push_flag, seq, be->d_xticket);
+    be_x_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const unsigned long long*>(be->x_local + L.push_flag), peers.world, seq, be->d_xfault, 0x20);
+  }));
+  // 4. blur of the own band (+ alpha IGp), S1 / S2 over its own rows
+  {
+    const int skip = be->sh_first - (be->sh_y0 - be->sh_hl);
+    const float* il = reinterpret_cast<const float*>(be->x_local + L.acc[par]) + (size_t)skip * W;
+    const float* igp = be->have_igp ? be->d_igp + (size_t)be->sh_first * W : nullptr;
+    ReduceOut ro{be->d_acc, be->d_ticket, be->d_result, be->d_mean};
+    ro.raw = be->d_sh_sums;
+    ro.sum_y0 = be->sh_y0 - be->sh_first; ro.sum_y1 = be->sh_y1 - be->sh_first;
+    const SrcBePlane src{il, igp, (float)be->alpha};
+    cudaError_t le = cudaSuccess;
+    CMAXB_TRY(be->prof.run(CMAXB_K_BLUR_REDUCE, s, true, [&] {
+      le = launch_blur_reduce<1, SrcBePlane, true>(s, 1, src, W, be->sh_rows, be->taps, be->d_sh_blur, 0, ro, be->cfg.contrast_measure);
+    }));
+    if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("blur_reduce launch: ") + cudaGetErrorString(le));
+  }
+  CMAXB_TRY(be->prof.run(CMAXB_K_BE_X_SUMS, s, true, [&] {
+    cudaMemsetAsync(be->x_local + L.acc[par], 0, sizeof(float) * (size_t)be->sh_ce * W, s);       // ready for evaluation seq + 2
+    be_x_sums_kernel<<<1, 32, 0, s>>>(be->d_sh_sums, peers, L.sums, seq, (double)W * (double)H, be->cfg.contrast_measure, be->d_result,
+                                      be->d_mean, be->d_xfault);
+  }));
+  if (g) {
+    // 5. adjoint image of the band; every rank pulls G for its dirty tiles; gather; gradient exchange
+    cudaError_t le = cudaSuccess;
+    CMAXB_TRY(be->prof.run(CMAXB_K_ADJOINT_BLUR, s, true, [&] {
+      le = launch_adjoint_blur<false>(s, 1, be->d_sh_blur, 0, W, be->sh_rows, be->taps, be->d_mean, be->cfg.contrast_measure,
+                                      reinterpret_cast<float*>(be->x_local + L.G), nullptr);
+    }));
+    if (le != cudaSuccess) return set_error(CMAXB_ERR_CUDA, std::string("adjoint_blur launch: ") + cudaGetErrorString(le));
+    CMAXB_TRY(be->prof.run(CMAXB_K_BE_X_PULL, s, true, [&] {
+      be_x_flag_kernel<<<1, 32, 0, s>>>(peers, L.g_flag, seq);
+      be_x_pull_kernel<<<tile_grid, 256, 0, s>>>(be->d_GQ, be->d_dirty, xg, peers, L.G,
+                                                 reinterpret_cast<const unsigned long long*>(be->x_local + L.g_flag), seq, be->d_xfault);
+    }));
+    CMAXB_TRY(be_gather_launch(be, nullptr, be->d_GQ));
+    CMAXB_TRY(be->prof.run(CMAXB_K_BE_X_GRAD, s, true, [&] {
+      be_x_grad_kernel<<<(P + 255) / 256, 256, 0, s>>>(be->d_grad, P, peers, L.grad, seq, be->d_xfault);
+    }));
+  }
+  if (x && n > 0) be->last_x.assign(x, x + n); else be->last_x.assign((size_t)(n > 0 ? n : 0), 0.0);
+  be->end_launched = true; be->end_grad = g;
+  CMAXB_TRY(cmaxb_be_eval_end_fetch(be, contrast, g ? grad : nullptr));
+  if (be->h_xfault[0]) {
+    const unsigned long long why = be->h_xfault[0];
+    be->h_xfault[0] = 0;
+    return set_error(CMAXB_ERR_CUDA, "peer exchange: a rank did not arrive (time-out), stage 0x" + std::to_string(why & 0xff) + " rank " + std::to_string((why >> 8) & 0xff));
+  }
+  if (grad && !g) for (int i = 0; i < P; ++i) grad[i] = 0.0;
   return CMAXB_OK;
 }
 

@@ -186,6 +186,7 @@ __device__ __forceinline__ BeWarp be_warp(const BeGeom& g, const double* R, uint
 }
 
 constexpr int kBeThreads = 256;
+constexpr int kBeDirtyWords = 1024;     // dirty-tile bitmap of the peer exchange: up to 32768 tiles of 32 x 32 (8192 x 4096 panorama)
 constexpr int kBeWarps = kBeThreads / 32;
 
 // value scatter, one THREAD per visited event (full lane efficiency; the batch pose is read through
@@ -197,7 +198,7 @@ constexpr int kBeWarps = kBeThreads / 32;
 template <int MODE, bool CACHE>
 __device__ __forceinline__ void be_scatter_range(const BeGeom& g, const BePose* __restrict__ poses, float* __restrict__ il_old,
                                                  float* __restrict__ il_new, float4* __restrict__ il_quad, const BeCache& cache,
-                                                 long long j0, long long stride) {
+                                                 long long j0, long long stride, int dirty_ntx = 0, unsigned int* s_dirty = nullptr) {
   for (long long j = j0; j < g.n_visit; j += stride) {
     long long b = j / g.m;
     if (b > g.nb - 1) b = g.nb - 1;
@@ -217,6 +218,11 @@ __device__ __forceinline__ void be_scatter_range(const BeGeom& g, const BePose* 
     const long long p = (long long)w.yy * g.W + w.xx;
     if (MODE == 2) {
       atomicAdd(il_quad + p, make_float4((1.f - dx) * (1.f - dy), dx * (1.f - dy), (1.f - dx) * dy, dx * dy));
+      if (s_dirty) {                        // 32x32 panorama tile touched (peer exchange, be_xchg.cuh): CTA-local bitmap, flushed once
+        const int t = (w.yy >> 5) * dirty_ntx + (w.xx >> 5);     // (millions of stores to a few global sectors would serialise in L2)
+        const unsigned int bit = 1u << (t & 31);
+        if (!(s_dirty[t >> 5] & bit)) atomicOr(&s_dirty[t >> 5], bit);
+      }
     } else {
       float* il = w.is_old ? il_old : il_new;
       atomicAdd(il + p, (1.f - dx) * (1.f - dy));
@@ -230,9 +236,24 @@ __device__ __forceinline__ void be_scatter_range(const BeGeom& g, const BePose* 
 template <int MODE, bool CACHE>
 __global__ void __launch_bounds__(kBeThreads)
 be_scatter_kernel(BeGeom g, const BePose* __restrict__ poses, float* __restrict__ il_old, float* __restrict__ il_new,
-                  float4* __restrict__ il_quad, BeCache cache) {
+                  float4* __restrict__ il_quad, BeCache cache, unsigned int* __restrict__ dirty = nullptr, int dirty_ntx = 0,
+                  int dirty_ntiles = 0) {
+  __shared__ unsigned int s_dirty[kBeDirtyWords];
+  const bool local = MODE == 2 && dirty != nullptr;           // dirty_ntiles <= 32 kBeDirtyWords (checked by cmaxb_be_exchange_init)
+  const int nwords = (dirty_ntiles + 31) >> 5;
+  if (local) {
+    for (int i = threadIdx.x; i < nwords; i += kBeThreads) s_dirty[i] = 0u;
+    __syncthreads();
+  }
   be_scatter_range<MODE, CACHE>(g, poses, il_old, il_new, il_quad, cache, blockIdx.x * (long long)kBeThreads + threadIdx.x,
-                                (long long)gridDim.x * kBeThreads);
+                                (long long)gridDim.x * kBeThreads, dirty_ntx, local ? s_dirty : nullptr);
+  if (local) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nwords; i += kBeThreads) {
+      const unsigned int m = s_dirty[i];
+      if (m && (m & ~__ldcg(dirty + i))) atomicOr(dirty + i, m);
+    }
+  }
 }
 
 // dense derivative bands (reference-faithful DENSE mode / parity): planar bands[P][A]
@@ -377,12 +398,16 @@ __global__ void be_segment_ranges_kernel(const BeBatchTime* __restrict__ bt, lon
   atomicMax(seg_hi + s, (int)b + 1);
 }
 
+// 1024 threads per knot: the loop below is a chain of dependent L2 round trips (index, then three partial sums per
+// batch), so its length in iterations is what the kernel costs (2 000 batches per knot in C5: 8 iterations at 256 threads)
+constexpr int kBeReduceThreads = 1024;
+
 // g[3*kk + c] = (1/Np) * sum over batches touching knot (kk + n_fixed) of wgrad[b][3*(knot-idx_b)+c].
 // One CTA per optimised knot; fixed summation order (deterministic).
 template <int N>
 __device__ __forceinline__ void be_grad_reduce_knot(int kk, const int* __restrict__ idx, const int* __restrict__ seg_lo,
                                                     const int* __restrict__ seg_hi, const double* __restrict__ wgrad, int n_fixed,
-                                                    double inv_np, double* __restrict__ grad, double* s_red /*[8*3]*/) {
+                                                    double inv_np, double* __restrict__ grad, double* s_red /*[warps*3]*/) {
   const int knot = kk + n_fixed;
   double a[3] = {0.0, 0.0, 0.0};
   for (int rel = 0; rel < N; ++rel) {
@@ -409,10 +434,10 @@ __device__ __forceinline__ void be_grad_reduce_knot(int kk, const int* __restric
 }
 
 template <int N>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBeReduceThreads)
 be_grad_reduce_kernel(const int* __restrict__ idx, const int* __restrict__ seg_lo, const int* __restrict__ seg_hi,
                       const double* __restrict__ wgrad, long long nb, int n_fixed, double inv_np, double* __restrict__ grad) {
-  __shared__ double s_red[8 * 3];
+  __shared__ double s_red[(kBeReduceThreads / 32) * 3];
   be_grad_reduce_knot<N>(blockIdx.x, idx, seg_lo, seg_hi, wgrad, n_fixed, inv_np, grad, s_red);
 }
 

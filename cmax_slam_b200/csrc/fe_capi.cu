@@ -1066,6 +1066,6 @@ extern "C" uint64_t cmaxb_launch_count(void) { return g_launch_count.load(); }
 extern "C" const char* cmaxb_kernel_name(int kind) {
   static const char* names[CMAXB_K_COUNT] = {"zero(memset)", "fe_scatter", "fe_gather", "blur_reduce", "adjoint_blur",
                                              "be_poses", "be_scatter", "be_gather", "be_grad_reduce", "misc",
-                                             "fe_eval_fused", "be_eval_fused"};
+                                             "fe_eval_fused", "be_eval_fused", "be_x_push", "be_x_sums", "be_x_pull", "be_x_grad"};
   return (kind >= 0 && kind < CMAXB_K_COUNT) ? names[kind] : "?";
 }

@@ -92,6 +92,9 @@ class ShardedEventWarper:
       mode "bands": the image phases are sharded too: reduce-scatter of the IL by row band (+ halo) -> blur of the band ->
                     all-reduce of (S1, S2) -> adjoint blur of the band -> all-gather of G -> gather -> gradient all-reduce.
                     Same bytes over NVLink, 1/world of the blur / adjoint work per rank (cmaxb_be_shard_*).
+      mode "p2p":   no collective call on the data path: the kernels exchange over peer memory (CUDA IPC, NVLink), and only
+                    the panorama tiles a rank's events touched travel (cmaxb_be_exchange_* / cmaxb_be_xeval, csrc/be_xchg.cuh).
+                    Needs connect() once (collective) and all ranks on one node.
     Results are identical on all ranks.  "auto" = bands when the bands are thick enough (>= 2 r + 1 rows), else plane."""
 
     def __init__(self, warper, group=None, mode="auto"):
@@ -111,8 +114,13 @@ class ShardedEventWarper:
         self.w.set_window(events[beg:end], knots_xyzw, t0_ns, dt_ns, n_fixed, t_next_win_beg, IGp, alpha)
         self._alpha_pending = isinstance(alpha, float) and math.isnan(alpha)
 
+    def connect(self):
+        """mode "p2p": open the peers' exchange blocks (collective)."""
+        self.w.exchange_connect(self.group)
+        self._connected = True
+
     def _use_bands(self, world):
-        if self.mode == "plane" or world < 2 or self._alpha_pending:
+        if self.mode in ("plane", "p2p") or world < 2 or self._alpha_pending:
             return False      # the window's first evaluation fixes alpha from the WHOLE summed IL: plane path
         r = self.w.blur_radius
         thick = -(-self.w.pano_height // world) >= 2 * r + 1 and (world - 1) * -(-self.w.pano_height // world) < self.w.pano_height
@@ -127,6 +135,10 @@ class ShardedEventWarper:
             self.w.eval_begin(x, want_grad)
             return self.w.eval_end()
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.mode == "p2p" and not self._alpha_pending:
+            if not getattr(self, "_connected", False):
+                raise RuntimeError("mode 'p2p': call connect() first")
+            return self.w.xeval(x, want_grad)
         if self._use_bands(world):
             return self._eval_bands(x, want_grad, world, rank)
         self.w.eval_begin(x, want_grad)

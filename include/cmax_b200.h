@@ -241,6 +241,22 @@ int cmaxb_be_shard_begin(cmaxb_be* be, const double* x, int n, int want_grad, in
 int cmaxb_be_shard_image(cmaxb_be* be, double** sums_dev);
 int cmaxb_be_shard_adjoint(cmaxb_be* be, float** g_own_dev, float** g_full_dev, size_t* own_floats);
 int cmaxb_be_shard_gather(cmaxb_be* be);
+/* The same time-sharded evaluation with the exchange done BY THE KERNELS over peer memory (NVLink / NVSwitch, CUDA IPC),
+ * and only for the panorama tiles a rank's events touched (csrc/be_xchg.cuh) -- no NCCL call on the data path:
+ *   cmaxb_be_exchange_init     allocates this rank's exchange block, returns its 64-byte IPC handle
+ *   cmaxb_be_exchange_connect  handles = world x 64 bytes in rank order (gathered by the caller through any channel)
+ *   cmaxb_be_xeval             collective: every rank calls it with the same x in the same order; contrast (and gradient,
+ *                              when grad != NULL) of the WHOLE window come back on every rank, bitwise identical
+ *   cmaxb_be_exchange_close    unmaps the peers' blocks
+ * Requirements: at most 8 ranks on one node with peer access; alpha fixed (first evaluation of a NaN-alpha window through
+ * cmaxb_be_eval_begin / _end); row bands at least 2 r + 1 rows; at most 1024 free control poses.  A rank that does not
+ * arrive within 5 s makes cmaxb_be_xeval fail with CMAXB_ERR_CUDA instead of hanging the GPU. */
+int cmaxb_be_exchange_init(cmaxb_be* be, int world, int rank, void* handle64_out);
+int cmaxb_be_exchange_connect(cmaxb_be* be, const void* handles);
+int cmaxb_be_exchange_close(cmaxb_be* be);
+int cmaxb_be_xeval(cmaxb_be* be, const double* x, int n, double* contrast, double* grad);
+/* tiles2[0] = 32x32 panorama tiles this rank's events touched in the last cmaxb_be_xeval, tiles2[1] = tiles of the panorama */
+int cmaxb_be_exchange_stats(cmaxb_be* be, int64_t* tiles2);
 /* IL_old_ / IL_new_ at x (needed by updateIG, event_pano_warper.cpp:109-126); either may be NULL */
 int cmaxb_be_get_il(cmaxb_be* be, const double* x, int n, float* il_old, float* il_new);
 /* final image I = blur(IL + alpha*IGp) at x */
@@ -464,6 +480,7 @@ enum {
   CMAXB_K_ZERO = 0, CMAXB_K_FE_SCATTER, CMAXB_K_FE_GATHER, CMAXB_K_BLUR_REDUCE, CMAXB_K_ADJOINT_BLUR,
   CMAXB_K_BE_POSES, CMAXB_K_BE_SCATTER, CMAXB_K_BE_GATHER, CMAXB_K_BE_GRAD_REDUCE, CMAXB_K_MISC,
   CMAXB_K_FE_EVAL_FUSED, CMAXB_K_BE_EVAL_FUSED,
+  CMAXB_K_BE_X_PUSH, CMAXB_K_BE_X_SUMS, CMAXB_K_BE_X_PULL, CMAXB_K_BE_X_GRAD,   /* peer exchange of cmaxb_be_xeval, waits for the peers included */
   CMAXB_K_COUNT
 };
 int cmaxb_fe_profile(cmaxb_fe* fe, int enable);

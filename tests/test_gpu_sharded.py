@@ -75,6 +75,18 @@ assert sh._use_bands(2)
 alpha = sh.w.alpha
 np.save(sys.argv[4] + f"/r{rank}.npy", np.concatenate([[c, c_f, alpha, sh.slab[0], sh.slab[1]], g]))
 np.save(sys.argv[4] + f"/b{rank}.npy", np.concatenate([[c_b], g_b]))
+# exchange by the kernels over peer memory (CUDA IPC between the two processes), sparse by dirty tile
+sh.mode = "p2p"
+sh.connect()
+outs = []
+for i, (xx, wg) in enumerate([(x, True), (x, False), (0.5 * x, True), (x, True)]):
+    c_p, g_p = sh.eval(xx, wg)
+    outs.append(np.concatenate([[c_p], g_p if wg else np.zeros(21)]))
+c_plain, g_plain = sh.w.eval(x, True)      # a plain (own-slab) evaluation in between breaks the tile invariant on purpose
+c_p, g_p = sh.eval(x, True)
+outs.append(np.concatenate([[c_p], g_p]))
+np.save(sys.argv[4] + f"/p{rank}.npy", np.stack(outs))
+sh.w.exchange_close()
 dist.barrier()
 dist.destroy_process_group()
 print("ok")
@@ -114,6 +126,14 @@ def test_two_ranks_time_sharded_equals_unsharded(oracle, tmp_path):
     b0, b1 = np.load(tmp_path / "b0.npy"), np.load(tmp_path / "b1.npy")
     assert np.allclose(b0, b1, rtol=1e-12)
     assert abs(b0[0] - c) <= 1e-6 * abs(c) and np.abs(b0[1:] - g).max() <= 1e-6 * np.abs(g).max()
+    # the peer-memory exchange: identical on both ranks bit for bit (sums formed in rank order), equal to the un-sharded numbers
+    p0, p1 = np.load(tmp_path / "p0.npy"), np.load(tmp_path / "p1.npy")
+    assert np.array_equal(p0, p1)
+    c_h, g_h = be.eval(0.5 * x, True)
+    for i in (0, 3, 4):
+        assert abs(p0[i, 0] - c) <= 1e-6 * abs(c) and np.abs(p0[i, 1:] - g).max() <= 1e-6 * np.abs(g).max()
+    assert abs(p0[1, 0] - c) <= 1e-6 * abs(c)
+    assert abs(p0[2, 0] - c_h) <= 1e-6 * abs(c_h) and np.abs(p0[2, 1:] - g_h).max() <= 1e-6 * np.abs(g_h).max()
     be.close()
 
 
@@ -216,3 +236,36 @@ def test_plain_eval_after_a_sharded_evaluation(oracle):
     a = oracle.be_args(w.events[:n2], w.lut, 64, 48, 128, 64, w.knots_xyzw, w.t0_ns, w.dt_ns, 2, w.n_fixed, w.tnext, IGp, 0.4)
     assert abs(c3 - oracle.be_eval(a, x2, False)["contrast"]) <= 1e-5 * abs(c3)
     be.close(); ref.close()
+
+
+@pytest.mark.parametrize("pano", [(128, 64), (256, 100), (132, 70)])
+def test_peer_exchange_single_rank_equals_eval(oracle, pano):
+    """cmaxb_be_xeval with a world of one rank (the rank is its own peer): dirty-tile clean / push / pull and the tagged-word
+    exchanges run exactly as at N ranks; result == plain evaluation == oracle, repeatedly and at changing parameters."""
+    from cmax_slam_b200.backend import EventWarperCMax
+    import ctypes as C
+    from cmax_slam_b200 import _capi
+    pw, ph = pano
+    w = synth.make_be_window(16001, 8, pw, ph, 78, order=2, sensor=(64, 48), K4=K_T, n_landmarks=300, n_fixed=1)
+    rng = np.random.default_rng(6)
+    IGp = np.abs(rng.normal(0, 0.3, (ph, pw))).astype(np.float32)
+    be = EventWarperCMax(64, 48, w.lut, pw, ph, spline_order=2)
+    be.set_window(w.events, w.knots_xyzw, w.t0_ns, w.dt_ns, w.n_fixed, w.tnext, IGp, 0.5)
+    h = C.create_string_buffer(64)
+    _capi.check(be._L.cmaxb_be_exchange_init(be._h, 1, 0, h))
+    _capi.check(be._L.cmaxb_be_exchange_connect(be._h, h.raw))
+    for k in range(4):
+        x = rng.normal(0, 0.02, 21)
+        c0, g0 = be.eval(x, True) if k % 2 == 0 else (None, None)     # interleaved plain evaluations (tile invariant reset)
+        c1, g1 = be.xeval(x, True)
+        c2, _ = be.xeval(x, False)
+        if c0 is None:
+            c0, g0 = be.eval(x, True)
+        assert abs(c1 - c0) <= 1e-6 * abs(c0) and abs(c2 - c0) <= 1e-6 * abs(c0)
+        assert np.abs(g1 - g0).max() <= 1e-6 * np.abs(g0).max()
+    a = oracle.be_args(w.events, w.lut, 64, 48, pw, ph, w.knots_xyzw, w.t0_ns, w.dt_ns, 2, w.n_fixed, w.tnext, IGp, 0.5)
+    ro = oracle.be_eval(a, x, True)
+    assert abs(c1 - ro["contrast"]) <= 1e-5 * ro["contrast"]
+    assert np.abs(g1 - ro["grad"]).max() <= 1e-5 * np.abs(ro["grad"]).max()
+    be.exchange_close()
+    be.close()
