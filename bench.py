@@ -545,7 +545,8 @@ def bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt
     nslots = 4
     FL = EventStream.PUSH_BORROW | EventStream.PUSH_SORTED
     state = {"msg": 0, "slot": 0, "out": 0, "packets": 0, "h2d": 0}
-    depth = 3
+    depth = int(os.environ.get("CMAXB_E2E_DEPTH", "3"))
+    no_eval = os.environ.get("CMAXB_E2E_SKIP") == "eval"        # diagnostics: uploads + packet preparation only
 
     # The per-tick sequence below goes through the C ABI directly (ctypes calls with pre-built argument objects): the
     # Python convenience wrappers of cmax_slam_b200/*.py cost ~3-5 us per call in conversions, which at ~80 us per tick would
@@ -567,18 +568,26 @@ def bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt
         if rc != 0:
             _capi.check(rc)
 
+    trace = os.environ.get("CMAXB_E2E_TRACE") == "1"      # host time per C-ABI call class, printed on stderr
+    tr = {"push": 0.0, "next": 0.0, "prep": 0.0, "launch": 0.0, "fetch": 0.0}
+    pc = time.perf_counter
+
     def step():
         """push the next message; evaluate every packet that became complete"""
         m = state["msg"]
         lo, hi = int(edges[m]), int(edges[m + 1])
+        t0 = pc()
         rc = L.cmaxb_stream_push_ex(ST, C.c_void_p(base + 16 * lo), hi - lo, FL, C.byref(k_ready))
+        tr["push"] += pc() - t0
         if rc != 0:
             _capi.check(rc)
         state["h2d"] += 16 * (hi - lo)
         state["msg"] = m + 1
         got = 0
         while True:
+            t0 = pc()
             rc = L.cmaxb_stream_next_packet_device(ST, C.byref(p_ev), C.byref(n_ev_c), C.byref(t_pk), C.byref(f_long))
+            t1 = pc(); tr["next"] += t1 - t0
             if rc == 1:
                 break
             if rc != 0:
@@ -587,8 +596,13 @@ def bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt
             state["slot"] += 1
             L.cmaxb_stream_wait_copied(ST, main_stream)
             rc = L.cmaxb_fe_set_packet_view(FE, p_ev, n_ev_c.value, float(t_pk.sec) + 1e-9 * float(t_pk.nsec))
+            t2 = pc(); tr["prep"] += t2 - t1
+            if no_eval:
+                got += 1
+                continue
             if rc == 0:
                 rc = L.cmaxb_fe_eval_launch(FE, om_c, 1, 1)
+            t3 = pc(); tr["launch"] += t3 - t2
             if rc != 0:
                 _capi.check(rc)
             state["out"] += 1
@@ -596,6 +610,7 @@ def bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt
             if state["out"] >= depth:
                 fetch()
                 state["out"] -= 1
+                tr["fetch"] += pc() - t3
         return got
 
     # fill the pipeline until packets come out steadily
@@ -612,9 +627,15 @@ def bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt
     fe.lanes_fork()
     done = 0
     n_steps = 0
+    for k_ in tr:
+        tr[k_] = 0.0
+    t_host0 = pc()
     while done < steps and state["msg"] + 1 < len(edges):
         done += step()
         n_steps += 1
+    if trace and rank == 0:
+        print("e2e host us/step:", {k_: round(v_ / max(done, 1) * 1e6, 1) for k_, v_ in tr.items()}, "loop total",
+              round((pc() - t_host0) / max(done, 1) * 1e6, 1), file=sys.stderr)
     while state["out"]:
         fetch(); state["out"] -= 1
     fe.lanes_join()

@@ -319,8 +319,10 @@ extern "C" int cmaxb_fe_create(const cmaxb_fe_cfg* cfg, cmaxb_fe** out) {
   const size_t k = (size_t)fe->kmax;
   bool ok = true;
   for (int s = 0; s < fe->npackets; ++s) {
-    ok = ok && dev_alloc(&fe->packets[s].d_flags, 1) == CMAXB_OK;
-    ok = ok && cudaMallocHost((void**)&fe->packets[s].h_flags, sizeof(int)) == cudaSuccess;
+    // verdict words of the packet in mapped host memory: [0] time order, [1] pixel range (written by the preparation kernels)
+    ok = ok && cudaHostAlloc((void**)&fe->packets[s].h_flags, 2 * sizeof(int), cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostGetDevicePointer((void**)&fe->packets[s].d_flags, fe->packets[s].h_flags, 0) == cudaSuccess;
+    if (ok) fe->packets[s].h_flags[0] = fe->packets[s].h_flags[1] = 0;
     ok = ok && cudaEventCreateWithFlags(&fe->packets[s].ready, cudaEventDisableTiming) == cudaSuccess;
   }
   ok = ok && dev_alloc(&fe->d_omegas, k * 3) == CMAXB_OK;
@@ -386,7 +388,7 @@ extern "C" void cmaxb_fe_destroy(cmaxb_fe* fe) {
   cudaFree(fe->d_lut); cudaFree(fe->d_tile_count); cudaFree(fe->d_adj_tab);
   for (int s = 0; s < kFeMaxPackets; ++s) {
     FePacket& pk = fe->packets[s];
-    cudaFree(pk.d_ev); cudaFree(pk.d_dt); cudaFree(pk.d_bev); cudaFree(pk.d_flags); cudaFree(pk.d_tile_end);
+    cudaFree(pk.d_ev); cudaFree(pk.d_dt); cudaFree(pk.d_bev); cudaFree(pk.d_tile_end);
     if (pk.h_flags) cudaFreeHost(pk.h_flags);
     if (pk.ready) cudaEventDestroy(pk.ready);
   }
@@ -428,8 +430,8 @@ static int fe_check_packet_flags(cmaxb_fe* fe, FePacket& pk) {
   // validation result of an asynchronous set_packet (its D2H copy precedes every later operation on the stream)
   if (!pk.flags_pending) return CMAXB_OK;
   pk.flags_pending = false;
-  if (*pk.h_flags & 2) { pk.have = false; return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor"); }
-  if (*pk.h_flags & 1) { pk.have = false; return set_error(CMAXB_ERR_TIME_ORDER, "Events must span a non-negative time interval"); }
+  if (pk.h_flags[1]) { pk.have = false; return set_error(CMAXB_ERR_EVENT_RANGE, "event pixel outside the sensor"); }
+  if (pk.h_flags[0]) { pk.have = false; return set_error(CMAXB_ERR_TIME_ORDER, "Events must span a non-negative time interval"); }
   return CMAXB_OK;
 }
 
@@ -480,7 +482,9 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
       CMAXB_CUDA_TRY(cudaMemcpyAsync(pk.d_ev, events, sizeof(cmaxb_event) * n, cudaMemcpyDefault, s));   // host (pinned: DMA) or device memory (UVA)
       pk.ev = pk.d_ev;
     }
-    CMAXB_CUDA_TRY(cudaMemsetAsync(pk.d_flags, 0, sizeof(int), s));
+    // verdict words: the previous packet of this slot must have delivered its own before they are cleared
+    if (pk.flags_pending) CMAXB_CUDA_TRY(cudaEventSynchronize(pk.ready));
+    pk.h_flags[0] = pk.h_flags[1] = 0;
     const uint4* ev = pk.ev; const long long nn = pk.n; int* flags = pk.d_flags;
     const int W = fe->cfg.width, H = fe->cfg.height; double* dt = pk.d_dt; const int ibs = (int)bs;
     // one-time spatial binning of the packet (reused by every evaluation until the next set_packet); its counting pass
@@ -490,12 +494,17 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
     const bool do_bins = fe->use_bins && fe->ntiles <= kBinMaxTiles && nn < (1LL << 32);
     if (!do_bins) {
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-        validate_events_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(ev, nn, W, H, flags);
+        fe_validate_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(ev, nn, W, H, flags);
       }));
     }
-    CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-      fe_batch_dt_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ev, nn, ibs, t_ref_sec, dt, nb, flags);
-    }));
+    // chunk of the binning kernels: a multiple of the batch size, so that the counting pass also forms the batch time offsets
+    const int chunk = (do_bins && ibs <= kBinChunk) ? (kBinChunk / ibs) * ibs : kBinChunk;
+    const bool dt_in_count = do_bins && chunk % ibs == 0;
+    if (!dt_in_count) {
+      CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
+        fe_batch_dt_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ev, nn, ibs, t_ref_sec, dt, nb, flags);
+      }));
+    }
     pk.have_bins = false;
     if (do_bins) {
       if (n > pk.bev_cap) {
@@ -504,25 +513,26 @@ static int fe_set_packet_impl(cmaxb_fe* fe, const cmaxb_event* events, size_t n,
         CMAXB_TRY(dev_alloc(&pk.d_bev, n));
         pk.bev_cap = n;
       }
-      if (!fe->d_tile_count) CMAXB_TRY(dev_alloc(&fe->d_tile_count, (size_t)kBinMaxTiles));
+      if (!fe->d_tile_count) {              // counts, cursors, ticket: zero here, left zero by every binning scatter pass
+        CMAXB_TRY(dev_alloc(&fe->d_tile_count, (size_t)2 * kBinMaxTiles + 1));
+        CMAXB_CUDA_TRY(cudaMemsetAsync(fe->d_tile_count, 0, sizeof(unsigned int) * (2 * kBinMaxTiles + 1), s));
+      }
       if (!pk.d_tile_end) CMAXB_TRY(dev_alloc(&pk.d_tile_end, (size_t)kBinMaxTiles));
       const int ntiles = fe->ntiles, ntx = fe->ntx;
-      const unsigned nchunks = (unsigned)((nn + kBinChunk - 1) / kBinChunk);
+      const unsigned nchunks = (unsigned)((nn + chunk - 1) / chunk);
       uint4* bev = pk.d_bev;
-      unsigned int* cursor = pk.d_tile_end;
-      CMAXB_CUDA_TRY(cudaMemsetAsync(fe->d_tile_count, 0, sizeof(unsigned int) * ntiles, s));
+      unsigned int* count = fe->d_tile_count;
+      unsigned int* cursor = fe->d_tile_count + kBinMaxTiles;
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-        fe_bin_count_kernel<<<nchunks, kBinThreads, sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, fe->d_tile_count, flags);
+        fe_bin_count_kernel<<<nchunks, kBinThreads, sizeof(unsigned int) * ntiles, s>>>(ev, nn, chunk, W, H, ntx, ntiles, count, flags, ibs,
+                                                                                       t_ref_sec, dt_in_count ? dt : nullptr, nb);
       }));
       CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-        fe_bin_scan_kernel<<<1, 1024, 0, s>>>(fe->d_tile_count, ntiles, cursor);
-      }));
-      CMAXB_TRY(fe->prof.run(CMAXB_K_MISC, s, true, [&] {
-        fe_bin_scatter_kernel<<<nchunks, kBinThreads, 2 * sizeof(unsigned int) * ntiles, s>>>(ev, nn, W, H, ntx, ntiles, ibs, dt, cursor, bev);
+        fe_bin_scatter_kernel<<<nchunks, kBinThreads, 2 * sizeof(unsigned int) * ntiles, s>>>(ev, nn, chunk, W, H, ntx, ntiles, ibs, dt, count,
+                                                                                              cursor, pk.d_tile_end, bev, fe->d_tile_count + 2 * kBinMaxTiles);
       }));
       pk.have_bins = true;
     }
-    CMAXB_CUDA_TRY(cudaMemcpyAsync(pk.h_flags, pk.d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
     CMAXB_CUDA_TRY(cudaEventRecord(pk.ready, s));
     pk.flags_pending = true;
     pk.have = true;

@@ -100,7 +100,18 @@ __device__ __forceinline__ FeWarp fe_warp(const FeGeom& g, uint4 e, double dt, d
   return fe_warp_b<GRAD>(g, bxy.x, bxy.y, bz, dt, ox, oy, oz);
 }
 
-// per-batch reference time offsets; flags[0] |= 1 on a negative batch span (:72)
+// Packet verdict words live in MAPPED host memory (no memset / copy on the stream): kernels raise them with plain stores.
+// flags[0] = 1: a batch spans a negative time interval (:72); flags[1] = 1: an event lies outside the sensor (:100)
+__device__ __forceinline__ void fe_flag_raise(int* flags, int which) { reinterpret_cast<volatile int*>(flags)[which] = 1; }
+
+__global__ void fe_validate_kernel(const uint4* __restrict__ ev, long long n, int W, int H, int* flags) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 e = ev[i];
+  if ((int)(e.x & 0xffff) >= W || (int)(e.x >> 16) >= H) fe_flag_raise(flags, 1);
+}
+
+// per-batch reference time offsets; flags[0] = 1 on a negative batch span (:72)
 __global__ void fe_batch_dt_kernel(const uint4* __restrict__ ev, long long n, int bs, double t_ref,
                                    double* __restrict__ dt_tab, long long nb, int* flags) {
   const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -110,7 +121,7 @@ __global__ void fe_batch_dt_kernel(const uint4* __restrict__ ev, long long n, in
   const uint4 e0 = ev[beg], e1 = ev[end - 1];
   RosTime mid;
   const bool ok = ros_batch_mid(RosTime{e0.y, e0.z}, RosTime{e1.y, e1.z}, &mid);
-  if (!ok) atomicOr(flags, 1);
+  if (!ok) fe_flag_raise(flags, 0);
   dt_tab[b] = ros_to_sec(mid.sec, mid.nsec) - t_ref;                       // (:75)
 }
 

@@ -199,7 +199,8 @@ static int stream_to_device(cmaxb_stream* s, long long abs0, const cmaxb_event* 
     CMAXB_CUDA_TRY(cudaMemcpyAsync(s->d_ring + pos, src + done, sizeof(cmaxb_event) * cnt, cudaMemcpyHostToDevice, s->cu_stream));
     if (pos < L) {
       const size_t mc = std::min(cnt, L - pos);
-      CMAXB_CUDA_TRY(cudaMemcpyAsync(s->d_ring + C + pos, src + done, sizeof(cmaxb_event) * mc, cudaMemcpyHostToDevice, s->cu_stream));
+      // the mirror of the ring's first events (packets stay contiguous across the wrap): device to device, not over PCIe again
+      CMAXB_CUDA_TRY(cudaMemcpyAsync(s->d_ring + C + pos, s->d_ring + pos, sizeof(cmaxb_event) * mc, cudaMemcpyDeviceToDevice, s->cu_stream));
     }
     done += cnt;
   }
