@@ -49,6 +49,9 @@ struct cmaxb_be {
   double* d_bacc = nullptr; unsigned int* d_bticket = nullptr; double* d_bresult = nullptr; double* d_bmean = nullptr; size_t bacc_cap = 0;
   double* d_alpha_sums = nullptr;
   double* h_result = nullptr; double* h_alpha_sums = nullptr;
+  double* d_hresult = nullptr; double* d_hgrad = nullptr;   // device aliases of the MAPPED h_result / h_grad (plain evaluations write them directly)
+  bool zeroed_by_poses = false;                             // the pose kernel of this evaluation cleared the accumulators
+  bool direct_out = false;                                  // this evaluation's kernels write h_result / h_grad themselves
   int* d_flags = nullptr; int* h_flags = nullptr;
   int* d_cells = nullptr; size_t cells_cap = 0;
   bool have_window = false;
@@ -129,7 +132,8 @@ extern "C" int cmaxb_be_create(const cmaxb_be_cfg* cfg, cmaxb_be** out) {
   ok = ok && dev_alloc(&be->d_alpha_sums, 8) == CMAXB_OK;
   ok = ok && dev_alloc(&be->d_flags, 1) == CMAXB_OK;
   if (!ok) return fail(CMAXB_ERR_CUDA);
-  ok = ok && cudaMallocHost((void**)&be->h_result, sizeof(double) * 4) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&be->h_result, sizeof(double) * 4, cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostGetDevicePointer((void**)&be->d_hresult, be->h_result, 0) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&be->h_alpha_sums, sizeof(double) * 8) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&be->h_flags, sizeof(int)) == cudaSuccess;
   ok = ok && cudaMemset(be->d_ticket, 0, sizeof(unsigned)) == cudaSuccess;
@@ -229,7 +233,8 @@ extern "C" int cmaxb_be_set_window(cmaxb_be* be, const cmaxb_be_window* w) {
     CMAXB_TRY(dev_alloc(&be->d_seg_lo, K));
     CMAXB_TRY(dev_alloc(&be->d_seg_hi, K));
     CMAXB_CUDA_TRY(cudaMallocHost((void**)&be->h_x, sizeof(double) * 3 * K));
-    CMAXB_CUDA_TRY(cudaMallocHost((void**)&be->h_grad, sizeof(double) * 3 * K));
+    CMAXB_CUDA_TRY(cudaHostAlloc((void**)&be->h_grad, sizeof(double) * 3 * K, cudaHostAllocMapped));
+    CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&be->d_hgrad, be->h_grad, 0));
     be->knots_cap = K;
   }
   be->n_knots = w->n_knots; be->n_fixed = w->n_fixed; be->n_opt = w->n_knots - w->n_fixed;
@@ -293,14 +298,23 @@ static int be_fill_x(cmaxb_be* be, const double* x, int n) {
   for (int i = 0; i < 3 * be->n_opt; ++i) be->h_x[i] = x ? x[i] : 0.0;
   return CMAXB_OK;
 }
-static int be_enqueue_poses(cmaxb_be* be, bool want_grad) {
+// zero_acc: the pose kernel also clears the accumulators of the scatter that follows (be_run_scatter(..., zeroed = true))
+static int be_enqueue_poses(cmaxb_be* be, bool want_grad, bool zero_acc = false) {
   cudaStream_t s = be->stream;
   if (be->n_opt > 0) CMAXB_CUDA_TRY(cudaMemcpyAsync(be->d_x, be->h_x, sizeof(double) * 3 * be->n_opt, cudaMemcpyHostToDevice, s));
+  be->zeroed_by_poses = false;
   if (be->nb > 0) {
-    const unsigned grid = (unsigned)((be->nb + 127) / 128);
+    unsigned grid = (unsigned)((be->nb + 127) / 128);
+    float4* za = nullptr; float4* zb = nullptr; long long na = 0, nbz = 0;
+    if (zero_acc && (be->A & 3) == 0) {
+      if (be->use_quad) { za = be->d_ilq; na = be->A; }
+      else { za = reinterpret_cast<float4*>(be->d_il_old); na = be->A / 4; zb = reinterpret_cast<float4*>(be->d_il_new); nbz = be->A / 4; }
+      grid = std::max(grid, 148u * 8u);
+      be->zeroed_by_poses = true;
+    }
     CMAXB_TRY(be->prof.run(CMAXB_K_BE_POSES, s, true, [&] {
-      if (be->N == 2) be_pose_kernel<2><<<grid, 128, 0, s>>>(be->d_knots0, be->d_x, be->n_fixed, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx);
-      else be_pose_kernel<4><<<grid, 128, 0, s>>>(be->d_knots0, be->d_x, be->n_fixed, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx);
+      if (be->N == 2) be_pose_kernel<2><<<grid, 128, 0, s>>>(be->d_knots0, be->d_x, be->n_fixed, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx, za, na, zb, nbz);
+      else be_pose_kernel<4><<<grid, 128, 0, s>>>(be->d_knots0, be->d_x, be->n_fixed, be->d_bt, be->nb, want_grad, be->d_poses, be->d_idx, za, na, zb, nbz);
     }));
   }
   return CMAXB_OK;
@@ -350,8 +364,10 @@ static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false
   const BeCache cache{be->d_ca, be->d_cb};
   be->il_is_quad = quad;
   be->il_is_plane = false;   // a fresh scatter supersedes the assembled plane of an earlier sharded evaluation (eval_begin re-sets it)
+  const bool zeroed = be->zeroed_by_poses && allow_quad;      // (the pose kernel cleared what allow_quad = true selects)
+  be->zeroed_by_poses = false;
   CMAXB_TRY(be->prof.run(CMAXB_K_ZERO, s, false, [&] {
-    if (dirty) return;                       // peer exchange: the caller cleaned the dirty tiles
+    if (dirty || zeroed) return;             // peer exchange: the caller cleaned the dirty tiles; plain evaluation: the pose kernel did
     if (quad) cudaMemsetAsync(be->d_ilq, 0, sizeof(float4) * be->A, s);
     else {
       cudaMemsetAsync(be->d_il_old, 0, sizeof(float) * be->A, s);
@@ -380,7 +396,8 @@ static int be_run_scatter(cmaxb_be* be, bool allow_quad, bool want_cache = false
 // blur(I) + contrast; leaves the blurred image in d_blur and its mean in d_mean
 static int be_run_image(cmaxb_be* be, const Taps& taps) {
   cudaStream_t s = be->stream;
-  const ReduceOut ro{be->d_acc, be->d_ticket, be->d_result, be->d_mean};
+  ReduceOut ro{be->d_acc, be->d_ticket, be->d_result, be->d_mean};
+  if (be->direct_out) ro.host_result = be->d_hresult;
   const int W = be->cfg.pano_width, H = be->cfg.pano_height;
   const float* igp = be->have_igp ? be->d_igp : nullptr;
   cudaError_t le = cudaSuccess;
@@ -470,8 +487,9 @@ static int be_gather_launch(cmaxb_be* be, const float* G, const float4* GQ) {
   }
   const double inv_np = 1.0 / ((double)W * (double)H);
   CMAXB_TRY(be->prof.run(CMAXB_K_BE_GRAD_REDUCE, s, true, [&] {
-    if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, kBeReduceThreads, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
-    else be_grad_reduce_kernel<4><<<be->n_opt, kBeReduceThreads, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad);
+    double* hg = be->direct_out ? be->d_hgrad : nullptr;
+    if (be->N == 2) be_grad_reduce_kernel<2><<<be->n_opt, kBeReduceThreads, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad, hg);
+    else be_grad_reduce_kernel<4><<<be->n_opt, kBeReduceThreads, 0, s>>>(be->d_idx, be->d_seg_lo, be->d_seg_hi, be->d_wgrad, be->nb, be->n_fixed, inv_np, be->d_grad, hg);
   }));
   return CMAXB_OK;
 }
@@ -506,6 +524,7 @@ static int be_finish_launch(cmaxb_be* be, bool want_grad) {
 static int be_enqueue_fetch(cmaxb_be* be, bool want_grad) {
   cudaStream_t s = be->stream;
   const int P = 3 * be->n_opt;
+  if (be->direct_out) return CMAXB_OK;      // the kernels wrote h_result / h_grad (mapped) themselves
   if (want_grad && P > 0) CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_grad, be->d_grad, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
   CMAXB_CUDA_TRY(cudaMemcpyAsync(be->h_result, be->d_result, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
   return CMAXB_OK;
@@ -535,6 +554,9 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
   const bool adjoint_grad = want_grad && P > 0 && be->cfg.grad_mode == CMAXB_GRAD_ADJOINT;
   be->split_pending = false;
   const int kind = want_grad ? 1 : 0;
+  // results straight into mapped host memory (ADJOINT gradient or value only; the dense-band reduction keeps its copies)
+  be->direct_out = !(want_grad && P > 0 && be->cfg.grad_mode == CMAXB_GRAD_DENSE);
+  struct Reset { cmaxb_be* b; ~Reset() { b->direct_out = false; } } reset_direct{be};
   CMAXB_TRY(be_fill_x(be, x, n));
   if (x && n > 0) be->last_x.assign(x, x + n); else be->last_x.assign((size_t)(n > 0 ? n : 0), 0.0);
   const bool replay = be->graph_on && !be->prof.enabled && !be->alpha_pending && be->evals_in_window[kind] >= 1 &&
@@ -545,7 +567,7 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
     if (!be->gexec[kind]) {
       cudaGraph_t graph = nullptr;
       CMAXB_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      int rc = be_enqueue_poses(be, want_grad);
+      int rc = be_enqueue_poses(be, want_grad, /*zero_acc=*/true);
       if (rc == CMAXB_OK) rc = be_run_scatter(be, true, adjoint_grad);
       if (rc == CMAXB_OK) rc = be_finish_launch(be, want_grad);
       if (rc == CMAXB_OK) rc = be_enqueue_fetch(be, want_grad);
@@ -565,7 +587,7 @@ extern "C" int cmaxb_be_eval(cmaxb_be* be, const double* x, int n, double* contr
     g_launch_count.fetch_add(want_grad ? 6 : 3, std::memory_order_relaxed);    // kernels replayed by the graph
     return be_wait_fetch(be, want_grad, contrast, grad);
   }
-  CMAXB_TRY(be_enqueue_poses(be, want_grad));
+  CMAXB_TRY(be_enqueue_poses(be, want_grad, /*zero_acc=*/true));
   CMAXB_TRY(be_run_scatter(be, true, adjoint_grad));
   return be_finish_eval(be, want_grad, contrast, grad);
 }

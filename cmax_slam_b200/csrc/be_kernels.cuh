@@ -115,8 +115,14 @@ __device__ __forceinline__ void be_pose_one(const Quat* __restrict__ knots0, con
 template <int N>
 __global__ void be_pose_kernel(const Quat* __restrict__ knots0, const double* __restrict__ x, int n_fixed,
                                const BeBatchTime* __restrict__ bt, long long nb, int want_grad, BePose* __restrict__ poses,
-                               int* __restrict__ idx_out) {
-  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+                               int* __restrict__ idx_out, float4* __restrict__ zero_a = nullptr, long long zero_na = 0,
+                               float4* __restrict__ zero_b = nullptr, long long zero_nb = 0) {
+  // the evaluation's accumulators are cleared here as well (one launch instead of a memset node per buffer)
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = tid; i < zero_na; i += nth) zero_a[i] = z4;
+  for (long long i = tid; i < zero_nb; i += nth) zero_b[i] = z4;
+  const long long b = tid;
   if (b >= nb) return;
   be_pose_one<N>(knots0, x, n_fixed, bt[b], want_grad, poses + b, idx_out + b);
 }
@@ -407,7 +413,8 @@ constexpr int kBeReduceThreads = 1024;
 template <int N>
 __device__ __forceinline__ void be_grad_reduce_knot(int kk, const int* __restrict__ idx, const int* __restrict__ seg_lo,
                                                     const int* __restrict__ seg_hi, const double* __restrict__ wgrad, int n_fixed,
-                                                    double inv_np, double* __restrict__ grad, double* s_red /*[warps*3]*/) {
+                                                    double inv_np, double* __restrict__ grad, double* s_red /*[warps*3]*/,
+                                                    double* __restrict__ host_grad = nullptr /* mapped host copy of the result */) {
   const int knot = kk + n_fixed;
   double a[3] = {0.0, 0.0, 0.0};
   for (int rel = 0; rel < N; ++rel) {
@@ -430,15 +437,17 @@ __device__ __forceinline__ void be_grad_reduce_knot(int kk, const int* __restric
     double s = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += s_red[w * 3 + threadIdx.x];
     grad[3 * kk + threadIdx.x] = s * inv_np;
+    if (host_grad) host_grad[3 * kk + threadIdx.x] = s * inv_np;
   }
 }
 
 template <int N>
 __global__ void __launch_bounds__(kBeReduceThreads)
 be_grad_reduce_kernel(const int* __restrict__ idx, const int* __restrict__ seg_lo, const int* __restrict__ seg_hi,
-                      const double* __restrict__ wgrad, long long nb, int n_fixed, double inv_np, double* __restrict__ grad) {
+                      const double* __restrict__ wgrad, long long nb, int n_fixed, double inv_np, double* __restrict__ grad,
+                      double* __restrict__ host_grad = nullptr) {
   __shared__ double s_red[(kBeReduceThreads / 32) * 3];
-  be_grad_reduce_knot<N>(blockIdx.x, idx, seg_lo, seg_hi, wgrad, n_fixed, inv_np, grad, s_red);
+  be_grad_reduce_knot<N>(blockIdx.x, idx, seg_lo, seg_hi, wgrad, n_fixed, inv_np, grad, s_red, host_grad);
 }
 
 // DENSE mode: reduce blurred bands against the blurred image.

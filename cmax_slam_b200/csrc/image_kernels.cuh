@@ -119,6 +119,7 @@ struct ReduceOut {
   unsigned int* ticket; // [n_planes]
   double* result;       // [n_planes][4]  contrast, g0, g1, g2
   double* mean;         // [n_planes]     mean of the blurred image (for the adjoint pass)
+  double* host_result = nullptr;   // optional mapped host copy of result[0] of plane 0 (no D2H copy on the stream)
   double* raw = nullptr;        // optional [n_planes][2]: the plain sums S1, S2 (row-band evaluation: summed across ranks by the caller)
   int sum_y0 = 0, sum_y1 = 0x7fffffff;   // rows whose pixels enter the sums (row-band evaluation: the band's own rows)
 };
@@ -323,6 +324,7 @@ blur_reduce_kernel(Src src, int W, int H, Taps taps, typename PixT<C>::type* out
       if constexpr (C == 4) for (int c = 0; c < 3; ++c) res[1 + c] = 2.0 * (t[5 + c] / Np - mean * (t[2 + c] / Np));
     }
     res[0] = contrast;
+    if (ro.host_result && h == 0) ro.host_result[0] = contrast;
     if (ro.raw) { ro.raw[2 * h] = S1; ro.raw[2 * h + 1] = S2; }
     ro.mean[h] = mean;
     ro.ticket[h] = 0u;

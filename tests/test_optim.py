@@ -55,13 +55,18 @@ def test_library_fe_solve_matches_restated_gsl_over_oracle(oracle):
         r = oracle.fe_eval(a, x, True)
         return -r["contrast"], -r["grad"]
 
-    x0 = np.array([0.3, -0.5, 1.0])
+    # Start point: GSL's Fletcher-Reeves is fragile under cost noise -- from (0.3, -0.5, 1.0) its line search sits on a knife
+    # edge at iteration 11 and reports "no progress" there in about 1 run of 6 on the device (whose cost varies by ~1e-8 run
+    # to run, f32 atomic order) and in 1 of 20 on the CPU oracle with 1e-8 relative noise injected
+    # (scratch/fr_noise_sensitivity.py, profiles/r02_fr_noise_sensitivity.txt).  From (0.4, -0.8, 1.8) all 20 noisy solves agree.
+    x0 = np.array([0.4, -0.8, 1.8])
     x_ref, st_ref = minimize_fr(f, fdf, x0)
     fe = AngVelEstimatorCMax(pk.width, pk.height, pk.K, pk.lut)
     fe.set_packet(pk.events, pk.t_ref_sec)
     x, st = fe.setupProblemAndOptimize(x0)
-    # The two cost functions agree to ~1e-9, but a line search is a chain of comparisons: a flipped branch changes
-    # the evaluation counts slightly, so the OUTCOME is compared (measured: same 24 iterations, omega equal to 2e-5).
+    # The two cost functions agree to ~1e-9, but a line search is a chain of comparisons and the device cost is not even
+    # reproducible run to run (f32 atomic order): a flipped branch changes the evaluation counts slightly, so the OUTCOME
+    # is compared.
     assert abs(st["iterations"] - st_ref["iterations"]) <= 5 and abs(st["f_evals"] - st_ref["f_evals"]) <= 15
     assert np.abs(x - x_ref).max() < 1e-2
     assert abs(st["cost_final"] - st_ref["cost_final"]) <= 1e-3 * abs(st_ref["cost_final"])
@@ -132,7 +137,7 @@ def test_fused_trials_on_device_same_outcome():
     pk = synth.fe_config("C1", scale=0.3)
     fe = AngVelEstimatorCMax(pk.width, pk.height, pk.K, pk.lut)
     fe.set_packet(pk.events, pk.t_ref_sec)
-    x0 = np.array([0.3, -0.5, 1.0])
+    x0 = np.array([0.4, -0.8, 1.8])      # a start point without a knife edge in the line search (see the test above)
     x, st = fe.setupProblemAndOptimize(x0)
     xf, stf = fe.setupProblemAndOptimize(x0, params=(0.1, 0.05, 50, 1e-3, 1e-4, 1))
     assert np.abs(x - xf).max() < 2e-3 and abs(st["iterations"] - stf["iterations"]) <= 3
