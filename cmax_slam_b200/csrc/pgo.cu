@@ -134,21 +134,25 @@ extern "C" int cmaxb_pgo_process_window(cmaxb_pgo* p, const cmaxb_event* events,
   auto ie = std::lower_bound(p->ang_vel.begin(), p->ang_vel.end(), p->t_av_end, [](const AngVel& a, cmaxb_stamp t) { return st_lt(a.t, t); });
   std::vector<AngVel> subset;
   if (ib < ie) subset.assign(ib, ie);
-  p->ang_vel.erase(p->ang_vel.begin(), ie);
+  const size_t n_erase = (size_t)(ie - p->ang_vel.begin());     // committed below, once nothing can fail any more
   r.n_ang_vel = (int)subset.size();
 
   // ---- processTimeWindow (:244-323)
   std::vector<cmaxb_stamp> st(subset.size()), pst(subset.size() + 1);
   std::vector<double> ws(3 * subset.size() + 3), pq(4 * subset.size() + 4);
   for (size_t i = 0; i < subset.size(); ++i) { st[i] = subset[i].t; for (int c = 0; c < 3; ++c) ws[3 * i + c] = subset[i].w[c]; }
-  int n_poses = 0;
-  CMAXB_TRY(cmaxb_traj_integrate_ang_vel(p->pose_latest_t, p->pose_latest_q, &p->ang_vel_prev.t, p->ang_vel_prev.w,
-                                         p->first_time_window ? 1 : 0, st.data(), ws.data(), (int)subset.size(), pst.data(), pq.data(), &n_poses));
-  r.n_frontend_poses = n_poses;
+  // everything that can reject the window runs on copies first: a failed call leaves the optimiser's state untouched
   const int num_new = cmaxb_traj_num_ctrl_poses(N, p->t_av_beg, p->t_av_end, p->cfg.dt_knots);
   if (num_new < 0) return num_new;
+  int n_poses = 0;
+  AngVel prev = p->ang_vel_prev;
+  CMAXB_TRY(cmaxb_traj_integrate_ang_vel(p->pose_latest_t, p->pose_latest_q, &prev.t, prev.w,
+                                         p->first_time_window ? 1 : 0, st.data(), ws.data(), (int)subset.size(), pst.data(), pq.data(), &n_poses));
+  r.n_frontend_poses = n_poses;
   std::vector<double> ctrl((size_t)4 * num_new);
   CMAXB_TRY(cmaxb_traj_fit_ctrl_poses(N, p->cfg.dt_knots, st_sec(p->t_av_beg), num_new, pst.data(), pq.data(), n_poses, ctrl.data()));
+  p->ang_vel_prev = prev;
+  p->ang_vel.erase(p->ang_vel.begin(), p->ang_vel.begin() + (long)n_erase);
   int first_new = 0;
   if (p->first_time_window) {
     p->idx_cp_opt_beg = (N == 4) ? 3 : 1;                                                       // (:259-263)
