@@ -63,8 +63,8 @@ fe_bin_count_kernel(const uint4* __restrict__ ev, long long n, int chunk, int W,
   if (bad) fe_flag_raise(flags, 1);
   if (dt_tab) {
     const int per = chunk / bs;
-    if ((int)threadIdx.x < per) {
-      const long long b = blockIdx.x * (long long)per + threadIdx.x;
+    for (int lb = threadIdx.x; lb < per; lb += kBinThreads) {     // (more than 256 batches per chunk when the batch size is < 8)
+      const long long b = blockIdx.x * (long long)per + lb;
       if (b < nb) {
         const long long b0 = b * bs;
         long long b1 = b0 + bs; if (b1 > n) b1 = n;

@@ -123,6 +123,18 @@ def test_fe_scatter_is_additive_over_packets(oracle):
     fe.close()
 
 
+@pytest.mark.parametrize("bs", [7, 100, 1024, 3000])
+def test_fe_batch_sizes_of_the_packet_preparation(oracle, bs):
+    """The binning's counting pass forms the batch time offsets when its chunk is a multiple of the batch size (7: more batches
+    per chunk than threads; 100: the reference's; 1024: two per chunk); 3000 exceeds the chunk: separate kernel."""
+    pk = synth.fe_config("C1", scale=0.2)
+    fe = _mk(pk, event_batch_size=bs)
+    a = oracle.fe_args(pk.events, pk.t_ref_sec, pk.lut, pk.width, pk.height, pk.K, batch_size=bs)
+    om = pk.omega_true + np.array([0.2, -0.1, 0.3])
+    _check(fe, oracle, a, om)
+    fe.close()
+
+
 def test_fe_edge_cases(oracle):
     from cmax_slam_b200._capi import CmaxbError
     from cmax_slam_b200.frontend import AngVelEstimatorCMax
