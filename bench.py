@@ -445,6 +445,10 @@ def run_ours(args, rank, world, local_rank):
         fe.exchange_close()
         barrier()
     e2e = bench_e2e(args, fe, stream, dev, rank, world, False, barrier, sampler, pkt, omega)
+    # the e2e loop left VIEWS of its (now released) device ring in the packet slots: put the resident packets back
+    for s_, p_ in enumerate(pkts):
+        fe.select_packet(s_)
+        fe.set_packet((pinned[s_].data_ptr(), n_ev), p_.t_ref_sec)
 
     # ---- dominant kernel: CUDA-event time of the fused launch (library profiler: serialised whole-GPU launches, L2 cold) -----
     fe.select_packet(0)
