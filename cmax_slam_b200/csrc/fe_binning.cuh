@@ -19,7 +19,7 @@ namespace cmaxb {
 constexpr int kBinTile = 32;          // source tile edge in pixels
 constexpr int kBinThreads = 256;
 constexpr int kBinChunk = 2048;       // events per CTA at most (8 per thread: ~490 CTAs for a 1M-event packet); rounded down to a multiple of the batch size
-constexpr int kBinMaxTiles = 6144;    // shared-memory histogram capacity: the scatter pass needs 2 x 4 B per tile within the 48 KB default limit (6144 x 8 = 48 KB; + 32 B static)
+constexpr int kBinMaxTiles = 6016;    // shared-memory histogram capacity: the scatter pass needs 2 x 4 B per tile + 40 B static within the 48 KB default limit
 
 __device__ __forceinline__ int bin_tile_of(uint4 e, int W, int H, int ntx) {
   int x = e.x & 0xffff, y = e.x >> 16;
