@@ -131,7 +131,7 @@ EXPORTS = [
     "cmaxb_pgo_create", "cmaxb_pgo_destroy", "cmaxb_pgo_push_ang_vel", "cmaxb_pgo_window", "cmaxb_pgo_process_window",
     "cmaxb_pgo_get_ctrl_poses", "cmaxb_be_last_eval_x",
     "cmaxb_last_error", "cmaxb_version", "cmaxb_device_count", "cmaxb_launch_count",
-    "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_fe_phase_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
+    "cmaxb_fe_profile", "cmaxb_fe_kernel_times", "cmaxb_fe_cta_times", "cmaxb_fe_phase_times", "cmaxb_be_profile", "cmaxb_be_kernel_times", "cmaxb_kernel_name",
 ]
 
 _lib = None
@@ -209,6 +209,7 @@ def lib():
     L.cmaxb_kernel_name.argtypes = [C.c_int]
     L.cmaxb_fe_profile.argtypes = [vp, C.c_int]
     L.cmaxb_fe_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
+    L.cmaxb_fe_cta_times.argtypes = [vp, dp, C.c_int, C.POINTER(C.c_int)]
     L.cmaxb_fe_phase_times.argtypes = [vp, dp]
     if not hasattr(L, "cmaxb_be_create"):
         raise RuntimeError("libcmax_b200.so is stale (no back-end symbols): rebuild with cmax_slam_b200/build.py --force")

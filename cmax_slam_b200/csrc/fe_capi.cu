@@ -234,8 +234,8 @@ static int fe_lane_prepare(cmaxb_fe* fe, int li) {
   CMAXB_CUDA_TRY(cudaHostAlloc((void**)&L.h_fault, sizeof(unsigned long long) * 8, cudaHostAllocMapped));
   CMAXB_CUDA_TRY(cudaHostGetDevicePointer((void**)&L.d_fault, L.h_fault, 0));
   L.h_fault[0] = 0;
-  CMAXB_TRY(dev_alloc(&L.d_phase, 16));
-  CMAXB_CUDA_TRY(cudaMemset(L.d_phase, 0, sizeof(unsigned long long) * 16));
+  CMAXB_TRY(dev_alloc(&L.d_phase, 16 + 4 * kCtaTraceMax));
+  CMAXB_CUDA_TRY(cudaMemset(L.d_phase, 0, sizeof(unsigned long long) * (16 + 4 * kCtaTraceMax)));
   if (fe->use_tma) {
     for (int m = 0; m < 2; ++m)
       for (int b = 0; b < 2; ++b)
@@ -1048,6 +1048,23 @@ extern "C" int cmaxb_fe_phase_times(cmaxb_fe* fe, double* us10) {
   unsigned long long ph[16];
   CMAXB_CUDA_TRY(cudaMemcpy(ph, fe->lanes[0].d_phase, sizeof(ph), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 10; ++i) us10[i] = (ph[i] && ph[0]) ? (double)(ph[i] - ph[0]) * 1e-3 : -1.0;
+  return CMAXB_OK;
+}
+// profiling aid: per-CTA stamps of the last profiled whole-grid launch, us since kernel entry: out[cta][4] = scatter end, image
+// phase end, gather start, gather end (0 where not reached); *n_ctas = CTAs of the launch (at most 1024 are traced)
+extern "C" int cmaxb_fe_cta_times(cmaxb_fe* fe, double* out, int max_ctas, int* n_ctas) {
+  if (!fe || !out || !n_ctas) return set_error(CMAXB_ERR_INVALID, "null argument");
+  fe->pending = true;
+  CMAXB_TRY(fe_drain(fe));
+  std::vector<unsigned long long> ph(16 + 4 * kCtaTraceMax);
+  CMAXB_CUDA_TRY(cudaMemcpy(ph.data(), fe->lanes[0].d_phase, sizeof(unsigned long long) * ph.size(), cudaMemcpyDeviceToHost));
+  const int n = std::min(std::min(fe->grid[0], kCtaTraceMax), max_ctas);
+  for (int c = 0; c < n; ++c)
+    for (int w = 0; w < 4; ++w) {
+      const unsigned long long v = ph[16 + 4 * c + w];
+      out[4 * c + w] = (v && ph[0]) ? (double)(v - ph[0]) * 1e-3 : 0.0;
+    }
+  *n_ctas = n;
   return CMAXB_OK;
 }
 extern "C" int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms, uint64_t* launches) {

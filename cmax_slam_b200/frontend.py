@@ -181,6 +181,13 @@ class AngVelEstimatorCMax:
         _capi.check(self._L.cmaxb_fe_phase_times(self._h, _capi.dptr(t)))
         return t
 
+    def cta_times(self):
+        """Fused kernel (profiling on): per-CTA us since kernel entry, array [ctas, 4] = scatter end, image end, gather start, gather end."""
+        out = np.zeros((1024, 4))
+        n = C.c_int(0)
+        _capi.check(self._L.cmaxb_fe_cta_times(self._h, _capi.dptr(out), 1024, C.byref(n)))
+        return out[: n.value].copy()
+
     def kernel_times(self):
         ms = np.zeros(_capi.K_COUNT)
         n = np.zeros(_capi.K_COUNT, np.uint64)

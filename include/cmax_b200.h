@@ -485,6 +485,9 @@ enum {
 };
 int cmaxb_fe_profile(cmaxb_fe* fe, int enable);
 int cmaxb_fe_kernel_times(cmaxb_fe* fe, double* ms /*CMAXB_K_COUNT*/, uint64_t* launches /*CMAXB_K_COUNT*/);
+/* profiling aid: per-CTA %globaltimer stamps of the last profiled whole-grid fused launch, us since kernel entry:
+ * out[cta][4] = scatter end, image phase end, gather start, gather end; *n_ctas = CTAs traced (<= max_ctas, <= 1024) */
+int cmaxb_fe_cta_times(cmaxb_fe* fe, double* out, int max_ctas, int* n_ctas);
 /* Fused evaluation kernel, profiling enabled: microseconds from kernel entry (CTA 0) to the phase boundaries of the LAST
  * synchronous evaluation: [1] scatter end, [2] grid barrier, [3] image phase end, [4] grid barrier, [5] gather end,
  * [6] last CTA starts the final sums, [7] result rows stored (all CTA 0 except [6], [7]); [8] / [9]: the SLOWEST CTA's
