@@ -546,10 +546,10 @@ def bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt
     copy_stream = torch.cuda.Stream(device=dev)       # uploads on their own stream: they overlap packet preparation and evaluation
     st.attach_device(dev.index, copy_stream.cuda_stream, ring_events=8 * per_packet)
     slots = fe._slots if hasattr(fe, "_slots") else None
-    nslots = 4
+    nslots = int(os.environ.get("CMAXB_E2E_SLOTS", str(max(2, min(getattr(args, "rotation", 6), 6)))))   # packet slots in flight (the handle has `rotation` of them)
     FL = EventStream.PUSH_BORROW | EventStream.PUSH_SORTED
     state = {"msg": 0, "slot": 0, "out": 0, "packets": 0, "h2d": 0}
-    depth = int(os.environ.get("CMAXB_E2E_DEPTH", "3"))
+    depth = int(os.environ.get("CMAXB_E2E_DEPTH", str(max(2, nslots - 1))))    # evaluations outstanding before the oldest is fetched (< slots)
     no_eval = os.environ.get("CMAXB_E2E_SKIP") == "eval"        # diagnostics: uploads + packet preparation only
 
     # The per-tick sequence below goes through the C ABI directly (ctypes calls with pre-built argument objects): the
@@ -663,7 +663,7 @@ def bench_e2e(args, fe, stream, dev, rank, world, use_p2p, barrier, sampler, pkt
                     "cmaxb_stream_next_packet_device (overlapping 1M-event packet = ring view) -> cmaxb_fe_set_packet_view (validate, "
                     "batch times, binning) -> cmaxb_fe_eval_launch / _fetch; one packet per step; the reference re-copies each packet "
                     "out of its host vector (ang_vel_estimator.cpp:137-147) -- here every event crosses PCIe once",
-            "events_per_packet": per_packet, "new_events_per_step": h2d / 16}
+            "events_per_packet": per_packet, "new_events_per_step": h2d / 16, "pipeline_depth": depth, "packet_slots": nslots}
 
 
 def bench_configs(args, rank, world, local_rank, dev, stream, peak, peak_src, barrier):
