@@ -65,10 +65,31 @@ class EventStore {
   // false when the store does not reach the end of the window yet
   bool window_events(cmaxb_stamp t_beg, cmaxb_stamp t_end, Span* out) {
     const int rc = cmaxb_stream_window_events(s_, t_beg, t_end, &out->data, &out->size);
-    if (rc == CMAXB_ERR_STATE) return false;
+    if (rc == 1) return false;                  // not an error: nothing consumed (CMAXB_ERR_STATE = inconsistent store, thrown below)
     check(rc, "cmaxb_stream_window_events");
     return true;
   }
+  // ---- device-resident store: every event crosses PCIe once, packets come out as views of a device ring --------------
+  // before the first push; cuda_stream = the stream the copies run on (its own, not the evaluator's: they overlap the kernels)
+  void attach_device(int device, void* cuda_stream, size_t ring_events = 0) {
+    check(cmaxb_stream_attach_device(s_, device, cuda_stream, ring_events), "cmaxb_stream_attach_device");
+  }
+  // flags: CMAXB_PUSH_BORROW (page-locked message, referenced in place until released() passes it), CMAXB_PUSH_SORTED
+  int push(const void* events, size_t n, int flags) {
+    int ready = 0;
+    check(cmaxb_stream_push_ex(s_, static_cast<const cmaxb_event*>(events), n, flags, &ready), "cmaxb_stream_push_ex");
+    return ready;
+  }
+  // device pointer + count for cmaxb_fe_set_packet_view; call wait_copied(evaluator stream) before using it
+  bool next_packet_device(const cmaxb_event** dev_events, size_t* n, cmaxb_stamp* time_packet, bool* span_too_long = nullptr) {
+    int flag = 0;
+    const int rc = cmaxb_stream_next_packet_device(s_, dev_events, n, time_packet, &flag);
+    if (rc == 1) return false;
+    check(rc, "cmaxb_stream_next_packet_device");
+    if (span_too_long) *span_too_long = flag != 0;
+    return true;
+  }
+  void wait_copied(void* consumer_stream) { check(cmaxb_stream_wait_copied(s_, consumer_stream), "cmaxb_stream_wait_copied"); }
   cmaxb_stream* handle() const { return s_; }
 
  private:

@@ -38,6 +38,10 @@ extern "C" int drive(const cmaxb_event* ev, size_t n, size_t msg, double dt_ang_
         *n_windows += solver.run_ready_windows(store, [](const cmaxb_pgo_report&) {});
       }
     }
+    // a window the store does not reach yet is "not ready" (false), not an error
+    Span far;
+    cmaxb_stamp tb{ev[n - 1].sec + 10, ev[n - 1].nsec}, te{ev[n - 1].sec + 11, ev[n - 1].nsec};
+    if (store.window_events(tb, te, &far)) return -101;
     std::vector<double> q = solver.ctrl_poses_xyzw();
     *n_ctrl = (int)(q.size() / 4);
     if ((int)q.size() > 4 * cap) return -100;
