@@ -165,3 +165,79 @@ def test_time_slabs_are_batch_aligned_and_cover_the_window():
         # the reference's trailing single-event batch can only ever sit in the LAST slab
         for b, e in sl[:-1]:
             assert (e - b) % bs == 0 or e == n      # a ragged slab is always the global tail
+
+
+# ---- time-sharded back-end window: the orchestration of ShardedEventWarper over gloo, world 2, with a numpy stand-in for the
+# device warper (the kernels themselves are covered by tests/test_gpu_sharded.py and tests/test_gpu_multi.py)
+_SHARD_WORKER = r'''
+import sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from cmax_slam_b200.dist import ShardedEventWarper
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=rank, world_size=2)
+
+class FakeWarper:
+    """IL = votes of the slab's events at pixel (x + round(10 * p0)) mod W; contrast = variance of the (summed) IL;
+    partial gradient = sum over OWN events of IL[pixel] * (x, y, 1) -- needs the SUMMED IL, like the adjoint gather."""
+    pano_width, pano_height, blur_radius = 32, 16, 4
+    def set_window(self, events, knots, t0, dt, n_fixed, tnext, IGp, alpha):
+        self.ev = events; self.n_params = 3
+    def _pix(self, x):
+        return (self.ev["y"] % 16) * 32 + (self.ev["x"] + int(round(10 * x[0]))) % 32
+    def eval_begin(self, x, want_grad):
+        self.x = np.asarray(x, float); self.want = want_grad
+        self.plane = torch.zeros(32 * 16, dtype=torch.float32)
+        np.add.at(self.plane.numpy(), self._pix(self.x), 1.0)
+    def il_plane_tensor(self):
+        return self.plane
+    def eval_end_launch(self):
+        il = self.plane.numpy().astype(np.float64)
+        self.c = float(il.var())
+        w = il[self._pix(self.x)]
+        self.g = torch.tensor([float((w * self.ev["x"]).sum()), float((w * self.ev["y"]).sum()), float(w.sum())], dtype=torch.float64)
+    def grad_tensor(self):
+        return self.g
+    def eval_end_fetch(self):
+        return self.c, (self.g.numpy().copy() if self.want else None)
+    def eval_end(self):
+        self.eval_end_launch(); return self.eval_end_fetch()
+
+rng = np.random.default_rng(5)
+ev = np.zeros(1001, dtype=[("x", np.int64), ("y", np.int64)])
+ev["x"] = rng.integers(0, 32, 1001); ev["y"] = rng.integers(0, 16, 1001)
+sh = ShardedEventWarper(FakeWarper(), mode="plane")
+sh.set_window(ev, None, 0, 0, 1, None, None, 0.5, batch_size=100)
+x = np.array([0.3, 0.0, 0.0])
+c, g = sh.eval(x, True)
+c_v, g_v = sh.eval(x, False)
+one = FakeWarper(); one.set_window(ev, None, 0, 0, 1, None, None, 0.5); one.eval_begin(x, True); c1, g1 = one.eval_end()
+assert sh.slab == ((0, 600) if rank == 0 else (600, 1001)), sh.slab      # 11 batches of 100: 6 + 5
+assert abs(c - c1) < 1e-12 and abs(c_v - c1) < 1e-12 and g_v is None
+assert np.allclose(g, g1, rtol=1e-12), (g, g1)
+try:
+    sh.mode = "p2p"; sh.eval(x, True)
+    raise SystemExit("p2p without connect() must be refused")
+except RuntimeError:
+    pass
+sh.mode = "bands"                              # 16 rows / 2 ranks = 8 < 2 r + 1 = 9: refused
+try:
+    sh._use_bands(2)
+    raise SystemExit("bands thinner than the halo must be refused")
+except ValueError:
+    pass
+dist.barrier(); dist.destroy_process_group()
+print("ok")
+'''
+
+
+def test_time_sharded_orchestration_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_SHARD_WORKER)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
