@@ -341,40 +341,54 @@ __device__ __forceinline__ void be_gather_range(const BeGeom& g, const BePose* _
     long long j1 = j0 + g.m;
     if (b == g.nb - 1 || j1 > g.n_visit) j1 = g.n_visit;
     double v0 = 0, v1 = 0, v2 = 0;
-    for (long long j = j0 + lane; j < j1; j += 32) {
-      const float4 ca4 = __ldcg(cache.a + j);
-      const int cell = __float_as_int(ca4.x);
-      if (cell < 0) continue;
-      const float2 cb2 = __ldcg(cache.b + j);
-      float dd[2][3];
-      {
-        const float rx = ca4.w, ry = cb2.x, rz = cb2.y;
-        const float s2 = rx * rx + rz * rz, rho2 = s2 + ry * ry;
-        const float sr = sqrtf(s2);
-        const float i_s2 = __fdividef(1.0f, s2), i_r2s = __fdividef(1.0f, rho2 * sr);
-        const float ffx = (float)g.fx, ffy = (float)g.fy;
-        const float j00 = ffx * rz * i_s2, j02 = -ffx * rx * i_s2;
-        const float j10 = -ffy * rx * ry * i_r2s, j11 = ffy * sr * __fdividef(1.0f, rho2), j12 = -ffy * ry * rz * i_r2s;
-        // dpm_ddrot = dpm_drb * (-[ray]x)
-        dd[0][0] = j02 * ry;               dd[0][1] = j00 * rz - j02 * rx;   dd[0][2] = -j00 * ry;
-        dd[1][0] = -j11 * rz + j12 * ry;   dd[1][1] = j10 * rz - j12 * rx;   dd[1][2] = -j10 * ry + j11 * rx;
+    // kGatherIl x 32 events per pass: the cache records of both first, then both adjoint-image cells, then the arithmetic
+    // (the kernel waits on loads: 12 stalled warps per issue in ncu; 4 x 32 cost too many registers, profiles/r02k_*)
+    constexpr int kGatherIl = 2;
+    for (long long jb = j0; jb < j1; jb += 32 * kGatherIl) {
+      float4 ca4[kGatherIl]; float2 cb2[kGatherIl]; float4 q4[kGatherIl]; int cell[kGatherIl];
+#pragma unroll
+      for (int k = 0; k < kGatherIl; ++k) {
+        const long long j = jb + k * 32 + lane;
+        ca4[k] = make_float4(__int_as_float(-1), 0.f, 0.f, 0.f);
+        cb2[k] = make_float2(0.f, 0.f);
+        if (j < j1) { ca4[k] = __ldcg(cache.a + j); cb2[k] = __ldcg(cache.b + j); }   // (b is only meaningful when the cell is valid)
       }
-      const float4 ca = make_float4(ca4.y, ca4.z, dd[0][0], dd[0][1]);
-      const float4 cb = make_float4(dd[0][2], dd[1][0], dd[1][1], dd[1][2]);
-      double g00, g01, g10, g11;
-      if (QUAD) {
-        const float4 q = __ldcg(GQ + cell);
-        g00 = q.x; g01 = q.y; g10 = q.z; g11 = q.w;
-      } else {
-        const float* p = G + cell;
-        g00 = __ldcg(p); g01 = __ldcg(p + 1); g10 = __ldcg(p + g.W); g11 = __ldcg(p + g.W + 1);
+#pragma unroll
+      for (int k = 0; k < kGatherIl; ++k) {
+        cell[k] = __float_as_int(ca4[k].x);
+        q4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cell[k] >= 0) {
+          if (QUAD) q4[k] = __ldcg(GQ + cell[k]);
+          else {
+            const float* p = G + cell[k];
+            q4[k] = make_float4(__ldcg(p), __ldcg(p + 1), __ldcg(p + g.W), __ldcg(p + g.W + 1));
+          }
+        }
       }
-      const double dx = ca.x, dy = ca.y;
-      const double a = (1.0 - dy) * (g01 - g00) + dy * (g11 - g10);
-      const double bb = (1.0 - dx) * (g10 - g00) + dx * (g11 - g01);
-      v0 += a * (double)ca.z + bb * (double)cb.y;
-      v1 += a * (double)ca.w + bb * (double)cb.z;
-      v2 += a * (double)cb.x + bb * (double)cb.w;
+#pragma unroll
+      for (int k = 0; k < kGatherIl; ++k) {
+        if (cell[k] < 0) continue;
+        float dd[2][3];
+        {
+          const float rx = ca4[k].w, ry = cb2[k].x, rz = cb2[k].y;
+          const float s2 = rx * rx + rz * rz, rho2 = s2 + ry * ry;
+          const float sr = sqrtf(s2);
+          const float i_s2 = __fdividef(1.0f, s2), i_r2s = __fdividef(1.0f, rho2 * sr);
+          const float ffx = (float)g.fx, ffy = (float)g.fy;
+          const float j00 = ffx * rz * i_s2, j02 = -ffx * rx * i_s2;
+          const float j10 = -ffy * rx * ry * i_r2s, j11 = ffy * sr * __fdividef(1.0f, rho2), j12 = -ffy * ry * rz * i_r2s;
+          // dpm_ddrot = dpm_drb * (-[ray]x)
+          dd[0][0] = j02 * ry;               dd[0][1] = j00 * rz - j02 * rx;   dd[0][2] = -j00 * ry;
+          dd[1][0] = -j11 * rz + j12 * ry;   dd[1][1] = j10 * rz - j12 * rx;   dd[1][2] = -j10 * ry + j11 * rx;
+        }
+        const double g00 = q4[k].x, g01 = q4[k].y, g10 = q4[k].z, g11 = q4[k].w;
+        const double dx = ca4[k].y, dy = ca4[k].z;
+        const double a = (1.0 - dy) * (g01 - g00) + dy * (g11 - g10);
+        const double bb = (1.0 - dx) * (g10 - g00) + dx * (g11 - g01);
+        v0 += a * (double)dd[0][0] + bb * (double)dd[1][0];
+        v1 += a * (double)dd[0][1] + bb * (double)dd[1][1];
+        v2 += a * (double)dd[0][2] + bb * (double)dd[1][2];
+      }
     }
     v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
     if (lane < 3 * N) {
